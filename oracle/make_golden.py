@@ -1,0 +1,168 @@
+"""Generate the frozen golden vectors under ``tests/golden/`` by running the REAL reference.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container only (needs /root/reference, loaded through
+``oracle/refshim.py``); the resulting ``.npz`` files are committed so that the GPU box -- which has no
+reference tree -- can check both the oracle and the CUDA path against outputs of the reference itself.
+
+    python -m oracle.make_golden            # writes tests/golden/kernels.npz and tests/golden/gp_*.npz
+
+While generating, every vector is also compared against the numpy restatement in ``oracle/`` and the
+largest deviation is printed (the restatement must agree to a few ulps).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import covfuncs as ocf  # noqa: E402
+from oracle import gp as ogp  # noqa: E402
+from oracle import refshim  # noqa: E402
+from tests.golden import cases as gcases  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+# ----------------------------------------------------------------------------------------
+# spec -> reference objects
+# ----------------------------------------------------------------------------------------
+def ref_base(base):
+    from linpde_gp.randprocs import covfuncs
+
+    kind = base["kind"]
+    if kind == "tensor_product":
+        return covfuncs.TensorProduct(*(ref_base(f) for f in base["factors"]))
+    shape = tuple(base["input_shape"])
+    ls = base["lengthscales"]
+    ls = np.asarray(ls, dtype=float) if isinstance(ls, (list, tuple)) else float(ls)
+    if kind == "matern":
+        return covfuncs.Matern(shape, nu=base["nu"], lengthscales=ls)
+    if kind == "expquad":
+        return covfuncs.ExpQuad(shape, lengthscales=ls)
+    raise ValueError(kind)
+
+
+def ref_kernel(kernel):
+    k = ref_base(kernel["base"])
+    if kernel.get("scale") is not None:
+        k = kernel["scale"] * k
+    return k
+
+
+def ref_op(L, input_shape):
+    from linpde_gp.linfuncops import SumLinearFunctionOperator, diffops
+
+    if L is None:
+        return None
+    summands = []
+    for scalar, (kind, payload) in L:
+        if kind == "wl":
+            op = diffops.WeightedLaplacian(np.asarray(payload, dtype=float))
+        elif kind == "dd":
+            op = diffops.DirectionalDerivative(np.asarray(payload, dtype=float))
+        else:
+            assert len(payload) == 1 and payload[0][1] == 1.0
+            op = diffops.PartialDerivative(diffops.MultiIndex(payload[0][0]))
+        if scalar != 1.0:
+            op = scalar * op
+        summands.append(op)
+    if len(summands) == 1:
+        return summands[0]
+    return SumLinearFunctionOperator(*summands)
+
+
+def ref_L0kL1(spec):
+    k = ref_kernel(spec["kernel"])
+    shape = gcases.kernel_input_shape(spec["kernel"])
+    L0, L1 = ref_op(spec["L0"], shape), ref_op(spec["L1"], shape)
+    kk = L1(k, argnum=1) if L1 is not None else k
+    return L0(kk, argnum=0) if L0 is not None else kk
+
+
+# ----------------------------------------------------------------------------------------
+def make_kernels():
+    out = {}
+    specs = gcases.build_cases()
+    worst = 0.0
+    for spec in specs:
+        name = spec["name"]
+        shape = gcases.kernel_input_shape(spec["kernel"])
+        X = gcases.sobol_points(shape)
+        X0, X1 = X[:32], X
+        kref = ref_L0kL1(spec)
+        K = np.asarray(kref.matrix(X0, X1))
+        diag = np.asarray(kref(X0, None))
+        # heat test-case style check of the un-flattened call too
+        assert K.shape == (32, 128)
+        o_op0, o_op1 = gcases.spec_to_oracle_op(spec["L0"]), gcases.spec_to_oracle_op(spec["L1"])
+        Ko = ocf.matrix(spec["kernel"], o_op0, o_op1, X0, X1)
+        do = ocf.diagonal(spec["kernel"], o_op0, o_op1, X0)
+        scale = max(np.max(np.abs(K)), 1e-300)
+        err = max(np.max(np.abs(K - Ko)) / scale, np.max(np.abs(diag - do)) / scale)
+        worst = max(worst, err)
+        print(f"{name:42s} type={type(kref).__name__:48s} max|K|={scale:10.3e} oracle-ref rel {err:.2e}")
+        out[f"{name}__K"] = K
+        out[f"{name}__diag"] = np.broadcast_to(diag, (32,)).copy()
+    out["__specs__"] = np.frombuffer(json.dumps(specs).encode(), dtype=np.uint8)
+    np.savez(os.path.join(GOLDEN, "kernels.npz"), **out)
+    print(f"kernels.npz: {len(specs)} cases, worst oracle-vs-reference deviation {worst:.2e}")
+    return worst
+
+
+def make_gp():
+    worst = 0.0
+    for name, problem in ogp.golden_problems().items():
+        res = run_reference_gp(problem)
+        ores = ogp.solve(problem)
+        for key in ("w", "mean", "var", "cov"):
+            sc = max(np.max(np.abs(res[key])), 1e-300)
+            err = np.max(np.abs(res[key] - ores[key])) / sc
+            worst = max(worst, err)
+            print(f"{name:28s} {key:5s} oracle-ref rel {err:.2e}")
+        np.savez(
+            os.path.join(GOLDEN, f"gp_{name}.npz"),
+            problem=np.frombuffer(json.dumps(problem).encode(), dtype=np.uint8),
+            **res,
+        )
+    return worst
+
+
+def run_reference_gp(problem):
+    """Run the unmodified reference: prior.condition_on_observations(...) block by block."""
+    pn, lg = refshim.load()
+    from linpde_gp import functions
+
+    kernel = problem["kernel"]
+    shape = gcases.kernel_input_shape(kernel)
+    k = ref_kernel(kernel)
+    prior = pn.randprocs.GaussianProcess(functions.Zero(input_shape=shape), k)
+    post = prior
+    for blk in problem["blocks"]:
+        X = np.asarray(blk["X"], dtype=float)
+        Y = np.asarray(blk["Y"], dtype=float)
+        L = ref_op(blk["L"], shape)
+        b = None
+        if blk.get("noise_var") is not None:
+            nv = np.asarray(blk["noise_var"], dtype=float)
+            b = pn.randvars.Normal(np.zeros_like(Y), pn.linops.Scaling(np.broadcast_to(nv, Y.shape).copy()))
+        post = post.condition_on_observations(Y, X=X, L=L, b=b)
+    Xt = np.asarray(problem["Xt"], dtype=float)
+    mean = np.asarray(post.mean(Xt))
+    var = np.asarray(post.cov(Xt, None))
+    Xc = Xt[: problem.get("n_cov", 16)]
+    cov = np.asarray(post.cov.matrix(Xc))  # the path GaussianProcess.__call__ takes (pn _gaussian_process.py:75-79)
+    w = np.asarray(post.representer_weights)
+    gram = np.asarray(post.gram.todense())
+    return {"w": w, "mean": mean, "var": var, "cov": cov, "gram": gram}
+
+
+if __name__ == "__main__":
+    refshim.load()
+    w1 = make_kernels()
+    w2 = make_gp()
+    print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}")

@@ -1,0 +1,98 @@
+"""The oracle (numpy restatement, ``oracle/``) against the frozen outputs of the REAL reference
+(``tests/golden/*.npz``, produced by ``oracle/make_golden.py``) and the reference's doctest known answers."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import covfuncs as ocf
+from oracle import gp as ogp
+from tests.golden import cases as gcases
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+_K = np.load(os.path.join(GOLDEN, "kernels.npz"))
+SPECS = json.loads(bytes(_K["__specs__"]).decode())
+
+
+@pytest.mark.parametrize("spec", SPECS, ids=[s["name"] for s in SPECS])
+def test_kernel_matrix_matches_reference(spec):
+    shape = gcases.kernel_input_shape(spec["kernel"])
+    X = gcases.sobol_points(shape)
+    K_ref, d_ref = _K[spec["name"] + "__K"], _K[spec["name"] + "__diag"]
+    L0, L1 = gcases.spec_to_oracle_op(spec["L0"]), gcases.spec_to_oracle_op(spec["L1"])
+    K = ocf.matrix(spec["kernel"], L0, L1, X[:32], X)
+    d = ocf.diagonal(spec["kernel"], L0, L1, X[:32])
+    scale = np.max(np.abs(K_ref))
+    # the restatement follows the reference operation by operation: a few ulps at most
+    assert np.max(np.abs(K - K_ref)) <= 4e-16 * scale
+    assert np.max(np.abs(d - d_ref)) <= 4e-16 * scale
+
+
+def test_generated_case_list_is_the_frozen_one():
+    assert json.loads(json.dumps(gcases.build_cases())) == SPECS
+
+
+def test_doctest_known_answers():
+    # pn/randprocs/covfuncs/_matern.py:89-96
+    k = {"scale": None, "base": {"kind": "matern", "input_shape": (), "nu": 2.5, "lengthscales": 0.1}}
+    K = ocf.matrix(k, None, None, np.linspace(0, 1, 3))
+    np.testing.assert_allclose(K[0], [1.0, 7.50933789e-04, 3.69569622e-08], rtol=1e-8)
+    # pn/randprocs/covfuncs/_exponentiated_quadratic.py:45-52
+    k = {"scale": None, "base": {"kind": "expquad", "input_shape": (), "lengthscales": 0.1}}
+    K = ocf.matrix(k, None, None, np.linspace(0, 1, 3))
+    np.testing.assert_allclose(K[0], [1.0, 3.72665317e-06, 1.92874985e-22], rtol=1e-8)
+
+
+def test_matern_derivative_polynomial_table():
+    """the table dumped from ``half_integer_matern_derivative_polynomial``."""
+    from fractions import Fraction as F
+
+    assert ocf.matern_derivative_polynomial(1, 4) == (F(-3), F(1))
+    assert ocf.matern_derivative_polynomial(2, 2) == (F(-1, 3), F(-1, 3), F(1, 3))
+    assert ocf.matern_derivative_polynomial(2, 4) == (F(1), F(-5, 3), F(1, 3))
+    assert ocf.matern_derivative_polynomial(3, 4) == (F(1, 5), F(1, 5), F(-2, 5), F(1, 15))
+
+
+def test_product_expquad_equals_ard_expquad():
+    """tests/linpde_gp/randprocs/kernels/test_tensor_product.py:39-47."""
+    X = gcases.sobol_points((3,))
+    ls = [0.8, 1.1, 1.7]
+    tp = {"scale": None, "base": {"kind": "tensor_product", "factors": [{"kind": "expquad", "input_shape": (), "lengthscales": l} for l in ls]}}
+    ard = {"scale": None, "base": {"kind": "expquad", "input_shape": (3,), "lengthscales": ls}}
+    np.testing.assert_allclose(ocf.matrix(tp, None, None, X), ocf.matrix(ard, None, None, X), rtol=1e-13, atol=1e-300)
+
+
+GP_FILES = sorted(glob.glob(os.path.join(GOLDEN, "gp_*.npz")))
+
+
+@pytest.mark.parametrize("path", GP_FILES, ids=[os.path.basename(p)[3:-4] for p in GP_FILES])
+def test_gp_conditioning_matches_reference(path):
+    g = np.load(path)
+    problem = json.loads(bytes(g["problem"]).decode())
+    res = ogp.solve(problem)
+    np.testing.assert_allclose(res["gram"], g["gram"], rtol=0, atol=4e-16 * np.max(np.abs(g["gram"])))
+    for key, tol in (("mean", 1e-9), ("var", 1e-8), ("cov", 1e-8)):
+        sc = np.max(np.abs(g[key]))
+        assert np.max(np.abs(res[key] - g[key])) <= tol * sc, key
+
+
+def test_iterative_equals_batch_conditioning():
+    """tests/linpde_gp/randprocs/test_posterior_gp.py:152-162 (iterative block conditioning == one shot)."""
+    prob = ogp.golden_problems()["expquad_iterative"]
+    it = ogp.solve(prob)
+    X = np.concatenate([np.asarray(b["X"]) for b in prob["blocks"]])
+    Y = np.concatenate([np.asarray(b["Y"]) for b in prob["blocks"]])
+    nv = np.concatenate([np.full(len(b["Y"]), b["noise_var"] or 0.0) for b in prob["blocks"]])
+    one = dict(prob, blocks=[{"X": X.tolist(), "Y": Y.tolist(), "L": None, "noise_var": nv.tolist()}])
+    ob = ogp.solve(one)
+    for key in ("mean", "var", "cov"):
+        np.testing.assert_allclose(it[key], ob[key], rtol=1e-7, atol=1e-12)
+
+
+def test_not_positive_definite_raises():
+    from oracle import linalg as ola
+
+    with pytest.raises(np.linalg.LinAlgError):
+        ola.cholesky_lower(np.array([[1.0, 2.0], [2.0, 1.0]]))
