@@ -1,0 +1,184 @@
+/*
+ * liblpgp -- C ABI of the B200-native GP-PDE conditioning hot path (sm_100a CUDA, FP64).
+ *
+ * This is the drop-in boundary for the ONE path of marvinpfoertner/linpde-gp this repository accelerates
+ * (BASELINE.json:north_star).  The reference is pure Python and has no FFI; each entry
+ * point below names the reference method(s) whose numerics it replaces (paths relative to the reference
+ * tree, "pn" = probnum/src/probnum).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer except `desc` / `blocks` (host structs) is a DEVICE pointer to FP64 data, row-major (C order),
+ *     leading dimension `ld*` in elements; the caller owns all buffers (torch CUDA tensors in the Python host);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous on that
+ *     stream unless stated otherwise; the library keeps no hidden device allocations;
+ *   - return value: 0 ok; >0 LAPACK-style info (leading minor of that order is not positive definite ->
+ *     the Python host raises numpy.linalg.LinAlgError like pn/linops/_linear_operator.py:823-839);
+ *     <0 : -k = argument k invalid (-> ValueError);  <= -1000 : -(1000+e) = CUDA runtime error e
+ *     (-> RuntimeError).  Only lower-triangular ("L L^T", row-major) factors are produced: the row-major
+ *     lower factor is bit-identical in memory to LAPACK's column-major upper factor that the reference
+ *     requests (pn/linops/_linear_operator.py:303-307).
+ */
+#ifndef LPGP_H_
+#define LPGP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPGP_MAX_DIM 4
+#define LPGP_MAX_COEF 512
+
+/* dimension types of the (product-form) kernel descriptor */
+#define LPGP_DIM_MATERN 0  /* half-integer Matern factor:  v = s*|dx|, weight exp(-v),  s = sqrt(2 nu)/ell   */
+#define LPGP_DIM_EXPQUAD 1 /* exponentiated-quadratic factor: v = dx/ell (signed), weight exp(-v^2/2)          */
+
+/* output modes of lpgp_gram */
+#define LPGP_GRAM_FULL 0  /* every entry of the n0 x n1 block                                             */
+#define LPGP_GRAM_LOWER 1 /* square symmetric block: only tiles intersecting the lower triangle are written */
+
+/*
+ * Flat description of  (L0 k L1^*)(x, x')  for product-form kernels, produced by the Python host from the
+ * reference-style objects (covfuncs.TensorProduct / ExpQuad / Matern  x  linfuncops.diffops.*):
+ *
+ *   value(x, x') = exp(-sum_d g_d) * sum_{b_0..b_{d-1}} coef[b_0,...,b_{d-1}] * prod_d basis_d[b_d]
+ *
+ *   Matern dim : u = s_d (x_d - x'_d), v = |u|, g_d = v,      basis = [1, v, .., v^(nb-1)] (+ [u, u v, .., u v^(nb-1)] if has_odd)
+ *   ExpQuad dim: v = (x_d - x'_d)/ell_d,        g_d = v^2/2,  basis = [1, v, .., v^(nb-1)]
+ *
+ * which is the closed form of   sigma^2 sum_{alpha in L0, beta in L1} c_alpha c_beta prod_d d^alpha_d d'^beta_d k_d
+ * evaluated by the reference in src/linpde_gp/randprocs/covfuncs/linfuncops/diffops/_tensor_product.py:84-119
+ * with 1-D factors from diffops/_matern.py:17-639 and diffops/_expquad.py:12-432, and of the base kernels
+ * pn/randprocs/covfuncs/_matern.py:175-195, _exponentiated_quadratic.py:89-100.
+ * `coef` is a dense C-order tensor of shape (nbtot_0, .., nbtot_{d-1}), nbtot_d = nbasis_d * (1 + has_odd_d).
+ */
+typedef struct lpgp_kernel_desc {
+  int32_t d;                      /* input dimension, 1..LPGP_MAX_DIM (input_shape=() -> d = 1)      */
+  int32_t dim_type[LPGP_MAX_DIM]; /* LPGP_DIM_*                                                      */
+  int32_t nbasis[LPGP_MAX_DIM];   /* number of monomials per dimension (1..5)                        */
+  int32_t has_odd[LPGP_MAX_DIM];  /* Matern only: signed half of the basis present                   */
+  int32_t reserved;
+  double scale[LPGP_MAX_DIM];     /* s_d (Matern) or 1/ell_d (ExpQuad)                               */
+  double diag_value;              /* closed-form value at x == x' (the reference's `x1=None` branch) */
+  double coef[LPGP_MAX_COEF];
+} lpgp_kernel_desc;
+
+/* library / build information ------------------------------------------------------------------- */
+int lpgp_version(void);              /* 100*major + minor                                               */
+const char* lpgp_build_arch(void);   /* "sm_100a"                                                       */
+const char* lpgp_error_string(int code);
+
+/* (1) Gram / cross-covariance assembly ---------------------------------------------------------------
+ * Replaces  pn CovarianceFunction._evaluate_matrix / matrix / linop(...).todense()
+ * (pn/randprocs/covfuncs/_covariance_function.py:359-488, 553-582; _covariance_linear_operator.py:75-76)
+ * for the kernel classes listed at lpgp_kernel_desc, and the cross-covariance blocks of
+ * src/linpde_gp/randprocs/crosscov/linfunctls/_evaluation.py:45-100,159-160.
+ *   out[i*ld + j] (+)= alpha * value(X0[i,:], X1[j,:]);   X1 == NULL -> X1 := X0 (symmetric block).       */
+int lpgp_gram(const lpgp_kernel_desc* desc, const double* X0, int64_t n0, const double* X1, int64_t n1,
+              double* out, int64_t ld, int mode, int accumulate, double alpha, void* stream);
+
+/* out[i] = alpha * k(X0[i], X0[i])  -- the reference's element-wise `k(x0, None)` (x1=None) semantics. */
+int lpgp_gram_diag(const lpgp_kernel_desc* desc, int64_t n0, double* out, double alpha, void* stream);
+
+/* A[i*ld+i] += scalar * (v ? v[i] : 1)  -- `gram + b.cov` for diagonal noise
+ * (src/linpde_gp/randprocs/_gaussian_process/_conditional.py:392-394).                                 */
+int lpgp_add_diag(double* A, int64_t n, int64_t ld, const double* v, double scalar, void* stream);
+
+/* mirror the lower triangle into the upper one (todense() of a block assembled in LOWER mode).        */
+int lpgp_symmetrize_lower(double* A, int64_t n, int64_t ld, void* stream);
+
+/* (2) dense FP64 linear algebra on the DMMA (FP64 tensor core) path ---------------------------------------
+ * C[m x n] = beta*C + alpha * A[m x k] * B[n x k]^T  (all row-major);  lower != 0: only tiles that intersect
+ * the lower triangle of the (square) C are updated (SYRK-style trailing update).                        */
+int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
+                 int64_t ldb, double beta, double* C, int64_t ldc, int lower, void* stream);
+
+/*
+ * Cached, appendable Cholesky factor  G = L L^T  (lower, row-major, in place in `L`).
+ *
+ * The reference grows its Gram matrix one observation batch at a time and factors it by bordering
+ * (nested BlockMatrix2x2 Schur complements, src/linpde_gp/linops/_block.py:191-242).
+ * Here the same structure is a list of SEGMENTS (one per observation batch): seg_off[0]=0 < ... < seg_off[nseg]=n.
+ * Inside a segment the factor is cut into leaves of at most LPGP_LEAF rows; `dinv` holds the explicit inverse
+ * of every leaf's diagonal block (LPGP_LEAF x LPGP_LEAF doubles per leaf, leaves counted across segments in
+ * order), which turns every triangular solve into DMMA GEMMs.  The caller owns L and dinv (torch tensors).
+ */
+#define LPGP_LEAF 128
+#define LPGP_MAX_SEG 64
+typedef struct lpgp_factor {
+  double* L;       /* device, n x n row-major, leading dimension ld (even, 16-byte aligned rows)        */
+  int64_t n;
+  int64_t ld;
+  double* dinv;    /* device, lpgp_factor_dinv_bytes(...) bytes (includes a small status area)          */
+  int32_t nseg;
+  int32_t reserved;
+  int64_t seg_off[LPGP_MAX_SEG + 1];
+} lpgp_factor;
+
+size_t lpgp_factor_dinv_bytes(const int64_t* seg_off, int nseg);
+
+/* Factor all segments from scratch (the lower triangle of f->L holds G on entry, L on exit; the strict upper
+ * triangle is not referenced and may be overwritten inside diagonal tiles).  Replaces
+ * scipy.linalg.cholesky(self.todense(), lower=...) in pn/linops/_linear_operator.py:784-865.
+ * Synchronises `stream`; returns LAPACK info (> 0: leading minor of that order not positive definite).     */
+int lpgp_potrf(lpgp_factor* f, void* stream);
+
+/* Bordered update: segments 0..nseg-2 already hold their factor; the rows of the last segment hold the new
+ * Gram rows [B^T | D] (lower part) and are replaced by [L_21 | L_22]:  L_21 = B^T L_11^{-T} (TRSM,
+ * _block.py:203-207), S = D - L_21 L_21^T (SYRK, :191-201), L_22 = chol(S) (:233-242).
+ * Synchronises `stream`; info > 0 refers to the position inside the whole matrix.                          */
+int lpgp_chol_append(lpgp_factor* f, void* stream);
+
+/* X[m x n] <- X L^{-T}  (right side, lower, transposed; row-major).  This is  L^{-1} B  of
+ * src/linpde_gp/linops/_block.py:203-207 / scipy solve_triangular in pn/linops/_linear_operator.py:296-299
+ * with the right-hand sides stored as ROWS of X (X = B^T), the natural layout of cross-covariance blocks
+ * k(x_test, X_obs).  `nlead` restricts the solve to the leading nlead columns/rows of the factor (must be a
+ * segment boundary; pass f->n for the whole factor).                                                       */
+int lpgp_trsm_rlt(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int64_t ldx, void* stream);
+
+/* B[r, :] <- G^{-1} B[r, :] for nrhs right-hand sides stored as rows of B (nrhs x n): forward and backward
+ * substitution = scipy.linalg.cho_solve of pn/linops/_linear_operator.py:303-307.                          */
+int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t ldb, void* stream);
+
+/* sum_i log L_ii^2 = log det G, written to *out (device double).                                           */
+int lpgp_logdet(const lpgp_factor* f, double* out, void* stream);
+
+/* (3) posterior evaluation -----------------------------------------------------------------------------
+ * One observation block of the conditioned process: descriptor of (k L_i^*) (test side x observation side),
+ * the observation points and the slice of the representer weights.                                      */
+typedef struct lpgp_obs_block {
+  const lpgp_kernel_desc* desc; /* host pointer: (k L_b^*) with the test side as argument 0            */
+  const double* X;              /* device, n x d observation points                                    */
+  int64_t n;
+  int64_t col_off;              /* first row/column of this block inside the factor / weight vector    */
+                                /* (segments are padded to even sizes by the host; gaps are zero)      */
+} lpgp_obs_block;
+
+/* out[i] = sum_blocks sum_j (k L_b^*)(Xt[i], X_b[j]) * w[off_b + j]   (matrix-free; never forms the M x N
+ * cross-covariance).  Replaces ConditionalGaussianProcess.Mean._evaluate
+ * (src/linpde_gp/randprocs/_gaussian_process/_conditional.py:193-197) minus the prior mean.             */
+int lpgp_post_mean(const lpgp_obs_block* blocks, int nblocks, const double* w, const double* Xt, int64_t m,
+                   double* out, int accumulate, void* stream);
+
+/* K[i, col_off_b + j] = (k L_b^*)(Xt[i], X_b[j]) for all blocks, gaps zeroed: the cross-covariance rows
+ * PriorPredictiveCrossCovariance._evaluate (_conditional.py:140-153) of m test points, n = factor size.      */
+int lpgp_crosscov(const lpgp_obs_block* blocks, int nblocks, int64_t n, const double* Xt, int64_t m, double* K,
+                  int64_t ldk, void* stream);
+
+/* out[i] = prior_diag - || row_i( K_tX L^{-T} ) ||^2  for a chunk of m test points: assembles the m x N
+ * cross-covariance chunk into `K` (m x ldk workspace supplied by the caller, ldk >= n even), solves in place
+ * on the DMMA path and reduces.  Replaces ConditionalGaussianProcess.CovarianceFunction._evaluate(x, None)
+ * (_conditional.py:223-231) / pn RandomProcess.var (pn/randprocs/_random_process.py:223-253).          */
+int lpgp_post_var(const lpgp_obs_block* blocks, int nblocks, const lpgp_factor* f, const double* Xt, int64_t m,
+                  double prior_diag, double* K, int64_t ldk, double* out, void* stream);
+
+/* out[i] (+)= scale * sum_j A[i*ld + j]^2   (row sums of squares; building block of lpgp_post_var).    */
+int lpgp_row_sumsq(const double* A, int64_t m, int64_t n, int64_t ld, double scale, double offset, double* out,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPGP_H_ */

@@ -1,0 +1,110 @@
+"""ctypes binding of ``liblpgp.so`` (the C-ABI boundary declared in ``include/lpgp.h``).
+
+There is no CPU fallback: if the shared library is missing the import fails loudly, and every compute entry
+point requires CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblpgp.so")
+
+MAX_DIM = 4
+MAX_COEF = 512
+LEAF = 128
+MAX_SEG = 64
+DIM_MATERN, DIM_EXPQUAD = 0, 1
+GRAM_FULL, GRAM_LOWER = 0, 1
+
+
+class KernelDesc(ctypes.Structure):
+    _fields_ = [
+        ("d", ctypes.c_int32),
+        ("dim_type", ctypes.c_int32 * MAX_DIM),
+        ("nbasis", ctypes.c_int32 * MAX_DIM),
+        ("has_odd", ctypes.c_int32 * MAX_DIM),
+        ("reserved", ctypes.c_int32),
+        ("scale", ctypes.c_double * MAX_DIM),
+        ("diag_value", ctypes.c_double),
+        ("coef", ctypes.c_double * MAX_COEF),
+    ]
+
+
+class Factor(ctypes.Structure):
+    _fields_ = [
+        ("L", ctypes.c_void_p),
+        ("n", ctypes.c_int64),
+        ("ld", ctypes.c_int64),
+        ("dinv", ctypes.c_void_p),
+        ("nseg", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("seg_off", ctypes.c_int64 * (MAX_SEG + 1)),
+    ]
+
+
+class ObsBlock(ctypes.Structure):
+    _fields_ = [
+        ("desc", ctypes.POINTER(KernelDesc)),
+        ("X", ctypes.c_void_p),
+        ("n", ctypes.c_int64),
+        ("col_off", ctypes.c_int64),
+    ]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). linpde_gp_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    i64, dbl, vp, ci = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
+    KD, FP, OB = ctypes.POINTER(KernelDesc), ctypes.POINTER(Factor), ctypes.POINTER(ObsBlock)
+    sigs = {
+        "lpgp_version": (ci, []),
+        "lpgp_build_arch": (ctypes.c_char_p, []),
+        "lpgp_error_string": (ctypes.c_char_p, [ci]),
+        "lpgp_gram": (ci, [KD, vp, i64, vp, i64, vp, i64, ci, ci, dbl, vp]),
+        "lpgp_gram_diag": (ci, [KD, i64, vp, dbl, vp]),
+        "lpgp_add_diag": (ci, [vp, i64, i64, vp, dbl, vp]),
+        "lpgp_symmetrize_lower": (ci, [vp, i64, i64, vp]),
+        "lpgp_gemm_nt": (ci, [i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, ci, vp]),
+        "lpgp_factor_dinv_bytes": (ctypes.c_size_t, [ctypes.POINTER(i64), ci]),
+        "lpgp_potrf": (ci, [FP, vp]),
+        "lpgp_chol_append": (ci, [FP, vp]),
+        "lpgp_trsm_rlt": (ci, [FP, i64, vp, i64, i64, vp]),
+        "lpgp_potrs": (ci, [FP, vp, i64, i64, vp]),
+        "lpgp_logdet": (ci, [FP, vp, vp]),
+        "lpgp_post_mean": (ci, [OB, ci, vp, vp, i64, vp, ci, vp]),
+        "lpgp_crosscov": (ci, [OB, ci, i64, vp, i64, vp, i64, vp]),
+        "lpgp_post_var": (ci, [OB, ci, FP, vp, i64, dbl, vp, i64, vp, vp]),
+        "lpgp_row_sumsq": (ci, [vp, i64, i64, i64, dbl, dbl, vp, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+EXPORTED = (
+    "lpgp_version lpgp_build_arch lpgp_error_string lpgp_gram lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
+    "lpgp_gemm_nt lpgp_factor_dinv_bytes lpgp_potrf lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_logdet "
+    "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq"
+).split()
+
+
+def check(rc: int, what: str = "liblpgp call") -> None:
+    """Map the C-ABI return convention onto the reference's exception types."""
+    if rc == 0:
+        return
+    if rc > 0:
+        raise np.linalg.LinAlgError(f"{what}: {rc}-th leading minor of the array is not positive definite")
+    if rc <= -1000:
+        raise RuntimeError(f"{what}: CUDA error {-rc - 1000}: {lib.lpgp_error_string(rc).decode()}")
+    raise ValueError(f"{what}: invalid argument #{-rc}")

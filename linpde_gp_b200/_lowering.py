@@ -1,0 +1,151 @@
+"""Lowering of (prior kernel, L0, L1) to the flat ``lpgp_kernel_desc`` consumed by the CUDA kernels.
+
+For stationary product kernels  k(x, x') = prod_d kappa_d(x_d - x'_d)  and operators given as sums of partial
+derivatives  L = sum_alpha c_alpha d^alpha,
+
+    (L0 k L1^*)(x, x') = sigma^2 sum_{alpha, beta} c_alpha c_beta prod_d (-1)^{beta_d} kappa_d^{(alpha_d + beta_d)}(delta_d)
+
+(reference: src/linpde_gp/randprocs/covfuncs/linfuncops/diffops/_tensor_product.py:34-119).  Every 1-D factor is
+"polynomial x exponential":
+
+  Matern nu = p + 1/2 : kappa^{(n)}(delta) = s^n sign(delta)^n P_{p,n}(r) e^{-r},  r = s |delta|, s = sqrt(2 nu)/ell,
+                        P_{p,n} = P'_{p,n-1} - P_{p,n-1}  (diffops/_matern.py:613-639)
+  ExpQuad            : kappa^{(n)}(delta) = (-1)^n ell^{-n} He_n(v) e^{-v^2/2},   v = delta/ell  (diffops/_expquad.py)
+
+so the whole double sum folds into ONE coefficient tensor over per-dimension monomial bases, evaluated on the
+device with a single exp() per matrix entry.  The fold happens here, on the host, in exact rational arithmetic for
+the polynomial parts.
+"""
+from __future__ import annotations
+
+import functools
+import itertools
+from fractions import Fraction
+
+import numpy as np
+
+from . import _lib
+
+
+@functools.lru_cache(maxsize=None)
+def matern_poly(p: int, n: int):
+    """Exact coefficients (ascending) of P_{p,n}: kappa_p^{(n)}(r) = P_{p,n}(r) e^{-r}."""
+    if n == 0:
+        c = [Fraction(1)]
+        for i in range(p - 1, -1, -1):
+            c.append(c[-1] * 2 * (i + 1) / (p + i + 1) / (p - i))
+        return tuple(c)
+    prev = matern_poly(p, n - 1)
+    d = [prev[k] * k for k in range(1, len(prev))] + [Fraction(0)]
+    return tuple(a - b for a, b in zip(d, prev))
+
+
+@functools.lru_cache(maxsize=None)
+def hermite_poly(n: int):
+    """Probabilists' Hermite polynomial He_n (ascending coefficients): He_{n+1} = x He_n - n He_{n-1}."""
+    if n == 0:
+        return (Fraction(1),)
+    if n == 1:
+        return (Fraction(0), Fraction(1))
+    a, b = hermite_poly(n - 1), hermite_poly(n - 2)
+    out = [Fraction(0)] * (n + 1)
+    for i, c in enumerate(a):
+        out[i + 1] += c
+    for i, c in enumerate(b):
+        out[i] -= (n - 1) * c
+    return tuple(out)
+
+
+class Factor1D:
+    """One stationary 1-D factor: ('matern', p, ell) or ('expquad', ell)."""
+
+    def __init__(self, kind: str, lengthscale: float, nu: float | None = None):
+        self.kind = kind
+        self.lengthscale = float(lengthscale)
+        self.nu = nu
+        if kind == "matern":
+            p = nu - 0.5
+            if p != int(p) or p < 0:
+                raise NotImplementedError("only half-integer Matern kernels have closed-form derivatives")
+            self.p = int(p)
+            self.scale = float(np.sqrt(2 * nu) / self.lengthscale)
+        elif kind == "expquad":
+            self.scale = 1.0 / self.lengthscale
+        else:
+            raise ValueError(kind)
+
+    def deriv_coeffs(self, n: int):
+        """(even, odd) coefficient vectors of kappa^{(n)} over [v^e] and [u v^e]."""
+        if self.kind == "matern":
+            P = matern_poly(self.p, n)
+            sn = self.scale**n
+            if n % 2 == 0:
+                return [sn * float(c) for c in P], None
+            if P[0] != 0:
+                raise NotImplementedError(
+                    f"derivative order {n} of a Matern-{self.nu} kernel is singular on the diagonal "
+                    "(the reference raises for this combination as well)"
+                )
+            return None, [sn * float(c) for c in P[1:]] + [0.0]
+        He = hermite_poly(n)
+        f = (-1.0) ** n * self.scale**n
+        return [f * float(c) for c in He], None
+
+
+def lower(factors, L0, L1, sigma2: float = 1.0) -> _lib.KernelDesc:
+    """Build the descriptor. ``L0``/``L1``: ``None`` (identity) or ``{multi_index_tuple: coeff}``."""
+    d = len(factors)
+    if not 1 <= d <= _lib.MAX_DIM:
+        raise NotImplementedError(f"input dimension {d} not supported (max {_lib.MAX_DIM})")
+    ident = {tuple([0] * d): 1.0}
+    L0 = ident if L0 is None else L0
+    L1 = ident if L1 is None else L1
+    orders = [set() for _ in range(d)]
+    for a, b in itertools.product(L0, L1):
+        for i in range(d):
+            orders[i].add(a[i] + b[i])
+    nbasis, has_odd = [], []
+    for i, f in enumerate(factors):
+        if f.kind == "matern":
+            nbasis.append(f.p + 1)
+            has_odd.append(any(n % 2 for n in orders[i]))
+        else:
+            nbasis.append(max(orders[i]) + 1)
+            has_odd.append(False)
+    nbt = [nb * (2 if od else 1) for nb, od in zip(nbasis, has_odd)]
+    if int(np.prod(nbt)) > _lib.MAX_COEF:
+        raise NotImplementedError("coefficient tensor too large for the device descriptor")
+    tensor = np.zeros(nbt, dtype=np.float64)
+    cache = [{} for _ in range(d)]
+
+    def vec(i, n):
+        if n not in cache[i]:
+            ev, od = factors[i].deriv_coeffs(n)
+            v = np.zeros(nbt[i])
+            if ev is not None:
+                v[: len(ev)] = ev[: nbasis[i]] if len(ev) > nbasis[i] else ev
+            if od is not None:
+                v[nbasis[i] : nbasis[i] + len(od)] = od
+            cache[i][n] = v
+        return cache[i][n]
+
+    for (a, ca), (b, cb) in itertools.product(L0.items(), L1.items()):
+        term = np.asarray(float(ca) * float(cb))
+        for i in range(d):
+            sign = -1.0 if (b[i] % 2) else 1.0
+            term = np.multiply.outer(term, sign * vec(i, a[i] + b[i]))
+        tensor += term
+    tensor *= float(sigma2)
+
+    desc = _lib.KernelDesc()
+    desc.d = d
+    for i, f in enumerate(factors):
+        desc.dim_type[i] = _lib.DIM_MATERN if f.kind == "matern" else _lib.DIM_EXPQUAD
+        desc.nbasis[i] = nbasis[i]
+        desc.has_odd[i] = int(has_odd[i])
+        desc.scale[i] = f.scale
+    flat = tensor.reshape(-1)
+    for i, c in enumerate(flat):
+        desc.coef[i] = float(c)
+    desc.diag_value = float(flat[0])
+    return desc

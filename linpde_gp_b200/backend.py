@@ -1,0 +1,262 @@
+"""Thin device layer: torch CUDA tensors as buffers, hand-written sm_100a kernels through ``liblpgp.so``.
+
+torch is used for device memory, streams and host<->device copies only; every numerical operation of the hot
+path goes through the C ABI (``include/lpgp.h``).  There is no CPU fallback: all functions require a CUDA
+device and raise otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+F64 = torch.float64
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "linpde_gp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback for the hot path"
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def to_device(x, *, pinned: bool = False) -> torch.Tensor:
+    """Host array (anything ``np.asarray`` accepts) -> contiguous float64 CUDA tensor."""
+    dev = _require_cuda()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=F64).contiguous()
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    t = torch.from_numpy(a)
+    if pinned:
+        t = t.pin_memory()
+    return t.to(dev, non_blocking=pinned)
+
+
+def points(X, d: int) -> torch.Tensor:
+    """Flatten the batch shape C-order (pn ``_preprocess_linop_input``, _covariance_function.py:676-693)."""
+    t = to_device(X)
+    return t.reshape(-1, d) if d > 0 else t.reshape(-1, 1)
+
+
+def alloc_matrix(rows: int, cols: int) -> torch.Tensor:
+    """(rows x cols) view into a buffer whose leading dimension is a multiple of 16 doubles (128-byte rows)."""
+    dev = _require_cuda()
+    ld = max(round_up(cols, 16), 16)
+    return torch.empty((max(rows, 1), ld), dtype=F64, device=dev)[:rows, :cols]
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and (t.shape[1] <= 1 or t.stride(1) == 1), "row-major matrix expected"
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+# ------------------------------------------------------------------------------------------------------------
+def gram(desc: _lib.KernelDesc, X0: torch.Tensor, X1: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         *, lower: bool = False, accumulate: bool = False, alpha: float = 1.0) -> torch.Tensor:
+    """K[i, j] (+)= alpha * (L0 k L1*)(X0[i], X1[j]);  X1=None -> symmetric block on X0."""
+    _require_cuda()
+    n0 = X0.shape[0]
+    n1 = n0 if X1 is None else X1.shape[0]
+    if out is None:
+        out = alloc_matrix(n0, n1)
+    assert out.shape == (n0, n1)
+    rc = lib.lpgp_gram(ctypes.byref(desc), _ptr(X0), n0, _ptr(X1), n1, _ptr(out), _ld(out),
+                       _lib.GRAM_LOWER if lower else _lib.GRAM_FULL, int(accumulate), float(alpha), _stream())
+    check(rc, "lpgp_gram")
+    return out
+
+
+def gram_diag(desc: _lib.KernelDesc, n: int, alpha: float = 1.0) -> torch.Tensor:
+    out = torch.empty(n, dtype=F64, device=_require_cuda())
+    check(lib.lpgp_gram_diag(ctypes.byref(desc), n, _ptr(out), float(alpha), _stream()), "lpgp_gram_diag")
+    return out
+
+
+def add_diag(A: torch.Tensor, v: Optional[torch.Tensor] = None, scalar: float = 1.0) -> None:
+    check(lib.lpgp_add_diag(_ptr(A), A.shape[0], _ld(A), _ptr(v), float(scalar), _stream()), "lpgp_add_diag")
+
+
+def symmetrize_lower(A: torch.Tensor) -> None:
+    check(lib.lpgp_symmetrize_lower(_ptr(A), A.shape[0], _ld(A), _stream()), "lpgp_symmetrize_lower")
+
+
+def gemm_nt(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, alpha: float = 1.0, beta: float = 0.0,
+            lower: bool = False) -> torch.Tensor:
+    """C = beta*C + alpha * A @ B.T on the DMMA path."""
+    m, k = A.shape
+    n = B.shape[0]
+    assert B.shape[1] == k and C.shape == (m, n)
+    rc = lib.lpgp_gemm_nt(m, n, k, float(alpha), _ptr(A), _ld(A), _ptr(B), _ld(B), float(beta), _ptr(C), _ld(C),
+                          int(lower), _stream())
+    check(rc, "lpgp_gemm_nt")
+    return C
+
+
+def row_sumsq(A: torch.Tensor, scale: float = 1.0, offset: float = 0.0) -> torch.Tensor:
+    out = torch.empty(A.shape[0], dtype=F64, device=A.device)
+    check(lib.lpgp_row_sumsq(_ptr(A), A.shape[0], A.shape[1], _ld(A), float(scale), float(offset), _ptr(out), _stream()),
+          "lpgp_row_sumsq")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+class DeviceFactor:
+    """Device-resident, appendable lower Cholesky factor (``lpgp_factor``).
+
+    ``seg_sizes`` are the (even) physical sizes of the observation batches.  The object owns ``L`` (n x n,
+    row-major, padded leading dimension) and ``dinv`` (inverted 128x128 diagonal blocks).  Appending never
+    mutates an existing factor: :meth:`extended` returns a new object (the reference's conditioning API is
+    functional)."""
+
+    def __init__(self, seg_sizes: Sequence[int]):
+        dev = _require_cuda()
+        seg_sizes = [int(s) for s in seg_sizes]
+        if any(s <= 0 or s % 2 for s in seg_sizes):
+            raise ValueError("segment sizes must be positive and even (pad odd batches)")
+        if len(seg_sizes) > _lib.MAX_SEG:
+            raise ValueError(f"at most {_lib.MAX_SEG} observation batches per factor")
+        self.seg_off = [0]
+        for s in seg_sizes:
+            self.seg_off.append(self.seg_off[-1] + s)
+        self.n = self.seg_off[-1]
+        self.L = alloc_matrix(self.n, self.n)
+        arr = (ctypes.c_int64 * len(self.seg_off))(*self.seg_off)
+        nbytes = lib.lpgp_factor_dinv_bytes(arr, len(seg_sizes))
+        if nbytes == 0:
+            raise ValueError("invalid segment layout")
+        self.dinv = torch.empty(round_up(nbytes, 8) // 8, dtype=F64, device=dev)
+        self.nleaves = sum((s + _lib.LEAF - 1) // _lib.LEAF for s in seg_sizes)
+        self.factored_segments = 0
+
+    @property
+    def ld(self) -> int:
+        return _ld(self.L)
+
+    def _struct(self, nseg: Optional[int] = None) -> _lib.Factor:
+        nseg = len(self.seg_off) - 1 if nseg is None else nseg
+        f = _lib.Factor()
+        f.L = self.L.data_ptr()
+        f.n = self.seg_off[nseg]
+        f.ld = self.ld
+        f.dinv = self.dinv.data_ptr()
+        f.nseg = nseg
+        for i in range(nseg + 1):
+            f.seg_off[i] = self.seg_off[i]
+        return f
+
+    def segment_rows(self, s: int) -> torch.Tensor:
+        return self.L[self.seg_off[s] : self.seg_off[s + 1]]
+
+    def potrf(self) -> None:
+        """Factor everything from scratch (all segments as one matrix)."""
+        f = self._struct()
+        check(lib.lpgp_potrf(ctypes.byref(f), _stream()), "lpgp_potrf")
+        self.factored_segments = len(self.seg_off) - 1
+
+    def append_last(self) -> None:
+        """Segments 0..nseg-2 are factored; the last segment's rows hold the new Gram rows."""
+        f = self._struct()
+        check(lib.lpgp_chol_append(ctypes.byref(f), _stream()), "lpgp_chol_append")
+        self.factored_segments = len(self.seg_off) - 1
+
+    def extended(self, new_size: int) -> "DeviceFactor":
+        """New factor object with one more (unfactored) segment; the existing factor is copied."""
+        sizes = [self.seg_off[i + 1] - self.seg_off[i] for i in range(len(self.seg_off) - 1)]
+        new = DeviceFactor(sizes + [int(new_size)])
+        new.L[: self.n, : self.n].copy_(self.L)
+        nold = self.nleaves * _lib.LEAF * _lib.LEAF  # all leaf blocks, without the status area
+        new.dinv[:nold].copy_(self.dinv[:nold])
+        new.factored_segments = self.factored_segments
+        return new
+
+    def trsm_rlt(self, X: torch.Tensor, nlead: Optional[int] = None) -> torch.Tensor:
+        """X <- X L^{-T} in place (rows of X are right-hand sides)."""
+        nlead = self.n if nlead is None else nlead
+        assert X.shape[1] == nlead
+        f = self._struct()
+        check(lib.lpgp_trsm_rlt(ctypes.byref(f), nlead, _ptr(X), X.shape[0], _ld(X), _stream()), "lpgp_trsm_rlt")
+        return X
+
+    def potrs(self, B: torch.Tensor) -> torch.Tensor:
+        """Rows of B <- G^{-1} rows of B, in place."""
+        if B.dim() == 1:
+            B = B.reshape(1, -1)
+        assert B.shape[1] == self.n
+        f = self._struct()
+        check(lib.lpgp_potrs(ctypes.byref(f), _ptr(B), B.shape[0], _ld(B), _stream()), "lpgp_potrs")
+        return B
+
+    def logdet(self) -> float:
+        out = torch.empty(1, dtype=F64, device=self.L.device)
+        f = self._struct()
+        check(lib.lpgp_logdet(ctypes.byref(f), _ptr(out), _stream()), "lpgp_logdet")
+        return float(out.item())
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ObsBlocks:
+    """ctypes array of ``lpgp_obs_block`` keeping the referenced descriptors / tensors alive."""
+
+    def __init__(self, descs, Xs, col_offs):
+        self.descs = list(descs)
+        self.Xs = list(Xs)
+        self.n = len(self.descs)
+        self.arr = (_lib.ObsBlock * self.n)()
+        for i, (dsc, X, off) in enumerate(zip(self.descs, self.Xs, col_offs)):
+            self.arr[i].desc = ctypes.pointer(dsc)
+            self.arr[i].X = X.data_ptr()
+            self.arr[i].n = X.shape[0]
+            self.arr[i].col_off = int(off)
+
+
+def post_mean(blocks: ObsBlocks, w: torch.Tensor, Xt: torch.Tensor, out: Optional[torch.Tensor] = None,
+              accumulate: bool = False) -> torch.Tensor:
+    m = Xt.shape[0]
+    if out is None:
+        out = torch.empty(m, dtype=F64, device=Xt.device)
+    rc = lib.lpgp_post_mean(blocks.arr, blocks.n, _ptr(w), _ptr(Xt), m, _ptr(out), int(accumulate), _stream())
+    check(rc, "lpgp_post_mean")
+    return out
+
+
+def crosscov(blocks: ObsBlocks, n: int, Xt: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    m = Xt.shape[0]
+    if out is None:
+        out = alloc_matrix(m, n)
+    check(lib.lpgp_crosscov(blocks.arr, blocks.n, n, _ptr(Xt), m, _ptr(out), _ld(out), _stream()), "lpgp_crosscov")
+    return out
+
+
+def post_var(blocks: ObsBlocks, factor: DeviceFactor, Xt: torch.Tensor, prior_diag: float, chunk: int = 8192,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Pointwise posterior variance, test points processed in chunks of ``chunk`` rows."""
+    m = Xt.shape[0]
+    if out is None:
+        out = torch.empty(m, dtype=F64, device=Xt.device)
+    chunk = max(1, min(chunk, m))
+    K = alloc_matrix(chunk, factor.n)
+    f = factor._struct()
+    for i0 in range(0, m, chunk):
+        mc = min(chunk, m - i0)
+        rc = lib.lpgp_post_var(blocks.arr, blocks.n, ctypes.byref(f), _ptr(Xt[i0:]), mc, float(prior_diag), _ptr(K),
+                               _ld(K), _ptr(out[i0:]), _stream())
+        check(rc, "lpgp_post_var")
+    return out

@@ -1,0 +1,232 @@
+// FP64 tensor-core (DMMA) "NT" GEMM:  C[m x n] = beta*C + alpha * A[m x k] * B[n x k]^T, all row-major.
+//
+// This one kernel carries every O(N^3) step of the path: the SYRK/GEMM
+// trailing updates of the blocked Cholesky, the blocked triangular solves (panel TRSM, factor append, the
+// N x M posterior-variance solve) and the multiplications with inverted diagonal blocks.
+//
+// Blackwell has no FP64 kind in tcgen05/TMEM; the FP64 tensor path on sm_100a is the warp-level
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; measured issue-rate peak 37.1 TFLOP/s on this pool's B200, see
+// profiles/fp64_peaks_r01.txt).  Design:
+//   * CTA tile 128 x 128, 8 consumer warps (2 x 4), warp tile 64 x 32 -> 64 FP64 accumulators per thread;
+//   * operands are streamed by one producer warp with TMA 2-D tensor copies (cp.async.bulk.tensor, SASS
+//     UTMALDG) into an 8-stage shared-memory ring of (128+128) x 8 doubles, full/empty mbarriers, no
+//     __syncthreads in the main loop; TMA zero-fills the m/n/k tails, so no edge predicates in the hot loop;
+//   * rows of a stage are 64 bytes: an LDS.128 of lane (g, t) fetches k = 2t, 2t+1 of row g -> two DMMAs per
+//     shared-memory load (the contraction index may be permuted as long as A and B agree), conflict-free
+//     without swizzling (lanes 0-7 cover two rows = one 128-byte bank window);
+//   * `lower != 0`: only tiles intersecting the lower triangle are launched (SYRK-style update).
+// Bound: FP64 tensor pipe.  Algorithmic flops 2*m*n*k (lower: ~m*n*k); operand traffic per CTA tile and k-step
+// is (128+128)*8*8 B for 262144 flops, i.e. 0.0625 B/flop from L2.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 8;
+constexpr int STAGES = 8;
+constexpr int NCONSUMER_WARPS = 8;
+constexpr int NTHREADS = (NCONSUMER_WARPS + 1) * 32;
+constexpr int STAGE_A_BYTES = BM * BK * 8;
+constexpr int STAGE_B_BYTES = BN * BK * 8;
+constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+    gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int m, int n,
+                   int k, double alpha, double beta, double* __restrict__ C, int64_t ldc, int lower, int tiles_n,
+                   int vec_ok) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // keeps the shared address space
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+
+  // ---- tile coordinates ----------------------------------------------------------------------------
+  int tm, tn;
+  if (lower) {  // linear index over the lower triangle of the tile grid, row-major
+    const long long x = blockIdx.x;
+    long long r = (long long)((sqrt(8.0 * (double)x + 1.0) - 1.0) * 0.5);
+    while (r * (r + 1) / 2 > x) --r;
+    while ((r + 1) * (r + 2) / 2 <= x) ++r;
+    tm = (int)r;
+    tn = (int)(x - r * (r + 1) / 2);
+  } else {
+    tm = blockIdx.x / tiles_n;
+    tn = blockIdx.x % tiles_n;
+  }
+  const int row0 = tm * BM, col0 = tn * BN;
+  const int nk = (k + BK - 1) / BK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == NCONSUMER_WARPS) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        if (kb >= STAGES) mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        unsigned char* st = smem + s * STAGE_BYTES;
+        tma_load_2d(st, &tmA, kb * BK, row0, &full[s]);
+        tma_load_2d(st + STAGE_A_BYTES, &tmB, kb * BK, col0, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ===== DMMA consumers =====
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int kb = 0; kb < nk; ++kb) {
+    const int s = kb % STAGES;
+    const uint32_t ph = (kb / STAGES) & 1;
+    mbar_wait(&full[s], ph);
+    const double* sA = (const double*)(smem + s * STAGE_BYTES);
+    const double* sB = (const double*)(smem + s * STAGE_BYTES + STAGE_A_BYTES);
+    double2 a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double2*>(sA + (wm0 + 8 * i + g) * BK + 2 * t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(sB + (wn0 + 8 * j + g) * BK + 2 * t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+        dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+      }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ===== epilogue: C = beta*C + alpha*acc =====
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row0 + wm0 + 8 * i + g;
+    if (row >= m) continue;
+    double* crow = C + (int64_t)row * ldc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = col0 + wn0 + 8 * j + 2 * t;
+      if (col >= n) continue;
+      double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+      if (vec_ok && col + 1 < n) {
+        double2* p = reinterpret_cast<double2*>(crow + col);
+        if (beta != 0.0) {
+          const double2 c = *p;
+          v0 = fma(beta, c.x, v0);
+          v1 = fma(beta, c.y, v1);
+        }
+        *p = make_double2(v0, v1);
+      } else {
+        if (beta != 0.0) v0 = fma(beta, crow[col], v0);
+        crow[col] = v0;
+        if (col + 1 < n) {
+          if (beta != 0.0) v1 = fma(beta, crow[col + 1], v1);
+          crow[col + 1] = v1;
+        }
+      }
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+std::once_flag g_once;
+int g_init_rc = 0;
+
+void init_once() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    g_init_rc = LPGP_CUDA_ERR(e != cudaSuccess ? e : cudaErrorNotSupported);
+    return;
+  }
+  g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) g_init_rc = LPGP_CUDA_ERR(e);
+}
+
+// row-major (rows x cols, ld) FP64 matrix -> 2-D tensor map with box (BK cols) x (box_rows rows)
+int make_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : LPGP_CUDA_ERR(cudaErrorInvalidValue);
+}
+
+}  // namespace
+
+extern "C" int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
+                            int64_t ldb, double beta, double* C, int64_t ldc, int lower, void* stream) {
+  if (m < 0) return -1;
+  if (n < 0) return -2;
+  if (k < 0) return -3;
+  if (m == 0 || n == 0) return 0;
+  if (!A || lda < k || (lda % 2) || ((uintptr_t)A % 16)) return -6;  // TMA: 16-byte aligned rows
+  if (!B || ldb < k || (ldb % 2) || ((uintptr_t)B % 16)) return -8;
+  if (!C || ldc < n) return -11;
+  if (lower && m != n) return -12;
+  if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return -1;
+  std::call_once(g_once, init_once);
+  if (g_init_rc) return g_init_rc;
+  if (k == 0) {
+    // pure scaling of C; reuse the kernel with an empty contraction (nk = 0)
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, A, m, k > 0 ? k : 1, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, B, n, k > 0 ? k : 1, ldb, BN);
+  if (rc) return rc;
+  const int64_t tiles_m = ceil_div64(m, BM), tiles_n = ceil_div64(n, BN);
+  const int64_t ntiles = lower ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
+  if (ntiles > INT32_MAX) return -1;
+  const int vec_ok = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
+  gemm_nt_kernel<<<(unsigned)ntiles, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+      tmA, tmB, (int)m, (int)n, (int)k, alpha, beta, C, ldc, lower, (int)tiles_n, vec_ok);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,255 @@
+// Gram / cross-covariance assembly: a tiled pairwise FP64 kernel.
+//
+// One CTA (256 threads) produces a TM x TN = 64 x 128 tile of the row-major output.  Both point tiles are
+// staged in shared memory by the TMA engine (1-D bulk copies, cp.async.bulk -> SASS UBLKCP, completion on an
+// mbarrier); every thread owns two adjacent columns (one 16-byte st.global per row -> each warp writes 512
+// contiguous bytes per row) and walks 16 rows, two at a time, so that 4 independent exp/Horner chains are in
+// flight per thread.  Algorithmic traffic: 8 B written per entry (+ 8*d*(n0+n1) B of points, negligible).
+// Bound: FP64 pipe (one exp ~ 23 DFMA slots + the polynomial) for derivative kernels, HBM writes otherwise.
+#include "kernel_eval.cuh"
+
+namespace {
+
+constexpr int TM = 64;
+constexpr int TN = 128;
+constexpr int NTHREADS = 256;
+constexpr int ROWS_PER_THREAD = TM / (NTHREADS / (TN / 2));  // 16
+
+template <int D, int NB, bool ODD>
+__global__ void __launch_bounds__(NTHREADS)
+    gram_tile_kernel(const __grid_constant__ EvalParams<D, NB, ODD> p, const double* __restrict__ X0, int64_t n0,
+                     const double* __restrict__ X1, int64_t n1, double* __restrict__ out, int64_t ld, int mode,
+                     int accumulate, double alpha, int vec_ok) {
+  const int64_t row0 = (int64_t)blockIdx.y * TM;
+  const int64_t col0 = (int64_t)blockIdx.x * TN;
+  if (mode == LPGP_GRAM_LOWER && col0 > row0 + (TM - 1)) return;  // tile strictly above the diagonal
+
+  __shared__ __align__(16) double sx0[TM * D];
+  __shared__ __align__(16) double sx1[TN * D];
+  __shared__ __align__(8) uint64_t bar;
+
+  const int rows = (int)min((int64_t)TM, n0 - row0);
+  const int cols = (int)min((int64_t)TN, n1 - col0);
+  const uint32_t bytes0 = (uint32_t)(rows * D * sizeof(double));
+  const uint32_t bytes1 = (uint32_t)(cols * D * sizeof(double));
+  const double* g0 = X0 + row0 * D;
+  const double* g1 = X1 + col0 * D;
+  // TMA bulk copies need 16-byte aligned addresses and sizes; otherwise (odd d with odd offsets/tails) fall
+  // back to plain cooperative loads.  The condition is block-uniform.
+  const bool tma_ok = ((bytes0 | bytes1) % 16 == 0) && (((uintptr_t)g0 | (uintptr_t)g1) % 16 == 0);
+  if (tma_ok) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(&bar, bytes0 + bytes1);
+      bulk_g2s(sx0, g0, bytes0, &bar);
+      bulk_g2s(sx1, g1, bytes1, &bar);
+    }
+    __syncthreads();  // barrier init visible to all waiters
+    mbar_wait(&bar, 0);
+  } else {
+    for (int i = threadIdx.x; i < rows * D; i += NTHREADS) sx0[i] = g0[i];
+    for (int i = threadIdx.x; i < cols * D; i += NTHREADS) sx1[i] = g1[i];
+    __syncthreads();
+  }
+
+  const int cpair = (threadIdx.x % (TN / 2)) * 2;  // first of my two columns inside the tile
+  const int rgrp = threadIdx.x / (TN / 2);         // 0..3
+  const bool c0_ok = cpair < cols, c1_ok = cpair + 1 < cols;
+  double xa[D], xb[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    xa[d] = c0_ok ? sx1[cpair * D + d] : 0.0;
+    xb[d] = c1_ok ? sx1[(cpair + 1) * D + d] : 0.0;
+  }
+  double* obase = out + (row0 + rgrp * ROWS_PER_THREAD) * ld + col0 + cpair;
+
+#pragma unroll 1
+  for (int r = 0; r < ROWS_PER_THREAD; r += 2) {
+    const int lr = rgrp * ROWS_PER_THREAD + r;
+    if (lr >= rows) break;
+    const bool r1_ok = lr + 1 < rows;
+    double y0[D], y1[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      y0[d] = sx0[lr * D + d];
+      y1[d] = r1_ok ? sx0[(lr + 1) * D + d] : y0[d];
+    }
+    double v00 = alpha * eval_pair<D, NB, ODD>(p, y0, xa);
+    double v01 = alpha * eval_pair<D, NB, ODD>(p, y0, xb);
+    double v10 = alpha * eval_pair<D, NB, ODD>(p, y1, xa);
+    double v11 = alpha * eval_pair<D, NB, ODD>(p, y1, xb);
+    double* o0 = obase + (int64_t)r * ld;
+    double* o1 = o0 + ld;
+    if (vec_ok && c1_ok) {
+      if (accumulate) {
+        double2 a = *reinterpret_cast<double2*>(o0);
+        v00 += a.x;
+        v01 += a.y;
+        if (r1_ok) {
+          double2 b = *reinterpret_cast<double2*>(o1);
+          v10 += b.x;
+          v11 += b.y;
+        }
+      }
+      *reinterpret_cast<double2*>(o0) = make_double2(v00, v01);
+      if (r1_ok) *reinterpret_cast<double2*>(o1) = make_double2(v10, v11);
+    } else {
+      if (c0_ok) {
+        o0[0] = accumulate ? o0[0] + v00 : v00;
+        if (r1_ok) o1[0] = accumulate ? o1[0] + v10 : v10;
+      }
+      if (c1_ok) {
+        o0[1] = accumulate ? o0[1] + v01 : v01;
+        if (r1_ok) o1[1] = accumulate ? o1[1] + v11 : v11;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    gram_generic_kernel(const __grid_constant__ lpgp_kernel_desc k, const double* __restrict__ X0, int64_t n0,
+                        const double* __restrict__ X1, int64_t n1, double* __restrict__ out, int64_t ld, int mode,
+                        int accumulate, double alpha) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= n1 || i >= n0) return;
+  if (mode == LPGP_GRAM_LOWER && j > i) return;
+  double x0[LPGP_MAX_DIM], x1[LPGP_MAX_DIM];
+  for (int d = 0; d < k.d; ++d) {
+    x0[d] = X0[i * k.d + d];
+    x1[d] = X1[j * k.d + d];
+  }
+  const double v = alpha * eval_pair_generic(k, x0, x1);
+  double* o = out + i * ld + j;
+  *o = accumulate ? *o + v : v;
+}
+
+template <int D, int NB, bool ODD>
+int launch_tile(const lpgp_kernel_desc& k, const double* X0, int64_t n0, const double* X1, int64_t n1, double* out,
+                int64_t ld, int mode, int accumulate, double alpha, cudaStream_t st) {
+  EvalParams<D, NB, ODD> p;
+  pack_params<D, NB, ODD>(k, p);
+  dim3 grid((unsigned)ceil_div64(n1, TN), (unsigned)ceil_div64(n0, TM));
+  const int vec_ok = (ld % 2 == 0) && ((uintptr_t)out % 16 == 0);
+  gram_tile_kernel<D, NB, ODD><<<grid, NTHREADS, 0, st>>>(p, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, vec_ok);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int D>
+int dispatch_nb(int NB, bool odd, const lpgp_kernel_desc& k, const double* X0, int64_t n0, const double* X1, int64_t n1,
+                double* out, int64_t ld, int mode, int accumulate, double alpha, cudaStream_t st) {
+#define LPGP_CASE(nb, od) \
+  if (NB == nb && odd == od) return launch_tile<D, nb, od>(k, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, st);
+  LPGP_CASE(3, false)
+  LPGP_CASE(3, true)
+  LPGP_CASE(4, false)
+  LPGP_CASE(4, true)
+  LPGP_CASE(5, false)
+  if constexpr (D < 3) { LPGP_CASE(5, true) }
+#undef LPGP_CASE
+  return -1;
+}
+
+__global__ void fill_kernel(double* out, int64_t n, double v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
+__global__ void add_diag_kernel(double* A, int64_t n, int64_t ld, const double* v, double scalar) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[i * ld + i] += scalar * (v ? v[i] : 1.0);
+}
+
+// A[j, i] = A[i, j] for j < i: 32x32 smem-transposed tiles, coalesced reads and writes
+__global__ void __launch_bounds__(256) symmetrize_kernel(double* A, int64_t n, int64_t ld) {
+  __shared__ double t[32][33];
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    int64_t i = bi * 32 + r, j = bj * 32 + tx;
+    t[r][tx] = (i < n && j < n) ? A[i * ld + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int64_t i = bj * 32 + r, j = bi * 32 + tx;  // destination (upper) element (i, j) <- source (j, i)
+    if (i < n && j < n && j > i) A[i * ld + j] = t[tx][r];
+  }
+}
+
+}  // namespace
+
+extern "C" int lpgp_gram(const lpgp_kernel_desc* desc, const double* X0, int64_t n0, const double* X1, int64_t n1,
+                         double* out, int64_t ld, int mode, int accumulate, double alpha, void* stream) {
+  if (validate_desc(desc)) return -1;
+  if (n0 < 0) return -3;
+  if (!X1) {
+    X1 = X0;
+    n1 = n0;
+  }
+  if (n1 < 0) return -5;
+  if (n0 == 0 || n1 == 0) return 0;  // empty blocks are legal (and may come with null pointers)
+  if (!X0) return -2;
+  if (!out) return -6;
+  if (ld < n1) return -7;
+  if (mode != LPGP_GRAM_FULL && mode != LPGP_GRAM_LOWER) return -8;
+  if (mode == LPGP_GRAM_LOWER && n0 != n1) return -8;
+  if (n0 == 0 || n1 == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool odd;
+  const int NB = pick_nb(*desc, odd);
+  int rc = -1;
+  if (NB) {
+    if (desc->d == 1) rc = dispatch_nb<1>(NB, odd, *desc, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, st);
+    if (desc->d == 2) rc = dispatch_nb<2>(NB, odd, *desc, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, st);
+    if (desc->d == 3) rc = dispatch_nb<3>(NB, odd, *desc, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, st);
+    if (rc != -1) return rc;
+  }
+  dim3 grid((unsigned)ceil_div64(n1, 256), (unsigned)n0);
+  if (n0 > 65535) {  // grid.y limit: process in row slabs
+    for (int64_t r = 0; r < n0; r += 65535) {
+      int64_t nr = n0 - r < 65535 ? n0 - r : 65535;
+      dim3 g((unsigned)ceil_div64(n1, 256), (unsigned)nr);
+      if (mode == LPGP_GRAM_LOWER) return -8;  // generic path: full blocks only at this size
+      gram_generic_kernel<<<g, 256, 0, st>>>(*desc, X0 + r * desc->d, nr, X1, n1, out + r * ld, ld, mode, accumulate, alpha);
+      LPGP_CHECK_LAUNCH();
+    }
+    return 0;
+  }
+  gram_generic_kernel<<<grid, 256, 0, st>>>(*desc, X0, n0, X1, n1, out, ld, mode, accumulate, alpha);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int lpgp_gram_diag(const lpgp_kernel_desc* desc, int64_t n0, double* out, double alpha, void* stream) {
+  if (validate_desc(desc)) return -1;
+  if (n0 < 0) return -2;
+  if (!out) return -3;
+  if (n0 == 0) return 0;
+  fill_kernel<<<(unsigned)ceil_div64(n0, 256), 256, 0, (cudaStream_t)stream>>>(out, n0, alpha * desc->diag_value);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int lpgp_add_diag(double* A, int64_t n, int64_t ld, const double* v, double scalar, void* stream) {
+  if (!A) return -1;
+  if (n < 0) return -2;
+  if (ld < n) return -3;
+  if (n == 0) return 0;
+  add_diag_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(A, n, ld, v, scalar);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int lpgp_symmetrize_lower(double* A, int64_t n, int64_t ld, void* stream) {
+  if (!A) return -1;
+  if (n < 0) return -2;
+  if (ld < n) return -3;
+  if (n == 0) return 0;
+  dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)ceil_div64(n, 32));
+  symmetrize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, n, ld);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,160 @@
+// Closed-form evaluation of (L0 k L1^*)(x, x') in the "polynomial x exponential" product form described at
+// lpgp_kernel_desc (include/lpgp.h).  One exp() per entry; the per-dimension polynomial factors of every
+// derivative order are folded on the host into one dense coefficient tensor, evaluated here by nested Horner
+// recursion with compile-time coefficient offsets (the coefficients are kernel parameters -> constant bank
+// operands of the DFMAs).
+//
+// Reference semantics reproduced: src/linpde_gp/randprocs/covfuncs/linfuncops/diffops/_tensor_product.py:84-119
+// (sum over operator terms of products of 1-D factors), diffops/_matern.py:403-410,476-483,64-86,558-571
+// (s^n P_{p,n}(r) e^{-r}, odd orders carry the signed s*dx), diffops/_expquad.py:187-201,280-312.
+#pragma once
+#include "common.cuh"
+
+template <int D, int NB, bool ODD>
+struct EvalParams {
+  static constexpr int NBT = ODD ? 2 * NB : NB;
+  static constexpr int NCOEF = (D == 1 ? NBT : (D == 2 ? NBT * NBT : NBT * NBT * NBT));
+  int32_t dim_type[D];
+  double scale[D];
+  double coef[NCOEF];
+};
+
+template <int D, int NB, bool ODD, int DIM>
+struct NestedHorner {
+  static constexpr int NBT = ODD ? 2 * NB : NB;
+  // stride (in coefficients) of one step along dimension DIM in the C-order tensor
+  static constexpr __host__ __device__ int stride() {
+    int s = 1;
+    for (int i = DIM + 1; i < D; ++i) s *= NBT;
+    return s;
+  }
+  template <typename P>
+  static __device__ __forceinline__ double run(const P& p, const double* v, const double* u, int base) {
+    constexpr int S = stride();
+    double acc = NestedHorner<D, NB, ODD, DIM + 1>::run(p, v, u, base + (NB - 1) * S);
+#pragma unroll
+    for (int b = NB - 2; b >= 0; --b) acc = fma(acc, v[DIM], NestedHorner<D, NB, ODD, DIM + 1>::run(p, v, u, base + b * S));
+    if (ODD) {
+      double acc_o = NestedHorner<D, NB, ODD, DIM + 1>::run(p, v, u, base + (2 * NB - 1) * S);
+#pragma unroll
+      for (int b = NB - 2; b >= 0; --b)
+        acc_o = fma(acc_o, v[DIM], NestedHorner<D, NB, ODD, DIM + 1>::run(p, v, u, base + (NB + b) * S));
+      acc = fma(acc_o, u[DIM], acc);
+    }
+    return acc;
+  }
+};
+template <int D, int NB, bool ODD>
+struct NestedHorner<D, NB, ODD, D> {
+  template <typename P>
+  static __device__ __forceinline__ double run(const P& p, const double*, const double*, int base) {
+    return p.coef[base];
+  }
+};
+
+// value of the transformed kernel for one pair of points (x0, x1 are D doubles each)
+template <int D, int NB, bool ODD, typename P>
+__device__ __forceinline__ double eval_pair(const P& p, const double* x0, const double* x1) {
+  double v[D], u[D];
+  double g = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double uu = (x0[d] - x1[d]) * p.scale[d];
+    const bool eq = p.dim_type[d] == LPGP_DIM_EXPQUAD;
+    u[d] = uu;
+    v[d] = eq ? uu : fabs(uu);
+    g += eq ? 0.5 * uu * uu : fabs(uu);
+  }
+  const double poly = NestedHorner<D, NB, ODD, 0>::run(p, v, u, 0);
+  return poly * exp(-g);
+}
+
+// Generic (runtime-shaped) evaluation straight from the descriptor: any d <= LPGP_MAX_DIM, any basis sizes.
+// Slow path used only for shapes without a specialised instantiation.
+__device__ __forceinline__ double eval_pair_generic(const lpgp_kernel_desc& k, const double* x0, const double* x1) {
+  double v[LPGP_MAX_DIM], u[LPGP_MAX_DIM];
+  int nbt[LPGP_MAX_DIM];
+  double g = 0.0;
+  int total = 1;
+  for (int d = 0; d < k.d; ++d) {
+    const double uu = (x0[d] - x1[d]) * k.scale[d];
+    const bool eq = k.dim_type[d] == LPGP_DIM_EXPQUAD;
+    u[d] = uu;
+    v[d] = eq ? uu : fabs(uu);
+    g += eq ? 0.5 * uu * uu : fabs(uu);
+    nbt[d] = k.nbasis[d] * (k.has_odd[d] ? 2 : 1);
+    total *= nbt[d];
+  }
+  double sum = 0.0;
+  for (int idx = 0; idx < total; ++idx) {
+    const double c = k.coef[idx];
+    if (c == 0.0) continue;
+    int rem = idx;
+    double term = c;
+    for (int d = k.d - 1; d >= 0; --d) {
+      int b = rem % nbt[d];
+      rem /= nbt[d];
+      if (b >= k.nbasis[d]) {
+        term *= u[d];
+        b -= k.nbasis[d];
+      }
+      for (int e = 0; e < b; ++e) term *= v[d];
+    }
+    sum += term;
+  }
+  return sum * exp(-g);
+}
+
+// Host: repack a descriptor into the zero-padded (NBT)^D tensor of a specialised instantiation.
+template <int D, int NB, bool ODD>
+static inline void pack_params(const lpgp_kernel_desc& k, EvalParams<D, NB, ODD>& p) {
+  constexpr int NBT = EvalParams<D, NB, ODD>::NBT;
+  for (int i = 0; i < EvalParams<D, NB, ODD>::NCOEF; ++i) p.coef[i] = 0.0;
+  int nbt[LPGP_MAX_DIM], total = 1;
+  for (int d = 0; d < D; ++d) {
+    p.dim_type[d] = k.dim_type[d];
+    p.scale[d] = k.scale[d];
+    nbt[d] = k.nbasis[d] * (k.has_odd[d] ? 2 : 1);
+    total *= nbt[d];
+  }
+  for (int idx = 0; idx < total; ++idx) {
+    int rem = idx, dst = 0, mul = 1;
+    for (int d = D - 1; d >= 0; --d) {
+      int b = rem % nbt[d];
+      rem /= nbt[d];
+      int bb = b < k.nbasis[d] ? b : NB + (b - k.nbasis[d]);
+      dst += bb * mul;
+      mul *= NBT;
+    }
+    p.coef[dst] = k.coef[idx];
+  }
+}
+
+// smallest specialised basis size covering the descriptor (0 = none, use the generic kernels)
+static inline int pick_nb(const lpgp_kernel_desc& k, bool& odd) {
+  int nb = 1;
+  odd = false;
+  for (int d = 0; d < k.d; ++d) {
+    if (k.nbasis[d] > nb) nb = k.nbasis[d];
+    if (k.has_odd[d]) odd = true;
+  }
+  if (k.d > 3 || nb > 5) return 0;
+  int NB = nb <= 3 ? 3 : nb;
+  if (k.d == 3 && NB == 5 && odd) return 0;  // 1000 coefficients: beyond the parameter budget
+  return NB;
+}
+
+static inline int validate_desc(const lpgp_kernel_desc* k) {
+  if (!k) return -1;
+  if (k->d < 1 || k->d > LPGP_MAX_DIM) return -1;
+  int64_t total = 1;
+  for (int d = 0; d < k->d; ++d) {
+    if (k->dim_type[d] != LPGP_DIM_MATERN && k->dim_type[d] != LPGP_DIM_EXPQUAD) return -1;
+    if (k->nbasis[d] < 1 || k->nbasis[d] > 8) return -1;
+    if (k->has_odd[d] && k->dim_type[d] != LPGP_DIM_MATERN) return -1;
+    if (!(k->scale[d] > 0.0)) return -1;
+    total *= k->nbasis[d] * (k->has_odd[d] ? 2 : 1);
+  }
+  if (total > LPGP_MAX_COEF) return -1;
+  return 0;
+}

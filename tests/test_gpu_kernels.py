@@ -1,0 +1,197 @@
+"""GPU parity tests of the raw C-ABI kernels (through ctypes) against the frozen reference outputs, the oracle
+and plain torch FP64 references.  Run on the B200 box: ``pytest -m gpu``."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers
+from tests.golden import cases as gcases
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+_K = np.load(os.path.join(GOLDEN, "kernels.npz"))
+SPECS = json.loads(bytes(_K["__specs__"]).decode())
+
+
+def _lowerable(spec):
+    base = spec["kernel"]["base"]
+    return not (base["kind"] == "matern" and int(np.prod(base.get("input_shape", ()) or (1,))) > 1)
+
+
+LOWERABLE = [s for s in SPECS if _lowerable(s)]
+GRAM_TOL = 1e-12  # north_star: Gram entries rel err <= 1e-12 (relative to max |G|)
+
+
+@pytest.fixture(scope="module")
+def be():
+    from linpde_gp_b200 import backend
+
+    return backend
+
+
+@pytest.mark.parametrize("spec", LOWERABLE, ids=[s["name"] for s in LOWERABLE])
+def test_gram_matches_reference_golden(be, spec):
+    desc = helpers.desc_from_spec(spec)
+    shape = gcases.kernel_input_shape(spec["kernel"])
+    X = gcases.sobol_points(shape)
+    d = desc.d
+    X0, X1 = be.points(X[:32], d), be.points(X, d)
+    K = be.gram(desc, X0, X1).cpu().numpy()
+    K_ref = _K[spec["name"] + "__K"]
+    scale = np.max(np.abs(K_ref))
+    assert np.max(np.abs(K - K_ref)) <= GRAM_TOL * scale
+    dg = be.gram_diag(desc, 32).cpu().numpy()
+    assert np.max(np.abs(dg - _K[spec["name"] + "__diag"])) <= GRAM_TOL * scale
+
+
+@pytest.mark.parametrize("n0,n1", [(1, 1), (63, 129), (64, 128), (200, 77), (513, 1025)])
+def test_gram_ragged_shapes_and_modes(be, n0, n1):
+    from oracle import covfuncs as ocf
+
+    spec = next(s for s in SPECS if s["name"] == "ns_poisson2d_LkL")
+    desc = helpers.desc_from_spec(spec)
+    rng = np.random.default_rng(n0 * 1000 + n1)
+    A, B = rng.uniform(0, 1, (n0, 2)), rng.uniform(0, 1, (n1, 2))
+    L = gcases.spec_to_oracle_op(spec["L0"])
+    K_ref = ocf.matrix(spec["kernel"], L, L, A, B)
+    scale = np.max(np.abs(K_ref))
+    K = be.gram(desc, be.points(A, 2), be.points(B, 2))
+    assert np.max(np.abs(K.cpu().numpy() - K_ref)) <= GRAM_TOL * scale
+    # accumulate + alpha
+    K2 = be.gram(desc, be.points(A, 2), be.points(B, 2), out=K.clone(), accumulate=True, alpha=-0.5)
+    assert np.max(np.abs(K2.cpu().numpy() - 0.5 * K_ref)) <= GRAM_TOL * scale
+    # odd leading dimension -> scalar store path
+    buf = torch.full((n0, n1 + 3), 7.0, dtype=torch.float64, device="cuda")[:, :n1]
+    if (n1 + 3) % 2 == 1:
+        be.gram(desc, be.points(A, 2), be.points(B, 2), out=buf)
+        assert np.max(np.abs(buf.cpu().numpy() - K_ref)) <= GRAM_TOL * scale
+
+
+def test_gram_lower_mode_and_symmetrize(be):
+    from oracle import covfuncs as ocf
+
+    spec = next(s for s in SPECS if s["name"] == "ns_heat_LkL")
+    desc = helpers.desc_from_spec(spec)
+    rng = np.random.default_rng(5)
+    A = rng.uniform(-1, 1, (333, 2))
+    L = gcases.spec_to_oracle_op(spec["L0"])
+    K_ref = ocf.matrix(spec["kernel"], L, L, A)
+    out = torch.full((333, 336), np.nan, dtype=torch.float64, device="cuda")[:, :333]
+    be.gram(desc, be.points(A, 2), None, out=out, lower=True)
+    be.symmetrize_lower(out)
+    assert np.max(np.abs(out.cpu().numpy() - K_ref)) <= GRAM_TOL * np.max(np.abs(K_ref))
+
+
+def test_gram_empty_input(be):
+    desc = helpers.desc_from_spec(next(s for s in SPECS if s["name"] == "ns_poisson2d_k"))
+    K = be.gram(desc, torch.empty((0, 2), dtype=torch.float64, device="cuda"), torch.zeros((5, 2), dtype=torch.float64, device="cuda"))
+    assert K.shape == (0, 5)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 8), (300, 200, 77), (1, 130, 1000), (1000, 1000, 512), (257, 511, 1030)])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (-1.0, 1.0), (0.5, -2.0)])
+def test_gemm_nt_vs_torch(be, m, n, k, alpha, beta):
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    A = be.alloc_matrix(m, k).normal_(generator=g)
+    B = be.alloc_matrix(n, k).normal_(generator=g)
+    C = be.alloc_matrix(m, n).normal_(generator=g)
+    ref = beta * C + alpha * (A @ B.T)
+    be.gemm_nt(A, B, C, alpha, beta)
+    err = (C - ref).abs().max().item()
+    assert err <= 1e-13 * max(1.0, k**0.5) * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_nt_lower_only_touches_lower_tiles(be):
+    n, k = 1000, 300
+    A = be.alloc_matrix(n, k).normal_()
+    C = be.alloc_matrix(n, n).zero_()
+    be.gemm_nt(A, A, C, -1.0, 1.0, lower=True)
+    ref = -(A @ A.T)
+    low = torch.tril(torch.ones(n, n, dtype=torch.bool, device="cuda"))
+    assert ((C - ref)[low]).abs().max().item() <= 1e-11
+    # tiles strictly above the diagonal were skipped
+    assert C[:128, 128:].abs().max().item() == 0.0
+
+
+def _spd(n, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    X = torch.randn(n, n + 16, dtype=torch.float64, device="cuda", generator=g)
+    return X @ X.T / n + 0.5 * torch.eye(n, dtype=torch.float64, device="cuda")
+
+
+@pytest.mark.parametrize("n", [2, 64, 128, 130, 200, 384, 1000, 2304, 4098])
+def test_potrf_vs_torch(be, n):
+    G = _spd(n, n)
+    f = be.DeviceFactor([n])
+    f.L.copy_(G)
+    f.potrf()
+    L = torch.tril(f.L)
+    L_ref = torch.linalg.cholesky(G)
+    assert (L - L_ref).abs().max().item() <= 1e-12 * L_ref.abs().max().item()
+    # valid square root + positive diagonal (probnum tests/test_linops/test_linop_decompositions.py:17-62)
+    assert (L @ L.T - G).abs().max().item() <= 1e-12 * G.abs().max().item()
+    assert (torch.diagonal(L) > 0).all()
+    assert abs(f.logdet() - torch.logdet(G).item()) <= 1e-9 * max(1.0, abs(torch.logdet(G).item()))
+
+
+def test_potrf_not_positive_definite_raises(be):
+    n = 300
+    G = _spd(n, 1)
+    G[200, 200] = -1.0
+    f = be.DeviceFactor([n])
+    f.L.copy_(G)
+    with pytest.raises(np.linalg.LinAlgError) as ei:
+        f.potrf()
+    assert "201" in str(ei.value)  # LAPACK-style info: order of the first non-PD leading minor
+
+
+@pytest.mark.parametrize("n,m", [(130, 5), (1000, 300), (2304, 1), (2304, 700)])
+def test_trsm_and_potrs_vs_torch(be, n, m):
+    G = _spd(n, n + m)
+    f = be.DeviceFactor([n])
+    f.L.copy_(G)
+    f.potrf()
+    L_ref = torch.linalg.cholesky(G)
+    B = torch.randn(m, n, dtype=torch.float64, device="cuda")
+    X = be.alloc_matrix(m, n)
+    X.copy_(B)
+    f.trsm_rlt(X)
+    ref = torch.linalg.solve_triangular(L_ref, B.T, upper=False).T
+    assert (X - ref).abs().max().item() <= 1e-10 * ref.abs().max().item()
+    Y = B[: min(m, 3)].clone()
+    f.potrs(Y)
+    ref2 = torch.cholesky_solve(B[: min(m, 3)].T.contiguous(), L_ref).T
+    assert (Y - ref2).abs().max().item() <= 1e-9 * ref2.abs().max().item()
+
+
+@pytest.mark.parametrize("sizes", [(128, 128), (200, 72, 300), (2, 4, 6, 130), (1000, 24, 1500)])
+def test_append_equals_full_factorisation(be, sizes):
+    n = sum(sizes)
+    G = _spd(n, n)
+    f = None
+    off = 0
+    for s in sizes:
+        f = be.DeviceFactor([s]) if f is None else f.extended(s)
+        f.L[off : off + s, : off + s].copy_(G[off : off + s, : off + s])
+        if off == 0:
+            f.potrf()
+        else:
+            f.append_last()
+        off += s
+    L_ref = torch.linalg.cholesky(G)
+    assert (torch.tril(f.L) - L_ref).abs().max().item() <= 1e-11 * L_ref.abs().max().item()
+    b = torch.randn(1, n, dtype=torch.float64, device="cuda")
+    x = f.potrs(b.clone())
+    ref = torch.cholesky_solve(b.T.contiguous(), L_ref).T
+    assert (x - ref).abs().max().item() <= 1e-9 * ref.abs().max().item()
+
+
+def test_row_sumsq(be):
+    A = be.alloc_matrix(37, 1001).normal_()
+    out = be.row_sumsq(A, -1.0, 3.0)
+    ref = 3.0 - (A * A).sum(dim=1)
+    assert (out - ref).abs().max().item() <= 1e-11 * ref.abs().max().item()
