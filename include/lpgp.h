@@ -79,6 +79,12 @@ const char* lpgp_error_string(int code);
 int lpgp_gram(const lpgp_kernel_desc* desc, const double* X0, int64_t n0, const double* X1, int64_t n1,
               double* out, int64_t ld, int mode, int accumulate, double alpha, void* stream);
 
+/* out[i] = alpha * value(X0[i], X1[i]) for n explicit pairs: general numpy-broadcast calls  k(x0, x1)  of
+ * pn CovarianceFunction.__call__ (pn/randprocs/covfuncs/_covariance_function.py:280-357) that are not an outer
+ * product of two point sets.                                                                           */
+int lpgp_gram_pairs(const lpgp_kernel_desc* desc, const double* X0, const double* X1, int64_t n, double* out,
+                    double alpha, void* stream);
+
 /* out[i] = alpha * k(X0[i], X0[i])  -- the reference's element-wise `k(x0, None)` (x1=None) semantics. */
 int lpgp_gram_diag(const lpgp_kernel_desc* desc, int64_t n0, double* out, double alpha, void* stream);
 

@@ -69,6 +69,7 @@ def _load() -> ctypes.CDLL:
         "lpgp_build_arch": (ctypes.c_char_p, []),
         "lpgp_error_string": (ctypes.c_char_p, [ci]),
         "lpgp_gram": (ci, [KD, vp, i64, vp, i64, vp, i64, ci, ci, dbl, vp]),
+        "lpgp_gram_pairs": (ci, [KD, vp, vp, i64, vp, dbl, vp]),
         "lpgp_gram_diag": (ci, [KD, i64, vp, dbl, vp]),
         "lpgp_add_diag": (ci, [vp, i64, i64, vp, dbl, vp]),
         "lpgp_symmetrize_lower": (ci, [vp, i64, i64, vp]),
@@ -93,7 +94,7 @@ def _load() -> ctypes.CDLL:
 
 lib = _load()
 EXPORTED = (
-    "lpgp_version lpgp_build_arch lpgp_error_string lpgp_gram lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
+    "lpgp_version lpgp_build_arch lpgp_error_string lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
     "lpgp_gemm_nt lpgp_factor_dinv_bytes lpgp_potrf lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_logdet "
     "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq"
 ).split()

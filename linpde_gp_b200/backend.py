@@ -84,6 +84,15 @@ def gram(desc: _lib.KernelDesc, X0: torch.Tensor, X1: Optional[torch.Tensor] = N
     return out
 
 
+def gram_pairs(desc: _lib.KernelDesc, X0: torch.Tensor, X1: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """out[i] = alpha * value(X0[i], X1[i]) (explicit pairs)."""
+    n = X0.shape[0]
+    assert X1.shape == X0.shape
+    out = torch.empty(n, dtype=F64, device=_require_cuda())
+    check(lib.lpgp_gram_pairs(ctypes.byref(desc), _ptr(X0), _ptr(X1), n, _ptr(out), float(alpha), _stream()), "lpgp_gram_pairs")
+    return out
+
+
 def gram_diag(desc: _lib.KernelDesc, n: int, alpha: float = 1.0) -> torch.Tensor:
     out = torch.empty(n, dtype=F64, device=_require_cuda())
     check(lib.lpgp_gram_diag(ctypes.byref(desc), n, _ptr(out), float(alpha), _stream()), "lpgp_gram_diag")

@@ -152,6 +152,20 @@ int dispatch_nb(int NB, bool odd, const lpgp_kernel_desc& k, const double* X0, i
   return -1;
 }
 
+// element-wise pairs: out[i] = alpha * value(X0[i], X1[i])  (general numpy-broadcast calls k(x0, x1); not a hot path)
+__global__ void __launch_bounds__(256)
+    gram_pairs_kernel(const __grid_constant__ lpgp_kernel_desc k, const double* __restrict__ X0,
+                      const double* __restrict__ X1, int64_t n, double* __restrict__ out, double alpha) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x0[LPGP_MAX_DIM], x1[LPGP_MAX_DIM];
+  for (int d = 0; d < k.d; ++d) {
+    x0[d] = X0[i * k.d + d];
+    x1[d] = X1[i * k.d + d];
+  }
+  out[i] = alpha * eval_pair_generic(k, x0, x1);
+}
+
 __global__ void fill_kernel(double* out, int64_t n, double v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = v;
@@ -219,6 +233,19 @@ extern "C" int lpgp_gram(const lpgp_kernel_desc* desc, const double* X0, int64_t
     return 0;
   }
   gram_generic_kernel<<<grid, 256, 0, st>>>(*desc, X0, n0, X1, n1, out, ld, mode, accumulate, alpha);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int lpgp_gram_pairs(const lpgp_kernel_desc* desc, const double* X0, const double* X1, int64_t n, double* out,
+                               double alpha, void* stream) {
+  if (validate_desc(desc)) return -1;
+  if (n < 0) return -4;
+  if (n == 0) return 0;
+  if (!X0) return -2;
+  if (!X1) return -3;
+  if (!out) return -5;
+  gram_pairs_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(*desc, X0, X1, n, out, alpha);
   LPGP_CHECK_LAUNCH();
   return 0;
 }

@@ -1,0 +1,370 @@
+"""``ConditionalGaussianProcess``: a GP conditioned on batches of linear (PDE-collocation, boundary, plain
+evaluation) observations, with a device-resident cached Cholesky factor of the Gram matrix that is EXTENDED
+when another batch is added.
+
+Mirrors src/linpde_gp/randprocs/_gaussian_process/_conditional.py (``from_observations`` :27-54,
+``condition_on_observations`` :253-294, ``_preprocess_observations`` :296-399, ``Mean`` :177-197,
+``CovarianceFunction`` :199-251, push-forwards :432-467).  Numerics: Gram blocks by the pairwise CUDA kernel,
+bordered FP64 Cholesky + triangular solves on the DMMA path, matrix-free posterior mean, chunked TRSM posterior
+variance -- all in ``liblpgp.so``.  Objects are immutable after construction (new conditionings copy the factor),
+like the reference's functional API.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import backend, functions, linfunctls, linops, randvars
+from ..linfuncops import LinearFunctionOperator
+from . import covfuncs
+from ._gaussian_process import GaussianProcess
+
+VAR_CHUNK_BYTES = 4 << 30  # cross-covariance workspace per chunk of test points
+
+
+def _descs(k: covfuncs.CovarianceFunction):
+    """Device descriptors of a (possibly sum) kernel."""
+    if isinstance(k, covfuncs.SumCovarianceFunction):
+        try:
+            return [k.descriptor()]
+        except NotImplementedError:
+            out = []
+            for s in k.summands:
+                out.extend(_descs(s))
+            return out
+    return [k.descriptor()]
+
+
+class _Block:
+    """One observation batch: points, operator, logical / physical (even-padded) size, offset in the factor."""
+
+    def __init__(self, X_host: np.ndarray, op: Optional[LinearFunctionOperator], d: int, col_off: int):
+        self.X_host = X_host
+        self.op = op
+        self.X = backend.points(X_host, d)
+        self.n = self.X.shape[0]
+        self.n_phys = self.n + (self.n % 2)
+        self.col_off = col_off
+
+
+class ConditionalGaussianProcess(GaussianProcess):
+    @classmethod
+    def from_observations(cls, prior: GaussianProcess, Y, X=None, *, L=None, b=None):
+        Y, Lf, b, op, Xobs, resid, noise = cls._preprocess_observations(prior=prior, Y=Y, X=X, L=L, b=b)
+        blk = _Block(Xobs, op, prior.cov.input_size, 0)
+        factor = backend.DeviceFactor([blk.n_phys])
+        cls._assemble_rows(prior, [], blk, factor, noise)
+        factor.potrf()
+        y = torch.zeros(factor.n, dtype=torch.float64, device=factor.L.device)
+        y[: blk.n].copy_(backend.to_device(resid))
+        w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
+        return cls(prior=prior, Ys=(Y,), Ls=(Lf,), bs=(b,), blocks=(blk,), factor=factor, resid=y, weights=w)
+
+    def __init__(self, *, prior, Ys, Ls, bs, blocks, factor, resid, weights, test_op=None, base_prior=None):
+        self._prior = prior
+        self._base_prior = prior if base_prior is None else base_prior  # the process the observations refer to
+        self._Ys = tuple(Ys)
+        self._Ls = tuple(Ls)
+        self._bs = tuple(bs)
+        self._blocks = tuple(blocks)
+        self._factor = factor
+        self._resid = resid
+        self._w = weights
+        self._test_op = test_op
+        self._gram_op = None
+        super().__init__(
+            mean=ConditionalGaussianProcess.Mean(self),
+            cov=ConditionalGaussianProcess.CovarianceFunction(self),
+        )
+
+    # -- state ---------------------------------------------------------------------------------------------
+    @property
+    def _logical_index(self) -> np.ndarray:
+        return np.concatenate([np.arange(b.col_off, b.col_off + b.n) for b in self._blocks])
+
+    @property
+    def gram(self) -> "GramFactorOperator":
+        if self._gram_op is None:
+            self._gram_op = GramFactorOperator(self._factor, self._logical_index)
+        return self._gram_op
+
+    @property
+    def representer_weights(self) -> np.ndarray:
+        return self._w.cpu().numpy()[self._logical_index]
+
+    # -- kernels between the test side and observation block j ------------------------------------------------
+    def _k_test_obs(self, blk: _Block):
+        k = self._base_prior.cov
+        kk = k if blk.op is None else blk.op(k, argnum=1)
+        return kk if self._test_op is None else self._test_op(kk, argnum=0)
+
+    def _obs_blocks(self) -> backend.ObsBlocks:
+        descs, Xs, offs = [], [], []
+        for blk in self._blocks:
+            for dsc in _descs(self._k_test_obs(blk)):
+                descs.append(dsc)
+                Xs.append(blk.X)
+                offs.append(blk.col_off)
+        return backend.ObsBlocks(descs, Xs, offs)
+
+    def _obs_blocks_unique(self) -> backend.ObsBlocks:
+        """One entry per observation block (sum kernels not supported for the variance workspace assembly)."""
+        descs, Xs, offs = [], [], []
+        for blk in self._blocks:
+            ds = _descs(self._k_test_obs(blk))
+            if len(ds) != 1:
+                raise NotImplementedError("posterior covariance of sum-kernels with different base factors")
+            descs.append(ds[0])
+            Xs.append(blk.X)
+            offs.append(blk.col_off)
+        return backend.ObsBlocks(descs, Xs, offs)
+
+    # -- posterior mean / covariance -----------------------------------------------------------------------------
+    class Mean(functions.Function):
+        def __init__(self, post: "ConditionalGaussianProcess"):
+            self._post = post
+            super().__init__(input_shape=post._prior.mean.input_shape, output_shape=())
+
+        def _evaluate(self, x: np.ndarray) -> np.ndarray:
+            post = self._post
+            batch = x.shape[: x.ndim - self.input_ndim]
+            m_x = post._prior.mean(x)
+            Xt = backend.points(x, post._base_prior.cov.input_size)
+            upd = backend.post_mean(post._obs_blocks(), post._w, Xt)
+            return m_x + upd.cpu().numpy().reshape(batch)
+
+    class CovarianceFunction(covfuncs.CovarianceFunction):
+        def __init__(self, post: "ConditionalGaussianProcess"):
+            self._post = post
+            super().__init__(post._prior.cov.input_shape)
+
+        def _evaluate(self, x0, x1, batch):
+            post = self._post
+            d = self.input_size
+            if x1 is None:  # pointwise variance
+                Xt = backend.points(x0, d)
+                prior_diag = _descs(post._prior.cov)
+                diag = sum(dsc.diag_value for dsc in prior_diag)
+                n = post._factor.n
+                chunk = int(max(256, min(Xt.shape[0], VAR_CHUNK_BYTES // (8 * backend.round_up(n, 16)))))
+                var = backend.post_var(post._obs_blocks_unique(), post._factor, Xt, diag, chunk=chunk)
+                return var.cpu().numpy().reshape(batch)
+            nd = self.input_ndim
+            b0, b1 = x0.shape[: x0.ndim - nd], x1.shape[: x1.ndim - nd]
+            nb = len(batch)
+            b0 = (1,) * (nb - len(b0)) + tuple(b0)
+            b1 = (1,) * (nb - len(b1)) + tuple(b1)
+            if not all(s0 == 1 or s1 == 1 for s0, s1 in zip(b0, b1)):
+                raise NotImplementedError("posterior covariance: only outer-product broadcasting is supported")
+            K = self._dense(x0.reshape((-1,) + self.input_shape), x1.reshape((-1,) + self.input_shape))
+            K = K.cpu().numpy().reshape(tuple(b0) + tuple(b1))
+            perm = [ax for pair in zip(range(nb), range(nb, 2 * nb)) for ax in pair]
+            return np.ascontiguousarray(np.transpose(K, perm)).reshape(batch)
+
+        def _dense(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> torch.Tensor:
+            """k(x0,x1) - K_0 G^{-1} K_1^T = k(x0,x1) - (K_0 L^{-T})(K_1 L^{-T})^T  (_conditional.py:245-251)."""
+            post = self._post
+            d = self.input_size
+            X0 = backend.points(x0, d)
+            blocks = post._obs_blocks_unique()
+            V0 = backend.crosscov(blocks, post._factor.n, X0)
+            post._factor.trsm_rlt(V0)
+            if x1 is None:
+                X1, V1 = None, V0
+            else:
+                X1 = backend.points(x1, d)
+                V1 = backend.crosscov(blocks, post._factor.n, X1)
+                post._factor.trsm_rlt(V1)
+            C = backend.alloc_matrix(X0.shape[0], V1.shape[0])
+            for i, dsc in enumerate(_descs(post._prior.cov)):
+                backend.gram(dsc, X0, X1, out=C, accumulate=i > 0)
+            backend.gemm_nt(V0, V1, C, -1.0, 1.0)
+            return C
+
+        def linop(self, x0, x1=None):
+            x0 = self._preprocess_linop_input(x0, 0)
+            x1 = None if x1 is None else self._preprocess_linop_input(x1, 1)
+            C = self._dense(x0, x1)
+            op = _DeviceMatrix(C)
+            if x1 is None:
+                op.is_symmetric = True
+            return op
+
+    # -- adding observations ----------------------------------------------------------------------------------
+    def condition_on_observations(self, Y, X=None, *, L=None, b=None):
+        if self._test_op is not None:
+            raise NotImplementedError("condition the original process, then apply the operator")
+        prior = self._base_prior
+        Y, Lf, b, op, Xobs, resid, noise = self._preprocess_observations(prior=prior, Y=Y, X=X, L=L, b=b)
+        blk = _Block(Xobs, op, prior.cov.input_size, self._factor.n)
+        factor = self._factor.extended(blk.n_phys)
+        self._assemble_rows(prior, self._blocks, blk, factor, noise)
+        factor.append_last()
+        y = torch.zeros(factor.n, dtype=torch.float64, device=factor.L.device)
+        y[: self._factor.n].copy_(self._resid)
+        y[blk.col_off : blk.col_off + blk.n].copy_(backend.to_device(resid))
+        # representer weights of the extended system.  The reference updates them with the Schur-complement
+        # formulas of BlockMatrix2x2.schur_update (_block.py:226-231); solving with the extended factor is the same
+        # linear system and costs the same O(N^2).
+        w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
+        return ConditionalGaussianProcess(
+            prior=prior, Ys=self._Ys + (Y,), Ls=self._Ls + (Lf,), bs=self._bs + (b,),
+            blocks=self._blocks + (blk,), factor=factor, resid=y, weights=w,
+        )
+
+    @staticmethod
+    def _assemble_rows(prior, prev_blocks, blk: _Block, factor: backend.DeviceFactor, noise) -> None:
+        """Fill rows [col_off, col_off + n_phys) of the factor buffer with [L_new k L_j^*(X_new, X_j) ... | D]."""
+        k = prior.cov
+        r0, n = blk.col_off, blk.n
+        rows = factor.L[r0 : r0 + blk.n_phys]
+        for pb in prev_blocks:
+            kj = k if pb.op is None else pb.op(k, argnum=1)
+            kij = kj if blk.op is None else blk.op(kj, argnum=0)
+            out = rows[:n, pb.col_off : pb.col_off + pb.n]
+            for i, dsc in enumerate(_descs(kij)):
+                backend.gram(dsc, blk.X, pb.X, out=out, accumulate=i > 0)
+            if pb.n_phys != pb.n:
+                rows[:, pb.col_off + pb.n] = 0.0
+        kj = k if blk.op is None else blk.op(k, argnum=1)
+        kii = kj if blk.op is None else blk.op(kj, argnum=0)
+        D = rows[:n, r0 : r0 + n]
+        for i, dsc in enumerate(_descs(kii)):
+            backend.gram(dsc, blk.X, None, out=D, lower=True, accumulate=i > 0)
+        if noise is not None:
+            kind, val = noise
+            if kind == "diag":
+                backend.add_diag(D, backend.to_device(val), 1.0)
+            else:
+                D.add_(backend.to_device(val))
+        if blk.n_phys != n:  # identity padding row keeps segment offsets even (16-byte aligned TMA rows)
+            rows[n, : r0 + n + 1] = 0.0
+            rows[n, r0 + n] = 1.0
+
+    @classmethod
+    def _preprocess_observations(cls, *, prior, Y, X, L, b):
+        """Argument handling and error behaviour of _conditional.py:296-399."""
+        if isinstance(L, linfunctls.LinearFunctional):
+            if X is not None:
+                raise TypeError("If `L` is a `LinearFunctional`, `X` must be `None`.")
+            Lf = L
+        elif isinstance(L, LinearFunctionOperator):
+            if X is None:
+                raise ValueError("`X` must not be omitted if `L` is a `LinearFunctionOperator`.")
+            Lf = L.to_linfunctl(X)
+        elif L is None:
+            if X is None:
+                raise ValueError("`X` and `L` can not be omitted at the same time.")
+            Lf = linfunctls._EvaluationFunctional(  # pylint: disable=protected-access
+                input_domain_shape=prior.input_shape, input_codomain_shape=prior.output_shape, X=X
+            )
+        else:
+            raise TypeError("`L` must be a `LinearFunctional`, a `LinearFunctionOperator` or `None`.")
+        op, Xobs = Lf._as_observation()  # pylint: disable=protected-access
+
+        if b is not None:
+            b = randvars.asrandvar(b)
+            if not isinstance(b, (randvars.Constant, randvars.Normal)):
+                raise TypeError(f"`b` must be a `Normal` or a `Constant` `RandomVariable` ({type(b)=})")
+            if tuple(b.shape) != tuple(Lf.output_shape):
+                raise ValueError(f"{b.shape=} must be equal to {Lf.output_shape}")
+
+        mean_fn = prior.mean if op is None else op(prior.mean)
+        pred_mean = np.asarray(mean_fn(Xobs), dtype=np.double).reshape(-1, order="C")
+        Y = np.asarray(Y, dtype=np.double)
+        if Y.shape != tuple(Lf.output_shape):
+            raise ValueError(f"Expected Y to have shape {Lf.output_shape}, got shape {Y.shape}.")
+        Y = Y.reshape(-1, order="C")
+
+        noise = None
+        if b is not None:
+            pred_mean = pred_mean + np.asarray(b.mean, dtype=np.double).reshape(-1, order="C")
+            cov = b.cov
+            if isinstance(cov, linops.Scaling):
+                noise = ("diag", cov.factors)
+            elif isinstance(cov, linops.LinearOperator):
+                noise = ("dense", cov.todense())
+            else:
+                noise = ("dense", np.asarray(cov, dtype=np.double))
+        return Y, Lf, b, op, Xobs, Y - pred_mean, noise
+
+    # -- push-forwards L(posterior) (_conditional.py:432-467) --------------------------------------------------------
+    def _apply_linfuncop(self, L: LinearFunctionOperator) -> "ConditionalGaussianProcess":
+        if self._test_op is not None:
+            raise NotImplementedError("composition of two operators on a conditioned process")
+        return ConditionalGaussianProcess(
+            prior=L(self._prior), Ys=self._Ys, Ls=self._Ls, bs=self._bs, blocks=self._blocks, factor=self._factor,
+            resid=self._resid, weights=self._w, test_op=L, base_prior=self._base_prior,
+        )
+
+    def _apply_linfunctl(self, Lf) -> randvars.Normal:
+        op, X = Lf._as_observation()  # pylint: disable=protected-access
+        gp = self if op is None else self._apply_linfuncop(op)
+        X = np.asarray(X, dtype=np.double)
+        return randvars.Normal(mean=np.asarray(gp.mean(X)).reshape(-1), cov=gp.cov.linop(X))
+
+
+class _DeviceMatrix(linops.LinearOperator):
+    def __init__(self, dev: torch.Tensor):
+        super().__init__(dev.shape)
+        self._dev = dev
+
+    def device_dense(self):
+        return self._dev
+
+
+class GramFactorOperator(linops.LinearOperator):
+    """The (factored) Gram matrix of all observation batches -- the reference's nested ``BlockMatrix2x2``
+    (src/linpde_gp/linops/_block.py:84-292) flattened into one device-resident bordered Cholesky factor."""
+
+    def __init__(self, factor: backend.DeviceFactor, logical_index: np.ndarray):
+        n = len(logical_index)
+        super().__init__((n, n))
+        self.factor = factor
+        self._idx = logical_index
+        self.is_symmetric = True
+        self.is_positive_definite = True
+
+    def device_dense(self) -> torch.Tensor:
+        f = self.factor
+        Lt = backend.alloc_matrix(f.n, f.n)
+        Lt.copy_(torch.tril(f.L))
+        G = backend.alloc_matrix(f.n, f.n)
+        backend.gemm_nt(Lt, Lt, G, 1.0, 0.0)
+        idx = torch.as_tensor(self._idx, device=G.device)
+        return G[idx][:, idx].contiguous()
+
+    def cholesky(self, lower: bool = True):
+        fac = _LogicalCholesky(self.factor, self._idx)
+        return fac if lower else fac.T
+
+    def solve(self, B):
+        B = np.asarray(B, dtype=np.double)
+        n, f = self.shape[0], self.factor
+        vec = B.ndim == 1
+        cols = B[:, None] if vec else B
+        if cols.shape[0] != n:
+            raise ValueError("`b` must be a vector or a (stack of) matrices.")
+        dev = torch.zeros((cols.shape[1], f.n), dtype=torch.float64, device=f.L.device)
+        idx = torch.as_tensor(self._idx, device=dev.device)
+        dev[:, idx] = backend.to_device(np.ascontiguousarray(cols.T))
+        f.potrs(dev)
+        res = dev[:, idx].cpu().numpy().T
+        return res[:, 0] if vec else res
+
+    def logdet(self) -> float:
+        return self.factor.logdet()
+
+
+class _LogicalCholesky(linops.LinearOperator):
+    def __init__(self, factor, idx):
+        super().__init__((len(idx), len(idx)))
+        self.factor = factor
+        self._idx = idx
+        self.is_lower_triangular = True
+
+    def device_dense(self):
+        idx = torch.as_tensor(self._idx, device=self.factor.L.device)
+        return torch.tril(self.factor.L)[idx][:, idx].contiguous()

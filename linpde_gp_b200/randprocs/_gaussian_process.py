@@ -1,0 +1,82 @@
+"""``GaussianProcess`` prior (pn/randprocs/_gaussian_process.py:15-79, _random_process.py:223-270) with the
+``condition_on_observations`` entry point that linpde-gp patches in
+(src/linpde_gp/randprocs/_gaussian_process/_conditional.py:402-406) and the ``L(gp)`` push-forwards of
+src/linpde_gp/randprocs/_gaussian_process/_lintransforms.py:9-31."""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import functions, randvars
+from . import covfuncs
+
+
+class GaussianProcess:
+    def __init__(self, mean, cov):
+        if not isinstance(mean, functions.Function):
+            raise TypeError("The mean function must have type `Function`.")
+        if not isinstance(cov, covfuncs.CovarianceFunction):
+            raise TypeError("The covariance function must have type `CovarianceFunction`.")
+        if mean.input_shape != cov.input_shape:
+            raise ValueError(
+                f"The mean and covariance functions must have the same input shapes ({mean.input_shape} and "
+                f"{cov.input_shape})."
+            )
+        if mean.output_shape != ():
+            raise NotImplementedError("only scalar-output processes are on the accelerated path")
+        self._mean = mean
+        self._cov = cov
+
+    @property
+    def mean(self):
+        return self._mean
+
+    @property
+    def cov(self):
+        return self._cov
+
+    @property
+    def input_shape(self):
+        return self._mean.input_shape
+
+    @property
+    def input_ndim(self):
+        return self._mean.input_ndim
+
+    @property
+    def output_shape(self):
+        return ()
+
+    @property
+    def output_ndim(self):
+        return 0
+
+    def __call__(self, args) -> randvars.Normal:
+        """Finite-dimensional marginal ``Normal(mean(x), cov.matrix(x))``."""
+        x = np.asarray(args, dtype=np.double)
+        return randvars.Normal(mean=np.array(self._mean(x), copy=False).reshape(-1), cov=self._cov.matrix(x))
+
+    def var(self, args) -> np.ndarray:
+        return self._cov(np.asarray(args, dtype=np.double), None)
+
+    def std(self, args) -> np.ndarray:
+        return np.sqrt(self.var(args))
+
+    def condition_on_observations(self, Y, X=None, *, L=None, b=None):
+        from ._conditional import ConditionalGaussianProcess
+
+        return ConditionalGaussianProcess.from_observations(self, Y, X, L=L, b=b)
+
+
+def apply_linfuncop_to_gp(L, gp: GaussianProcess) -> GaussianProcess:
+    """``L(gp)`` for a LinearFunctionOperator (_lintransforms.py:25-31)."""
+    mean = L(gp.mean)
+    cov = L(L(gp.cov, argnum=1), argnum=0)
+    return GaussianProcess(mean, cov)
+
+
+def apply_linfunctl_to_gp(Lf, gp: GaussianProcess) -> randvars.Normal:
+    """``L(gp)`` for a LinearFunctional: the (lazy) Gaussian ``Normal(L m, L k L^*)`` (_lintransforms.py:9-22)."""
+    op, X = Lf._as_observation()  # pylint: disable=protected-access
+    mean_fn = gp.mean if op is None else op(gp.mean)
+    k = gp.cov if op is None else op(op(gp.cov, argnum=1), argnum=0)
+    return randvars.Normal(mean=np.asarray(mean_fn(X)).reshape(-1), cov=k.linop(X))

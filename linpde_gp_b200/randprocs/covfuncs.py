@@ -1,0 +1,473 @@
+"""Covariance functions of the hot path with the reference's API; numerics on the GPU.
+
+Mirrors ``linpde_gp.randprocs.covfuncs`` / ``probnum.randprocs.covfuncs``:
+``CovarianceFunction.__call__/matrix/linop`` (pn/randprocs/covfuncs/_covariance_function.py:280-488),
+``Matern`` (pn …/_matern.py), ``ExpQuad`` (pn …/_exponentiated_quadratic.py), ``TensorProduct``
+(src/linpde_gp/randprocs/covfuncs/_tensor_product.py:15-95), the scalar / sum wrappers
+(src/linpde_gp/randprocs/covfuncs/_jax_arithmetic.py:16-66) and the operator-transformed kernels selected by
+the dispatch registry src/linpde_gp/randprocs/covfuncs/linfuncops/diffops/_registry.py.
+
+Every kernel that can be evaluated is *lowered* to a flat descriptor (``_lowering.py``) and evaluated by the
+hand-written CUDA kernels behind ``liblpgp.so``; there is no numpy evaluation path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _lowering, backend
+from ..functions import _as_shape
+from ..linops import CovarianceLinearOperator
+
+
+class CovarianceFunction:
+    """Scalar-output covariance function ``k: R^input_shape x R^input_shape -> R``."""
+
+    def __init__(self, input_shape=()):
+        self._input_shape = _as_shape(input_shape)
+
+    # -- shapes ------------------------------------------------------------------------------------------
+    @property
+    def input_shape(self):
+        return self._input_shape
+
+    input_shape_0 = input_shape
+    input_shape_1 = input_shape
+
+    @property
+    def input_ndim(self):
+        return len(self._input_shape)
+
+    @property
+    def input_size(self):
+        return int(np.prod(self._input_shape)) if self._input_shape else 1
+
+    output_shape_0 = ()
+    output_shape_1 = ()
+    output_shape = ()
+
+    # -- lowering ------------------------------------------------------------------------------------------
+    def _product_form(self):
+        """``(factors, L0_terms, L1_terms, scale)`` or raise ``NotImplementedError``."""
+        raise NotImplementedError(f"{type(self).__name__} has no closed product form on the device path")
+
+    def descriptor(self):
+        if getattr(self, "_desc", None) is None:
+            factors, t0, t1, scale = self._product_form()
+            self._desc = _lowering.lower(factors, t0, t1, scale)
+        return self._desc
+
+    # -- evaluation ----------------------------------------------------------------------------------------
+    def _check_shapes(self, x0_shape, x1_shape=None):
+        err = (
+            "The shape of the input array `x{argnum}` must match `input_shape_{argnum}`, i.e. `{input_shape}`, "
+            "along its trailing dimensions, but an array with shape `{shape}` was given."
+        )
+        nd = self.input_ndim
+        if tuple(x0_shape[len(x0_shape) - nd :]) != self._input_shape:
+            raise ValueError(err.format(argnum=0, input_shape=self._input_shape, shape=x0_shape))
+        batch = tuple(x0_shape[: len(x0_shape) - nd])
+        if x1_shape is not None:
+            if tuple(x1_shape[len(x1_shape) - nd :]) != self._input_shape:
+                raise ValueError(err.format(argnum=1, input_shape=self._input_shape, shape=x1_shape))
+            try:
+                batch = np.broadcast_shapes(batch, tuple(x1_shape[: len(x1_shape) - nd]))
+            except ValueError as ve:
+                raise ValueError(
+                    f"The input arrays `x0` and `x1` with shapes {x0_shape} and {x1_shape} can not be broadcast "
+                    "to a common shape."
+                ) from ve
+        return batch
+
+    def __call__(self, x0, x1=None):
+        """``k(x0, x1)`` with numpy broadcasting over batch shapes; ``x1=None`` evaluates ``k(x0_i, x0_i)``
+        (pn …/_covariance_function.py:280-357)."""
+        x0 = np.asarray(x0, dtype=np.double)
+        x1 = None if x1 is None else np.asarray(x1, dtype=np.double)
+        batch = self._check_shapes(x0.shape, None if x1 is None else x1.shape)
+        return self._evaluate(x0, x1, batch)
+
+    def _evaluate(self, x0, x1, batch):
+        desc = self.descriptor()
+        d = self.input_size
+        nd = self.input_ndim
+        if x1 is None:
+            n = int(np.prod(batch)) if batch else 1
+            return backend.gram_diag(desc, n).cpu().numpy().reshape(batch)
+        b0, b1 = x0.shape[: x0.ndim - nd], x1.shape[: x1.ndim - nd]
+        nb = len(batch)
+        b0 = (1,) * (nb - len(b0)) + tuple(b0)
+        b1 = (1,) * (nb - len(b1)) + tuple(b1)
+        # outer-product pattern: every batch axis varies in at most one of the arguments
+        if all(s0 == 1 or s1 == 1 for s0, s1 in zip(b0, b1)):
+            X0 = backend.points(x0, d)
+            X1 = backend.points(x1, d)
+            K = backend.gram(desc, X0, X1).cpu().numpy()  # (prod b0, prod b1)
+            # pair up axis i of x0's batch with axis i of x1's batch (one of them is a singleton) and merge
+            K = K.reshape(tuple(b0) + tuple(b1))
+            perm = [ax for pair in zip(range(nb), range(nb, 2 * nb)) for ax in pair]
+            return np.ascontiguousarray(np.transpose(K, perm)).reshape(batch)
+        full0 = np.broadcast_to(x0, batch + self._input_shape).reshape(-1, d)
+        full1 = np.broadcast_to(x1, batch + self._input_shape).reshape(-1, d)
+        out = backend.gram_pairs(desc, backend.to_device(full0), backend.to_device(full1))
+        return out.cpu().numpy().reshape(batch)
+
+    def _preprocess_linop_input(self, x, argnum):
+        x = np.asarray(x, dtype=np.double)
+        nd = self.input_ndim
+        if not (x.ndim >= nd and x.shape[x.ndim - nd :] == self._input_shape):
+            raise ValueError(
+                f"The shape of `x{argnum}` must must match `input_shape_{argnum}`, i.e. `{self._input_shape}`, of "
+                f"the covariance function along its trailing dimensions, but an array with shape `{x.shape}` was given."
+            )
+        return x.reshape((-1,) + self._input_shape, order="C")
+
+    def linop(self, x0, x1=None) -> CovarianceLinearOperator:
+        """Lazy device-resident covariance matrix (pn …/_covariance_function.py:415-488); ``x1=None`` means
+        ``x1 := x0`` (full symmetric matrix), unlike ``__call__``."""
+        x0 = self._preprocess_linop_input(x0, 0)
+        x1 = None if x1 is None else self._preprocess_linop_input(x1, 1)
+        return CovarianceLinearOperator(self, x0, x1)
+
+    def matrix(self, x0, x1=None) -> np.ndarray:
+        """Dense covariance matrix as a host array (pn …/_covariance_function.py:359-413)."""
+        return self.linop(x0, x1).todense()
+
+    # -- arithmetic ----------------------------------------------------------------------------------------
+    def __rmul__(self, other):
+        if np.ndim(other) == 0:
+            return ScaledCovarianceFunction(self, scalar=other)
+        return NotImplemented
+
+    def __add__(self, other):
+        if isinstance(other, CovarianceFunction):
+            return SumCovarianceFunction(self, other)
+        return NotImplemented
+
+
+class _Stationary1DMixin:
+    def _factors(self):
+        raise NotImplementedError
+
+
+class Matern(CovarianceFunction):
+    """Matern covariance function (pn/randprocs/covfuncs/_matern.py:25-195); half-integer ``nu`` on the device."""
+
+    def __init__(self, input_shape=(), nu=1.5, *, lengthscales=None):
+        super().__init__(input_shape)
+        nu = float(nu)
+        if nu <= 0:
+            raise ValueError(f"Hyperparameter nu={nu} must be positive.")
+        self._nu = nu
+        ls = np.asarray(1.0 if lengthscales is None else lengthscales, dtype=np.double)
+        if np.any(ls <= 0):
+            raise ValueError(f"All lengthscales l={ls} must be positive.")
+        np.broadcast_to(ls, self.input_shape)
+        self._lengthscales = ls
+
+    @property
+    def nu(self):
+        return self._nu
+
+    @property
+    def p(self):
+        q = self._nu - 0.5
+        return int(q) if q == int(q) else None
+
+    @property
+    def is_half_integer(self):
+        return self.p is not None
+
+    @property
+    def lengthscales(self):
+        return self._lengthscales
+
+    def _product_form(self):
+        if self.input_size != 1:
+            raise NotImplementedError(
+                "isotropic multi-dimensional Matern kernels are not of product form; use "
+                "TensorProduct(Matern((), ...), ...) like the reference's PDE examples"
+            )
+        if not self.is_half_integer:
+            raise NotImplementedError("only half-integer Matern kernels are supported on the device")
+        ell = float(np.broadcast_to(self._lengthscales, (1,))[0])
+        return [_lowering.Factor1D("matern", ell, nu=self._nu)], None, None, 1.0
+
+
+class ExpQuad(CovarianceFunction):
+    """Exponentiated quadratic (pn/randprocs/covfuncs/_exponentiated_quadratic.py:14-100), ARD lengthscales."""
+
+    def __init__(self, input_shape=(), *, lengthscales=None):
+        super().__init__(input_shape)
+        ls = np.asarray(1.0 if lengthscales is None else lengthscales, dtype=np.double)
+        if np.any(ls <= 0):
+            raise ValueError(f"Lengthscales l={ls} must be positive.")
+        np.broadcast_to(ls, self.input_shape)
+        self._lengthscales = ls
+
+    @property
+    def lengthscales(self):
+        return self._lengthscales
+
+    def _product_form(self):
+        if self.input_ndim > 1:
+            raise NotImplementedError("ExpQuad inputs must be scalars or vectors")
+        ls = np.broadcast_to(self._lengthscales, (self.input_size,))
+        return [_lowering.Factor1D("expquad", float(l)) for l in ls], None, None, 1.0
+
+
+class TensorProduct(CovarianceFunction):
+    """Product of univariate kernels (src/linpde_gp/randprocs/covfuncs/_tensor_product.py:15-48)."""
+
+    def __init__(self, *factors):
+        if len(factors) < 1:
+            raise ValueError("At least one factor is required.")
+        if not all(isinstance(k, CovarianceFunction) and k.input_shape == () for k in factors):
+            raise ValueError("The input shape of all factors must be `()`.")
+        self._factors = tuple(factors)
+        super().__init__((len(self._factors),))
+
+    @property
+    def factors(self):
+        return self._factors
+
+    def _product_form(self):
+        fs, scale = [], 1.0
+        for k in self._factors:
+            f, t0, t1, s = k._product_form()
+            if t0 is not None or t1 is not None or len(f) != 1:
+                raise NotImplementedError("TensorProduct factors must be plain univariate kernels")
+            fs.extend(f)
+            scale *= s
+        return fs, None, None, scale
+
+
+class ScaledCovarianceFunction(CovarianceFunction):
+    """``scalar * k`` (reference: ``JaxScaledCovarianceFunction``, _jax_arithmetic.py:16-44)."""
+
+    def __init__(self, covfunc, scalar):
+        if np.ndim(scalar) != 0:
+            raise TypeError()
+        super().__init__(covfunc.input_shape)
+        self._covfunc = covfunc
+        self._scalar = np.asarray(scalar, dtype=np.double)
+
+    @property
+    def scalar(self):
+        return self._scalar
+
+    @property
+    def covfunc(self):
+        return self._covfunc
+
+    def _product_form(self):
+        f, t0, t1, s = self._covfunc._product_form()
+        return f, t0, t1, s * float(self._scalar)
+
+    def __rmul__(self, other):
+        if np.ndim(other) == 0:
+            return ScaledCovarianceFunction(self._covfunc, scalar=np.asarray(other) * self._scalar)
+        return NotImplemented
+
+
+# reference-compatible aliases (src/linpde_gp/randprocs/covfuncs/__init__.py:1-19)
+JaxScaledCovarianceFunction = ScaledCovarianceFunction
+
+
+class SumCovarianceFunction(CovarianceFunction):
+    """``k1 + k2 + ...`` (reference: ``JaxSumCovarianceFunction``, _jax_arithmetic.py:47-66).  Summands sharing
+    the same base factors are folded into ONE device descriptor; otherwise blocks are accumulated."""
+
+    def __init__(self, *summands):
+        if not all(isinstance(s, CovarianceFunction) for s in summands):
+            raise TypeError()
+        if not all(s.input_shape == summands[0].input_shape for s in summands):
+            raise ValueError("All summands must have the same input shape")
+        super().__init__(summands[0].input_shape)
+        self._summands = tuple(summands)
+
+    @property
+    def summands(self):
+        return self._summands
+
+    def _product_form(self):
+        raise NotImplementedError("sum of kernels with different base factors: evaluated block-wise")
+
+    def descriptors(self):
+        return [s.descriptor() for s in self._summands]
+
+    def _evaluate(self, x0, x1, batch):
+        out = None
+        for s in self._summands:
+            v = s._evaluate(x0, x1, batch)
+            out = v if out is None else out + v
+        return out
+
+
+JaxSumCovarianceFunction = SumCovarianceFunction
+
+
+class LinDiffOpCovarianceFunction(CovarianceFunction):
+    """``L0 k L1^*`` for a product-form base kernel ``k`` and partial-derivative operators ``L0`` / ``L1``.
+
+    Generic carrier of what the reference spreads over ``TensorProduct_LinDiffOp_LinDiffOp`` and the
+    ``ExpQuad_* / *HalfIntegerMatern_*`` closed-form classes (diffops/_tensor_product.py, _expquad.py, _matern.py);
+    the named subclasses below only record WHICH reference class the dispatcher would have produced."""
+
+    def __init__(self, k, *, L0=None, L1=None):
+        super().__init__(k.input_shape)
+        self._k = k
+        self._L0 = L0
+        self._L1 = L1
+
+    @property
+    def k(self):
+        return self._k
+
+    @property
+    def L0(self):
+        return self._L0
+
+    @property
+    def L1(self):
+        return self._L1
+
+    def _product_form(self):
+        f, t0, t1, s = self._k._product_form()
+        assert t0 is None and t1 is None
+        d = len(f)
+
+        def terms(L):
+            if L is None:
+                return None
+            t = L._terms()
+            if any(len(mi) != d for mi in t):
+                raise ValueError("operator and kernel input dimensions differ")
+            return t
+
+        return f, terms(self._L0), terms(self._L1), s
+
+
+class TensorProduct_LinDiffOp_LinDiffOp(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_tensor_product.py:21"""
+
+
+class ExpQuad_Identity_DirectionalDerivative(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_expquad.py:12"""
+
+
+class ExpQuad_DirectionalDerivative_DirectionalDerivative(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_expquad.py:76"""
+
+
+class ExpQuad_Identity_WeightedLaplacian(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_expquad.py:145"""
+
+
+class ExpQuad_WeightedLaplacian_WeightedLaplacian(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_expquad.py:221"""
+
+
+class ExpQuad_DirectionalDerivative_WeightedLaplacian(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_expquad.py:348"""
+
+
+class HalfIntegerMatern_Identity_DirectionalDerivative(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_matern.py:17"""
+
+
+class UnivariateHalfIntegerMatern_DirectionalDerivative_DirectionalDerivative(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_matern.py:267"""
+
+
+class UnivariateHalfIntegerMatern_Identity_WeightedLaplacian(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_matern.py:358"""
+
+
+class UnivariateHalfIntegerMatern_WeightedLaplacian_WeightedLaplacian(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_matern.py:439"""
+
+
+class UnivariateHalfIntegerMatern_DirectionalDerivative_WeightedLaplacian(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_matern.py:512"""
+
+
+def _kind_of(L):
+    from ..linfuncops import diffops
+
+    if L is None:
+        return "Identity"
+    if isinstance(L, diffops.ScaledLinearDifferentialOperator):
+        return _kind_of(L.lindiffop)
+    if isinstance(L, diffops.WeightedLaplacian):
+        return "WeightedLaplacian"
+    if isinstance(L, diffops.DirectionalDerivative):
+        return "DirectionalDerivative"
+    if isinstance(L, diffops.PartialDerivative) and L.order == 0:
+        return "Identity"
+    return "LinDiffOp"
+
+
+def _select_class(k, L0, L1):
+    """Which closed-form class the reference's registry produces for (L0, k, L1)."""
+    if isinstance(k, TensorProduct):
+        return TensorProduct_LinDiffOp_LinDiffOp
+    kinds = tuple(sorted((_kind_of(L0), _kind_of(L1))))
+    table_eq = {
+        ("DirectionalDerivative", "Identity"): ExpQuad_Identity_DirectionalDerivative,
+        ("DirectionalDerivative", "DirectionalDerivative"): ExpQuad_DirectionalDerivative_DirectionalDerivative,
+        ("Identity", "WeightedLaplacian"): ExpQuad_Identity_WeightedLaplacian,
+        ("WeightedLaplacian", "WeightedLaplacian"): ExpQuad_WeightedLaplacian_WeightedLaplacian,
+        ("DirectionalDerivative", "WeightedLaplacian"): ExpQuad_DirectionalDerivative_WeightedLaplacian,
+    }
+    table_m = {
+        ("DirectionalDerivative", "Identity"): HalfIntegerMatern_Identity_DirectionalDerivative,
+        ("DirectionalDerivative", "DirectionalDerivative"): UnivariateHalfIntegerMatern_DirectionalDerivative_DirectionalDerivative,
+        ("Identity", "WeightedLaplacian"): UnivariateHalfIntegerMatern_Identity_WeightedLaplacian,
+        ("WeightedLaplacian", "WeightedLaplacian"): UnivariateHalfIntegerMatern_WeightedLaplacian_WeightedLaplacian,
+        ("DirectionalDerivative", "WeightedLaplacian"): UnivariateHalfIntegerMatern_DirectionalDerivative_WeightedLaplacian,
+    }
+    if isinstance(k, ExpQuad):
+        return table_eq.get(kinds, LinDiffOpCovarianceFunction)
+    if isinstance(k, Matern):
+        return table_m.get(kinds, LinDiffOpCovarianceFunction)
+    return LinDiffOpCovarianceFunction
+
+
+def _compose(L_old, L_new):
+    """Operators acting on the same argument compose; only ``identity`` is composable without a product rule."""
+    if L_old is None:
+        return L_new
+    raise NotImplementedError(
+        "an operator was already applied to this argument (the reference returns NotImplemented as well, "
+        "diffops/_registry.py:54-72)"
+    )
+
+
+def apply_linfuncop(L, k: CovarianceFunction, argnum: int = 0) -> CovarianceFunction:
+    """``L(k, argnum=...)``: the dispatch of src/linpde_gp/randprocs/covfuncs/linfuncops/_registry.py:14-31 (scalar
+    and sum linearity) and diffops/_registry.py:15-370 (closed forms)."""
+    from ..linfuncops import _linfuncop
+
+    if argnum not in (0, 1):
+        raise ValueError("`argnum` must either be 0 or 1.")
+    if tuple(L.input_domain_shape) != tuple(k.input_shape):
+        raise ValueError(f"operator input domain shape {L.input_domain_shape} != kernel input shape {k.input_shape}")
+    if isinstance(L, _linfuncop.Identity):
+        return k
+    if isinstance(k, ScaledCovarianceFunction):
+        return k.scalar * apply_linfuncop(L, k.covfunc, argnum)
+    if isinstance(k, SumCovarianceFunction):
+        return SumCovarianceFunction(*(apply_linfuncop(L, s, argnum) for s in k.summands))
+    if isinstance(k, LinDiffOpCovarianceFunction):
+        L0, L1 = k.L0, k.L1
+        if argnum == 0:
+            L0 = _compose(L0, L)
+        else:
+            L1 = _compose(L1, L)
+        return _select_class(k.k, L0, L1)(k.k, L0=L0, L1=L1)
+    if isinstance(k, (Matern, ExpQuad, TensorProduct)):
+        L0, L1 = (L, None) if argnum == 0 else (None, L)
+        out = _select_class(k, L0, L1)(k, L0=L0, L1=L1)
+        out._product_form()  # validate now: raise NotImplementedError for unsupported combinations
+        return out
+    raise NotImplementedError(f"{type(L).__name__} applied to {type(k).__name__}")

@@ -90,3 +90,81 @@ def eval_desc_numpy(desc, X0, X1):
             term = term * basis[i][bi]
         out += term
     return out * np.exp(-g)
+
+
+# ---- JSON spec -> objects of the product's reference-style API ---------------------------------------------
+def api_base(base):
+    from linpde_gp_b200.randprocs import covfuncs
+
+    kind = base["kind"]
+    if kind == "tensor_product":
+        return covfuncs.TensorProduct(*(api_base(f) for f in base["factors"]))
+    shape = tuple(base.get("input_shape", ()))
+    ls = base["lengthscales"]
+    ls = np.asarray(ls, dtype=float) if isinstance(ls, (list, tuple)) else float(ls)
+    if kind == "matern":
+        return covfuncs.Matern(shape, nu=base["nu"], lengthscales=ls)
+    return covfuncs.ExpQuad(shape, lengthscales=ls)
+
+
+def api_kernel(kernel):
+    k = api_base(kernel["base"])
+    if kernel.get("scale") is not None:
+        k = kernel["scale"] * k
+    return k
+
+
+def api_op(L):
+    from linpde_gp_b200.linfuncops import SumLinearFunctionOperator, diffops
+
+    if L is None:
+        return None
+    summands = []
+    for scalar, (kind, payload) in L:
+        if kind == "wl":
+            op = diffops.WeightedLaplacian(np.asarray(payload, dtype=float))
+        elif kind == "dd":
+            op = diffops.DirectionalDerivative(np.asarray(payload, dtype=float))
+        else:
+            assert len(payload) == 1 and payload[0][1] == 1.0
+            op = diffops.PartialDerivative(diffops.MultiIndex(payload[0][0]))
+        if scalar != 1.0:
+            op = scalar * op
+        summands.append(op)
+    return summands[0] if len(summands) == 1 else SumLinearFunctionOperator(*summands)
+
+
+def api_L0kL1(spec):
+    k = api_kernel(spec["kernel"])
+    L0, L1 = api_op(spec["L0"]), api_op(spec["L1"])
+    kk = L1(k, argnum=1) if L1 is not None else k
+    return L0(kk, argnum=0) if L0 is not None else kk
+
+
+def api_solve(problem):
+    """Run a golden GP problem through the product API, block by block (like oracle/make_golden.py does with the
+    real reference)."""
+    import linpde_gp_b200 as lg
+    from tests.golden import cases as gcases
+
+    kernel = problem["kernel"]
+    shape = gcases.kernel_input_shape(kernel)
+    prior = lg.GaussianProcess(lg.functions.Zero(input_shape=shape), api_kernel(kernel))
+    post = prior
+    for blk in problem["blocks"]:
+        X = np.asarray(blk["X"], dtype=float)
+        Y = np.asarray(blk["Y"], dtype=float)
+        b = None
+        if blk.get("noise_var") is not None:
+            nv = np.broadcast_to(np.asarray(blk["noise_var"], dtype=float), Y.shape).copy()
+            b = lg.randvars.Normal(np.zeros_like(Y), lg.linops.Scaling(nv))
+        post = post.condition_on_observations(Y, X=X, L=api_op(blk["L"]), b=b)
+    Xt = np.asarray(problem["Xt"], dtype=float)
+    Xc = Xt[: problem.get("n_cov", 16)]
+    return post, {
+        "w": post.representer_weights,
+        "mean": post.mean(Xt),
+        "var": post.cov(Xt, None),
+        "cov": post.cov.matrix(Xc),
+        "gram": post.gram.todense(),
+    }

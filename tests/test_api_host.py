@@ -1,0 +1,148 @@
+"""Host-side logic of the reference-style API that needs no GPU: symbolic operator algebra, dispatch types,
+argument validation / error behaviour, the C-ABI library's exported symbols."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import linpde_gp_b200 as lg
+from linpde_gp_b200.linfuncops import diffops
+from linpde_gp_b200.randprocs import covfuncs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "lpgp.h")).read()
+    declared = set(re.findall(r"\b(lpgp_[a-z0-9_]+)\s*\(", header))
+    lib = ctypes.CDLL(os.path.join(ROOT, "linpde_gp_b200", "lib", "liblpgp.so"))
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(lg._lib.EXPORTED) == declared
+    assert lib.lpgp_version() >= 100
+    lib.lpgp_build_arch.restype = ctypes.c_char_p
+    assert lib.lpgp_build_arch() == b"sm_100a"
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(lg._lib.KernelDesc) == 4 + 3 * 16 + 4 + 4 * 8 + 8 + 512 * 8
+    assert ctypes.sizeof(lg._lib.Factor) == 8 + 8 + 8 + 8 + 4 + 4 + 65 * 8
+    assert ctypes.sizeof(lg._lib.ObsBlock) == 32
+
+
+def test_coefficients_algebra():
+    """tests/linpde_gp/linfuncops/diffops/test_coefficients.py, test_laplacian.py"""
+    lap = diffops.Laplacian((2,))
+    c = lap.coefficients
+    assert c.num_entries == 2 and not c.has_mixed
+    assert c[()][diffops.MultiIndex((2, 0))] == 1.0 and c[()][diffops.MultiIndex((0, 2))] == 1.0
+    neg = (-2.0 * lap).coefficients
+    assert neg[()][diffops.MultiIndex((0, 2))] == -2.0
+    s = c + diffops.DirectionalDerivative([1.0, 0.0]).coefficients
+    assert s.num_entries == 3
+    with pytest.raises(ValueError):
+        c + diffops.Laplacian((3,)).coefficients
+    with pytest.raises(ValueError):
+        diffops.MultiIndex((-1, 0))
+    wl = diffops.WeightedLaplacian([0.0, 3.0])
+    assert wl.coefficients.num_entries == 1  # zero weights dropped (_laplacian.py:31-41)
+    assert diffops.SpatialLaplacian((3,)).weights.tolist() == [0.0, 1.0, 1.0]
+    with pytest.raises(ValueError):
+        diffops.SpatialLaplacian((1,))
+    heat = diffops.HeatOperator((2,), alpha=0.1)
+    assert heat._terms() == {(1, 0): 1.0, (0, 2): -0.1}
+    with pytest.raises(ValueError):
+        diffops.HeatOperator((2, 2))
+    assert diffops.TimeDerivative((3,)).multi_index.as_tuple() == (1, 0, 0)
+    assert (3.0 * (2.0 * lap)).scalar == 6.0
+
+
+def test_dispatch_types_follow_the_reference_registry():
+    """test_diffops.py::test_L0kL1_expected_type / SURVEY Appendix A."""
+    eq = covfuncs.ExpQuad((3,))
+    wl, dd = diffops.WeightedLaplacian(np.ones(3)), diffops.DirectionalDerivative(np.ones(3))
+    assert type(wl(eq, argnum=1)) is covfuncs.ExpQuad_Identity_WeightedLaplacian
+    assert type(wl(wl(eq, argnum=1), argnum=0)) is covfuncs.ExpQuad_WeightedLaplacian_WeightedLaplacian
+    assert type(dd(eq, argnum=0)) is covfuncs.ExpQuad_Identity_DirectionalDerivative
+    assert type(dd(dd(eq, argnum=1), argnum=0)) is covfuncs.ExpQuad_DirectionalDerivative_DirectionalDerivative
+    assert type(dd(wl(eq, argnum=1), argnum=0)) is covfuncs.ExpQuad_DirectionalDerivative_WeightedLaplacian
+    m = covfuncs.Matern((), nu=2.5)
+    w1, d1 = diffops.WeightedLaplacian(2.0), diffops.DirectionalDerivative(1.5)
+    assert type(w1(m, argnum=1)) is covfuncs.UnivariateHalfIntegerMatern_Identity_WeightedLaplacian
+    assert type(w1(w1(m, argnum=1), argnum=0)) is covfuncs.UnivariateHalfIntegerMatern_WeightedLaplacian_WeightedLaplacian
+    assert type(d1(m, argnum=1)) is covfuncs.HalfIntegerMatern_Identity_DirectionalDerivative
+    assert type(d1(w1(m, argnum=1), argnum=0)) is covfuncs.UnivariateHalfIntegerMatern_DirectionalDerivative_WeightedLaplacian
+    tp = covfuncs.TensorProduct(covfuncs.Matern((), nu=1.5), covfuncs.Matern((), nu=2.5))
+    heat = diffops.HeatOperator((2,), 0.1)
+    assert type(heat(heat(tp, argnum=1), argnum=0)) is covfuncs.TensorProduct_LinDiffOp_LinDiffOp
+    scaled = 4.0 * tp
+    out = (-1.0 * diffops.Laplacian((2,)))(scaled, argnum=1)
+    assert type(out) is covfuncs.ScaledCovarianceFunction and float(out.scalar) == 4.0
+    assert type(out.covfunc) is covfuncs.TensorProduct_LinDiffOp_LinDiffOp  # the -1 is folded into the operator terms
+    assert out.covfunc.L1._terms() == {(2, 0): -1.0, (0, 2): -1.0}
+    # isotropic multi-d Matern x Laplacian: no closed form (reference falls back to jax, _registry.py:270-280)
+    with pytest.raises(NotImplementedError):
+        diffops.Laplacian((2,))(covfuncs.Matern((2,), nu=2.5), argnum=1)
+    with pytest.raises(ValueError):
+        diffops.Laplacian((3,))(tp, argnum=0)
+    with pytest.raises(ValueError):
+        tp_bad = covfuncs.TensorProduct(covfuncs.Matern((2,), nu=1.5))
+
+
+def test_covfunc_argument_validation():
+    with pytest.raises(ValueError):
+        covfuncs.Matern((), nu=-1.0)
+    with pytest.raises(ValueError):
+        covfuncs.ExpQuad((2,), lengthscales=[1.0, -1.0])
+    k = covfuncs.ExpQuad((2,))
+    with pytest.raises(ValueError):
+        k(np.zeros((4, 3)), None)
+    with pytest.raises(ValueError):
+        k(np.zeros((4, 2)), np.zeros((3, 2)))  # batch shapes do not broadcast
+    with pytest.raises(ValueError):
+        k.linop(np.zeros((4, 3)))
+
+
+def test_condition_on_observations_error_behaviour():
+    """_conditional.py:317-387: the same exception types as the reference."""
+    prior = lg.GaussianProcess(lg.functions.Zero(input_shape=(2,)), covfuncs.ExpQuad((2,)))
+    X = np.zeros((5, 2))
+    L = diffops.Laplacian((2,))
+    with pytest.raises(ValueError):
+        prior.condition_on_observations(np.zeros(5))  # X and L both omitted
+    with pytest.raises(ValueError):
+        prior.condition_on_observations(np.zeros(5), L=L)  # operator without X
+    with pytest.raises(TypeError):
+        prior.condition_on_observations(np.zeros(5), X=X, L=L.to_linfunctl(X))  # functional with X
+    with pytest.raises(TypeError):
+        prior.condition_on_observations(np.zeros(5), X=X, L="laplacian")
+    with pytest.raises(ValueError):
+        prior.condition_on_observations(np.zeros(4), X=X, L=L)  # Y shape mismatch
+    with pytest.raises(ValueError):
+        prior.condition_on_observations(np.zeros(5), X=X, b=lg.randvars.Normal(np.zeros(4), np.eye(4)))
+    with pytest.raises(ValueError):
+        lg.GaussianProcess(lg.functions.Zero(input_shape=(3,)), covfuncs.ExpQuad((2,)))
+    with pytest.raises(TypeError):
+        lg.GaussianProcess(lambda x: x, covfuncs.ExpQuad((2,)))
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    k = covfuncs.ExpQuad((2,))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        k.matrix(np.zeros((3, 2)))
+    # the product never imports the oracle
+    import sys
+
+    src = []
+    for root, _, files in os.walk(os.path.join(ROOT, "linpde_gp_b200")):
+        src += [os.path.join(root, f) for f in files if f.endswith((".py", ".cu", ".cuh"))]
+    for path in src:
+        text = open(path).read()
+        assert "import oracle" not in text and "from oracle" not in text, path
