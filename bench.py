@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py -- seconds per GP-PDE solve (2-D Poisson, N = 65,536) on B200, with roofline and CPU baseline.
+
+One *step* = one full pass of the hot path over one synthetic problem (BASELINE.json configs[3]):
+  2-D Poisson-Dirichlet on [0,1]^2, prior 4 * TensorProduct(Matern-5/2(l), Matern-5/2(l)), l = 4/sqrt(N_pde);
+  4 boundary batches (N_bc = 2,048) + 1 PDE-collocation batch (N_pde = 63,488, seed 2) => N = 65,536;
+  assemble all Gram blocks -> bordered FP64 Cholesky -> representer weights -> posterior mean AND pointwise
+  variance on the 512 x 512 test grid.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--npde ..] [--nbc-edge ..] [--grid ..]
+
+`value`      device-timed seconds per solve with all inputs already resident in HBM (CUDA events, max over ranks);
+`e2e`        the same solve through the public Python API with HOST numpy buffers (pinned H2D of the points /
+             right-hand sides and D2H of mean + variance inside the timed region);
+`roofline`   the DMMA GEMM kernel (Cholesky trailing updates + posterior-variance triangular solve) against the
+             FP64 tensor-pipe issue rate measured live on the box (lpgp_dmma_peak_probe);
+`cpu_baseline` the oracle (numpy/scipy restatement of the reference) timed on the box's host cores on a bounded
+             sample and extrapolated to the full solve.
+With --gpus N > 1 (torchrun) every rank assembles and factorises the (replicated) Gram matrix and the test grid is
+sharded N ways (strong scaling of a fixed problem); results are gathered with NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIGMA2 = 4.0
+NU = 2.5
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------------
+def make_problem(n_pde: int, n_bc_edge: int, grid: int, seed: int = 2):
+    rng = np.random.default_rng(seed)
+    ell = 4.0 / np.sqrt(n_pde)
+    s = np.linspace(0.0, 1.0, n_bc_edge, endpoint=False)
+    h = 1.0 / n_bc_edge
+    edges = [
+        np.stack([s, np.zeros_like(s)], -1),
+        np.stack([np.ones_like(s), s], -1),
+        np.stack([s + h, np.ones_like(s)], -1),
+        np.stack([np.zeros_like(s), s + h], -1),
+    ]
+    Xp = rng.uniform(0.0, 1.0, size=(n_pde, 2))
+    g = np.linspace(0.0, 1.0, grid)
+    Xt = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    return {
+        "ell": ell,
+        "edges": [np.ascontiguousarray(e) for e in edges],
+        "Y_bc": [np.zeros(len(e)) for e in edges],
+        "X_pde": Xp,
+        "Y_pde": np.full(n_pde, 2.0),
+        "Xt": Xt,
+        "N": n_pde + 4 * n_bc_edge,
+        "M": Xt.shape[0],
+    }
+
+
+def oracle_kernel(ell):
+    f = {"kind": "matern", "input_shape": [], "nu": NU, "lengthscales": float(ell)}
+    return {"scale": SIGMA2, "base": {"kind": "tensor_product", "factors": [f, dict(f)]}}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on the host cores, bounded sample, extrapolated to one full solve
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_sample(prob, budget_s: float = 20.0):
+    import scipy.linalg
+
+    from oracle import covfuncs as ocf
+
+    N, M = prob["N"], prob["M"]
+    kern = oracle_kernel(prob["ell"])
+    lap = [(-1.0, ("wl", np.ones(2)))]
+    X = prob["X_pde"]
+    t_budget = budget_s / 3.0
+    # (a) Gram assembly L k L^* on row tiles (the un-tiled reference needs ~10 N x N temporaries)
+    rows, t0, done = 256, time.perf_counter(), 0
+    while True:
+        ocf.matrix(kern, lap, lap, X[done % 4096 : done % 4096 + rows], X)
+        done += rows
+        if time.perf_counter() - t0 > t_budget or done >= 4096:
+            break
+    t_asm = time.perf_counter() - t0
+    eps = done * len(X) / t_asm
+    # (b) dpotrf via scipy at a host-sized N
+    nc = 6144
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((nc, nc))
+    G = A @ A.T / nc + 2.0 * np.eye(nc)
+    t0 = time.perf_counter()
+    Lc = scipy.linalg.cholesky(G, lower=True)
+    t_chol = time.perf_counter() - t0
+    chol_flops = nc**3 / 3.0 / t_chol
+    # (c) dtrsm (posterior variance in the N x M_c form, _conditional.py:245-251)
+    mc = 2048
+    B = rng.standard_normal((nc, mc))
+    t0 = time.perf_counter()
+    scipy.linalg.solve_triangular(Lc, B, lower=True, check_finite=False)
+    t_trsm = time.perf_counter() - t0
+    trsm_flops = nc * nc * mc / t_trsm
+    est = N * N / eps + M * N / eps + (N**3 / 3.0) / chol_flops + (float(M) * N * N) / trsm_flops
+    detail = {
+        "gram_entries_per_s": eps,
+        "cholesky_gflops": chol_flops * 1e-9,
+        "trsm_gflops": trsm_flops * 1e-9,
+        "sample": f"LkL assembly of {done}x{len(X)} row tiles ({t_asm:.1f} s), scipy dpotrf n={nc} ({t_chol:.1f} s), "
+                  f"dtrsm {nc}x{mc} ({t_trsm:.1f} s); extrapolated to N={N}, M={M}",
+    }
+    return est, detail
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
+    except Exception:  # pragma: no cover
+        n = 1
+    return int(n), len(os.sched_getaffinity(0))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU clocks during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.path = tempfile.mktemp(prefix="lpgp_clocks_", suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+                power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        load = [c for c, w in zip(sm, power) if w > 0.5 * max(power)] if power else sm
+        return {
+            "sm_mhz": float(np.median(load)) if load else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "power_w_max": float(max(power)) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+class DeviceSolve:
+    """The hot path driven at the device-buffer level (inputs resident in HBM): this is what `value` times."""
+
+    def __init__(self, prob, rank: int, world: int):
+        import torch
+
+        import linpde_gp_b200 as lg
+        from linpde_gp_b200 import backend
+        from linpde_gp_b200._lowering import Factor1D, lower
+
+        self.torch, self.be = torch, backend
+        fac = [Factor1D("matern", prob["ell"], nu=NU), Factor1D("matern", prob["ell"], nu=NU)]
+        lap = {(2, 0): -1.0, (0, 2): -1.0}
+        self.d_k = lower(fac, None, None, SIGMA2)
+        self.d_kL = lower(fac, None, lap, SIGMA2)   # test/boundary side x PDE side
+        self.d_Lk = lower(fac, lap, None, SIGMA2)   # PDE rows x boundary columns
+        self.d_LkL = lower(fac, lap, lap, SIGMA2)
+        self.edges = [backend.to_device(e) for e in prob["edges"]]
+        self.Xp = backend.to_device(prob["X_pde"])
+        self.y = torch.cat([backend.to_device(y) for y in prob["Y_bc"]] + [backend.to_device(prob["Y_pde"])])
+        Xt = prob["Xt"]
+        self.shard = np.array_split(np.arange(len(Xt)), world)[rank]
+        self.Xt = backend.to_device(Xt[self.shard])
+        self.N, self.M = prob["N"], prob["M"]
+        self.t = {}
+
+    def _timed(self, name, fn):
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.t.setdefault(name, []).append((e0, e1))
+        return out
+
+    def step(self):
+        be = self.be
+        sizes = [e.shape[0] for e in self.edges] + [self.Xp.shape[0]]
+        blocksX = self.edges + [self.Xp]
+        factor = None
+        off = 0
+        for i, (X, n) in enumerate(zip(blocksX, sizes)):
+            is_pde = i == len(sizes) - 1
+            factor = be.DeviceFactor([n]) if factor is None else factor.extended(n)
+
+            def assemble():
+                rows = factor.L[off : off + n]
+                c = 0
+                for Xj, nj in zip(blocksX[:i], sizes[:i]):
+                    be.gram(self.d_Lk if is_pde else self.d_k, X, Xj, out=rows[:, c : c + nj])
+                    c += nj
+                be.gram(self.d_LkL if is_pde else self.d_k, X, None, out=rows[:, off : off + n], lower=True)
+
+            self._timed("assemble", assemble)
+            self._timed("factor", factor.potrf if i == 0 else factor.append_last)
+            off += n
+        w = self._timed("solve", lambda: factor.potrs(self.y.clone().reshape(1, -1)).reshape(-1))
+        descs = [self.d_k] * len(self.edges) + [self.d_kL]
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+        blocks = be.ObsBlocks(descs, blocksX, offs)
+        mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
+        chunk = int(max(256, min(self.Xt.shape[0], (4 << 30) // (8 * be.round_up(factor.n, 16)))))
+        var = self._timed("var", lambda: be.post_var(blocks, factor, self.Xt, self.d_k.diag_value, chunk=chunk))
+        return mean, var
+
+    def phase_ms(self, last_k: int):
+        self.torch.cuda.synchronize()
+        return {k: sum(e0.elapsed_time(e1) for e0, e1 in v[-last_k * (5 if k in ("assemble", "factor") else 1):]) / last_k
+                for k, v in self.t.items()}
+
+
+def api_solve(prob, rank: int, world: int):
+    """The same solve through the public reference-style API with host (numpy) buffers -> `e2e`."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.linfuncops import diffops
+    from linpde_gp_b200.randprocs import covfuncs
+
+    k = SIGMA2 * covfuncs.TensorProduct(covfuncs.Matern((), nu=NU, lengthscales=prob["ell"]),
+                                        covfuncs.Matern((), nu=NU, lengthscales=prob["ell"]))
+    post = lg.GaussianProcess(lg.functions.Zero(input_shape=(2,)), k)
+    for Xb, Yb in zip(prob["edges"], prob["Y_bc"]):
+        post = post.condition_on_observations(Yb, X=Xb)
+    post = post.condition_on_observations(prob["Y_pde"], X=prob["X_pde"], L=-1.0 * diffops.Laplacian((2,)))
+    shard = np.array_split(np.arange(prob["M"]), world)[rank]
+    Xt = prob["Xt"][shard]
+    return post.mean(Xt), post.var(Xt)
+
+
+def dmma_peak_tflops(torch, backend):
+    import ctypes
+
+    from linpde_gp_b200._lib import lib
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    scratch = torch.empty(sms * 2 * 256, dtype=torch.float64, device="cuda")
+    flops = ctypes.c_double(0.0)
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = lib.lpgp_dmma_peak_probe(ctypes.c_void_p(scratch.data_ptr()), sms * 2, 20000, ctypes.byref(flops),
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        e1.record()
+        torch.cuda.synchronize()
+        assert rc == 0
+        best = max(best, flops.value / e0.elapsed_time(e1) * 1e-9)
+    return best
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from linpde_gp_b200 import backend
+    from linpde_gp_b200._lib import lib
+
+    prob = make_problem(args.npde, args.nbc_edge, args.grid)
+    N, M = prob["N"], prob["M"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(mean, var):
+        if world == 1:
+            return mean, var
+        outs = [None] * world
+        dist.all_gather_object(outs, (mean.cpu().numpy() if hasattr(mean, "cpu") else mean,
+                                      var.cpu().numpy() if hasattr(var, "cpu") else var))
+        return np.concatenate([o[0] for o in outs]), np.concatenate([o[1] for o in outs])
+
+    peak = dmma_peak_tflops(torch, backend) if rank == 0 else None
+    ds = DeviceSolve(prob, rank, world)
+    for _ in range(args.warmup):
+        m, v = ds.step()
+        gather(m, v)
+    barrier()
+    lib.lpgp_launch_count(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        m, v = ds.step()
+        gm, gv = gather(m, v)
+    e1.record()
+    barrier()
+    launches = lib.lpgp_launch_count(0)
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    phases = ds.phase_ms(args.steps)
+    del ds
+    torch.cuda.empty_cache()
+
+    # ---- e2e through the public API, host buffers (pinned H2D + D2H inside the timed region) ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        em, ev = api_solve(prob, rank, world)
+        gem, gev = gather(em, ev)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    times = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = (float(x) for x in times.cpu())
+
+    if rank == 0:
+        gm = gm.cpu().numpy() if hasattr(gm, "cpu") else gm
+        gv = gv.cpu().numpy() if hasattr(gv, "cpu") else gv
+        agree = float(max(np.max(np.abs(gm - gem)), np.max(np.abs(gv - gev))))
+        m_shard = len(np.array_split(np.arange(M), world)[0])
+        flops_tensor = N**3 / 3.0 + float(m_shard) * N * N          # per rank: Cholesky + variance TRSM
+        t_tensor = (phases["factor"] + phases["var"]) * 1e-3
+        achieved = flops_tensor / t_tensor * 1e-12
+        h2d = sum(e.nbytes for e in prob["edges"]) + sum(y.nbytes for y in prob["Y_bc"]) + prob["X_pde"].nbytes \
+            + prob["Y_pde"].nbytes + prob["Xt"].nbytes * 2 // world
+        cpu_est, cpu_detail = cpu_sample(prob, budget_s=20.0)
+        threads, cores = host_threads()
+        out = {
+            "metric": "s per GP-PDE solve (2D Poisson N=64k)",
+            "value": ms_dev * 1e-3,
+            "unit": "s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_dev,
+            "higher_is_better": False,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"2D Poisson Dirichlet synthetic N={N} (N_pde={args.npde} seed 2, N_bc={4 * args.nbc_edge}), "
+                            f"product Matern-5/2 prior, 5 conditioning batches, mean+variance on {args.grid}x{args.grid} grid "
+                            "(BASELINE.json configs[3])",
+                "parallelism": "replicated factor, test grid sharded" if world > 1 else "single GPU",
+                "l2": f"working set {N * N * 8 / 1e9:.1f} GB Gram >> 126 MB L2 (no flush needed)",
+            },
+            "phases_ms": phases,
+            "gram_entries_per_s": (N * (N + 1) / 2 + 0.0) / (phases["assemble"] * 1e-3),
+            "cholesky_tflops": N**3 / 3.0 / (phases["factor"] * 1e-3) * 1e-12,
+            "variance_trsm_tflops": float(m_shard) * N * N / (phases["var"] * 1e-3) * 1e-12,
+            "e2e": {"value": ms_e2e * 1e-3, "unit": "s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(2 * 8 * M // world), "api_vs_device_max_abs_diff": agree},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "kernel": "gemm_nt_kernel (DMMA m8n8k4.f64) inside lpgp_potrf/lpgp_chol_append + lpgp_post_var",
+                "peak_source": "FP64 tensor-pipe issue rate measured live (lpgp_dmma_peak_probe); MEASURED_PEAKS.json "
+                               "holds no FP64 figure",
+                "flops": flops_tensor,
+            },
+            "cpu_baseline": {"value": cpu_est, "unit": "s", "cores": cores, "threads": threads, "kind": "port",
+                             **cpu_detail},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    prob = make_problem(args.npde, args.nbc_edge, args.grid)
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(prob, budget_s=6.0)
+    vals, detail = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, detail = cpu_sample(prob, budget_s=20.0)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    threads, cores = host_threads()
+    val = float(np.mean(vals))
+    out = {
+        "impl": "reference",
+        "metric": "s per GP-PDE solve (2D Poisson N=64k)",
+        "value": val, "unit": "s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(args.steps, 1), "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"2D Poisson Dirichlet synthetic N={prob['N']}, mean+variance on {args.grid}x{args.grid} grid "
+                               "(BASELINE.json configs[3]); bounded sample extrapolated to the full solve"},
+        "cpu_baseline": {"value": val, "unit": "s", "cores": cores, "threads": threads, "kind": "port", **detail},
+        "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--npde", type=int, default=63488)
+    ap.add_argument("--nbc-edge", type=int, default=512)
+    ap.add_argument("--grid", type=int, default=512)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

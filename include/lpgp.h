@@ -69,6 +69,11 @@ typedef struct lpgp_kernel_desc {
 int lpgp_version(void);              /* 100*major + minor                                               */
 const char* lpgp_build_arch(void);   /* "sm_100a"                                                       */
 const char* lpgp_error_string(int code);
+long long lpgp_launch_count(int reset); /* kernels launched by the library so far (optionally reset)      */
+/* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and
+ * reports the flop count; timed by the caller it yields the roofline denominator of the DMMA kernels on the
+ * box at hand (bench.py).  `scratch`: device, blocks*256 doubles.                                          */
+int lpgp_dmma_peak_probe(double* scratch, int blocks, int iters, double* flops, void* stream);
 
 /* (1) Gram / cross-covariance assembly ---------------------------------------------------------------
  * Replaces  pn CovarianceFunction._evaluate_matrix / matrix / linop(...).todense()

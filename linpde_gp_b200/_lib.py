@@ -68,6 +68,8 @@ def _load() -> ctypes.CDLL:
         "lpgp_version": (ci, []),
         "lpgp_build_arch": (ctypes.c_char_p, []),
         "lpgp_error_string": (ctypes.c_char_p, [ci]),
+        "lpgp_launch_count": (ctypes.c_longlong, [ci]),
+        "lpgp_dmma_peak_probe": (ci, [vp, ci, ci, ctypes.POINTER(dbl), vp]),
         "lpgp_gram": (ci, [KD, vp, i64, vp, i64, vp, i64, ci, ci, dbl, vp]),
         "lpgp_gram_pairs": (ci, [KD, vp, vp, i64, vp, dbl, vp]),
         "lpgp_gram_diag": (ci, [KD, i64, vp, dbl, vp]),
@@ -94,7 +96,7 @@ def _load() -> ctypes.CDLL:
 
 lib = _load()
 EXPORTED = (
-    "lpgp_version lpgp_build_arch lpgp_error_string lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
+    "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
     "lpgp_gemm_nt lpgp_factor_dinv_bytes lpgp_potrf lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_logdet "
     "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq"
 ).split()

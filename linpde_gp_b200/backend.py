@@ -43,7 +43,7 @@ def to_device(x, *, pinned: bool = False) -> torch.Tensor:
     dev = _require_cuda()
     if isinstance(x, torch.Tensor):
         return x.to(device=dev, dtype=F64).contiguous()
-    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    a = np.array(x, dtype=np.float64, order="C", copy=True)  # private, writable host staging copy
     t = torch.from_numpy(a)
     if pinned:
         t = t.pin_memory()
@@ -52,7 +52,7 @@ def to_device(x, *, pinned: bool = False) -> torch.Tensor:
 
 def points(X, d: int) -> torch.Tensor:
     """Flatten the batch shape C-order (pn ``_preprocess_linop_input``, _covariance_function.py:676-693)."""
-    t = to_device(X)
+    t = to_device(X, pinned=True)
     return t.reshape(-1, d) if d > 0 else t.reshape(-1, 1)
 
 

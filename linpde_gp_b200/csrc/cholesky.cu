@@ -333,7 +333,9 @@ extern "C" int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t
     for (int l = 0; l < nl; ++l) {  // forward: L y = b
       const int64_t c0 = lv.off[l], c1 = lv.off[l + 1];
       leaf_apply_kernel<<<1, LEAF, 0, st>>>(dinv_block(f, l), b + c0, (int)(c1 - c0), 0);
+      LPGP_COUNT(1);
       if (c1 < n) {
+        LPGP_COUNT(1);
         const int64_t rows = n - c1;
         const unsigned grid = (unsigned)(rows / 8 + 1 < 1184 ? rows / 8 + 1 : 1184);
         fwd_update_kernel<<<grid, 256, 0, st>>>(f->L, f->ld, c0, (int)(c1 - c0), c1, n, b);
@@ -342,9 +344,11 @@ extern "C" int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t
     for (int l = nl - 1; l >= 0; --l) {  // backward: L^T x = y
       const int64_t c0 = lv.off[l], c1 = lv.off[l + 1];
       leaf_apply_kernel<<<1, LEAF, 0, st>>>(dinv_block(f, l), b + c0, (int)(c1 - c0), 1);
+      LPGP_COUNT(c0 > 0 ? 2 : 1);
       if (c0 > 0) bwd_update_kernel<<<(unsigned)ceil_div64(c0, 256), 256, 0, st>>>(f->L, f->ld, c0, (int)(c1 - c0), b);
     }
   }
+  LPGP_COUNT(-1);  // the check below counts one launch itself
   LPGP_CHECK_LAUNCH();
   return 0;
 }

@@ -7,8 +7,13 @@
 
 #define LPGP_CUDA_ERR(e) (-(1000 + (int)(e)))
 
+// every kernel launch of the library is counted (bench.py reports the number as `gpu_launches`)
+extern long long g_lpgp_launches;
+#define LPGP_COUNT(n) (g_lpgp_launches += (n))
+
 #define LPGP_CHECK_LAUNCH()                            \
   do {                                                 \
+    LPGP_COUNT(1);                                     \
     cudaError_t e__ = cudaGetLastError();              \
     if (e__ != cudaSuccess) return LPGP_CUDA_ERR(e__); \
   } while (0)
