@@ -210,8 +210,10 @@ class DeviceSolve:
         self.Xp = backend.to_device(prob["X_pde"])
         self.y = torch.cat([backend.to_device(y) for y in prob["Y_bc"]] + [backend.to_device(prob["Y_pde"])])
         Xt = prob["Xt"]
-        self.shard = np.array_split(np.arange(len(Xt)), world)[rank]
-        self.Xt = backend.to_device(Xt[self.shard])
+        from linpde_gp_b200 import parallel
+
+        lo, hi = parallel.shard_bounds(len(Xt), rank, world)
+        self.Xt = backend.to_device(Xt[lo:hi])
         self.N, self.M = prob["N"], prob["M"]
         self.t = {}
 
@@ -272,8 +274,10 @@ def api_solve(prob, rank: int, world: int):
     for Xb, Yb in zip(prob["edges"], prob["Y_bc"]):
         post = post.condition_on_observations(Yb, X=Xb)
     post = post.condition_on_observations(prob["Y_pde"], X=prob["X_pde"], L=-1.0 * diffops.Laplacian((2,)))
-    shard = np.array_split(np.arange(prob["M"]), world)[rank]
-    Xt = prob["Xt"][shard]
+    from linpde_gp_b200 import parallel
+
+    lo, hi = parallel.shard_bounds(prob["M"], rank, world)
+    Xt = prob["Xt"][lo:hi]
     return post.mean(Xt), post.var(Xt)
 
 
@@ -321,13 +325,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from linpde_gp_b200 import parallel
+
     def gather(mean, var):
+        """the path's only exchange step: all-gather the sharded result rows (NCCL)"""
         if world == 1:
             return mean, var
-        outs = [None] * world
-        dist.all_gather_object(outs, (mean.cpu().numpy() if hasattr(mean, "cpu") else mean,
-                                      var.cpu().numpy() if hasattr(var, "cpu") else var))
-        return np.concatenate([o[0] for o in outs]), np.concatenate([o[1] for o in outs])
+        if not hasattr(mean, "cpu"):
+            mean, var = backend.to_device(mean), backend.to_device(var)
+        return parallel.gather_concat(mean, M), parallel.gather_concat(var, M)
 
     peak = dmma_peak_tflops(torch, backend) if rank == 0 else None
     ds = DeviceSolve(prob, rank, world)
@@ -370,7 +376,7 @@ def run_b200(args):
         gm = gm.cpu().numpy() if hasattr(gm, "cpu") else gm
         gv = gv.cpu().numpy() if hasattr(gv, "cpu") else gv
         agree = float(max(np.max(np.abs(gm - gem)), np.max(np.abs(gv - gev))))
-        m_shard = len(np.array_split(np.arange(M), world)[0])
+        m_shard = parallel.shard_bounds(M, 0, world)[1]
         flops_tensor = N**3 / 3.0 + float(m_shard) * N * N          # per rank: Cholesky + variance TRSM
         t_tensor = (phases["factor"] + phases["var"]) * 1e-3
         achieved = flops_tensor / t_tensor * 1e-12
