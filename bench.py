@@ -373,8 +373,8 @@ def run_b200(args):
     ms_dev, ms_e2e = (float(x) for x in times.cpu())
 
     if rank == 0:
-        gm = gm.cpu().numpy() if hasattr(gm, "cpu") else gm
-        gv = gv.cpu().numpy() if hasattr(gv, "cpu") else gv
+        tonp = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+        gm, gv, gem, gev = tonp(gm), tonp(gv), tonp(gem), tonp(gev)
         agree = float(max(np.max(np.abs(gm - gem)), np.max(np.abs(gv - gev))))
         m_shard = parallel.shard_bounds(M, 0, world)[1]
         flops_tensor = N**3 / 3.0 + float(m_shard) * N * N          # per rank: Cholesky + variance TRSM
