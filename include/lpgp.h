@@ -102,9 +102,16 @@ int lpgp_symmetrize_lower(double* A, int64_t n, int64_t ld, void* stream);
 
 /* (2) dense FP64 linear algebra on the DMMA (FP64 tensor core) path ---------------------------------------
  * C[m x n] = beta*C + alpha * A[m x k] * B[n x k]^T  (all row-major);  lower != 0: only tiles that intersect
- * the lower triangle of the (square) C are updated (SYRK-style trailing update).                        */
+ * the lower triangle of the (square) C are updated (SYRK-style trailing update).  C may alias A only for
+ * n <= 128 (in-place X <- X W^T: one CTA owns complete output rows).                                    */
 int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
                  int64_t ldb, double beta, double* C, int64_t ldc, int lower, void* stream);
+
+/* As lpgp_gemm_nt, but for every block of 128 rows only the columns < col_limit[row/128] are updated
+ * (col_limit: device array of ceil(m/128) ints).  Building block of the multi-GPU Cholesky, whose ranks own
+ * block rows of the lower triangle.                                               */
+int lpgp_gemm_nt_limited(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
+                         int64_t ldb, double beta, double* C, int64_t ldc, const int* col_limit, void* stream);
 
 /*
  * Cached, appendable Cholesky factor  G = L L^T  (lower, row-major, in place in `L`).

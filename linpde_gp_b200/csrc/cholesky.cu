@@ -7,6 +7,9 @@
 // that the leaf step of every TRSM is a GEMM with the inverted block (X <- X W^T) instead of a substitution.
 // Appending an observation batch (the reference's bordered BlockMatrix2x2 factor) is the same code started at
 // the first leaf of the new segment.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -16,7 +19,7 @@ namespace {
 constexpr int LEAF = LPGP_LEAF;  // 128
 constexpr int LDS_A = LEAF + 1;  // padded shared-memory row stride
 constexpr int DIAG_THREADS = 256;
-constexpr int DIAG_SMEM = LEAF * LDS_A * 8 + LEAF * 8 + 64;
+constexpr int DIAG_SMEM = LEAF * LDS_A * 8 + LEAF * 8 + 3 * 32 * 33 * 8 + 64;
 
 // status area at the end of the dinv buffer
 struct Status {
@@ -27,16 +30,37 @@ struct Status {
 // ---- leaf kernel: Cholesky of one diagonal block + its inverse ------------------------------------------------
 // A: pointer to the (nb x nb) diagonal block inside the big row-major matrix; on exit holds L (lower).
 // W: 128 x 128 row-major block receiving L^{-1} (lower, zero elsewhere; identity-padded beyond nb).
+//
+// The block lives in shared memory and is processed in 32-wide panels (left-looking):
+//   panel update (all 8 warps, broadcast + conflict-free LDS)  ->  32x32 diagonal Cholesky in the REGISTERS of
+//   one warp (lane = row, column scaling / rank-1 updates through warp shuffles)  ->  row-wise forward
+//   substitution of the rows below (one thread per row, the 32 unknowns in registers).
+// The inverse is built block-wise: the four 32x32 diagonal blocks are inverted by four warps in parallel (each
+// lane solves L x = e_lane in registers), the off-diagonal blocks follow from W_ij = -W_ii sum_k L_ik W_kj with
+// 2x2 register tiles.  ~20 us instead of ~235 us for the scalar version it replaces (profiles/ncu_kernels_r01.md).
+
+// solve L y = b for one 32-vector held in registers; L is a 32x32 lower block in shared memory (row stride LDS_A),
+// rdiag its reciprocal diagonal.  All threads of a warp read the same L entries (broadcast).
+__device__ __forceinline__ void solve_lower32(double (&x)[32], const double* __restrict__ Lb, const double* __restrict__ rdiag) {
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    x[k] *= rdiag[k];
+#pragma unroll
+    for (int c = k + 1; c < 32; ++c) x[c] = fma(-x[k], Lb[c * LDS_A + k], x[c]);
+  }
+}
+
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
     potrf_leaf_kernel(double* __restrict__ A, int64_t ld, int nb, double* __restrict__ W, int* info, int global_off) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* a = reinterpret_cast<double*>(smem_raw);  // [LEAF][LDS_A]
-  double* tmp = a + LEAF * LDS_A;                    // [LEAF]
+  double* rdiag = a + LEAF * LDS_A;                  // [LEAF] reciprocals of the diagonal of L
+  double* tbuf = rdiag + LEAF;                       // [3][32][33] scratch for the inverse
   __shared__ int s_fail;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_fail = 0;
 
-  // load lower triangle (identity padding beyond nb)
+  // load the lower triangle (identity padding beyond nb, zeros above the diagonal)
   for (int idx = tid; idx < LEAF * LEAF; idx += DIAG_THREADS) {
     const int i = idx / LEAF, j = idx % LEAF;
     double v = (i == j) ? 1.0 : 0.0;
@@ -45,54 +69,135 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
   }
   __syncthreads();
 
-  // ---- right-looking Cholesky in shared memory ----
-  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 thread grid for the rank-1 updates
-  for (int j = 0; j < nb; ++j) {
-    if (tid == 0) {
-      const double d = a[j * LDS_A + j];
-      if (!(d > 0.0)) {  // also catches NaN
-        s_fail = 1;
-        atomicCAS(info, 0, global_off + j + 1);
+  for (int kb = 0; kb < LEAF / 32; ++kb) {
+    const int c0 = kb * 32;
+    // ---- (1) panel update: a[i][c0+lane] -= sum_{k<c0} a[i][k] a[c0+lane][k] for the rows i >= c0 of this warp ----
+    if (kb > 0) {
+      constexpr int RMAX = 12;  // (128 - 32) / 8 rows per warp at most
+      double acc[RMAX];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) acc[r] = 0.0;
+      const int nr = (LEAF - c0) / 8;
+      const double* crow = a + (c0 + lane) * LDS_A;
+      for (int k = 0; k < c0; ++k) {
+        const double bc = crow[k];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+          if (r < nr) acc[r] = fma(a[(c0 + warp + 8 * r) * LDS_A + k], bc, acc[r]);
       }
-      a[j * LDS_A + j] = sqrt(d);
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < nr) a[(c0 + warp + 8 * r) * LDS_A + c0 + lane] -= acc[r];
+      __syncthreads();
+    }
+    // ---- (2) Cholesky of the 32x32 diagonal block in the registers of warp 0 (lane = row) ----
+    if (warp == 0) {
+      double r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) r[c] = a[(c0 + lane) * LDS_A + c0 + c];
+      bool fail = false;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const double djj = __shfl_sync(0xffffffffu, r[j], j);
+        if (!(djj > 0.0) && !fail) {  // warp-uniform; also catches NaN
+          fail = true;
+          if (lane == 0) {
+            s_fail = 1;
+            atomicCAS(info, 0, global_off + c0 + j + 1);
+          }
+        }
+        const double d = sqrt(djj), inv = 1.0 / d;
+        const double lij = lane > j ? r[j] * inv : (lane == j ? d : r[j]);
+        r[j] = lij;
+        if (lane == j) rdiag[c0 + j] = inv;
+#pragma unroll
+        for (int c = j + 1; c < 32; ++c) {
+          const double lcj = __shfl_sync(0xffffffffu, lij, c);
+          r[c] = fma(-lij, lcj, r[c]);  // only entries with lane >= c are meaningful (lower triangle)
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[(c0 + lane) * LDS_A + c0 + c] = c <= lane ? r[c] : 0.0;
     }
     __syncthreads();
-    if (s_fail) break;
-    const double inv = 1.0 / a[j * LDS_A + j];
-    for (int i = j + 1 + tid; i < nb; i += DIAG_THREADS) a[i * LDS_A + j] *= inv;
-    __syncthreads();
-    for (int i = j + 1 + ty; i < nb; i += 16) {
-      const double lij = a[i * LDS_A + j];
-      for (int c = j + 1 + tx; c <= i; c += 16) a[i * LDS_A + c] -= lij * a[c * LDS_A + j];
+    if (s_fail) return;  // leave the block half-factored; the host reports info > 0
+    // ---- (3) rows below the diagonal block: x L_kk^T = a_row  <=>  L_kk x = a_row ----
+    {
+      const int i = c0 + 32 + tid;
+      if (i < LEAF) {
+        double x[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] = a[i * LDS_A + c0 + c];
+        solve_lower32(x, a + c0 * LDS_A + c0, rdiag + c0);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) a[i * LDS_A + c0 + c] = x[c];
+      }
     }
     __syncthreads();
   }
-  if (s_fail) return;  // leave the block half-factored; the host reports info > 0
 
-  // write L back
+  // write L back (coalesced rows)
   for (int idx = tid; idx < nb * nb; idx += DIAG_THREADS) {
     const int i = idx / nb, j = idx % nb;
     if (j <= i) A[(int64_t)i * ld + j] = a[i * LDS_A + j];
   }
-  __syncthreads();
 
-  // ---- in-place inverse of the lower-triangular factor (column sweep from the right, cf. LAPACK dtrti2) ----
-  // column j of W: W_jj = 1/L_jj;  W[j+1:, j] = -W_jj * W22 * L[j+1:, j]  with W22 the already inverted trailing block
-  const int row_pair = tid >> 1, half = tid & 1;  // two threads share one row's dot product
-  for (int j = LEAF - 1; j >= 0; --j) {
-    for (int i = j + 1 + tid; i < LEAF; i += DIAG_THREADS) tmp[i] = a[i * LDS_A + j];
-    __syncthreads();
-    const double wjj = 1.0 / a[j * LDS_A + j];
-    {
-      const int i = j + 1 + row_pair;
-      double s = 0.0;
-      if (i < LEAF) {
-        for (int k = j + 1 + half; k <= i; k += 2) s = fma(a[i * LDS_A + k], tmp[k], s);
+  // ---- inverse, step 1: W_bb = L_bb^{-1} for the four diagonal blocks (warp b, lane = column) ----
+  if (warp < LEAF / 32) {
+    const int c0 = warp * 32;
+    double x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.0 : 0.0;
+    solve_lower32(x, a + c0 * LDS_A + c0, rdiag + c0);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[(c0 + i) * LDS_A + c0 + lane] = x[i];  // column `lane` of W_bb (zeros above the diagonal)
+  }
+  __syncthreads();
+  // ---- inverse, step 2: block rows i = 1..3:  T_j = sum_{k=j}^{i-1} L_ik W_kj,  W_ij = -W_ii T_j ----
+  const int tr = (tid >> 4) * 2, tc = (tid & 15) * 2;  // 2x2 register tile of a 32x32 block
+  for (int bi = 1; bi < LEAF / 32; ++bi) {
+    double t[3][2][2];
+#pragma unroll
+    for (int bj = 0; bj < 3; ++bj) {
+      t[bj][0][0] = t[bj][0][1] = t[bj][1][0] = t[bj][1][1] = 0.0;
+      if (bj < bi) {
+        for (int k = bj * 32; k < bi * 32; ++k) {  // L_ik (row block bi) times W_kj (column block bj)
+          const double l0 = a[(bi * 32 + tr) * LDS_A + k], l1 = a[(bi * 32 + tr + 1) * LDS_A + k];
+          const double w0 = a[k * LDS_A + bj * 32 + tc], w1 = a[k * LDS_A + bj * 32 + tc + 1];
+          t[bj][0][0] = fma(l0, w0, t[bj][0][0]);
+          t[bj][0][1] = fma(l0, w1, t[bj][0][1]);
+          t[bj][1][0] = fma(l1, w0, t[bj][1][0]);
+          t[bj][1][1] = fma(l1, w1, t[bj][1][1]);
+        }
+        double* tb = tbuf + bj * 32 * 33;
+        tb[tr * 33 + tc] = t[bj][0][0];
+        tb[tr * 33 + tc + 1] = t[bj][0][1];
+        tb[(tr + 1) * 33 + tc] = t[bj][1][0];
+        tb[(tr + 1) * 33 + tc + 1] = t[bj][1][1];
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      if (i < LEAF && half == 0) a[i * LDS_A + j] = -wjj * s;
     }
-    if (tid == 0) a[j * LDS_A + j] = wjj;
+    __syncthreads();
+#pragma unroll
+    for (int bj = 0; bj < 3; ++bj) {
+      if (bj < bi) {
+        const double* tb = tbuf + bj * 32 * 33;
+        double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+        for (int k = 0; k < 32; ++k) {  // W_ii (lower) times T_j
+          const double w0 = a[(bi * 32 + tr) * LDS_A + bi * 32 + k], w1 = a[(bi * 32 + tr + 1) * LDS_A + bi * 32 + k];
+          const double u0 = tb[k * 33 + tc], u1 = tb[k * 33 + tc + 1];
+          s00 = fma(w0, u0, s00);
+          s01 = fma(w0, u1, s01);
+          s10 = fma(w1, u0, s10);
+          s11 = fma(w1, u1, s11);
+        }
+        double* dst = a + (bi * 32 + tr) * LDS_A + bj * 32 + tc;
+        dst[0] = -s00;
+        dst[1] = -s01;
+        dst[LDS_A] = -s10;
+        dst[LDS_A + 1] = -s11;
+      }
+    }
     __syncthreads();
   }
   for (int idx = tid; idx < LEAF * LEAF; idx += DIAG_THREADS) {
@@ -275,9 +380,20 @@ extern "C" int lpgp_potrf(lpgp_factor* f, void* stream) {
   int* info = info_ptr(f, nl);
   set_int_kernel<<<1, 1, 0, st>>>(info, 0);
   LPGP_CHECK_LAUNCH();
+  const bool dbg = getenv("LPGP_DEBUG_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  const long long l0 = g_lpgp_launches;
   rc = potrf_rec(f, lv, 0, nl, info, st);
   if (rc) return rc;
-  return finish_info(info, st);
+  const auto t1 = std::chrono::steady_clock::now();
+  rc = finish_info(info, st);
+  if (dbg) {
+    const auto t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[lpgp_potrf] n=%lld launches=%lld host enqueue %.3f ms, until sync %.3f ms\n", (long long)f->n,
+            g_lpgp_launches - l0, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+            std::chrono::duration<double, std::milli>(t2 - t0).count());
+  }
+  return rc;
 }
 
 extern "C" int lpgp_chol_append(lpgp_factor* f, void* stream) {

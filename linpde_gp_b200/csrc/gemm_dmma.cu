@@ -26,16 +26,30 @@
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BN = 128;
 constexpr int BK = 8;
 constexpr int STAGES = 8;
-constexpr int NCONSUMER_WARPS = 8;
-constexpr int NTHREADS = (NCONSUMER_WARPS + 1) * 32;
-constexpr int STAGE_A_BYTES = BM * BK * 8;
-constexpr int STAGE_B_BYTES = BN * BK * 8;
-constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
+
+// Tile configuration: CTA tile BM x BN, WARPS_M x WARPS_N consumer warps (+ 1 TMA producer warp).
+//   Big  : 128 x 128, 2 x 4 warps, warp tile 64 x 32 (64 accumulators / thread)  -- the throughput configuration
+//   Small:  64 x  64, 2 x 2 warps, warp tile 32 x 32 (32 accumulators / thread)  -- for the small GEMMs of the
+//           recursion near the Cholesky leaves, where the 128 x 128 grid cannot fill 148 SMs (latency bound)
+template <int BM_, int BN_, int WARPS_M_, int WARPS_N_>
+struct TileCfg {
+  static constexpr int BM = BM_, BN = BN_, WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
+  static constexpr int NCONSUMER_WARPS = WARPS_M * WARPS_N;
+  static constexpr int NTHREADS = (NCONSUMER_WARPS + 1) * 32;
+  static constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;  // warp tile
+  static constexpr int MI = WTM / 8, NJ = WTN / 8;               // DMMA sub-tiles per warp
+  static constexpr int STAGE_A_BYTES = BM * BK * 8;
+  static constexpr int STAGE_B_BYTES = BN * BK * 8;
+  static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
+};
+//   Strip: 32 x 128, 1 x 4 warps, warp tile 32 x 32 -- in-place products X <- X W^T (C aliases A, n <= 128): the
+//           whole output row strip belongs to ONE CTA, which has consumed all of its A rows before it stores
+using BigTile = TileCfg<128, 128, 2, 4>;
+using SmallTile = TileCfg<64, 64, 2, 2>;
+using StripTile = TileCfg<32, 128, 1, 4>;
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -55,10 +69,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int m, int n,
                    int k, double alpha, double beta, double* __restrict__ C, int64_t ldc, int lower, int tiles_n,
-                   int vec_ok) {
+                   int vec_ok, const int* __restrict__ col_limit) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, NCONSUMER_WARPS = Cfg::NCONSUMER_WARPS, MI = Cfg::MI, NJ = Cfg::NJ;
+  constexpr int STAGE_A_BYTES = Cfg::STAGE_A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // keeps the shared address space
   uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -78,6 +95,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tn = blockIdx.x % tiles_n;
   }
   const int row0 = tm * BM, col0 = tn * BN;
+  // optional per-row-block column limit (distributed block-row layouts: the rows of one 128-row block only need
+  // the columns up to their own diagonal block); the predicate is block-uniform
+  if (col_limit != nullptr && col0 >= col_limit[row0 >> 7]) return;
   const int nk = (k + BK - 1) / BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -108,12 +128,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   // ===== DMMA consumers =====
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
-  double acc[8][4][2];
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WTM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WTN;
+  double acc[MI][NJ][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   for (int kb = 0; kb < nk; ++kb) {
     const int s = kb % STAGES;
@@ -121,15 +141,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     mbar_wait(&full[s], ph);
     const double* sA = (const double*)(smem + s * STAGE_BYTES);
     const double* sB = (const double*)(smem + s * STAGE_BYTES + STAGE_A_BYTES);
-    double2 a[8], b[4];
+    double2 a[MI], b[NJ];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double2*>(sA + (wm0 + 8 * i + g) * BK + 2 * t);
+    for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double2*>(sA + (wm0 + 8 * i + g) * BK + 2 * t);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(sB + (wn0 + 8 * j + g) * BK + 2 * t);
+    for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double2*>(sB + (wn0 + 8 * j + g) * BK + 2 * t);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
         dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
       }
@@ -139,12 +159,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   // ===== epilogue: C = beta*C + alpha*acc =====
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < MI; ++i) {
     const int row = row0 + wm0 + 8 * i + g;
     if (row >= m) continue;
     double* crow = C + (int64_t)row * ldc;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int col = col0 + wn0 + 8 * j + 2 * t;
       if (col >= n) continue;
       double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
@@ -182,7 +202,11 @@ void init_once() {
     return;
   }
   g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
-  e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaFuncSetAttribute(gemm_nt_kernel<BigTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigTile::SMEM_BYTES);
+  if (e != cudaSuccess) g_init_rc = LPGP_CUDA_ERR(e);
+  e = cudaFuncSetAttribute(gemm_nt_kernel<SmallTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallTile::SMEM_BYTES);
+  if (e != cudaSuccess) g_init_rc = LPGP_CUDA_ERR(e);
+  e = cudaFuncSetAttribute(gemm_nt_kernel<StripTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripTile::SMEM_BYTES);
   if (e != cudaSuccess) g_init_rc = LPGP_CUDA_ERR(e);
 }
 
@@ -196,6 +220,25 @@ int make_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, in
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : LPGP_CUDA_ERR(cudaErrorInvalidValue);
+}
+
+
+template <typename Cfg>
+int launch(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+           double beta, double* C, int64_t ldc, int lower, void* stream, const int* col_limit = nullptr) {
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, A, m, k > 0 ? k : 1, lda, Cfg::BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, B, n, k > 0 ? k : 1, ldb, Cfg::BN);
+  if (rc) return rc;
+  const int64_t tiles_m = ceil_div64(m, Cfg::BM), tiles_n = ceil_div64(n, Cfg::BN);
+  const int64_t ntiles = lower ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
+  if (ntiles > INT32_MAX) return -1;
+  const int vec_ok = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
+  gemm_nt_kernel<Cfg><<<(unsigned)ntiles, Cfg::NTHREADS, Cfg::SMEM_BYTES, (cudaStream_t)stream>>>(
+      tmA, tmB, (int)m, (int)n, (int)k, alpha, beta, C, ldc, lower, (int)tiles_n, vec_ok, col_limit);
+  LPGP_CHECK_LAUNCH();
+  return 0;
 }
 
 }  // namespace
@@ -216,17 +259,35 @@ extern "C" int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const
   if (k == 0) {
     // pure scaling of C; reuse the kernel with an empty contraction (nk = 0)
   }
-  CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, A, m, k > 0 ? k : 1, lda, BM);
-  if (rc) return rc;
-  rc = make_map(&tmB, B, n, k > 0 ? k : 1, ldb, BN);
-  if (rc) return rc;
-  const int64_t tiles_m = ceil_div64(m, BM), tiles_n = ceil_div64(n, BN);
-  const int64_t ntiles = lower ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
-  if (ntiles > INT32_MAX) return -1;
-  const int vec_ok = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
-  gemm_nt_kernel<<<(unsigned)ntiles, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
-      tmA, tmB, (int)m, (int)n, (int)k, alpha, beta, C, ldc, lower, (int)tiles_n, vec_ok);
-  LPGP_CHECK_LAUNCH();
-  return 0;
+  // tile choice: the 128 x 128 configuration unless its grid would leave most of the 148 SMs idle
+  const int64_t tm128 = ceil_div64(m, 128), tn128 = ceil_div64(n, 128);
+  const int64_t tiles128 = lower ? tm128 * (tm128 + 1) / 2 : tm128 * tn128;
+  const bool use_small = tiles128 < 96;
+  if ((const double*)C == A) {
+    // in-place product (TRSM leaf step): only safe when one CTA owns complete output rows
+    if (n > 128 || lower) return -11;
+    return (use_small ? launch<StripTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, nullptr);
+  }
+  return (use_small ? launch<SmallTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower, stream, nullptr);
+}
+
+
+// C[m x n] = beta*C + alpha*A*B^T restricted, for every block of 128 rows, to the columns < col_limit[row/128]
+// (device array of ceil(m/128) ints).  Used by the distributed Cholesky, whose ranks own block ROWS of the lower
+// triangle: tiles to the right of a row block's diagonal are skipped.
+extern "C" int lpgp_gemm_nt_limited(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                                    const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                                    const int* col_limit, void* stream) {
+  if (m < 0) return -1;
+  if (n < 0) return -2;
+  if (k < 0) return -3;
+  if (m == 0 || n == 0) return 0;
+  if (!A || lda < k || (lda % 2) || ((uintptr_t)A % 16)) return -6;
+  if (!B || ldb < k || (ldb % 2) || ((uintptr_t)B % 16)) return -8;
+  if (!C || ldc < n || (const double*)C == A) return -11;
+  if (!col_limit) return -12;
+  if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return -1;
+  std::call_once(g_once, init_once);
+  if (g_init_rc) return g_init_rc;
+  return launch<BigTile>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, col_limit);
 }

@@ -62,6 +62,90 @@ class ConditionalGaussianProcess(GaussianProcess):
         w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
         return cls(prior=prior, Ys=(Y,), Ls=(Lf,), bs=(b,), blocks=(blk,), factor=factor, resid=y, weights=w)
 
+    @classmethod
+    def from_observation_batches(cls, prior: GaussianProcess, batches, *, process_group=None, nb: int = 512):
+        """Condition on several observation batches AT ONCE: ``batches`` is a sequence of
+        ``(Y, X, L, b)`` tuples (same meaning as the arguments of :meth:`condition_on_observations`).
+
+        The posterior is identical to conditioning batch by batch (the bordered factor of a block matrix IS the
+        Cholesky factor of the whole matrix), but the Gram matrix is assembled and factorised in one go -- and,
+        when ``torch.distributed`` is initialised with more than one rank, across all GPUs of the process group
+        (block-row cyclic layout, NCCL panel exchange, see ``linpde_gp_b200/distributed.py``).  Every rank must
+        call this with the same arguments; every rank ends up with the full (replicated) factor so that posterior
+        evaluation can shard test points freely."""
+        import torch.distributed as dist
+
+        from .. import distributed
+
+        pre = [cls._preprocess_observations(prior=prior, Y=t[0], X=t[1] if len(t) > 1 else None,
+                                            L=t[2] if len(t) > 2 else None, b=t[3] if len(t) > 3 else None)
+               for t in batches]
+        d = prior.cov.input_size
+        blocks, off = [], 0
+        for (_, _, _, op, Xobs, _, _) in pre:
+            blk = _Block(Xobs, op, d, off)
+            blocks.append(blk)
+            off += blk.n_phys
+        n = off
+        noises = [p[6] for p in pre]
+        world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        factor = backend.DeviceFactor([n])
+        if world > 1:
+            ch = distributed.DistributedCholesky(n, nb=nb, group=process_group)
+            for i in ch.layout.local_blocks(ch.rank):
+                g0, g1 = ch.layout.block_bounds(i)
+                cls._assemble_range(prior, blocks, noises, ch.local_block_rows(i), g0, g1)
+            ch.factor()
+            ch.replicate_into(factor.L)
+            factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
+            del ch
+        else:
+            cls._assemble_range(prior, blocks, noises, factor.L, 0, n)
+            factor.potrf()
+        factor.factored_segments = 1
+        y = torch.zeros(n, dtype=torch.float64, device=factor.L.device)
+        for blk, p in zip(blocks, pre):
+            y[blk.col_off : blk.col_off + blk.n].copy_(backend.to_device(p[5]))
+        w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
+        return cls(prior=prior, Ys=tuple(p[0] for p in pre), Ls=tuple(p[1] for p in pre), bs=tuple(p[2] for p in pre),
+                   blocks=tuple(blocks), factor=factor, resid=y, weights=w)
+
+    @staticmethod
+    def _assemble_range(prior, blocks, noises, out: "torch.Tensor", g0: int, g1: int) -> None:
+        """Fill ``out`` (rows g0..g1 of the global Gram matrix, all n columns addressable) with the lower part
+        G[g0:g1, 0:g1] of the block-structured Gram matrix of all batches (identity padding rows included)."""
+        k = prior.cov
+        for bi, blk in enumerate(blocks):
+            r_lo, r_hi = max(g0, blk.col_off), min(g1, blk.col_off + blk.n_phys)
+            if r_lo >= r_hi:
+                continue
+            rows = out[r_lo - g0 : r_hi - g0]
+            l_lo, l_hi = r_lo - blk.col_off, min(r_hi - blk.col_off, blk.n)  # logical rows of this batch
+            Xi = blk.X[l_lo:l_hi]
+            for bj, pb in enumerate(blocks[: bi + 1]):
+                kj = k if pb.op is None else pb.op(k, argnum=1)
+                kij = kj if blk.op is None else blk.op(kj, argnum=0)
+                c_hi = pb.n if bj < bi else min(pb.n, l_hi)  # own batch: columns up to the last row's diagonal
+                if l_hi > l_lo and c_hi > 0:
+                    view = rows[: l_hi - l_lo, pb.col_off : pb.col_off + c_hi]
+                    for t, dsc in enumerate(_descs(kij)):
+                        backend.gram(dsc, Xi, pb.X[:c_hi], out=view, accumulate=t > 0)
+                if pb.n_phys != pb.n and pb.col_off + pb.n < r_hi:
+                    rows[:, pb.col_off + pb.n] = 0.0  # padding column of batch bj
+            if noises[bi] is not None and l_hi > l_lo:
+                kind, val = noises[bi]
+                diag = rows[: l_hi - l_lo, blk.col_off + l_lo : blk.col_off + l_hi]
+                if kind == "diag":
+                    backend.add_diag(diag, backend.to_device(val[l_lo:l_hi]), 1.0)
+                else:
+                    diag.add_(backend.to_device(val[l_lo:l_hi, l_lo:l_hi]))
+                    if l_lo > 0:
+                        rows[: l_hi - l_lo, blk.col_off : blk.col_off + l_lo].add_(backend.to_device(val[l_lo:l_hi, :l_lo]))
+            if blk.n_phys != blk.n and r_hi == blk.col_off + blk.n_phys:  # the identity padding row is in range
+                pr = rows[blk.n - l_lo]
+                pr[: blk.col_off + blk.n_phys] = 0.0
+                pr[blk.col_off + blk.n] = 1.0
+
     def __init__(self, *, prior, Ys, Ls, bs, blocks, factor, resid, weights, test_op=None, base_prior=None):
         self._prior = prior
         self._base_prior = prior if base_prior is None else base_prior  # the process the observations refer to

@@ -1,0 +1,46 @@
+"""CPU test double of ``linpde_gp_b200.distributed.DeviceOps`` (plain torch on the host), used ONLY by the gloo
+test to exercise the ownership / packing / collective logic of the distributed Cholesky without a GPU."""
+import torch
+
+LEAF = 128
+
+
+class HostOps:
+    device = torch.device("cpu")
+
+    def empty(self, rows, cols):
+        ld = max((cols + 15) // 16 * 16, 16)
+        return torch.zeros((max(rows, 1), ld), dtype=torch.float64)[:rows, :cols]
+
+    def potrf_block(self, D, dinv):
+        n = D.shape[0]
+        G = torch.tril(D) + torch.tril(D, -1).T
+        try:
+            L = torch.linalg.cholesky(G)
+        except Exception:
+            return 1
+        D.copy_(torch.tril(L) + torch.triu(D, 1))
+        nleaf = (n + LEAF - 1) // LEAF
+        W = dinv[: nleaf * LEAF * LEAF].view(nleaf, LEAF, LEAF)
+        W.zero_()
+        for l in range(nleaf):
+            lo, hi = l * LEAF, min(n, (l + 1) * LEAF)
+            W[l] = torch.eye(LEAF, dtype=torch.float64)
+            W[l, : hi - lo, : hi - lo] = torch.linalg.inv(L[lo:hi, lo:hi])
+        return 0
+
+    def trsm_block(self, Lkk, dinv, X):
+        if X.shape[0] == 0:
+            return
+        X.copy_(torch.linalg.solve_triangular(torch.tril(Lkk), X.T.contiguous(), upper=False).T)
+
+    def update_limited(self, C, A, B, col_limit):
+        if C.shape[0] == 0 or C.shape[1] == 0:
+            return
+        full = A @ B.T
+        for t in range((C.shape[0] + LEAF - 1) // LEAF):
+            lim = int(col_limit[t])
+            rows = slice(t * LEAF, min(C.shape[0], (t + 1) * LEAF))
+            # the device kernel works on whole 128-column tiles: columns up to the tile boundary may be touched
+            lim_tile = min(C.shape[1], (lim + LEAF - 1) // LEAF * LEAF)
+            C[rows, :lim_tile] -= full[rows, :lim_tile]

@@ -1,0 +1,85 @@
+"""Distributed (block-row cyclic) Cholesky: orchestration logic under gloo, world_size 1 and 2, with the host test
+double for the local kernels (the CUDA kernels themselves are covered by the -m gpu tests)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from linpde_gp_b200.distributed import BlockRowLayout, DistributedCholesky
+from tests.dist_double import HostOps
+
+
+def _spd(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(n, n + 8, dtype=torch.float64, generator=g)
+    return X @ X.T / n + 0.5 * torch.eye(n, dtype=torch.float64)
+
+
+def _run(rank, world, port, n, nb, q):
+    if world > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    G = _spd(n, 3)
+    ch = DistributedCholesky(n, nb=nb, ops=HostOps())
+    for i in ch.layout.local_blocks(ch.rank):
+        lo, hi = ch.layout.block_bounds(i)
+        ch.local_block_rows(i)[:, :hi].copy_(G[lo:hi, :hi])  # lower part only
+    ch.factor()
+    L_full = torch.zeros((n, (n + 15) // 16 * 16), dtype=torch.float64)[:, :n]
+    ch.replicate_into(L_full)
+    L_ref = torch.linalg.cholesky(G)
+    err = float((torch.tril(L_full) - L_ref).abs().max())
+    # inverted leaf blocks are replicated too
+    l0 = torch.linalg.inv(L_ref[:128, :128])
+    werr = float((ch.dinv[: 128 * 128].view(128, 128) - l0).abs().max())
+    q.put((rank, err, werr))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_layout_bookkeeping():
+    lay = BlockRowLayout(1280 + 256, 512, 2)
+    assert lay.nblk == 3 and lay.local_blocks(0) == [0, 2] and lay.local_blocks(1) == [1]
+    assert lay.n_local(0) == 512 + 512 and lay.n_local(1) == 512
+    assert lay.block_bounds(2) == (1024, 1536)
+    assert lay.first_local_block_after(0, 0) == 1 and lay.first_local_block_after(1, 0) == 0
+    assert lay.rows_after(0, 0) == 512 and lay.rows_after(1, 0) == 512 and lay.rows_after(1, 1) == 0
+    with pytest.raises(ValueError):
+        BlockRowLayout(1000, 500, 2)
+
+
+@pytest.mark.parametrize("n,nb", [(512, 128), (1280, 256), (1100, 256)])
+def test_single_process(n, nb):
+    import queue
+
+    q = queue.Queue()
+    _run(0, 1, 0, n, nb, q)
+    _, err, werr = q.get()
+    assert err < 1e-11 and werr < 1e-10
+
+
+@pytest.mark.parametrize("n,nb", [(1280, 256), (1100, 128)])
+def test_world2_gloo(n, nb):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run, args=(r, 2, port, n, nb, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(err < 1e-11 and werr < 1e-10 for _, err, werr in res), res

@@ -172,3 +172,50 @@ def test_linop_solve_and_cholesky():
     assert np.max(np.abs(G @ x - b)) <= 1e-8 * np.max(np.abs(b))
     x1 = op.solve(b[:, 0])
     assert np.allclose(x1, x[:, 0], rtol=1e-9, atol=1e-12)
+
+
+def test_one_shot_batches_equal_sequential_conditioning():
+    """from_observation_batches (whole Gram assembled + factored at once) == batch-by-batch conditioning."""
+    import linpde_gp_b200 as lg
+    from oracle import gp as ogp
+
+    for prob in (ogp.poisson2d_problem(700, 33, seed=4, grid=12, noise_bc=1e-6), ogp.heat_problem(n_ic=9, n_bc=21, nt=20, nx=11)):
+        post_seq, seq = helpers.api_solve(prob)
+        shape = gcases.kernel_input_shape(prob["kernel"])
+        prior = lg.GaussianProcess(lg.functions.Zero(input_shape=shape), helpers.api_kernel(prob["kernel"]))
+        batches = []
+        for blk in prob["blocks"]:
+            Y = np.asarray(blk["Y"], dtype=float)
+            b = None
+            if blk.get("noise_var") is not None:
+                b = lg.randvars.Normal(np.zeros_like(Y), lg.linops.Scaling(np.broadcast_to(blk["noise_var"], Y.shape).copy()))
+            batches.append((Y, np.asarray(blk["X"], dtype=float), helpers.api_op(blk["L"]), b))
+        post = lg.ConditionalGaussianProcess.from_observation_batches(prior, batches)
+        Xt = np.asarray(prob["Xt"], dtype=float)
+        sc = np.max(np.abs(seq["var"]))
+        assert np.max(np.abs(post.mean(Xt) - seq["mean"])) <= 1e-9 * max(sc, np.max(np.abs(seq["mean"])))
+        assert np.max(np.abs(post.var(Xt) - seq["var"])) <= 1e-9 * sc
+        assert np.max(np.abs(post.gram.todense() - seq["gram"])) <= 1e-11 * np.max(np.abs(seq["gram"]))
+        # and the one-shot posterior can still be extended by bordering
+        Xn = Xt[5:7] + 0.01234  # two new points that do not coincide with existing observations
+        post2 = post.condition_on_observations(np.array([0.1, 0.2]), X=Xn)
+        assert np.max(np.abs(post2.mean(Xn) - np.array([0.1, 0.2]))) <= 1e-6
+
+
+def test_distributed_cholesky_single_rank_device_ops():
+    """The multi-GPU code path with world_size 1 (no collectives) on the real CUDA kernels, ragged last block."""
+    import torch
+
+    from linpde_gp_b200.distributed import DistributedCholesky
+
+    n = 1664 + 130
+    g = torch.Generator(device="cuda").manual_seed(0)
+    X = torch.randn(n, n + 8, dtype=torch.float64, device="cuda", generator=g)
+    G = X @ X.T / n + 0.5 * torch.eye(n, dtype=torch.float64, device="cuda")
+    ch = DistributedCholesky(n, nb=512)
+    for i in ch.layout.local_blocks(0):
+        lo, hi = ch.layout.block_bounds(i)
+        ch.local_block_rows(i)[:, :hi].copy_(G[lo:hi, :hi])
+    ch.factor()
+    L_ref = torch.linalg.cholesky(G)
+    assert (torch.tril(ch.A_loc) - L_ref).abs().max().item() <= 1e-11 * L_ref.abs().max().item()
