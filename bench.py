@@ -16,8 +16,9 @@ One *step* = one full pass of the hot path over one synthetic problem (BASELINE.
              FP64 tensor-pipe issue rate measured live on the box (lpgp_dmma_peak_probe);
 `cpu_baseline` the oracle (numpy/scipy restatement of the reference) timed on the box's host cores on a bounded
              sample and extrapolated to the full solve.
-With --gpus N > 1 (torchrun) every rank assembles and factorises the (replicated) Gram matrix and the test grid is
-sharded N ways (strong scaling of a fixed problem); results are gathered with NCCL.
+With --gpus N > 1 (torchrun) the Gram matrix is assembled and factorised over all ranks (block-row cyclic layout,
+NCCL panel exchange, linpde_gp_b200/distributed.py), the factor is then replicated and the test grid is sharded N
+ways (strong scaling of the fixed N = 65,536 problem); result rows are gathered with NCCL.
 """
 from __future__ import annotations
 
@@ -216,6 +217,7 @@ class DeviceSolve:
         self.Xt = backend.to_device(Xt[lo:hi])
         self.N, self.M = prob["N"], prob["M"]
         self.t = {}
+        self.distributed = world > 1
 
     def _timed(self, name, fn):
         torch = self.torch
@@ -256,13 +258,62 @@ class DeviceSolve:
         var = self._timed("var", lambda: be.post_var(blocks, factor, self.Xt, self.d_k.diag_value, chunk=chunk))
         return mean, var
 
+    # -- multi-GPU step: block-row cyclic assembly + distributed Cholesky, replicated factor, sharded test grid --
+    def _desc_for(self, bi: int, bj: int):
+        last = len(self.edges)
+        if bi == last:
+            return self.d_LkL if bj == last else self.d_Lk
+        return self.d_k
+
+    def _assemble_block_rows(self, out, g0: int, g1: int, blocksX, offs, sizes):
+        """rows g0..g1 of the lower triangle of the block-structured Gram matrix -> out[:, :g1]"""
+        be = self.be
+        for bi, (Xi, oi, ni) in enumerate(zip(blocksX, offs, sizes)):
+            r_lo, r_hi = max(g0, oi), min(g1, oi + ni)
+            if r_lo >= r_hi:
+                continue
+            rows = out[r_lo - g0 : r_hi - g0]
+            Xr = Xi[r_lo - oi : r_hi - oi]
+            for bj in range(bi + 1):
+                oj, nj = offs[bj], sizes[bj]
+                c_hi = nj if bj < bi else r_hi - oi
+                be.gram(self._desc_for(bi, bj), Xr, blocksX[bj][:c_hi], out=rows[:, oj : oj + c_hi])
+
+    def step_distributed(self, nb: int):
+        from linpde_gp_b200 import distributed
+
+        be, torch = self.be, self.torch
+        sizes = [e.shape[0] for e in self.edges] + [self.Xp.shape[0]]
+        blocksX = self.edges + [self.Xp]
+        offs = [int(o) for o in np.concatenate([[0], np.cumsum(sizes)[:-1]])]
+        n = int(sum(sizes))
+        factor = be.DeviceFactor([n])
+        ch = distributed.DistributedCholesky(n, nb=nb)
+
+        def assemble():
+            for i in ch.layout.local_blocks(ch.rank):
+                g0, g1 = ch.layout.block_bounds(i)
+                self._assemble_block_rows(ch.local_block_rows(i), g0, g1, blocksX, offs, sizes)
+
+        self._timed("assemble", assemble)
+        self._timed("factor", lambda: ch.factor(factor.L))  # every rank ends up with the whole factor
+        factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
+        del ch
+        w = self._timed("solve", lambda: factor.potrs(self.y.clone().reshape(1, -1)).reshape(-1))
+        descs = [self.d_k] * len(self.edges) + [self.d_kL]
+        blocks = be.ObsBlocks(descs, blocksX, offs)
+        mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
+        chunk = int(max(256, min(self.Xt.shape[0], (4 << 30) // (8 * be.round_up(factor.n, 16)))))
+        var = self._timed("var", lambda: be.post_var(blocks, factor, self.Xt, self.d_k.diag_value, chunk=chunk))
+        return mean, var
+
     def phase_ms(self, last_k: int):
         self.torch.cuda.synchronize()
-        return {k: sum(e0.elapsed_time(e1) for e0, e1 in v[-last_k * (5 if k in ("assemble", "factor") else 1):]) / last_k
-                for k, v in self.t.items()}
+        per = lambda k: 5 if (k in ("assemble", "factor") and not self.distributed) else 1
+        return {k: sum(e0.elapsed_time(e1) for e0, e1 in v[-last_k * per(k):]) / last_k for k, v in self.t.items()}
 
 
-def api_solve(prob, rank: int, world: int):
+def api_solve(prob, rank: int, world: int, nb: int = 1024):
     """The same solve through the public reference-style API with host (numpy) buffers -> `e2e`."""
     import linpde_gp_b200 as lg
     from linpde_gp_b200.linfuncops import diffops
@@ -271,9 +322,14 @@ def api_solve(prob, rank: int, world: int):
     k = SIGMA2 * covfuncs.TensorProduct(covfuncs.Matern((), nu=NU, lengthscales=prob["ell"]),
                                         covfuncs.Matern((), nu=NU, lengthscales=prob["ell"]))
     post = lg.GaussianProcess(lg.functions.Zero(input_shape=(2,)), k)
-    for Xb, Yb in zip(prob["edges"], prob["Y_bc"]):
-        post = post.condition_on_observations(Yb, X=Xb)
-    post = post.condition_on_observations(prob["Y_pde"], X=prob["X_pde"], L=-1.0 * diffops.Laplacian((2,)))
+    lap = -1.0 * diffops.Laplacian((2,))
+    if world > 1:  # one-shot conditioning on all batches, Gram assembly + Cholesky distributed over the ranks
+        batches = [(Yb, Xb) for Xb, Yb in zip(prob["edges"], prob["Y_bc"])] + [(prob["Y_pde"], prob["X_pde"], lap)]
+        post = lg.ConditionalGaussianProcess.from_observation_batches(post, batches, nb=nb)
+    else:
+        for Xb, Yb in zip(prob["edges"], prob["Y_bc"]):
+            post = post.condition_on_observations(Yb, X=Xb)
+        post = post.condition_on_observations(prob["Y_pde"], X=prob["X_pde"], L=lap)
     from linpde_gp_b200 import parallel
 
     lo, hi = parallel.shard_bounds(prob["M"], rank, world)
@@ -337,8 +393,9 @@ def run_b200(args):
 
     peak = dmma_peak_tflops(torch, backend) if rank == 0 else None
     ds = DeviceSolve(prob, rank, world)
+    step = ds.step if world == 1 else (lambda: ds.step_distributed(args.nb))
     for _ in range(args.warmup):
-        m, v = ds.step()
+        m, v = step()
         gather(m, v)
     barrier()
     lib.lpgp_launch_count(1)
@@ -348,7 +405,7 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        m, v = ds.step()
+        m, v = step()
         gm, gv = gather(m, v)
     e1.record()
     barrier()
@@ -362,7 +419,7 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        em, ev = api_solve(prob, rank, world)
+        em, ev = api_solve(prob, rank, world, args.nb)
         gem, gev = gather(em, ev)
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -377,7 +434,7 @@ def run_b200(args):
         gm, gv, gem, gev = tonp(gm), tonp(gv), tonp(gem), tonp(gev)
         agree = float(max(np.max(np.abs(gm - gem)), np.max(np.abs(gv - gev))))
         m_shard = parallel.shard_bounds(M, 0, world)[1]
-        flops_tensor = N**3 / 3.0 + float(m_shard) * N * N          # per rank: Cholesky + variance TRSM
+        flops_tensor = N**3 / 3.0 / world + float(m_shard) * N * N  # per rank: Cholesky share + variance TRSM
         t_tensor = (phases["factor"] + phases["var"]) * 1e-3
         achieved = flops_tensor / t_tensor * 1e-12
         h2d = sum(e.nbytes for e in prob["edges"]) + sum(y.nbytes for y in prob["Y_bc"]) + prob["X_pde"].nbytes \
@@ -401,12 +458,13 @@ def run_b200(args):
                 "workload": f"2D Poisson Dirichlet synthetic N={N} (N_pde={args.npde} seed 2, N_bc={4 * args.nbc_edge}), "
                             f"product Matern-5/2 prior, 5 conditioning batches, mean+variance on {args.grid}x{args.grid} grid "
                             "(BASELINE.json configs[3])",
-                "parallelism": "replicated factor, test grid sharded" if world > 1 else "single GPU",
+                "parallelism": (f"block-row cyclic Gram assembly + Cholesky over {world} ranks (nb={args.nb}, NCCL panel "
+                                "exchange), factor replicated, test grid sharded") if world > 1 else "single GPU",
                 "l2": f"working set {N * N * 8 / 1e9:.1f} GB Gram >> 126 MB L2 (no flush needed)",
             },
             "phases_ms": phases,
             "gram_entries_per_s": (N * (N + 1) / 2 + 0.0) / (phases["assemble"] * 1e-3),
-            "cholesky_tflops": N**3 / 3.0 / (phases["factor"] * 1e-3) * 1e-12,
+            "cholesky_tflops": N**3 / 3.0 / (phases["factor"] * 1e-3) * 1e-12,  # aggregate over all ranks
             "variance_trsm_tflops": float(m_shard) * N * N / (phases["var"] * 1e-3) * 1e-12,
             "e2e": {"value": ms_e2e * 1e-3, "unit": "s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(2 * 8 * M // world), "api_vs_device_max_abs_diff": agree},
@@ -467,6 +525,7 @@ def main():
     ap.add_argument("--npde", type=int, default=63488)
     ap.add_argument("--nbc-edge", type=int, default=512)
     ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--nb", type=int, default=1024, help="block-row height of the distributed Cholesky (N > 1 GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

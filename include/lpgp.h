@@ -107,11 +107,13 @@ int lpgp_symmetrize_lower(double* A, int64_t n, int64_t ld, void* stream);
 int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
                  int64_t ldb, double beta, double* C, int64_t ldc, int lower, void* stream);
 
-/* As lpgp_gemm_nt, but for every block of 128 rows only the columns < col_limit[row/128] are updated
- * (col_limit: device array of ceil(m/128) ints).  Building block of the multi-GPU Cholesky, whose ranks own
- * block rows of the lower triangle.                                               */
+/* As lpgp_gemm_nt, but for every block of 128 rows only the columns j with col_base + j < col_limit[row/128] are
+ * updated (col_limit: device array of ceil(m/128) ints; col_base: position of C's first column in the coordinates
+ * of the limits).  Building block of the multi-GPU Cholesky, whose ranks own block rows of the lower triangle
+ * (SURVEY.md section 8e).                                                                                 */
 int lpgp_gemm_nt_limited(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
-                         int64_t ldb, double beta, double* C, int64_t ldc, const int* col_limit, void* stream);
+                         int64_t ldb, double beta, double* C, int64_t ldc, const int* col_limit, int64_t col_base,
+                         void* stream);
 
 /*
  * Cached, appendable Cholesky factor  G = L L^T  (lower, row-major, in place in `L`).
@@ -142,6 +144,11 @@ size_t lpgp_factor_dinv_bytes(const int64_t* seg_off, int nseg);
  * scipy.linalg.cholesky(self.todense(), lower=...) in pn/linops/_linear_operator.py:784-865.
  * Synchronises `stream`; returns LAPACK info (> 0: leading minor of that order not positive definite).     */
 int lpgp_potrf(lpgp_factor* f, void* stream);
+
+/* As lpgp_potrf without the stream synchronisation (for pipelines that must not stall the host, e.g. the
+ * multi-GPU panel loop): always returns 0 on a successful enqueue; the LAPACK info is left on the device in the
+ * int32 at byte offset lpgp_factor_dinv_bytes(...) - 64 of `dinv`.                                          */
+int lpgp_potrf_async(lpgp_factor* f, void* stream);
 
 /* Bordered update: segments 0..nseg-2 already hold their factor; the rows of the last segment hold the new
  * Gram rows [B^T | D] (lower part) and are replaced by [L_21 | L_22]:  L_21 = B^T L_11^{-T} (TRSM,

@@ -76,9 +76,10 @@ def _load() -> ctypes.CDLL:
         "lpgp_add_diag": (ci, [vp, i64, i64, vp, dbl, vp]),
         "lpgp_symmetrize_lower": (ci, [vp, i64, i64, vp]),
         "lpgp_gemm_nt": (ci, [i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, ci, vp]),
-        "lpgp_gemm_nt_limited": (ci, [i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, vp, vp]),
+        "lpgp_gemm_nt_limited": (ci, [i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, vp, i64, vp]),
         "lpgp_factor_dinv_bytes": (ctypes.c_size_t, [ctypes.POINTER(i64), ci]),
         "lpgp_potrf": (ci, [FP, vp]),
+        "lpgp_potrf_async": (ci, [FP, vp]),
         "lpgp_chol_append": (ci, [FP, vp]),
         "lpgp_trsm_rlt": (ci, [FP, i64, vp, i64, i64, vp]),
         "lpgp_potrs": (ci, [FP, vp, i64, i64, vp]),
@@ -98,7 +99,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTED = (
     "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
-    "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_logdet "
+    "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_logdet "
     "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq"
 ).split()
 

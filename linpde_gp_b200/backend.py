@@ -120,13 +120,14 @@ def gemm_nt(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, alpha: float = 1.
 
 
 def gemm_nt_limited(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, col_limit: torch.Tensor, alpha: float = 1.0,
-                    beta: float = 0.0) -> torch.Tensor:
-    """C = beta*C + alpha * A @ B.T, each block of 128 rows restricted to columns < col_limit[block] (int32, device)."""
+                    beta: float = 0.0, col_base: int = 0) -> torch.Tensor:
+    """C = beta*C + alpha * A @ B.T, each block of 128 rows restricted to the columns j with
+    col_base + j < col_limit[block] (int32, device)."""
     m, k = A.shape
     n = B.shape[0]
     assert B.shape[1] == k and C.shape == (m, n) and col_limit.dtype == torch.int32 and col_limit.numel() >= (m + 127) // 128
     rc = lib.lpgp_gemm_nt_limited(m, n, k, float(alpha), _ptr(A), _ld(A), _ptr(B), _ld(B), float(beta), _ptr(C), _ld(C),
-                                  _ptr(col_limit), _stream())
+                                  _ptr(col_limit), int(col_base), _stream())
     check(rc, "lpgp_gemm_nt_limited")
     return C
 

@@ -369,7 +369,8 @@ extern "C" size_t lpgp_factor_dinv_bytes(const int64_t* seg_off, int nseg) {
   return (size_t)(lv.off.size() - 1) * LEAF * LEAF * sizeof(double) + sizeof(Status);
 }
 
-extern "C" int lpgp_potrf(lpgp_factor* f, void* stream) {
+namespace {
+int potrf_impl(lpgp_factor* f, void* stream, bool sync) {
   if (check_factor(f)) return -1;
   Leaves lv;
   if (build_leaves(f->seg_off, f->nseg, lv)) return -1;
@@ -385,6 +386,7 @@ extern "C" int lpgp_potrf(lpgp_factor* f, void* stream) {
   const long long l0 = g_lpgp_launches;
   rc = potrf_rec(f, lv, 0, nl, info, st);
   if (rc) return rc;
+  if (!sync) return 0;
   const auto t1 = std::chrono::steady_clock::now();
   rc = finish_info(info, st);
   if (dbg) {
@@ -395,6 +397,13 @@ extern "C" int lpgp_potrf(lpgp_factor* f, void* stream) {
   }
   return rc;
 }
+}  // namespace
+
+extern "C" int lpgp_potrf(lpgp_factor* f, void* stream) { return potrf_impl(f, stream, true); }
+
+// as lpgp_potrf, but never synchronises: the LAPACK info stays on the device, in the int32 at byte offset
+// lpgp_factor_dinv_bytes(...) - 64 of `dinv` (0 = ok, > 0 = order of the failing leading minor)
+extern "C" int lpgp_potrf_async(lpgp_factor* f, void* stream) { return potrf_impl(f, stream, false); }
 
 extern "C" int lpgp_chol_append(lpgp_factor* f, void* stream) {
   if (check_factor(f)) return -1;

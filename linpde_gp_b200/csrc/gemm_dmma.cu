@@ -73,7 +73,7 @@ template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int m, int n,
                    int k, double alpha, double beta, double* __restrict__ C, int64_t ldc, int lower, int tiles_n,
-                   int vec_ok, const int* __restrict__ col_limit) {
+                   int vec_ok, const int* __restrict__ col_limit, int col_base) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, NCONSUMER_WARPS = Cfg::NCONSUMER_WARPS, MI = Cfg::MI, NJ = Cfg::NJ;
   constexpr int STAGE_A_BYTES = Cfg::STAGE_A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   const int row0 = tm * BM, col0 = tn * BN;
   // optional per-row-block column limit (distributed block-row layouts: the rows of one 128-row block only need
   // the columns up to their own diagonal block); the predicate is block-uniform
-  if (col_limit != nullptr && col0 >= col_limit[row0 >> 7]) return;
+  if (col_limit != nullptr && col0 + col_base >= col_limit[row0 >> 7]) return;
   const int nk = (k + BK - 1) / BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -225,7 +225,8 @@ int make_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, in
 
 template <typename Cfg>
 int launch(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
-           double beta, double* C, int64_t ldc, int lower, void* stream, const int* col_limit = nullptr) {
+           double beta, double* C, int64_t ldc, int lower, void* stream, const int* col_limit = nullptr,
+           int col_base = 0) {
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, A, m, k > 0 ? k : 1, lda, Cfg::BM);
   if (rc) return rc;
@@ -236,7 +237,7 @@ int launch(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64
   if (ntiles > INT32_MAX) return -1;
   const int vec_ok = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
   gemm_nt_kernel<Cfg><<<(unsigned)ntiles, Cfg::NTHREADS, Cfg::SMEM_BYTES, (cudaStream_t)stream>>>(
-      tmA, tmB, (int)m, (int)n, (int)k, alpha, beta, C, ldc, lower, (int)tiles_n, vec_ok, col_limit);
+      tmA, tmB, (int)m, (int)n, (int)k, alpha, beta, C, ldc, lower, (int)tiles_n, vec_ok, col_limit, col_base);
   LPGP_CHECK_LAUNCH();
   return 0;
 }
@@ -266,18 +267,19 @@ extern "C" int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const
   if ((const double*)C == A) {
     // in-place product (TRSM leaf step): only safe when one CTA owns complete output rows
     if (n > 128 || lower) return -11;
-    return (use_small ? launch<StripTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, nullptr);
+    return (use_small ? launch<StripTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, nullptr, 0);
   }
-  return (use_small ? launch<SmallTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower, stream, nullptr);
+  return (use_small ? launch<SmallTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower, stream, nullptr, 0);
 }
 
 
-// C[m x n] = beta*C + alpha*A*B^T restricted, for every block of 128 rows, to the columns < col_limit[row/128]
-// (device array of ceil(m/128) ints).  Used by the distributed Cholesky, whose ranks own block ROWS of the lower
+// C[m x n] = beta*C + alpha*A*B^T restricted, for every block of 128 rows, to the columns j with
+// col_base + j < col_limit[row/128] (device array of ceil(m/128) ints; col_base = position of C's first column in
+// the coordinate system of the limits).  Used by the distributed Cholesky, whose ranks own block ROWS of the lower
 // triangle: tiles to the right of a row block's diagonal are skipped.
 extern "C" int lpgp_gemm_nt_limited(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                                     const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
-                                    const int* col_limit, void* stream) {
+                                    const int* col_limit, int64_t col_base, void* stream) {
   if (m < 0) return -1;
   if (n < 0) return -2;
   if (k < 0) return -3;
@@ -286,8 +288,9 @@ extern "C" int lpgp_gemm_nt_limited(int64_t m, int64_t n, int64_t k, double alph
   if (!B || ldb < k || (ldb % 2) || ((uintptr_t)B % 16)) return -8;
   if (!C || ldc < n || (const double*)C == A) return -11;
   if (!col_limit) return -12;
+  if (col_base < 0 || col_base > INT32_MAX) return -13;
   if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return -1;
   std::call_once(g_once, init_once);
   if (g_init_rc) return g_init_rc;
-  return launch<BigTile>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, col_limit);
+  return launch<BigTile>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, col_limit, (int)col_base);
 }

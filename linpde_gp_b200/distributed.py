@@ -70,19 +70,43 @@ class BlockRowLayout:
 
 
 class DeviceOps:
-    """Local numerical kernels on the GPU (C ABI through ctypes)."""
+    """Local numerical kernels on the GPU (C ABI through ctypes) + the two CUDA streams of the panel pipeline."""
 
     def __init__(self):
         from . import _lib, backend
 
         self._lib, self.be = _lib, backend
         self.device = backend._require_cuda()  # pylint: disable=protected-access
+        # panel chain (critical path) on a high-priority stream, bulk trailing updates on a normal one
+        self.panel_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.update_stream = torch.cuda.Stream(device=self.device, priority=0)
 
+    # -- streams / events (no-ops in the host test double) -----------------------------------------------------
+    def on(self, which: str):
+        return torch.cuda.stream(self.panel_stream if which == "panel" else self.update_stream)
+
+    def fork(self) -> None:
+        cur = torch.cuda.current_stream()
+        self.panel_stream.wait_stream(cur)
+        self.update_stream.wait_stream(cur)
+
+    def join(self) -> None:
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.panel_stream)
+        cur.wait_stream(self.update_stream)
+
+    def record(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def wait(self, ev) -> None:
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    # -- buffers ---------------------------------------------------------------------------------------------------
     def empty(self, rows: int, cols: int) -> torch.Tensor:
         return self.be.alloc_matrix(rows, cols)
-
-    def zeros_i32(self, n: int) -> torch.Tensor:
-        return torch.zeros(n, dtype=torch.int32, device=self.device)
 
     def _factor_struct(self, L: torch.Tensor, dinv: torch.Tensor):
         f = self._lib.Factor()
@@ -94,14 +118,14 @@ class DeviceOps:
         f.seg_off[0], f.seg_off[1] = 0, L.shape[0]
         return f
 
-    def potrf_block(self, D: torch.Tensor, dinv: torch.Tensor) -> int:
-        """Cholesky of the square view ``D`` in place; ``dinv`` receives the inverted leaf blocks (+ status).
-        Returns the LAPACK info (0 = ok, > 0 = order of the first non-positive-definite leading minor)."""
+    def potrf_block(self, D: torch.Tensor, dinv: torch.Tensor, info_out: torch.Tensor) -> None:
+        """Cholesky of the square view ``D`` in place, WITHOUT synchronising the host; ``dinv`` receives the
+        inverted leaf blocks (+ 8 doubles of status area); ``info_out`` (1 double, device) receives the LAPACK
+        info (0 = ok, > 0 = order of the first non-positive-definite leading minor of ``D``)."""
         f = self._factor_struct(D, dinv)
-        rc = self._lib.lib.lpgp_potrf(ctypes.byref(f), self.be._stream())  # pylint: disable=protected-access
-        if rc < 0:
-            self._lib.check(rc, "lpgp_potrf")
-        return int(rc)
+        rc = self._lib.lib.lpgp_potrf_async(ctypes.byref(f), self.be._stream())  # pylint: disable=protected-access
+        self._lib.check(rc, "lpgp_potrf_async")
+        info_out.copy_(dinv[-8:].view(torch.int32)[:1])
 
     def trsm_block(self, Lkk: torch.Tensor, dinv: torch.Tensor, X: torch.Tensor) -> None:
         """X <- X Lkk^{-T} in place."""
@@ -112,15 +136,26 @@ class DeviceOps:
                                          self.be._ld(X), self.be._stream())  # pylint: disable=protected-access
         self._lib.check(rc, "lpgp_trsm_rlt")
 
-    def update_limited(self, C: torch.Tensor, A: torch.Tensor, B: torch.Tensor, col_limit: torch.Tensor) -> None:
-        """C -= A B^T, each block of 128 rows restricted to the columns < col_limit[block]."""
+    def update_limited(self, C: torch.Tensor, A: torch.Tensor, B: torch.Tensor, col_limit: torch.Tensor,
+                       col_base: int) -> None:
+        """C -= A B^T, each block of 128 rows restricted to the columns j with col_base + j < col_limit[block]."""
         if C.shape[0] == 0 or C.shape[1] == 0:
             return
-        self.be.gemm_nt_limited(A, B, C, col_limit, alpha=-1.0, beta=1.0)
+        self.be.gemm_nt_limited(A, B, C, col_limit, alpha=-1.0, beta=1.0, col_base=col_base)
 
 
 class DistributedCholesky:
-    def __init__(self, n: int, nb: int = 512, group=None, ops=None):
+    """Right-looking block-row cyclic Cholesky with one panel of lookahead.
+
+    Two CUDA streams per rank: the *panel* stream (high priority) carries the critical path of panel ``k`` --
+    diagonal-block factorisation on the owner, broadcast, local TRSM, all-gather, and the update of block column
+    ``k+1`` --, the *update* stream carries the bulk of the trailing update (block columns ``>= k+2``), so that the
+    panel chain of step ``k+1`` (latency-bound kernels and NCCL) hides behind the DMMA GEMMs of step ``k``.  The
+    host never synchronises inside the loop (the LAPACK info travels with the broadcast and is read once at the
+    end).  Every gathered panel IS a block column of the factor in global row order: when ``L_full`` is passed to
+    :meth:`factor`, it is filled on the fly, i.e. replicating the factor costs no additional communication."""
+
+    def __init__(self, n: int, nb: int = 1024, group=None, ops=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -131,6 +166,11 @@ class DistributedCholesky:
         nleaves = (n + LEAF - 1) // LEAF
         # inverted diagonal leaf blocks of the WHOLE factor (replicated) + status area, as lpgp_factor expects
         self.dinv = torch.empty(nleaves * LEAF * LEAF + 8, dtype=torch.float64, device=self.A_loc.device)
+        # global end column of the diagonal block of every local 128-row block (row-limited trailing updates)
+        lim = []
+        for i in self.layout.local_blocks(self.rank):
+            lim += [self.layout.block_bounds(i)[1]] * ((self.layout.block_size(i) + LEAF - 1) // LEAF)
+        self.col_limit = torch.tensor(lim or [0], dtype=torch.int32).to(self.A_loc.device)
 
     # -- views ---------------------------------------------------------------------------------------------
     def local_block_rows(self, i: int) -> torch.Tensor:
@@ -142,72 +182,109 @@ class DistributedCholesky:
             dist.broadcast(t, src=dist.get_global_rank(self.group, src) if self.group is not None else src, group=self.group)
 
     # -- factorisation -------------------------------------------------------------------------------------
-    def factor(self) -> None:
-        lay, ops, P, rank, nb = self.layout, self.ops, self.world, self.rank, self.nb
+    def factor(self, L_full: Optional[torch.Tensor] = None) -> None:
+        """Factor in place (``A_loc`` holds this rank's block rows of L afterwards).  ``L_full`` (n x n row-major,
+        optional): receives the lower triangle of the complete factor on every rank."""
+        lay, ops, P, rank, nb, n = self.layout, self.ops, self.world, self.rank, self.nb, self.n
         dev = self.A_loc.device
-        pack = torch.zeros(nb * nb + nb * LEAF + 2, dtype=torch.float64, device=dev)  # [L_kk | W leaves | info]
-        for k in range(lay.nblk):
+        nblk = lay.nblk
+        jmax0 = (nblk - 1 + P - 1) // P if nblk > 1 else 0          # most blocks any rank owns below block 0
+        wlen = (nb // LEAF) * LEAF * LEAF
+        # preallocated, reused buffers (kept alive until the streams are joined)
+        packs = [torch.zeros(nb * nb + wlen + 2, dtype=torch.float64, device=dev) for _ in range(2)]
+        dtmp = torch.zeros(wlen + 8, dtype=torch.float64, device=dev)
+        info_all = torch.zeros(1, dtype=torch.float64, device=dev)
+        send = torch.zeros(max(jmax0, 1) * nb * nb, dtype=torch.float64, device=dev)
+        recv = torch.zeros(max(jmax0, 1) * P * nb * nb, dtype=torch.float64, device=dev) if P > 1 else send
+        panels = [torch.zeros(max(jmax0, 1) * P * nb * nb, dtype=torch.float64, device=dev) for _ in range(2)]
+        ev_first = [None, None]   # update stream: block column k+2 of step k done
+        ev_rest = [None, None]    # update stream: all of step k done (panel buffer k%2 free again)
+
+        ops.fork()
+        for k in range(nblk):
             k0, k1 = lay.block_bounds(k)
             bk = k1 - k0
             nleaf = (bk + LEAF - 1) // LEAF
             leaf0 = k0 // LEAF
             owner = lay.owner(k)
+            pack = packs[k % 2]
             Lkk = pack[: bk * bk].view(bk, bk)
             Wk = pack[nb * nb : nb * nb + nleaf * LEAF * LEAF]
-            dinv_k = self.dinv[leaf0 * LEAF * LEAF : (leaf0 + nleaf) * LEAF * LEAF + 8]
-            if rank == owner:
-                D = self.local_block_rows(k)[:, k0:k1]
-                info = ops.potrf_block(D, dinv_k)
-                pack[-1] = float(info + k0 if info > 0 else 0)
-                Lkk.copy_(D)
-                Wk.copy_(dinv_k[: nleaf * LEAF * LEAF])
-            self._bcast(pack, owner)
-            info = int(pack[-1].item())
-            if info > 0:  # every rank raises together (pn/linops/_linear_operator.py:823-839 semantics)
-                import numpy as np
+            dinv_k = self.dinv[leaf0 * LEAF * LEAF : (leaf0 + nleaf) * LEAF * LEAF]
+            with ops.on("panel"):
+                ops.wait(ev_rest[k % 2])  # step k-2 no longer reads pack / panel buffer k%2
+                # (1) diagonal block on its owner; [L_kk | inverted leaves | info] travels in one broadcast
+                if rank == owner:
+                    D = self.local_block_rows(k)[:, k0:k1]
+                    dt = dtmp[: nleaf * LEAF * LEAF + 8]
+                    ops.potrf_block(D, dt, pack[-1:])
+                    pack[-1:].add_(float(k0) * (pack[-1:] > 0))  # position inside the whole matrix
+                    Lkk.copy_(D)
+                    Wk.copy_(dt[: nleaf * LEAF * LEAF])
+                self._bcast(pack, owner)
+                info_all.copy_(torch.where(info_all > 0, info_all, pack[-1:]))
+                dinv_k.copy_(Wk)
+                if L_full is not None:
+                    L_full[k0:k1, k0:k1].copy_(Lkk)
+                if k == nblk - 1:
+                    break
+                # (2) my rows of the panel:  X <- X L_kk^{-T}
+                first = lay.first_local_block_after(rank, k)
+                r_lo = first * nb
+                m_loc = lay.rows_after(rank, k)
+                X = self.A_loc[r_lo : r_lo + m_loc, k0:k1]
+                ops.trsm_block(Lkk, Wk, X)
+                # (3) all-gather the panel pieces; slot (r, j) = j-th block below k of rank r.  Global block
+                #     k+1+t sits in slot ((k+1+t) % P, t // P): rotating the rank axis and swapping it with the
+                #     slot axis puts the panel into global row order.
+                J = (nblk - 1 - k + P - 1) // P
+                sview = send[: J * nb * bk].view(J * nb, bk)
+                sview[:m_loc].copy_(X)
+                pbuf = panels[k % 2]
+                if P > 1:
+                    rview = recv[: P * J * nb * bk]
+                    dist.all_gather_into_tensor(rview, send[: J * nb * bk], group=self.group)
+                    R = rview.view(P, J, nb, bk)
+                    pv = pbuf[: J * P * nb * bk].view(J, P, nb, bk)
+                    s = (k + 1) % P
+                    pv[:, : P - s].copy_(R[s:].permute(1, 0, 2, 3))
+                    if s:
+                        pv[:, P - s :].copy_(R[:s].permute(1, 0, 2, 3))
+                else:
+                    pbuf[: J * nb * bk].copy_(send[: J * nb * bk])
+                panel = pbuf[: (n - k1) * bk].view(n - k1, bk)
+                ev_panel = ops.record()
+                # (4a) block column k+1 (the next panel) right away, on the panel stream
+                k2 = lay.block_bounds(k + 1)[1]
+                lim = self.col_limit[r_lo // LEAF :]
+                if m_loc > 0:
+                    ops.wait(ev_first[(k + 1) % 2])  # step k-1 has finished with block column k+1
+                    ops.update_limited(self.A_loc[r_lo : r_lo + m_loc, k1:k2], X, panel[: k2 - k1], lim, k1)
+            with ops.on("update"):
+                ops.wait(ev_panel)
+                if L_full is not None:
+                    L_full[k1:n, k0:k1].copy_(panel)
+                # (4b) block column k+2, then everything to the right of it
+                if m_loc > 0 and k2 < n:
+                    k3 = lay.block_bounds(k + 2)[1]
+                    ops.update_limited(self.A_loc[r_lo : r_lo + m_loc, k2:k3], X, panel[k2 - k1 : k3 - k1], lim, k2)
+                    ev_first[k % 2] = ops.record()
+                    if k3 < n:
+                        ops.update_limited(self.A_loc[r_lo : r_lo + m_loc, k3:n], X, panel[k3 - k1 :], lim, k3)
+                else:
+                    ev_first[k % 2] = ops.record()
+                ev_rest[k % 2] = ops.record()
+        ops.join()
+        info = int(info_all.item())
+        if info > 0:  # every rank raises together (pn/linops/_linear_operator.py:823-839 semantics)
+            import numpy as np
 
-                raise np.linalg.LinAlgError(f"{info}-th leading minor of the array is not positive definite")
-            if rank != owner:
-                dinv_k[: nleaf * LEAF * LEAF].copy_(Wk)
-            if k == lay.nblk - 1:
-                break
-            # (2) my rows of the panel
-            first = lay.first_local_block_after(rank, k)
-            r_lo = first * nb
-            m_loc = lay.rows_after(rank, k)
-            X = self.A_loc[r_lo : r_lo + m_loc, k0:k1]
-            ops.trsm_block(Lkk, pack[nb * nb : nb * nb + nleaf * LEAF * LEAF], X)
-            # (3) all-gather the panel, global row order
-            m_all = [lay.rows_after(r, k) for r in range(P)]
-            m_max = max(m_all)
-            send = torch.zeros((m_max, bk), dtype=torch.float64, device=dev)
-            send[:m_loc].copy_(X)
-            if P > 1:
-                recv = torch.empty((P * m_max, bk), dtype=torch.float64, device=dev)
-                dist.all_gather_into_tensor(recv, send, group=self.group)
-                g = torch.arange(k1, self.n, device=dev)
-                blk = torch.div(g, nb, rounding_mode="floor")
-                rk = blk % P
-                firsts = torch.tensor([lay.first_local_block_after(r, k) for r in range(P)], device=dev)
-                idx = rk * m_max + (torch.div(blk, P, rounding_mode="floor") - firsts[rk]) * nb + g % nb
-                panel = ops.empty(self.n - k1, bk)
-                panel.copy_(recv.index_select(0, idx))
-            else:
-                panel = ops.empty(self.n - k1, bk)
-                panel.copy_(send[:m_loc])
-            # (4) trailing update of my block rows
-            if m_loc > 0:
-                C = self.A_loc[r_lo : r_lo + m_loc, k1 : self.n]
-                lim = []
-                for i in lay.local_blocks(rank):
-                    if i > k:
-                        lim += [lay.block_bounds(i)[1] - k1] * ((lay.block_size(i) + LEAF - 1) // LEAF)
-                col_limit = torch.tensor(lim, dtype=torch.int32, device=dev)
-                ops.update_limited(C, X, panel, col_limit)
+            raise np.linalg.LinAlgError(f"{info}-th leading minor of the array is not positive definite")
 
     # -- replication ---------------------------------------------------------------------------------------
     def replicate_into(self, L_full: torch.Tensor) -> None:
-        """Every rank receives every block row of the factor, straight into ``L_full`` (n x n row-major)."""
+        """Every rank receives every block row of the factor, straight into ``L_full`` (n x n row-major).  Only
+        needed when :meth:`factor` ran without ``L_full``."""
         lay = self.layout
         for i in range(lay.nblk):
             lo, hi = lay.block_bounds(i)

@@ -63,7 +63,7 @@ class ConditionalGaussianProcess(GaussianProcess):
         return cls(prior=prior, Ys=(Y,), Ls=(Lf,), bs=(b,), blocks=(blk,), factor=factor, resid=y, weights=w)
 
     @classmethod
-    def from_observation_batches(cls, prior: GaussianProcess, batches, *, process_group=None, nb: int = 512):
+    def from_observation_batches(cls, prior: GaussianProcess, batches, *, process_group=None, nb: int = 1024):
         """Condition on several observation batches AT ONCE: ``batches`` is a sequence of
         ``(Y, X, L, b)`` tuples (same meaning as the arguments of :meth:`condition_on_observations`).
 
@@ -95,8 +95,7 @@ class ConditionalGaussianProcess(GaussianProcess):
             for i in ch.layout.local_blocks(ch.rank):
                 g0, g1 = ch.layout.block_bounds(i)
                 cls._assemble_range(prior, blocks, noises, ch.local_block_rows(i), g0, g1)
-            ch.factor()
-            ch.replicate_into(factor.L)
+            ch.factor(factor.L)  # the gathered panels are the block columns of L: replicated on the fly
             factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
             del ch
         else:

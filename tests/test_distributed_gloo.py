@@ -29,11 +29,12 @@ def _run(rank, world, port, n, nb, q):
     for i in ch.layout.local_blocks(ch.rank):
         lo, hi = ch.layout.block_bounds(i)
         ch.local_block_rows(i)[:, :hi].copy_(G[lo:hi, :hi])  # lower part only
-    ch.factor()
     L_full = torch.zeros((n, (n + 15) // 16 * 16), dtype=torch.float64)[:, :n]
-    ch.replicate_into(L_full)
+    ch.factor(L_full)                      # the gathered panels fill the replicated factor on the fly
+    L_rep = torch.zeros_like(L_full)
+    ch.replicate_into(L_rep)               # explicit replication of the distributed block rows: same result
     L_ref = torch.linalg.cholesky(G)
-    err = float((torch.tril(L_full) - L_ref).abs().max())
+    err = max(float((torch.tril(L_full) - L_ref).abs().max()), float((torch.tril(L_rep) - L_ref).abs().max()))
     # inverted leaf blocks are replicated too
     l0 = torch.linalg.inv(L_ref[:128, :128])
     werr = float((ch.dinv[: 128 * 128].view(128, 128) - l0).abs().max())
@@ -71,7 +72,19 @@ def test_single_process(n, nb):
     assert err < 1e-11 and werr < 1e-10
 
 
-@pytest.mark.parametrize("n,nb", [(1280, 256), (1100, 128)])
+def test_not_positive_definite_raises():
+    n, nb = 640, 128
+    G = _spd(n, 5)
+    G[300, 300] = -1.0
+    ch = DistributedCholesky(n, nb=nb, ops=HostOps())
+    for i in ch.layout.local_blocks(0):
+        lo, hi = ch.layout.block_bounds(i)
+        ch.local_block_rows(i)[:, :hi].copy_(G[lo:hi, :hi])
+    with pytest.raises(np.linalg.LinAlgError):
+        ch.factor()
+
+
+@pytest.mark.parametrize("n,nb", [(1280, 256), (1100, 128), (1666, 128)])
 def test_world2_gloo(n, nb):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -216,6 +216,23 @@ def test_distributed_cholesky_single_rank_device_ops():
     for i in ch.layout.local_blocks(0):
         lo, hi = ch.layout.block_bounds(i)
         ch.local_block_rows(i)[:, :hi].copy_(G[lo:hi, :hi])
-    ch.factor()
+    from linpde_gp_b200 import backend
+
+    L_full = backend.alloc_matrix(n, n)
+    L_full.zero_()
+    ch.factor(L_full)
     L_ref = torch.linalg.cholesky(G)
     assert (torch.tril(ch.A_loc) - L_ref).abs().max().item() <= 1e-11 * L_ref.abs().max().item()
+    assert (torch.tril(L_full) - L_ref).abs().max().item() <= 1e-11 * L_ref.abs().max().item()
+    # inverted leaves of the whole factor are available for the triangular solves that follow
+    W0 = ch.dinv[: 128 * 128].view(128, 128)
+    assert (W0 @ L_ref[:128, :128] - torch.eye(128, dtype=torch.float64, device="cuda")).abs().max().item() <= 1e-10
+    # not positive definite: LinAlgError with the position of the failing leading minor, no host sync inside the loop
+    G2 = G.clone()
+    G2[700, 700] = -1.0
+    ch2 = DistributedCholesky(n, nb=512)
+    for i in ch2.layout.local_blocks(0):
+        lo, hi = ch2.layout.block_bounds(i)
+        ch2.local_block_rows(i)[:, :hi].copy_(G2[lo:hi, :hi])
+    with pytest.raises(np.linalg.LinAlgError, match="701-th"):
+        ch2.factor()
