@@ -70,6 +70,12 @@ int lpgp_version(void);              /* 100*major + minor                       
 const char* lpgp_build_arch(void);   /* "sm_100a"                                                       */
 const char* lpgp_error_string(int code);
 long long lpgp_launch_count(int reset); /* kernels launched by the library so far (optionally reset)      */
+/* Diagnostics switches.  LPGP_OPT_DIRECT_EXP != 0: Matern exponentials are evaluated entry by entry
+ * (exp(-r), the textbook form) instead of the separable per-point form a(y) b(x) the assembly and posterior-mean
+ * kernels use by default; both agree to a few ulp (tests/test_gpu_kernels.py), the switch exists so that
+ * the two can be compared and profiled against each other.                                               */
+#define LPGP_OPT_DIRECT_EXP 1
+int lpgp_set_option(int key, int value);
 /* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and
  * reports the flop count; timed by the caller it yields the roofline denominator of the DMMA kernels on the
  * box at hand (bench.py).  `scratch`: device, blocks*256 doubles.                                          */

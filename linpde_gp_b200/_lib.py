@@ -19,6 +19,7 @@ LEAF = 128
 MAX_SEG = 64
 DIM_MATERN, DIM_EXPQUAD = 0, 1
 GRAM_FULL, GRAM_LOWER = 0, 1
+OPT_DIRECT_EXP = 1
 
 
 class KernelDesc(ctypes.Structure):
@@ -69,6 +70,7 @@ def _load() -> ctypes.CDLL:
         "lpgp_build_arch": (ctypes.c_char_p, []),
         "lpgp_error_string": (ctypes.c_char_p, [ci]),
         "lpgp_launch_count": (ctypes.c_longlong, [ci]),
+        "lpgp_set_option": (ci, [ci, ci]),
         "lpgp_dmma_peak_probe": (ci, [vp, ci, ci, ctypes.POINTER(dbl), vp]),
         "lpgp_gram": (ci, [KD, vp, i64, vp, i64, vp, i64, ci, ci, dbl, vp]),
         "lpgp_gram_pairs": (ci, [KD, vp, vp, i64, vp, dbl, vp]),
@@ -98,7 +100,7 @@ def _load() -> ctypes.CDLL:
 
 lib = _load()
 EXPORTED = (
-    "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
+    "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_set_option lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
     "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_logdet "
     "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq"
 ).split()

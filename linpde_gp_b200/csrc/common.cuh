@@ -10,6 +10,8 @@
 // every kernel launch of the library is counted (bench.py reports the number as `gpu_launches`)
 extern long long g_lpgp_launches;
 #define LPGP_COUNT(n) (g_lpgp_launches += (n))
+// diagnostics switch (lpgp_set_option): 1 = evaluate Matern exponentials directly instead of the separable form
+extern int g_lpgp_no_sep;
 
 #define LPGP_CHECK_LAUNCH()                            \
   do {                                                 \

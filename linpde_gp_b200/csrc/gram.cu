@@ -107,6 +107,155 @@ __global__ void __launch_bounds__(NTHREADS)
   }
 }
 
+// ---- all-Matern product kernels: separable exponentials (see kernel_eval.cuh) -----------------------------------
+// 128 x 128 tile per CTA.  After the TMA stage-in, thread i turns point i of the tile (128 row + 128 column points)
+// into its record (x, a, b) per dimension -- 2 exp per point and dimension, i.e. 4 exp per thread for d = 2 against
+// 64 matrix entries per thread -- and the entry loop is exp-free: ~16 FP64-pipe operations per entry (2-D
+// Matern-5/2, any operator pair of even orders) instead of ~40, which puts the kernel at the HBM-write bound.
+constexpr int TMS = 128;
+constexpr int TNS = 256;
+constexpr int SEP_ROWS_PER_THREAD = TMS / (NTHREADS / (TNS / 2));  // 64
+
+// direct evaluation of one entry, kept out of line so that the (rare) fallback path does not inflate the
+// register allocation of the separable hot loop
+template <int D>
+struct Coords {
+  double v[D];
+};
+template <int D, int NB, bool ODD>
+__device__ __noinline__ double eval_pair_outofline(const EvalParams<D, NB, ODD>& p, Coords<D> y, Coords<D> x) {
+  return eval_pair<D, NB, ODD>(p, y.v, x.v);
+}
+
+// resident CTAs per SM the register allocation is tuned for: 3 (<= 80 registers) while the coefficient tensor is
+// small enough not to spill, else 2 or 1
+template <int D, int NB, bool ODD>
+constexpr int sep_min_blocks() {
+  return EvalParams<D, NB, ODD>::NCOEF <= 25 ? 3 : (EvalParams<D, NB, ODD>::NCOEF <= 64 ? 2 : 1);
+}
+
+template <int D, int NB, bool ODD>
+__global__ void __launch_bounds__(NTHREADS, sep_min_blocks<D, NB, ODD>())
+    gram_sep_kernel(const __grid_constant__ EvalParams<D, NB, ODD> p, const double* __restrict__ X0, int64_t n0,
+                    const double* __restrict__ X1, int64_t n1, double* __restrict__ out, int64_t ld, int mode,
+                    int accumulate, double alpha, int vec_ok) {
+  const int64_t row0 = (int64_t)blockIdx.y * TMS;
+  const int64_t col0 = (int64_t)blockIdx.x * TNS;
+  if (mode == LPGP_GRAM_LOWER && col0 > row0 + (TMS - 1)) return;  // tile strictly above the diagonal
+
+  __shared__ __align__(16) double sx0[TMS * D];
+  __shared__ __align__(16) double sx1[TNS * D];
+  __shared__ __align__(16) double sp0[TMS * 3 * D];
+  __shared__ __align__(16) double sp1[TNS * 3 * D];
+  __shared__ __align__(8) uint64_t bar;
+
+  const int rows = (int)min((int64_t)TMS, n0 - row0);
+  const int cols = (int)min((int64_t)TNS, n1 - col0);
+  const uint32_t bytes0 = (uint32_t)(rows * D * sizeof(double));
+  const uint32_t bytes1 = (uint32_t)(cols * D * sizeof(double));
+  const double* g0 = X0 + row0 * D;
+  const double* g1 = X1 + col0 * D;
+  const bool tma_ok = ((bytes0 | bytes1) % 16 == 0) && (((uintptr_t)g0 | (uintptr_t)g1) % 16 == 0);
+  if (tma_ok) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(&bar, bytes0 + bytes1);
+      bulk_g2s(sx0, g0, bytes0, &bar);
+      bulk_g2s(sx1, g1, bytes1, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+  } else {
+    for (int i = threadIdx.x; i < rows * D; i += NTHREADS) sx0[i] = g0[i];
+    for (int i = threadIdx.x; i < cols * D; i += NTHREADS) sx1[i] = g1[i];
+    __syncthreads();
+  }
+
+  // point records relative to the tile's first row point
+  bool ok = true;
+  for (int i = threadIdx.x; i < rows + cols; i += NTHREADS) {
+    const bool isrow = i < rows;
+    const int q = isrow ? i : i - rows;
+    const double* src = isrow ? sx0 + q * D : sx1 + q * D;
+    double* dst = isrow ? sp0 + q * 3 * D : sp1 + q * 3 * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) ok = sep_point(src[d], sx0[d], p.scale[d], dst + 3 * d) && ok;
+  }
+  const bool sep = !__syncthreads_or(!ok);  // block-uniform; also publishes the records
+
+  const int cpair = (threadIdx.x % (TNS / 2)) * 2;
+  const int rgrp = threadIdx.x / (TNS / 2);  // 0..1
+  const bool c0_ok = cpair < cols, c1_ok = cpair + 1 < cols;
+  double xa[3 * D], xb[3 * D];
+#pragma unroll
+  for (int i = 0; i < 3 * D; ++i) {
+    xa[i] = c0_ok ? sp1[cpair * 3 * D + i] : 1.0;
+    xb[i] = c1_ok ? sp1[(cpair + 1) * 3 * D + i] : 1.0;
+  }
+  if (sep) {  // fold alpha into the first exponential factor of my two columns
+    xa[1] *= alpha;
+    xa[2] *= alpha;
+    xb[1] *= alpha;
+    xb[2] *= alpha;
+  }
+  double* obase = out + (row0 + rgrp * SEP_ROWS_PER_THREAD) * ld + col0 + cpair;
+
+#pragma unroll 1
+  for (int r = 0; r < SEP_ROWS_PER_THREAD; r += 2) {
+    const int lr = rgrp * SEP_ROWS_PER_THREAD + r;
+    if (lr >= rows) break;
+    const bool r1_ok = lr + 1 < rows;
+    const double* y0 = sp0 + lr * 3 * D;
+    const double* y1 = r1_ok ? y0 + 3 * D : y0;
+    double v00, v01, v10, v11;
+    if (sep) {
+      v00 = eval_pair_sep<D, NB, ODD>(p, y0, xa);
+      v01 = eval_pair_sep<D, NB, ODD>(p, y0, xb);
+      v10 = eval_pair_sep<D, NB, ODD>(p, y1, xa);
+      v11 = eval_pair_sep<D, NB, ODD>(p, y1, xb);
+    } else {
+      Coords<D> z0, z1, ca, cb;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        z0.v[d] = y0[3 * d];
+        z1.v[d] = y1[3 * d];
+        ca.v[d] = xa[3 * d];
+        cb.v[d] = xb[3 * d];
+      }
+      v00 = alpha * eval_pair_outofline<D, NB, ODD>(p, z0, ca);
+      v01 = alpha * eval_pair_outofline<D, NB, ODD>(p, z0, cb);
+      v10 = alpha * eval_pair_outofline<D, NB, ODD>(p, z1, ca);
+      v11 = alpha * eval_pair_outofline<D, NB, ODD>(p, z1, cb);
+    }
+    double* o0 = obase + (int64_t)r * ld;
+    double* o1 = o0 + ld;
+    if (vec_ok && c1_ok) {
+      if (accumulate) {
+        double2 a = *reinterpret_cast<double2*>(o0);
+        v00 += a.x;
+        v01 += a.y;
+        if (r1_ok) {
+          double2 b = *reinterpret_cast<double2*>(o1);
+          v10 += b.x;
+          v11 += b.y;
+        }
+      }
+      *reinterpret_cast<double2*>(o0) = make_double2(v00, v01);
+      if (r1_ok) *reinterpret_cast<double2*>(o1) = make_double2(v10, v11);
+    } else {
+      if (c0_ok) {
+        o0[0] = accumulate ? o0[0] + v00 : v00;
+        if (r1_ok) o1[0] = accumulate ? o1[0] + v10 : v10;
+      }
+      if (c1_ok) {
+        o0[1] = accumulate ? o0[1] + v01 : v01;
+        if (r1_ok) o1[1] = accumulate ? o1[1] + v11 : v11;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
     gram_generic_kernel(const __grid_constant__ lpgp_kernel_desc k, const double* __restrict__ X0, int64_t n0,
                         const double* __restrict__ X1, int64_t n1, double* __restrict__ out, int64_t ld, int mode,
@@ -130,8 +279,14 @@ int launch_tile(const lpgp_kernel_desc& k, const double* X0, int64_t n0, const d
                 int64_t ld, int mode, int accumulate, double alpha, cudaStream_t st) {
   EvalParams<D, NB, ODD> p;
   pack_params<D, NB, ODD>(k, p);
-  dim3 grid((unsigned)ceil_div64(n1, TN), (unsigned)ceil_div64(n0, TM));
   const int vec_ok = (ld % 2 == 0) && ((uintptr_t)out % 16 == 0);
+  if (all_matern<D>(p) && !g_lpgp_no_sep) {
+    dim3 grid((unsigned)ceil_div64(n1, TNS), (unsigned)ceil_div64(n0, TMS));
+    gram_sep_kernel<D, NB, ODD><<<grid, NTHREADS, 0, st>>>(p, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, vec_ok);
+    LPGP_CHECK_LAUNCH();
+    return 0;
+  }
+  dim3 grid((unsigned)ceil_div64(n1, TN), (unsigned)ceil_div64(n0, TM));
   gram_tile_kernel<D, NB, ODD><<<grid, NTHREADS, 0, st>>>(p, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, vec_ok);
   LPGP_CHECK_LAUNCH();
   return 0;

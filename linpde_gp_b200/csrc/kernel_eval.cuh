@@ -69,6 +69,67 @@ __device__ __forceinline__ double eval_pair(const P& p, const double* x0, const 
   return poly * exp(-g);
 }
 
+// ---- separable exponentials (all-Matern product kernels) ------------------------------------------------------
+// For a Matern dimension the exponential factor is  exp(-s |y - x|) = a(y) b(x)  if y >= x  (b(y) a(x) otherwise)
+// with  a(z) = exp(-s (z - c)),  b(z) = exp(+s (z - c))  for any common centre c.  a, b are computed ONCE per point
+// of a tile (2 exp per point and dimension instead of one per matrix entry), which moves the assembly kernel
+// from the FP64-pipe bound (exp ~ 23 DFMA slots per entry) to the HBM-write bound.  t = s (z - c) is formed in
+// double-double (TwoSum of the difference, FMA residual of the product) and the low part is applied as a
+// first-order correction, so a(y) b(x) agrees with the exactly-rounded exp(-s|y-x|) to a few ulp, independent of
+// |t| -- the same accuracy class as evaluating exp(-r) directly.  Valid while |t| < LPGP_SEP_MAX_T (no overflow
+// of a or b); tiles violating that (block-uniform test) use the direct evaluation.
+#define LPGP_SEP_MAX_T 600.0
+
+// point record in shared memory / registers: for every dimension the triple (x, a, b)
+__device__ __forceinline__ bool sep_point(double x, double c, double s, double* rec) {
+  const double dx = x - c;
+  const double bp = dx - x;
+  const double err = (x - (dx - bp)) + (-c - bp);  // TwoSum: (x - c) = dx + err exactly
+  const double hi = s * dx;
+  const double lo = fma(s, dx, -hi) + s * err;     // s (x - c) = hi + lo to ~1e-32 relative
+  rec[0] = x;
+  rec[1] = exp(-hi) * (1.0 - lo);
+  rec[2] = exp(hi) * (1.0 + lo);
+  return fabs(hi) < LPGP_SEP_MAX_T;  // false also for NaN / inf coordinates
+}
+
+__device__ __forceinline__ double selp_f64(double a, double b, int p) {
+  double r;
+  asm("{\n.reg .pred q;\nsetp.ne.s32 q, %3, 0;\nselp.f64 %0, %1, %2, q;\n}" : "=d"(r) : "d"(a), "d"(b), "r"(p));
+  return r;
+}
+
+// value for one pair of point records y (argument 0; lives in shared memory, shared by the whole warp) and x
+// (argument 1; lives in registers), each 3*D doubles.  The instruction mix matters here (the loop is issue-bound
+// once the exp is gone): the warp-uniform side is selected by ADDRESS (one LDS from y + 8 or y + 16), the
+// per-thread side with one 64-bit select; |u| rides on the DFMA source modifiers.
+template <int D, int NB, bool ODD, typename P>
+__device__ __forceinline__ double eval_pair_sep(const P& p, const double* y, const double* x) {
+  double v[D], u[D];
+  double E = 1.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double delta = y[3 * d] - x[3 * d];
+    const double uu = delta * p.scale[d];
+    const int pos = __double2hiint(delta) >= 0;  // sign bit only: integer pipe (delta = -0 picks exp(0) either way)
+    const double pa = y[3 * d + 2 - pos];           // pos: a(y) else b(y)
+    const double qb = selp_f64(x[3 * d + 2], x[3 * d + 1], pos);  // pos: b(x) else a(x)
+    const double e = pa * qb;
+    E = d == 0 ? e : E * e;
+    u[d] = uu;
+    v[d] = fabs(uu);
+  }
+  return NestedHorner<D, NB, ODD, 0>::run(p, v, u, 0) * E;
+}
+
+template <int D, typename P>
+__host__ __device__ __forceinline__ bool all_matern(const P& p) {
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < D; ++d) ok = ok && (p.dim_type[d] == LPGP_DIM_MATERN);
+  return ok;
+}
+
 // Generic (runtime-shaped) evaluation straight from the descriptor: any d <= LPGP_MAX_DIM, any basis sizes.
 // Slow path used only for shapes without a specialised instantiation.
 __device__ __forceinline__ double eval_pair_generic(const lpgp_kernel_desc& k, const double* x0, const double* x1) {

@@ -49,6 +49,69 @@ __global__ void __launch_bounds__(PM_THREADS)
     if (i0 + q < m) atomicAdd(out + i0 + q, acc[q]);
 }
 
+// all-Matern product kernels: separable exponentials (kernel_eval.cuh).  The centre is the CTA's first test point;
+// each test point's record is built once, each staged observation tile is converted cooperatively (2 exp per
+// point and dimension against PM_THREADS * PM_PTS evaluations per observation point).
+template <int D, int NB, bool ODD>
+__global__ void __launch_bounds__(PM_THREADS)
+    post_mean_sep_kernel(const __grid_constant__ EvalParams<D, NB, ODD> p, const double* __restrict__ Xobs, int64_t nobs,
+                         const double* __restrict__ w, const double* __restrict__ Xt, int64_t m, double* __restrict__ out) {
+  __shared__ __align__(16) double sx[PM_TILE * D];
+  __shared__ __align__(16) double sp[PM_TILE * 3 * D];
+  __shared__ double sw[PM_TILE];
+  const int64_t ib = (int64_t)blockIdx.x * PM_THREADS * PM_PTS;  // first test point of this CTA (< m)
+  const int64_t i0 = ib + (int64_t)threadIdx.x * PM_PTS;
+  double c[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) c[d] = Xt[ib * D + d];
+  double xt[PM_PTS][D], rt[PM_PTS][3 * D], acc[PM_PTS];
+  bool ok_t = true;
+#pragma unroll
+  for (int q = 0; q < PM_PTS; ++q) {
+    acc[q] = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      xt[q][d] = (i0 + q < m) ? Xt[(i0 + q) * D + d] : c[d];
+      ok_t = sep_point(xt[q][d], c[d], p.scale[d], &rt[q][3 * d]) && ok_t;
+    }
+  }
+  const int64_t j_begin = (int64_t)blockIdx.y * PM_CHUNK;
+  const int64_t j_end = min(nobs, j_begin + PM_CHUNK);
+  for (int64_t j0 = j_begin; j0 < j_end; j0 += PM_TILE) {
+    const int cnt = (int)min((int64_t)PM_TILE, j_end - j0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * D; i += PM_THREADS) sx[i] = Xobs[j0 * D + i];
+    for (int i = threadIdx.x; i < cnt; i += PM_THREADS) sw[i] = w[j0 + i];
+    __syncthreads();
+    bool ok = ok_t;
+    for (int i = threadIdx.x; i < cnt; i += PM_THREADS) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) ok = sep_point(sx[i * D + d], c[d], p.scale[d], sp + i * 3 * D + 3 * d) && ok;
+    }
+    if (!__syncthreads_or(!ok)) {
+#pragma unroll 2
+      for (int j = 0; j < cnt; ++j) {
+        const double wj = sw[j];
+#pragma unroll
+        for (int q = 0; q < PM_PTS; ++q) acc[q] = fma(eval_pair_sep<D, NB, ODD>(p, rt[q], sp + j * 3 * D), wj, acc[q]);
+      }
+    } else {  // some |s (x - c)| too large for the separable form in this tile: direct evaluation
+#pragma unroll 2
+      for (int j = 0; j < cnt; ++j) {
+        double xo[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xo[d] = sx[j * D + d];
+        const double wj = sw[j];
+#pragma unroll
+        for (int q = 0; q < PM_PTS; ++q) acc[q] = fma(eval_pair<D, NB, ODD>(p, xt[q], xo), wj, acc[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PM_PTS; ++q)
+    if (i0 + q < m) atomicAdd(out + i0 + q, acc[q]);
+}
+
 __global__ void __launch_bounds__(PM_THREADS)
     post_mean_generic_kernel(const __grid_constant__ lpgp_kernel_desc k, const double* __restrict__ Xobs, int64_t nobs,
                              const double* __restrict__ w, const double* __restrict__ Xt, int64_t m,
@@ -73,6 +136,11 @@ int launch_mean(const lpgp_kernel_desc& k, const double* Xobs, int64_t nobs, con
   EvalParams<D, NB, ODD> p;
   pack_params<D, NB, ODD>(k, p);
   dim3 grid((unsigned)ceil_div64(m, PM_THREADS * PM_PTS), (unsigned)ceil_div64(nobs, PM_CHUNK));
+  if (all_matern<D>(p) && !g_lpgp_no_sep) {
+    post_mean_sep_kernel<D, NB, ODD><<<grid, PM_THREADS, 0, st>>>(p, Xobs, nobs, w, Xt, m, out);
+    LPGP_CHECK_LAUNCH();
+    return 0;
+  }
   post_mean_kernel<D, NB, ODD><<<grid, PM_THREADS, 0, st>>>(p, Xobs, nobs, w, Xt, m, out);
   LPGP_CHECK_LAUNCH();
   return 0;

@@ -86,6 +86,46 @@ def test_gram_lower_mode_and_symmetrize(be):
     assert np.max(np.abs(out.cpu().numpy() - K_ref)) <= GRAM_TOL * np.max(np.abs(K_ref))
 
 
+def _set_direct_exp(flag):
+    from linpde_gp_b200 import _lib
+
+    assert _lib.lib.lpgp_set_option(_lib.OPT_DIRECT_EXP, int(flag)) == 0
+
+
+@pytest.mark.parametrize("ell,offset", [(0.3, 0.0), (0.016, 0.0), (0.004, 0.0), (0.016, 1000.0), (0.0008, 0.0)])
+def test_separable_matern_exponentials_match_direct_evaluation(be, ell, offset):
+    """The assembly / posterior-mean kernels factor exp(-s|y-x|) = a(y) b(x) per tile (kernel_eval.cuh).  Both forms
+    must agree to a few ulp of the matrix scale (far inside the 1e-12 Gram tolerance), for short lengthscales
+    (|s (x - c)| up to ~560), for coordinates far from the origin, and beyond the overflow guard
+    (ell = 8e-4: s * range = 2800 -> the kernel falls back to the direct form, bitwise equal)."""
+    from linpde_gp_b200._lowering import Factor1D, lower
+
+    fac = [Factor1D("matern", ell, nu=2.5), Factor1D("matern", 1.7 * ell, nu=1.5)]
+    heat = {(1, 0): 1.0, (0, 2): -0.1}
+    lap = {(2, 0): -1.0, (0, 2): -1.0}
+    rng = np.random.default_rng(7)
+    A = be.points(rng.uniform(0, 1, (300, 2)) + offset, 2)
+    B = be.points(rng.uniform(0, 1, (517, 2)) + offset, 2)
+    w = be.to_device(rng.standard_normal(517))
+    for L0, L1 in ((None, None), (None, heat), (heat, heat), (None, {(0, 2): 1.0})):
+        desc = lower(fac, L0, L1, 1.3)
+        try:
+            _set_direct_exp(True)
+            K_dir = be.gram(desc, A, B).cpu().numpy()
+            m_dir = be.post_mean(be.ObsBlocks([desc], [B], [0]), w, A).cpu().numpy()
+        finally:
+            _set_direct_exp(False)
+        K_sep = be.gram(desc, A, B).cpu().numpy()
+        m_sep = be.post_mean(be.ObsBlocks([desc], [B], [0]), w, A).cpu().numpy()
+        scale = np.max(np.abs(K_dir))
+        if ell < 0.001:
+            assert np.array_equal(K_sep, K_dir)
+        # 5e-15: the direct form itself carries ~|r| ulp of argument rounding (r up to ~40 where entries matter)
+        assert np.max(np.abs(K_sep - K_dir)) <= 5e-15 * scale, (ell, offset, np.max(np.abs(K_sep - K_dir)) / scale)
+        assert np.max(np.abs(m_sep - m_dir)) <= 1e-13 * np.max(np.abs(m_dir))
+    del lap
+
+
 def test_gram_empty_input(be):
     desc = helpers.desc_from_spec(next(s for s in SPECS if s["name"] == "ns_poisson2d_k"))
     K = be.gram(desc, torch.empty((0, 2), dtype=torch.float64, device="cuda"), torch.zeros((5, 2), dtype=torch.float64, device="cuda"))
