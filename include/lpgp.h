@@ -173,6 +173,17 @@ int lpgp_trsm_rlt(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int
  * substitution = scipy.linalg.cho_solve of pn/linops/_linear_operator.py:303-307.                          */
 int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t ldb, void* stream);
 
+/* One right-hand side, one triangular factor:  trans == 0: b <- L^{-1} b (forward substitution),
+ * trans == 1: b <- L^{-T} b (backward substitution) -- the two halves of lpgp_potrs, exposed for the multi-GPU
+ * solve, whose ranks own block rows of L (scipy.linalg.solve_triangular, pn/linops/_linear_operator.py:296-299). */
+int lpgp_trsv(const lpgp_factor* f, int trans, double* b, void* stream);
+
+/* y += alpha * A x (trans == 0; A is m x n row-major, x has n entries, y has m) or y += alpha * A^T x
+ * (trans == 1; x has m entries, y has n): the off-diagonal part of a block-row forward / backward substitution.
+ * HBM-bound (reads A once).                                                                               */
+int lpgp_gemv(int trans, int64_t m, int64_t n, double alpha, const double* A, int64_t lda, const double* x, double* y,
+              void* stream);
+
 /* sum_i log L_ii^2 = log det G, written to *out (device double).                                           */
 int lpgp_logdet(const lpgp_factor* f, double* out, void* stream);
 

@@ -85,6 +85,8 @@ def _load() -> ctypes.CDLL:
         "lpgp_chol_append": (ci, [FP, vp]),
         "lpgp_trsm_rlt": (ci, [FP, i64, vp, i64, i64, vp]),
         "lpgp_potrs": (ci, [FP, vp, i64, i64, vp]),
+        "lpgp_trsv": (ci, [FP, ci, vp, vp]),
+        "lpgp_gemv": (ci, [ci, i64, i64, dbl, vp, i64, vp, vp, vp]),
         "lpgp_logdet": (ci, [FP, vp, vp]),
         "lpgp_post_mean": (ci, [OB, ci, vp, vp, i64, vp, ci, vp]),
         "lpgp_crosscov": (ci, [OB, ci, i64, vp, i64, vp, i64, vp]),
@@ -101,7 +103,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTED = (
     "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_set_option lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
-    "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_logdet "
+    "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
     "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq"
 ).split()
 

@@ -132,6 +132,16 @@ def gemm_nt_limited(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, col_limit
     return C
 
 
+def gemv(A: torch.Tensor, x: torch.Tensor, y: torch.Tensor, alpha: float = 1.0, trans: bool = False) -> torch.Tensor:
+    """y += alpha * A @ x  (or A.T @ x) in place; A row-major (view with unit column stride)."""
+    m, n = A.shape
+    assert x.numel() == (m if trans else n) and y.numel() == (n if trans else m)
+    assert x.is_contiguous() and y.is_contiguous()
+    rc = lib.lpgp_gemv(int(trans), m, n, float(alpha), _ptr(A), _ld(A), _ptr(x), _ptr(y), _stream())
+    check(rc, "lpgp_gemv")
+    return y
+
+
 def row_sumsq(A: torch.Tensor, scale: float = 1.0, offset: float = 0.0) -> torch.Tensor:
     out = torch.empty(A.shape[0], dtype=F64, device=A.device)
     check(lib.lpgp_row_sumsq(_ptr(A), A.shape[0], A.shape[1], _ld(A), float(scale), float(offset), _ptr(out), _stream()),

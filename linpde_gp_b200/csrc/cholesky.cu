@@ -271,6 +271,46 @@ __global__ void __launch_bounds__(256)
   b[c] -= s;
 }
 
+// ---- general matrix-vector products (building blocks of the multi-GPU triangular solves) ----------------------
+// y[r] += alpha * sum_c A[r, c] x[c]   (one warp per row, coalesced 16-byte row reads when aligned)
+__global__ void __launch_bounds__(256)
+    gemv_n_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, double alpha,
+                  const double* __restrict__ x, double* __restrict__ y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp;
+  if (r >= m) return;
+  const double* row = A + r * lda;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t c = lane;
+  for (; c + 32 < n; c += 64) {
+    s0 = fma(row[c], x[c], s0);
+    s1 = fma(row[c + 32], x[c + 32], s1);
+  }
+  if (c < n) s0 = fma(row[c], x[c], s0);
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[r] = fma(alpha, s, y[r]);
+}
+
+// y[c] += alpha * sum_r A[r, c] x[r]   (one thread per column, the m rows split over gridDim.y slices + atomics)
+__global__ void __launch_bounds__(256)
+    gemv_t_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, double alpha,
+                  const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t rows_per = (m + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(m, r0 + rows_per);
+  if (c >= n) return;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t r = r0;
+  for (; r + 1 < r1; r += 2) {
+    s0 = fma(A[r * lda + c], x[r], s0);
+    s1 = fma(A[(r + 1) * lda + c], x[r + 1], s1);
+  }
+  if (r < r1) s0 = fma(A[r * lda + c], x[r], s0);
+  atomicAdd(y + c, alpha * (s0 + s1));
+}
+
 // ---- host-side leaf bookkeeping ---------------------------------------------------------------------------
 struct Leaves {
   std::vector<int64_t> off;     // leaf start offsets, off.back() == n
@@ -443,18 +483,12 @@ extern "C" int lpgp_trsm_rlt(const lpgp_factor* f, int64_t nlead, double* X, int
   return trsm_rec(f, lv, 0, hi, X, m, ldx, (cudaStream_t)stream);
 }
 
-extern "C" int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t ldb, void* stream) {
-  if (check_factor(f)) return -1;
-  if (!B) return -2;
-  if (nrhs < 0) return -3;
-  if (ldb < f->n) return -4;
-  Leaves lv;
-  if (build_leaves(f->seg_off, f->nseg, lv)) return -1;
-  cudaStream_t st = (cudaStream_t)stream;
+namespace {
+// single right-hand-side substitution with the leaves of `f`: trans == 0: b <- L^{-1} b, else b <- L^{-T} b
+int trsv_impl(const lpgp_factor* f, const Leaves& lv, int trans, double* b, cudaStream_t st) {
   const int nl = (int)lv.off.size() - 1;
   const int64_t n = f->n;
-  for (int64_t r = 0; r < nrhs; ++r) {
-    double* b = B + r * ldb;
+  if (!trans) {
     for (int l = 0; l < nl; ++l) {  // forward: L y = b
       const int64_t c0 = lv.off[l], c1 = lv.off[l + 1];
       leaf_apply_kernel<<<1, LEAF, 0, st>>>(dinv_block(f, l), b + c0, (int)(c1 - c0), 0);
@@ -466,6 +500,7 @@ extern "C" int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t
         fwd_update_kernel<<<grid, 256, 0, st>>>(f->L, f->ld, c0, (int)(c1 - c0), c1, n, b);
       }
     }
+  } else {
     for (int l = nl - 1; l >= 0; --l) {  // backward: L^T x = y
       const int64_t c0 = lv.off[l], c1 = lv.off[l + 1];
       leaf_apply_kernel<<<1, LEAF, 0, st>>>(dinv_block(f, l), b + c0, (int)(c1 - c0), 1);
@@ -474,6 +509,56 @@ extern "C" int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t
     }
   }
   LPGP_COUNT(-1);  // the check below counts one launch itself
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}
+}  // namespace
+
+extern "C" int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t ldb, void* stream) {
+  if (check_factor(f)) return -1;
+  if (!B) return -2;
+  if (nrhs < 0) return -3;
+  if (ldb < f->n) return -4;
+  Leaves lv;
+  if (build_leaves(f->seg_off, f->nseg, lv)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t r = 0; r < nrhs; ++r) {
+    int rc = trsv_impl(f, lv, 0, B + r * ldb, st);
+    if (rc) return rc;
+    rc = trsv_impl(f, lv, 1, B + r * ldb, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int lpgp_trsv(const lpgp_factor* f, int trans, double* b, void* stream) {
+  if (check_factor(f)) return -1;
+  if (trans != 0 && trans != 1) return -2;
+  if (!b) return -3;
+  Leaves lv;
+  if (build_leaves(f->seg_off, f->nseg, lv)) return -1;
+  return trsv_impl(f, lv, trans, b, (cudaStream_t)stream);
+}
+
+extern "C" int lpgp_gemv(int trans, int64_t m, int64_t n, double alpha, const double* A, int64_t lda, const double* x,
+                         double* y, void* stream) {
+  if (trans != 0 && trans != 1) return -1;
+  if (m < 0) return -2;
+  if (n < 0) return -3;
+  if (m == 0 || n == 0) return 0;
+  if (!A || lda < n) return -5;
+  if (!x) return -7;
+  if (!y) return -8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!trans) {
+    gemv_n_kernel<<<(unsigned)ceil_div64(m, 8), 256, 0, st>>>(A, lda, m, n, alpha, x, y);
+  } else {
+    const int64_t col_blocks = ceil_div64(n, 256);
+    int64_t slices = 1;  // enough CTAs to stream A at HBM speed even for short, wide panels
+    while (col_blocks * slices < 592 && slices * 64 < m) slices *= 2;
+    dim3 grid((unsigned)col_blocks, (unsigned)slices);
+    gemv_t_kernel<<<grid, 256, 0, st>>>(A, lda, m, n, alpha, x, y);
+  }
   LPGP_CHECK_LAUNCH();
   return 0;
 }

@@ -136,6 +136,25 @@ class DeviceOps:
                                          self.be._ld(X), self.be._stream())  # pylint: disable=protected-access
         self._lib.check(rc, "lpgp_trsm_rlt")
 
+    def trsv_block(self, Lkk: torch.Tensor, dinv: torch.Tensor, b: torch.Tensor, trans: bool) -> None:
+        """b <- Lkk^{-1} b (trans False) or Lkk^{-T} b (trans True) in place, one right-hand side."""
+        f = self._factor_struct(Lkk, dinv)
+        rc = self._lib.lib.lpgp_trsv(ctypes.byref(f), int(trans), ctypes.c_void_p(b.data_ptr()), self.be._stream())  # pylint: disable=protected-access
+        self._lib.check(rc, "lpgp_trsv")
+
+    def gemv(self, A: torch.Tensor, x: torch.Tensor, y: torch.Tensor, alpha: float, trans: bool) -> None:
+        """y += alpha * A x  (A^T x if trans)."""
+        if A.shape[0] and A.shape[1]:
+            self.be.gemv(A, x, y, alpha=alpha, trans=trans)
+
+    def gemm_update(self, C: torch.Tensor, A: torch.Tensor, B: torch.Tensor) -> None:
+        """C -= A B^T (full tiles)."""
+        if C.shape[0] and C.shape[1] and A.shape[1]:
+            self.be.gemm_nt(A, B, C, alpha=-1.0, beta=1.0)
+
+    def row_sumsq(self, A: torch.Tensor, scale: float, offset: float) -> torch.Tensor:
+        return self.be.row_sumsq(A, scale, offset)
+
     def update_limited(self, C: torch.Tensor, A: torch.Tensor, B: torch.Tensor, col_limit: torch.Tensor,
                        col_base: int) -> None:
         """C -= A B^T, each block of 128 rows restricted to the columns j with col_base + j < col_limit[block]."""
@@ -281,6 +300,81 @@ class DistributedCholesky:
 
             raise np.linalg.LinAlgError(f"{info}-th leading minor of the array is not positive definite")
 
+    # -- solves with the DISTRIBUTED factor (nothing replicated) ---------------------------------------------------
+    def _dinv_block(self, k: int) -> torch.Tensor:
+        k0, k1 = self.layout.block_bounds(k)
+        nleaf = (k1 - k0 + LEAF - 1) // LEAF
+        return self.dinv[(k0 // LEAF) * LEAF * LEAF : (k0 // LEAF + nleaf) * LEAF * LEAF]
+
+    def solve(self, b: torch.Tensor) -> torch.Tensor:
+        """x = G^{-1} b = L^{-T} L^{-1} b for ONE replicated right-hand side (the representer weights,
+        _conditional.py:44), with L left in its block-row cyclic distribution.  Owner-computes: block k's owner
+        does the GEMV with its rows and the substitution with its diagonal block, then broadcasts the nb new
+        entries (forward); the transposed products of the backward sweep are accumulated per rank and summed with
+        one small all-reduce per block.  O(n^2) flops, n/nb latency-bound steps."""
+        lay, ops, rank = self.layout, self.ops, self.rank
+        y = b.detach().clone().reshape(-1).contiguous()
+        assert y.numel() == self.n
+        for k in range(lay.nblk):  # forward: L y = b
+            k0, k1 = lay.block_bounds(k)
+            yk = y[k0:k1]
+            if rank == lay.owner(k):
+                rows = self.local_block_rows(k)
+                ops.gemv(rows[:, :k0], y[:k0], yk, -1.0, False)
+                ops.trsv_block(rows[:, k0:k1], self._dinv_block(k), yk, False)
+            self._bcast(yk, lay.owner(k))
+        acc = torch.zeros_like(y)
+        for k in reversed(range(lay.nblk)):  # backward: L^T x = y
+            k0, k1 = lay.block_bounds(k)
+            yk = y[k0:k1]
+            part = acc[k0:k1]
+            if self.world > 1:
+                dist.all_reduce(part, group=self.group)
+            if rank == lay.owner(k):
+                rows = self.local_block_rows(k)
+                yk.sub_(part)
+                ops.trsv_block(rows[:, k0:k1], self._dinv_block(k), yk, True)
+            self._bcast(yk, lay.owner(k))
+            if rank == lay.owner(k):
+                ops.gemv(rows[:, :k0], yk, acc[:k0], 1.0, True)
+        return y
+
+    def solve_rows(self, K: torch.Tensor) -> torch.Tensor:
+        """K <- K L^{-T} in place for the rows ``K`` (m_loc x n) held by THIS rank (cross-covariance rows of its
+        test points, ``_conditional.py:245-251``), with the factor streamed instead of replicated: block row k of
+        L is broadcast by its owner (double-buffered, on the panel stream) while every rank applies block row
+        k-1 to its own rows -- left-looking,  K[:, k] <- (K[:, k] - K[:, :k0] L[k, :k0]^T) L_kk^{-T} -- so the
+        N^2 M flops shard over the test points and the factor crosses NVLink exactly once per call.  Collective:
+        every rank must call it (with its own, possibly empty, set of rows)."""
+        lay, ops, P, rank, nb, n = self.layout, self.ops, self.world, self.rank, self.nb, self.n
+        dev = self.A_loc.device
+        bufs = [torch.empty(nb * n, dtype=torch.float64, device=dev) for _ in range(2)]
+        ev_ready, ev_free = [None, None], [None, None]
+        ops.fork()
+        for k in range(lay.nblk):
+            k0, k1 = lay.block_bounds(k)
+            bk = k1 - k0
+            row = bufs[k % 2][: bk * k1].view(bk, k1)
+            with ops.on("panel"):
+                ops.wait(ev_free[k % 2])
+                if rank == lay.owner(k):
+                    row.copy_(self.local_block_rows(k)[:, :k1])
+                self._bcast(row, lay.owner(k))
+                ev_ready[k % 2] = ops.record()
+            with ops.on("update"):
+                ops.wait(ev_ready[k % 2])
+                if K.shape[0] > 0:
+                    Kk = K[:, k0:k1]
+                    ops.gemm_update(Kk, K[:, :k0], row[:, :k0])
+                    ops.trsm_block(row[:, k0:k1], self._dinv_block(k), Kk)
+                ev_free[k % 2] = ops.record()
+        ops.join()
+        return K
+
+    def post_var(self, K: torch.Tensor, prior_diag: float) -> torch.Tensor:
+        """var_i = prior_diag - || K_i L^{-T} ||^2 (``_conditional.py:223-231``); ``K`` is overwritten.  Collective."""
+        return self.ops.row_sumsq(self.solve_rows(K), -1.0, prior_diag)
+
     # -- replication ---------------------------------------------------------------------------------------
     def replicate_into(self, L_full: torch.Tensor) -> None:
         """Every rank receives every block row of the factor, straight into ``L_full`` (n x n row-major).  Only
@@ -295,3 +389,39 @@ class DistributedCholesky:
                 # the slab view covers whole (padded) rows of the buffer: contiguous memory
                 flat = torch.as_strided(slab, (hi - lo, slab.stride(0)), (slab.stride(0), 1)) if hi - lo > 1 else slab
                 self._bcast(flat, lay.owner(i))
+
+
+class DistributedFactor:
+    """The interface of ``backend.DeviceFactor`` that posterior evaluation needs, on top of a factor that STAYS
+    distributed (block rows spread over the ranks; nothing replicated): N = 131,072 (137 GB Gram, BASELINE.json
+    configs[4]) does not fit one GPU.  All methods are collective."""
+
+    distributed = True
+
+    def __init__(self, ch: DistributedCholesky):
+        self.ch = ch
+        self.n = ch.n
+
+    def potrs(self, B: torch.Tensor) -> torch.Tensor:
+        if B.dim() == 1:
+            B = B.reshape(1, -1)
+        for r in range(B.shape[0]):
+            B[r].copy_(self.ch.solve(B[r]))
+        return B
+
+    def trsm_rlt(self, X: torch.Tensor, nlead: Optional[int] = None) -> torch.Tensor:
+        if nlead is not None and nlead != self.n:
+            raise NotImplementedError("partial solves with a distributed factor")
+        return self.ch.solve_rows(X)
+
+    def extended(self, new_size: int):
+        raise NotImplementedError(
+            "a posterior whose factor is distributed over several GPUs cannot be extended by bordering; "
+            "pass all batches to from_observation_batches, or use replicate=True")
+
+    def passes(self, m_loc: int, chunk: int) -> int:
+        """number of chunk passes every rank must make so that the collective solves line up"""
+        t = torch.tensor([(m_loc + chunk - 1) // chunk], dtype=torch.int64, device=self.ch.A_loc.device)
+        if self.ch.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.ch.group)
+        return int(t.item())

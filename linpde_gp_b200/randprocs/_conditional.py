@@ -63,7 +63,8 @@ class ConditionalGaussianProcess(GaussianProcess):
         return cls(prior=prior, Ys=(Y,), Ls=(Lf,), bs=(b,), blocks=(blk,), factor=factor, resid=y, weights=w)
 
     @classmethod
-    def from_observation_batches(cls, prior: GaussianProcess, batches, *, process_group=None, nb: int = 1024):
+    def from_observation_batches(cls, prior: GaussianProcess, batches, *, process_group=None, nb: int = 1024,
+                                 replicate: bool = True):
         """Condition on several observation batches AT ONCE: ``batches`` is a sequence of
         ``(Y, X, L, b)`` tuples (same meaning as the arguments of :meth:`condition_on_observations`).
 
@@ -71,8 +72,11 @@ class ConditionalGaussianProcess(GaussianProcess):
         Cholesky factor of the whole matrix), but the Gram matrix is assembled and factorised in one go -- and,
         when ``torch.distributed`` is initialised with more than one rank, across all GPUs of the process group
         (block-row cyclic layout, NCCL panel exchange, see ``linpde_gp_b200/distributed.py``).  Every rank must
-        call this with the same arguments; every rank ends up with the full (replicated) factor so that posterior
-        evaluation can shard test points freely."""
+        call this with the same arguments.  ``replicate=True``: every rank ends up with the full factor, so that
+        posterior evaluation can shard test points freely and without further communication.  ``replicate=False``:
+        the factor stays distributed (N beyond one GPU's memory); ``mean`` works as usual, ``var`` / ``cov`` become
+        COLLECTIVE calls in which every rank passes its own shard of test points and block rows of the factor are
+        streamed over NVLink (``DistributedCholesky.solve_rows``)."""
         import torch.distributed as dist
 
         from .. import distributed
@@ -89,20 +93,25 @@ class ConditionalGaussianProcess(GaussianProcess):
         n = off
         noises = [p[6] for p in pre]
         world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        factor = backend.DeviceFactor([n])
-        if world > 1:
+        if world > 1 or not replicate:
             ch = distributed.DistributedCholesky(n, nb=nb, group=process_group)
             for i in ch.layout.local_blocks(ch.rank):
                 g0, g1 = ch.layout.block_bounds(i)
                 cls._assemble_range(prior, blocks, noises, ch.local_block_rows(i), g0, g1)
-            ch.factor(factor.L)  # the gathered panels are the block columns of L: replicated on the fly
-            factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
-            del ch
+            if replicate:
+                factor = backend.DeviceFactor([n])
+                ch.factor(factor.L)  # the gathered panels are the block columns of L: replicated on the fly
+                factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
+                del ch
+            else:
+                ch.factor()
+                factor = distributed.DistributedFactor(ch)
         else:
+            factor = backend.DeviceFactor([n])
             cls._assemble_range(prior, blocks, noises, factor.L, 0, n)
             factor.potrf()
         factor.factored_segments = 1
-        y = torch.zeros(n, dtype=torch.float64, device=factor.L.device)
+        y = torch.zeros(n, dtype=torch.float64, device=backend._require_cuda())  # pylint: disable=protected-access
         for blk, p in zip(blocks, pre):
             y[blk.col_off : blk.col_off + blk.n].copy_(backend.to_device(p[5]))
         w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
@@ -169,6 +178,8 @@ class ConditionalGaussianProcess(GaussianProcess):
 
     @property
     def gram(self) -> "GramFactorOperator":
+        if getattr(self._factor, "distributed", False):
+            raise NotImplementedError("the Gram factor is distributed over several GPUs (replicate=False)")
         if self._gram_op is None:
             self._gram_op = GramFactorOperator(self._factor, self._logical_index)
         return self._gram_op
@@ -231,6 +242,8 @@ class ConditionalGaussianProcess(GaussianProcess):
                 prior_diag = _descs(post._prior.cov)
                 diag = sum(dsc.diag_value for dsc in prior_diag)
                 n = post._factor.n
+                if getattr(post._factor, "distributed", False):
+                    return post._var_distributed(Xt, diag).cpu().numpy().reshape(batch)
                 chunk = int(max(256, min(Xt.shape[0], VAR_CHUNK_BYTES // (8 * backend.round_up(n, 16)))))
                 var = backend.post_var(post._obs_blocks_unique(), post._factor, Xt, diag, chunk=chunk)
                 return var.cpu().numpy().reshape(batch)
@@ -274,6 +287,28 @@ class ConditionalGaussianProcess(GaussianProcess):
             if x1 is None:
                 op.is_symmetric = True
             return op
+
+    def _var_distributed(self, Xt: "torch.Tensor", prior_diag: float) -> "torch.Tensor":
+        """Pointwise variance of THIS rank's test points with a distributed factor (collective)."""
+        fac = self._factor
+        n = fac.n
+        free = torch.cuda.mem_get_info()[0]
+        budget = max(VAR_CHUNK_BYTES, min(int(0.5 * free), 64 << 30))
+        chunk = int(max(256, budget // (8 * backend.round_up(n, 16))))
+        m = Xt.shape[0]
+        out = torch.empty(m, dtype=torch.float64, device=Xt.device)
+        blocks = self._obs_blocks_unique()
+        rows = min(chunk, max(m, 1))
+        K = backend.alloc_matrix(rows, n)
+        for p in range(fac.passes(m, chunk)):
+            lo, hi = min(m, p * chunk), min(m, (p + 1) * chunk)
+            Kc = K[: hi - lo]
+            if hi > lo:
+                backend.crosscov(blocks, n, Xt[lo:hi], out=Kc)
+            v = fac.ch.post_var(Kc, prior_diag)
+            if hi > lo:
+                out[lo:hi].copy_(v)
+        return out
 
     # -- adding observations ----------------------------------------------------------------------------------
     def condition_on_observations(self, Y, X=None, *, L=None, b=None):

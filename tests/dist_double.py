@@ -53,6 +53,21 @@ class HostOps:
             return
         X.copy_(torch.linalg.solve_triangular(torch.tril(Lkk), X.T.contiguous(), upper=False).T)
 
+    def trsv_block(self, Lkk, dinv, b, trans):
+        L = torch.tril(Lkk)
+        b.copy_(torch.linalg.solve_triangular(L.T if trans else L, b.reshape(-1, 1), upper=bool(trans)).reshape(-1))
+
+    def gemv(self, A, x, y, alpha, trans):
+        if A.shape[0] and A.shape[1]:
+            y.add_(alpha * ((A.T if trans else A) @ x))
+
+    def gemm_update(self, C, A, B):
+        if C.shape[0] and C.shape[1] and A.shape[1]:
+            C.sub_(A @ B.T)
+
+    def row_sumsq(self, A, scale, offset):
+        return offset + scale * (A * A).sum(dim=1)
+
     def update_limited(self, C, A, B, col_limit, col_base):
         if C.shape[0] == 0 or C.shape[1] == 0:
             return

@@ -38,6 +38,16 @@ def _run(rank, world, port, n, nb, q):
     # inverted leaf blocks are replicated too
     l0 = torch.linalg.inv(L_ref[:128, :128])
     werr = float((ch.dinv[: 128 * 128].view(128, 128) - l0).abs().max())
+    # distributed solve and streamed posterior variance (nothing replicated) against dense references
+    g = torch.Generator().manual_seed(11)
+    b = torch.randn(n, dtype=torch.float64, generator=g)
+    x = ch.solve(b)
+    err = max(err, float((x - torch.cholesky_solve(b[:, None], L_ref)[:, 0]).abs().max()))
+    m = 37 + 5 * rank  # ragged, different per rank
+    K = torch.randn(m, (n + 15) // 16 * 16, dtype=torch.float64, generator=g)[:, :n]
+    V_ref = torch.linalg.solve_triangular(L_ref, K.T.contiguous(), upper=False).T
+    var = ch.post_var(K, 3.0)
+    err = max(err, float((var - (3.0 - (V_ref * V_ref).sum(1))).abs().max()) * 1e-2)
     q.put((rank, err, werr))
     if world > 1:
         dist.destroy_process_group()

@@ -236,3 +236,24 @@ def test_distributed_cholesky_single_rank_device_ops():
         ch2.local_block_rows(i)[:, :hi].copy_(G2[lo:hi, :hi])
     with pytest.raises(np.linalg.LinAlgError, match="701-th"):
         ch2.factor()
+
+
+def test_one_shot_with_distributed_factor_not_replicated():
+    """replicate=False keeps the factor in its block-row layout (the N = 131,072 code path): representer weights by
+    the owner-computes substitution, variance / covariance by streaming block rows of L -- here with world_size 1
+    (no collectives) against sequential conditioning with the local factor."""
+    import linpde_gp_b200 as lg
+    from oracle import gp as ogp
+
+    prob = ogp.poisson2d_problem(1500, 40, seed=9, grid=20)
+    post_seq, seq = helpers.api_solve(prob)
+    prior = lg.GaussianProcess(lg.functions.Zero(input_shape=(2,)), helpers.api_kernel(prob["kernel"]))
+    batches = [(np.asarray(b["Y"], dtype=float), np.asarray(b["X"], dtype=float), helpers.api_op(b["L"])) for b in prob["blocks"]]
+    post = lg.ConditionalGaussianProcess.from_observation_batches(prior, batches, nb=256, replicate=False)
+    Xt = np.asarray(prob["Xt"], dtype=float)
+    sc = max(np.max(np.abs(seq["var"])), np.max(np.abs(seq["mean"])))
+    assert np.max(np.abs(post.mean(Xt) - seq["mean"])) <= 1e-9 * sc
+    assert np.max(np.abs(post.var(Xt) - seq["var"])) <= 1e-9 * sc
+    assert np.max(np.abs(post.cov.matrix(Xt[:50]) - post_seq.cov.matrix(Xt[:50]))) <= 1e-9 * sc
+    with pytest.raises(NotImplementedError):
+        post.condition_on_observations(np.zeros(2), X=Xt[:2] + 0.0123)

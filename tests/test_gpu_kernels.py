@@ -235,3 +235,40 @@ def test_row_sumsq(be):
     out = be.row_sumsq(A, -1.0, 3.0)
     ref = 3.0 - (A * A).sum(dim=1)
     assert (out - ref).abs().max().item() <= 1e-11 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (130, 77), (512, 4099), (1000, 1000), (7, 20000)])
+def test_gemv_vs_torch(be, m, n):
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    A = torch.randn(m, n + 3, dtype=torch.float64, device="cuda", generator=g)[:, :n]
+    x = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    z = torch.randn(m, dtype=torch.float64, device="cuda", generator=g)
+    y0 = torch.randn(m, dtype=torch.float64, device="cuda", generator=g)
+    y = be.gemv(A, x, y0.clone(), alpha=-0.75)
+    assert (y - (y0 - 0.75 * (A @ x))).abs().max().item() <= 1e-12 * max(1.0, (A.abs() @ x.abs()).max().item())
+    w0 = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    w = be.gemv(A, z, w0.clone(), alpha=1.5, trans=True)
+    assert (w - (w0 + 1.5 * (A.T @ z))).abs().max().item() <= 1e-12 * max(1.0, (A.abs().T @ z.abs()).max().item())
+
+
+@pytest.mark.parametrize("n", [2, 128, 300, 1664])
+def test_trsv_forward_backward_vs_torch(be, n):
+    import ctypes
+
+    from linpde_gp_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    X = torch.randn(n, n + 8, dtype=torch.float64, device="cuda", generator=g)
+    G = X @ X.T / n + 0.5 * torch.eye(n, dtype=torch.float64, device="cuda")
+    f = be.DeviceFactor([n])
+    f.L.copy_(G)
+    f.potrf()
+    L = torch.tril(f.L)
+    b = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    for trans in (0, 1):
+        x = b.clone()
+        st = f._struct()
+        rc = _lib.lib.lpgp_trsv(ctypes.byref(st), trans, ctypes.c_void_p(x.data_ptr()), be._stream())
+        assert rc == 0
+        ref = torch.linalg.solve_triangular(L.T if trans else L, b[:, None], upper=bool(trans))[:, 0]
+        assert (x - ref).abs().max().item() <= 1e-10 * ref.abs().max().item()

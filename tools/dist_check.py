@@ -30,4 +30,14 @@ sc = max(np.max(np.abs(v_1)), np.max(np.abs(m_1)))
 err = max(np.max(np.abs(m_d - m_1)), np.max(np.abs(v_d - v_1))) / sc
 print(f"rank {rank}/{world}: N={prob['N']} distributed one-shot {t1 - t0:.3f} s, posterior rel diff vs sequential single-GPU {err:.2e}", flush=True)
 assert err < 1e-9, err
+# factor left distributed (replicate=False): collective var on this rank's shard of the test points
+from linpde_gp_b200 import parallel
+post_d = lg.ConditionalGaussianProcess.from_observation_batches(prior, batches, nb=512, replicate=False)
+lo, hi = parallel.shard_bounds(len(prob["Xt"]), rank, world)
+m_s, v_s = post_d.mean(prob["Xt"][lo:hi]), post_d.var(prob["Xt"][lo:hi])
+err2 = max(np.max(np.abs(m_s - m_1[lo:hi])), np.max(np.abs(v_s - v_1[lo:hi]))) / sc
+c_s = post_d.cov.matrix(prob["Xt"][:40])
+err3 = np.max(np.abs(c_s - post1.cov.matrix(prob["Xt"][:40]))) / sc
+print(f"rank {rank}/{world}: distributed factor (not replicated): mean/var rel diff {err2:.2e}, cov rel diff {err3:.2e}", flush=True)
+assert err2 < 1e-9 and err3 < 1e-9, (err2, err3)
 dist.destroy_process_group()
