@@ -78,59 +78,76 @@ def oracle_kernel(ell):
 # reference arm / cpu baseline: the oracle on the host cores, bounded sample, extrapolated to one full solve
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_sample(prob, budget_s: float = 20.0):
+    """Bounded sample of the reference's CPU path (the oracle port) on ALL host cores, extrapolated to one solve:
+    Gram assembly on independent row tiles spread over a thread pool (numpy releases the GIL inside its ufuncs; the
+    reference itself is single-threaded here), LAPACK dpotrf / dtrsm through scipy with every BLAS thread."""
+    import concurrent.futures as cf
+
     import scipy.linalg
+    from threadpoolctl import threadpool_limits
 
     from oracle import covfuncs as ocf
 
+    cores = len(os.sched_getaffinity(0))
     N, M = prob["N"], prob["M"]
     kern = oracle_kernel(prob["ell"])
     lap = [(-1.0, ("wl", np.ones(2)))]
     X = prob["X_pde"]
     t_budget = budget_s / 3.0
     # (a) Gram assembly L k L^* on row tiles (the un-tiled reference needs ~10 N x N temporaries)
-    rows, t0, done = 256, time.perf_counter(), 0
-    while True:
-        ocf.matrix(kern, lap, lap, X[done % 4096 : done % 4096 + rows], X)
-        done += rows
-        if time.perf_counter() - t0 > t_budget or done >= 4096:
-            break
-    t_asm = time.perf_counter() - t0
+    rows = 64
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        ocf.matrix(kern, lap, lap, X[:rows], X)
+        t_one = max(time.perf_counter() - t0, 1e-3)
+        per_worker = max(1, int(t_budget / t_one))
+        workers = max(1, min(cores, 32))
+
+        def work(wid):
+            for i in range(per_worker):
+                r0 = ((wid * per_worker + i) * rows) % (len(X) - rows)
+                ocf.matrix(kern, lap, lap, X[r0 : r0 + rows], X)
+            return per_worker * rows
+
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(workers) as ex:
+            done = sum(ex.map(work, range(workers)))
+        t_asm = time.perf_counter() - t0
     eps = done * len(X) / t_asm
-    # (b) dpotrf via scipy at a host-sized N
-    nc = 6144
-    rng = np.random.default_rng(0)
-    A = rng.standard_normal((nc, nc))
-    G = A @ A.T / nc + 2.0 * np.eye(nc)
-    t0 = time.perf_counter()
-    Lc = scipy.linalg.cholesky(G, lower=True)
-    t_chol = time.perf_counter() - t0
-    chol_flops = nc**3 / 3.0 / t_chol
-    # (c) dtrsm (posterior variance in the N x M_c form, _conditional.py:245-251)
-    mc = 2048
-    B = rng.standard_normal((nc, mc))
-    t0 = time.perf_counter()
-    scipy.linalg.solve_triangular(Lc, B, lower=True, check_finite=False)
-    t_trsm = time.perf_counter() - t0
-    trsm_flops = nc * nc * mc / t_trsm
+    with threadpool_limits(limits=cores):
+        # (b) dpotrf via scipy at a host-sized N
+        nc = 8192
+        rng = np.random.default_rng(0)
+        A = rng.standard_normal((nc, nc))
+        G = A @ A.T / nc + 2.0 * np.eye(nc)
+        t0 = time.perf_counter()
+        Lc = scipy.linalg.cholesky(G, lower=True)
+        t_chol = time.perf_counter() - t0
+        chol_flops = nc**3 / 3.0 / t_chol
+        # (c) dtrsm (posterior variance in the N x M_c form, _conditional.py:245-251)
+        mc = 4096
+        B = rng.standard_normal((nc, mc))
+        t0 = time.perf_counter()
+        scipy.linalg.solve_triangular(Lc, B, lower=True, check_finite=False)
+        t_trsm = time.perf_counter() - t0
+        trsm_flops = nc * nc * mc / t_trsm
     est = N * N / eps + M * N / eps + (N**3 / 3.0) / chol_flops + (float(M) * N * N) / trsm_flops
     detail = {
         "gram_entries_per_s": eps,
         "cholesky_gflops": chol_flops * 1e-9,
         "trsm_gflops": trsm_flops * 1e-9,
-        "sample": f"LkL assembly of {done}x{len(X)} row tiles ({t_asm:.1f} s), scipy dpotrf n={nc} ({t_chol:.1f} s), "
-                  f"dtrsm {nc}x{mc} ({t_trsm:.1f} s); extrapolated to N={N}, M={M}",
+        "sample": f"LkL assembly of {done}x{len(X)} entries in {rows}-row tiles on {workers} threads ({t_asm:.1f} s), "
+                  f"scipy dpotrf n={nc} ({t_chol:.1f} s), dtrsm {nc}x{mc} ({t_trsm:.1f} s), BLAS threads {cores}; "
+                  f"extrapolated to N={N}, M={M}",
     }
     return est, detail
 
 
 def host_threads():
-    try:
-        from threadpoolctl import threadpool_info
-
-        n = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
-    except Exception:  # pragma: no cover
-        n = 1
-    return int(n), len(os.sched_getaffinity(0))
+    """(threads used by the sample, host cores available): cpu_sample drives every core explicitly, whatever
+    OMP_NUM_THREADS torchrun may have exported."""
+    cores = len(os.sched_getaffinity(0))
+    return cores, cores
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -279,7 +296,7 @@ class DeviceSolve:
                 c_hi = nj if bj < bi else r_hi - oi
                 be.gram(self._desc_for(bi, bj), Xr, blocksX[bj][:c_hi], out=rows[:, oj : oj + c_hi])
 
-    def step_distributed(self, nb: int):
+    def step_distributed(self, nb: int, replicate: bool = True):
         from linpde_gp_b200 import distributed
 
         be, torch = self.be, self.torch
@@ -287,7 +304,6 @@ class DeviceSolve:
         blocksX = self.edges + [self.Xp]
         offs = [int(o) for o in np.concatenate([[0], np.cumsum(sizes)[:-1]])]
         n = int(sum(sizes))
-        factor = be.DeviceFactor([n])
         ch = distributed.DistributedCholesky(n, nb=nb)
 
         def assemble():
@@ -296,15 +312,23 @@ class DeviceSolve:
                 self._assemble_block_rows(ch.local_block_rows(i), g0, g1, blocksX, offs, sizes)
 
         self._timed("assemble", assemble)
-        self._timed("factor", lambda: ch.factor(factor.L))  # every rank ends up with the whole factor
-        factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
-        del ch
-        w = self._timed("solve", lambda: factor.potrs(self.y.clone().reshape(1, -1)).reshape(-1))
         descs = [self.d_k] * len(self.edges) + [self.d_kL]
         blocks = be.ObsBlocks(descs, blocksX, offs)
-        mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
-        chunk = int(max(256, min(self.Xt.shape[0], (4 << 30) // (8 * be.round_up(factor.n, 16)))))
-        var = self._timed("var", lambda: be.post_var(blocks, factor, self.Xt, self.d_k.diag_value, chunk=chunk))
+        if replicate:
+            factor = be.DeviceFactor([n])
+            self._timed("factor", lambda: ch.factor(factor.L))  # every rank ends up with the whole factor
+            factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
+            del ch
+            w = self._timed("solve", lambda: factor.potrs(self.y.clone().reshape(1, -1)).reshape(-1))
+            mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
+            chunk = int(max(256, min(self.Xt.shape[0], (4 << 30) // (8 * be.round_up(factor.n, 16)))))
+            var = self._timed("var", lambda: be.post_var(blocks, factor, self.Xt, self.d_k.diag_value, chunk=chunk))
+        else:  # the factor stays distributed: owner-computes solve, block rows of L streamed for the variance
+            self._timed("factor", ch.factor)
+            fac = distributed.DistributedFactor(ch)
+            w = self._timed("solve", lambda: ch.solve(self.y))
+            mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
+            var = self._timed("var", lambda: fac.post_var(blocks, self.Xt, self.d_k.diag_value))
         return mean, var
 
     def phase_ms(self, last_k: int):
@@ -313,7 +337,7 @@ class DeviceSolve:
         return {k: sum(e0.elapsed_time(e1) for e0, e1 in v[-last_k * per(k):]) / last_k for k, v in self.t.items()}
 
 
-def api_solve(prob, rank: int, world: int, nb: int = 1024):
+def api_solve(prob, rank: int, world: int, nb: int = 1024, replicate: bool = True):
     """The same solve through the public reference-style API with host (numpy) buffers -> `e2e`."""
     import linpde_gp_b200 as lg
     from linpde_gp_b200.linfuncops import diffops
@@ -325,7 +349,7 @@ def api_solve(prob, rank: int, world: int, nb: int = 1024):
     lap = -1.0 * diffops.Laplacian((2,))
     if world > 1:  # one-shot conditioning on all batches, Gram assembly + Cholesky distributed over the ranks
         batches = [(Yb, Xb) for Xb, Yb in zip(prob["edges"], prob["Y_bc"])] + [(prob["Y_pde"], prob["X_pde"], lap)]
-        post = lg.ConditionalGaussianProcess.from_observation_batches(post, batches, nb=nb)
+        post = lg.ConditionalGaussianProcess.from_observation_batches(post, batches, nb=nb, replicate=replicate)
     else:
         for Xb, Yb in zip(prob["edges"], prob["Y_bc"]):
             post = post.condition_on_observations(Yb, X=Xb)
@@ -369,6 +393,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")  # panel broadcasts / all-gathers are the critical path
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from linpde_gp_b200 import backend
     from linpde_gp_b200._lib import lib
@@ -393,7 +418,12 @@ def run_b200(args):
 
     peak = dmma_peak_tflops(torch, backend) if rank == 0 else None
     ds = DeviceSolve(prob, rank, world)
-    step = ds.step if world == 1 else (lambda: ds.step_distributed(args.nb))
+    # the replicated n x n factor, this rank's block rows and the variance workspace must fit next to each other
+    if args.replicate == "auto":
+        replicate = (N * N * 8) * (1.0 + 1.0 / world) + (8 << 30) < 0.9 * torch.cuda.get_device_properties(local).total_memory
+    else:
+        replicate = args.replicate == "yes"
+    step = ds.step if world == 1 else (lambda: ds.step_distributed(args.nb, replicate))
     for _ in range(args.warmup):
         m, v = step()
         gather(m, v)
@@ -419,7 +449,7 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        em, ev = api_solve(prob, rank, world, args.nb)
+        em, ev = api_solve(prob, rank, world, args.nb, replicate)
         gem, gev = gather(em, ev)
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -439,7 +469,8 @@ def run_b200(args):
         achieved = flops_tensor / t_tensor * 1e-12
         h2d = sum(e.nbytes for e in prob["edges"]) + sum(y.nbytes for y in prob["Y_bc"]) + prob["X_pde"].nbytes \
             + prob["Y_pde"].nbytes + prob["Xt"].nbytes * 2 // world
-        cpu_est, cpu_detail = cpu_sample(prob, budget_s=20.0)
+        # the CPU baseline is reported by the single-GPU run only (rank 0 at N = 1)
+        cpu_est, cpu_detail = cpu_sample(prob, budget_s=20.0) if world == 1 else (None, {})
         threads, cores = host_threads()
         out = {
             "metric": "s per GP-PDE solve (2D Poisson N=64k)",
@@ -459,7 +490,8 @@ def run_b200(args):
                             f"product Matern-5/2 prior, 5 conditioning batches, mean+variance on {args.grid}x{args.grid} grid "
                             "(BASELINE.json configs[3])",
                 "parallelism": (f"block-row cyclic Gram assembly + Cholesky over {world} ranks (nb={args.nb}, NCCL panel "
-                                "exchange), factor replicated, test grid sharded") if world > 1 else "single GPU",
+                                f"exchange), factor {'replicated' if replicate else 'left distributed (block rows streamed for the variance)'}, "
+                                "test grid sharded") if world > 1 else "single GPU",
                 "l2": f"working set {N * N * 8 / 1e9:.1f} GB Gram >> 126 MB L2 (no flush needed)",
             },
             "phases_ms": phases,
@@ -478,8 +510,8 @@ def run_b200(args):
                                "holds no FP64 figure",
                 "flops": flops_tensor,
             },
-            "cpu_baseline": {"value": cpu_est, "unit": "s", "cores": cores, "threads": threads, "kind": "port",
-                             **cpu_detail},
+            "cpu_baseline": ({"value": cpu_est, "unit": "s", "cores": cores, "threads": threads, "kind": "port",
+                              **cpu_detail} if cpu_est is not None else None),
         }
         print(json.dumps(out))
     if world > 1:
@@ -525,6 +557,8 @@ def main():
     ap.add_argument("--npde", type=int, default=63488)
     ap.add_argument("--nbc-edge", type=int, default=512)
     ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--replicate", default="auto", choices=["auto", "yes", "no"],
+                    help="N > 1 GPU: replicate the factor on every rank (auto: if it fits) or keep it distributed")
     ap.add_argument("--nb", type=int, default=1024, help="block-row height of the distributed Cholesky (N > 1 GPU)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -419,6 +419,29 @@ class DistributedFactor:
             "a posterior whose factor is distributed over several GPUs cannot be extended by bordering; "
             "pass all batches to from_observation_batches, or use replicate=True")
 
+    def post_var(self, blocks, Xt: torch.Tensor, prior_diag: float, min_chunk_bytes: int = 4 << 30) -> torch.Tensor:
+        """Pointwise posterior variance of THIS rank's test points ``Xt`` (m_loc x d, device): cross-covariance
+        rows are assembled chunk by chunk (as many rows as fit half of the free device memory, so that the factor
+        is streamed as few times as possible) and solved against the distributed factor.  Collective."""
+        from . import backend
+
+        n = self.n
+        free = torch.cuda.mem_get_info()[0]
+        budget = max(min_chunk_bytes, min(int(0.5 * free), 64 << 30))
+        chunk = int(max(256, budget // (8 * backend.round_up(n, 16))))
+        m = Xt.shape[0]
+        out = torch.empty(m, dtype=torch.float64, device=Xt.device)
+        K = backend.alloc_matrix(min(chunk, max(m, 1)), n)
+        for p in range(self.passes(m, chunk)):
+            lo, hi = min(m, p * chunk), min(m, (p + 1) * chunk)
+            Kc = K[: hi - lo]
+            if hi > lo:
+                backend.crosscov(blocks, n, Xt[lo:hi], out=Kc)
+            v = self.ch.post_var(Kc, prior_diag)
+            if hi > lo:
+                out[lo:hi].copy_(v)
+        return out
+
     def passes(self, m_loc: int, chunk: int) -> int:
         """number of chunk passes every rank must make so that the collective solves line up"""
         t = torch.tensor([(m_loc + chunk - 1) // chunk], dtype=torch.int64, device=self.ch.A_loc.device)

@@ -290,25 +290,7 @@ class ConditionalGaussianProcess(GaussianProcess):
 
     def _var_distributed(self, Xt: "torch.Tensor", prior_diag: float) -> "torch.Tensor":
         """Pointwise variance of THIS rank's test points with a distributed factor (collective)."""
-        fac = self._factor
-        n = fac.n
-        free = torch.cuda.mem_get_info()[0]
-        budget = max(VAR_CHUNK_BYTES, min(int(0.5 * free), 64 << 30))
-        chunk = int(max(256, budget // (8 * backend.round_up(n, 16))))
-        m = Xt.shape[0]
-        out = torch.empty(m, dtype=torch.float64, device=Xt.device)
-        blocks = self._obs_blocks_unique()
-        rows = min(chunk, max(m, 1))
-        K = backend.alloc_matrix(rows, n)
-        for p in range(fac.passes(m, chunk)):
-            lo, hi = min(m, p * chunk), min(m, (p + 1) * chunk)
-            Kc = K[: hi - lo]
-            if hi > lo:
-                backend.crosscov(blocks, n, Xt[lo:hi], out=Kc)
-            v = fac.ch.post_var(Kc, prior_diag)
-            if hi > lo:
-                out[lo:hi].copy_(v)
-        return out
+        return self._factor.post_var(self._obs_blocks_unique(), Xt, prior_diag, min_chunk_bytes=VAR_CHUNK_BYTES)
 
     # -- adding observations ----------------------------------------------------------------------------------
     def condition_on_observations(self, Y, X=None, *, L=None, b=None):
