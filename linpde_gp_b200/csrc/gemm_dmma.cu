@@ -7,10 +7,11 @@
 // Blackwell has no FP64 kind in tcgen05/TMEM; the FP64 tensor path on sm_100a is the warp-level
 // mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; measured issue-rate peak 37.1 TFLOP/s on this pool's B200, see
 // profiles/fp64_peaks_r01.txt).  Design:
-//   * CTA tile 128 x 128, 8 consumer warps (2 x 4), warp tile 64 x 32 -> 64 FP64 accumulators per thread;
-//   * operands are streamed by one producer warp with TMA 2-D tensor copies (cp.async.bulk.tensor, SASS
-//     UTMALDG) into an 8-stage shared-memory ring of (128+128) x 8 doubles, full/empty mbarriers, no
-//     __syncthreads in the main loop; TMA zero-fills the m/n/k tails, so no edge predicates in the hot loop;
+//   * CTA tile 128 x 128, 8 warps (2 x 4), warp tile 64 x 32 -> 64 FP64 accumulators per thread;
+//   * operands are streamed with TMA 2-D tensor copies (cp.async.bulk.tensor, SASS UTMALDG), issued by one elected
+//     thread six k-blocks ahead of the DMMA loop, into an 8-stage shared-memory ring of (128+128) x 8 doubles,
+//     full/empty mbarriers, no __syncthreads in the main loop; TMA zero-fills the m/n/k tails, so no edge
+//     predicates in the hot loop;
 //   * rows of a stage are 64 bytes: an LDS.128 of lane (g, t) fetches k = 2t, 2t+1 of row g -> two DMMAs per
 //     shared-memory load (the contraction index may be permuted as long as A and B agree), conflict-free
 //     without swizzling (lanes 0-7 cover two rows = one 128-byte bank window);
@@ -37,7 +38,7 @@ template <int BM_, int BN_, int WARPS_M_, int WARPS_N_>
 struct TileCfg {
   static constexpr int BM = BM_, BN = BN_, WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
   static constexpr int NCONSUMER_WARPS = WARPS_M * WARPS_N;
-  static constexpr int NTHREADS = (NCONSUMER_WARPS + 1) * 32;
+  static constexpr int NTHREADS = NCONSUMER_WARPS * 32;
   static constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;  // warp tile
   static constexpr int MI = WTM / 8, NJ = WTN / 8;               // DMMA sub-tiles per warp
   static constexpr int STAGE_A_BYTES = BM * BK * 8;
@@ -110,20 +111,31 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   }
   __syncthreads();
 
-  if (warp == NCONSUMER_WARPS) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        if (kb >= STAGES) mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        unsigned char* st = smem + s * STAGE_BYTES;
-        tma_load_2d(st, &tmA, kb * BK, row0, &full[s]);
-        tma_load_2d(st + STAGE_A_BYTES, &tmB, kb * BK, col0, &full[s]);
-      }
+  // pull the C tile (read-modify-write in the epilogue) into L2 while the main loop runs: one 128-byte line per
+  // prefetch, BM rows x BN*8/128 lines
+  if (beta != 0.0) {
+    constexpr int LINES = BN * 8 / 128;
+    for (int idx = threadIdx.x; idx < BM * LINES; idx += Cfg::NTHREADS) {
+      const int r = row0 + idx / LINES, c = col0 + (idx % LINES) * 16;
+      if (r < m && c < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (int64_t)r * ldc + c));
     }
-    return;
+  }
+
+  // ===== TMA producer = lane 0 of warp 0, PREFETCH k-blocks ahead of the DMMA loop =====
+  // (no dedicated producer warp: a ninth warp would put three warps on one SM sub-partition and cap every thread
+  //  at 168 registers -- less than the 128 accumulator + 48 fragment registers of the 128 x 128 tile)
+  constexpr int PREFETCH = STAGES - 2;  // the slot refilled at step kb was consumed at step kb - 2
+  const bool producer = (threadIdx.x == 0);
+  auto issue = [&](int kf) {
+    const int s = kf % STAGES;
+    if (kf >= STAGES) mbar_wait(&empty[s], ((kf / STAGES) & 1) ^ 1);
+    mbar_expect_tx(&full[s], STAGE_BYTES);
+    unsigned char* st = smem + s * STAGE_BYTES;
+    tma_load_2d(st, &tmA, kf * BK, row0, &full[s]);
+    tma_load_2d(st + STAGE_A_BYTES, &tmB, kf * BK, col0, &full[s]);
+  };
+  if (producer) {
+    for (int kf = 0; kf < PREFETCH && kf < nk; ++kf) issue(kf);
   }
 
   // ===== DMMA consumers =====
@@ -136,6 +148,8 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   for (int kb = 0; kb < nk; ++kb) {
+    if (producer && kb + PREFETCH < nk) issue(kb + PREFETCH);
+    __syncwarp();
     const int s = kb % STAGES;
     const uint32_t ph = (kb / STAGES) & 1;
     mbar_wait(&full[s], ph);
@@ -158,31 +172,71 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   }
 
   // ===== epilogue: C = beta*C + alpha*acc =====
+  // The C values of MH row groups of accumulators are loaded as ONE batch of independent 16-byte loads before any
+  // store is issued (the compiler cannot hoist a load above a store through the same pointer by itself): MI / MH
+  // L2 round trips per tile instead of one per element pair.  The tile was prefetched into L2 at kernel start.
+  // (the opaque copies keep the compiler from hoisting the epilogue's address arithmetic above the main loop, where
+  //  it would cost registers the accumulators need)
+  int row0e = row0, col0e = col0;
+  double* Ce = C;
+  asm volatile("" : "+r"(row0e), "+r"(col0e), "+l"(Ce));
+  if (vec_ok) {
+    constexpr int MH = MI >= 8 ? 4 : 2;
+    static_assert(MI % MH == 0, "row groups per batch must divide MI");
+#pragma unroll
+    for (int h = 0; h < MI / MH; ++h) {
+      double2 cv[MH][NJ];
+      if (beta != 0.0) {
+#pragma unroll
+        for (int ii = 0; ii < MH; ++ii) {
+          const int i = h * MH + ii;
+          const int row = row0e + wm0 + 8 * i + g;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int col = col0e + wn0 + 8 * j + 2 * t;
+            cv[ii][j] = make_double2(0.0, 0.0);
+            if (i < MI && row < m && col + 1 < n) cv[ii][j] = *reinterpret_cast<const double2*>(Ce + (int64_t)row * ldc + col);
+            else if (i < MI && row < m && col < n) cv[ii][j].x = Ce[(int64_t)row * ldc + col];
+          }
+        }
+      }
+#pragma unroll
+      for (int ii = 0; ii < MH; ++ii) {
+        const int i = h * MH + ii;
+        const int row = row0e + wm0 + 8 * i + g;
+        if (i >= MI || row >= m) continue;
+        double* crow = Ce + (int64_t)row * ldc;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int col = col0e + wn0 + 8 * j + 2 * t;
+          if (col >= n) continue;
+          double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+          if (beta != 0.0) {
+            v0 = fma(beta, cv[ii][j].x, v0);
+            v1 = fma(beta, cv[ii][j].y, v1);
+          }
+          if (col + 1 < n) *reinterpret_cast<double2*>(crow + col) = make_double2(v0, v1);
+          else crow[col] = v0;
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < MI; ++i) {
-    const int row = row0 + wm0 + 8 * i + g;
+    const int row = row0e + wm0 + 8 * i + g;
     if (row >= m) continue;
-    double* crow = C + (int64_t)row * ldc;
+    double* crow = Ce + (int64_t)row * ldc;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int col = col0 + wn0 + 8 * j + 2 * t;
+      const int col = col0e + wn0 + 8 * j + 2 * t;
       if (col >= n) continue;
       double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
-      if (vec_ok && col + 1 < n) {
-        double2* p = reinterpret_cast<double2*>(crow + col);
-        if (beta != 0.0) {
-          const double2 c = *p;
-          v0 = fma(beta, c.x, v0);
-          v1 = fma(beta, c.y, v1);
-        }
-        *p = make_double2(v0, v1);
-      } else {
-        if (beta != 0.0) v0 = fma(beta, crow[col], v0);
-        crow[col] = v0;
-        if (col + 1 < n) {
-          if (beta != 0.0) v1 = fma(beta, crow[col + 1], v1);
-          crow[col + 1] = v1;
-        }
+      if (beta != 0.0) v0 = fma(beta, crow[col], v0);
+      crow[col] = v0;
+      if (col + 1 < n) {
+        if (beta != 0.0) v1 = fma(beta, crow[col + 1], v1);
+        crow[col + 1] = v1;
       }
     }
   }
