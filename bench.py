@@ -400,6 +400,8 @@ def run_b200(args):
 
     prob = make_problem(args.npde, args.nbc_edge, args.grid)
     N, M = prob["N"], prob["M"]
+    if args.nb <= 0:
+        args.nb = 1024 if world <= 2 else 512
 
     def barrier():
         if world > 1:
@@ -420,7 +422,7 @@ def run_b200(args):
     ds = DeviceSolve(prob, rank, world)
     # the replicated n x n factor, this rank's block rows and the variance workspace must fit next to each other
     if args.replicate == "auto":
-        replicate = (N * N * 8) * (1.0 + 1.0 / world) + (8 << 30) < 0.9 * torch.cuda.get_device_properties(local).total_memory
+        replicate = (N * N * 8) * (1.0 + 1.0 / world) + (8 << 30) < 0.5 * torch.cuda.get_device_properties(local).total_memory
     else:
         replicate = args.replicate == "yes"
     step = ds.step if world == 1 else (lambda: ds.step_distributed(args.nb, replicate))
@@ -442,6 +444,28 @@ def run_b200(args):
     launches = lib.lpgp_launch_count(0)
     ms_dev = e0.elapsed_time(e1) / args.steps
     phases = ds.phase_ms(args.steps)
+    # the assembly kernel on its own (one L k L* block of 16,384 x N_pde entries, written to HBM), best of 3
+    gram_kernel = None
+    if rank == 0:
+        nrow = min(16384, ds.Xp.shape[0])
+        blk = backend.alloc_matrix(nrow, ds.Xp.shape[0])
+        best = 1e30
+        for _ in range(4):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            backend.gram(ds.d_LkL, ds.Xp[:nrow], ds.Xp, out=blk)
+            g1.record()
+            torch.cuda.synchronize()
+            best = min(best, g0.elapsed_time(g1))
+        ent = nrow * ds.Xp.shape[0] / (best * 1e-3)
+        gram_kernel = {"entries_per_s": ent, "hbm_write_gbps": ent * 8e-9, "block": [int(nrow), int(ds.Xp.shape[0])],
+                       "kernel": "gram_sep_kernel<2,3,false> (L k L*, product Matern-5/2)"}
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm = json.load(open(peaks_path)).get("hbm_gbs") if os.path.exists(peaks_path) else None
+        gram_kernel["hbm_peak_gbps"] = hbm if hbm else 6650.0
+        gram_kernel["hbm_peak_source"] = "MEASURED_PEAKS.json" if hbm else "fallback (B200_PROFILING.md: 6.65 TB/s)"
+        gram_kernel["frac_of_hbm_peak"] = gram_kernel["hbm_write_gbps"] / gram_kernel["hbm_peak_gbps"]
+        del blk
     del ds
     torch.cuda.empty_cache()
 
@@ -488,14 +512,15 @@ def run_b200(args):
             "config": {
                 "workload": f"2D Poisson Dirichlet synthetic N={N} (N_pde={args.npde} seed 2, N_bc={4 * args.nbc_edge}), "
                             f"product Matern-5/2 prior, 5 conditioning batches, mean+variance on {args.grid}x{args.grid} grid "
-                            "(BASELINE.json configs[3])",
+                            f"(BASELINE.json configs[{4 if N >= 131072 else 3 if N >= 65536 else 1}])",
                 "parallelism": (f"block-row cyclic Gram assembly + Cholesky over {world} ranks (nb={args.nb}, NCCL panel "
                                 f"exchange), factor {'replicated' if replicate else 'left distributed (block rows streamed for the variance)'}, "
                                 "test grid sharded") if world > 1 else "single GPU",
                 "l2": f"working set {N * N * 8 / 1e9:.1f} GB Gram >> 126 MB L2 (no flush needed)",
             },
             "phases_ms": phases,
-            "gram_entries_per_s": (N * (N + 1) / 2 + 0.0) / (phases["assemble"] * 1e-3),
+            "gram_entries_per_s": (N * (N + 1) / 2 + 0.0) / (phases["assemble"] * 1e-3),  # whole assembly phase
+            "gram_kernel": gram_kernel,
             "cholesky_tflops": N**3 / 3.0 / (phases["factor"] * 1e-3) * 1e-12,  # aggregate over all ranks
             "variance_trsm_tflops": float(m_shard) * N * N / (phases["var"] * 1e-3) * 1e-12,
             "e2e": {"value": ms_e2e * 1e-3, "unit": "s", "h2d_bytes_per_step": int(h2d),
@@ -559,7 +584,9 @@ def main():
     ap.add_argument("--grid", type=int, default=512)
     ap.add_argument("--replicate", default="auto", choices=["auto", "yes", "no"],
                     help="N > 1 GPU: replicate the factor on every rank (auto: if it fits) or keep it distributed")
-    ap.add_argument("--nb", type=int, default=1024, help="block-row height of the distributed Cholesky (N > 1 GPU)")
+    ap.add_argument("--nb", type=int, default=0,
+                    help="block-row height of the distributed Cholesky (N > 1 GPU); 0 = 1024 up to 2 GPUs, 512 beyond "
+                         "(shorter panel chain / better balance, profiles/dist_cholesky_r01.txt)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
