@@ -142,8 +142,9 @@ class CovarianceLinearOperator(LinearOperator):
     def covfunc(self):
         return self._covfunc
 
-    def assemble_into(self, out: torch.Tensor, lower: bool = False, X0=None, X1=None) -> torch.Tensor:
-        """Write the block into ``out`` (a view into a larger device buffer) with the Gram kernel."""
+    def assemble_into(self, out: torch.Tensor, lower: bool = False, X0=None, X1=None, accumulate: bool = False) -> torch.Tensor:
+        """Write (or add, ``accumulate=True``) the block into ``out`` (a view into a larger device buffer) with the
+        Gram kernel."""
         from .randprocs import covfuncs
 
         d = self._covfunc.input_size
@@ -159,7 +160,7 @@ class CovarianceLinearOperator(LinearOperator):
         else:
             descs = [k.descriptor()]
         for i, desc in enumerate(descs):
-            backend.gram(desc, X0, X1, out=out, lower=lower, accumulate=i > 0)
+            backend.gram(desc, X0, X1, out=out, lower=lower, accumulate=accumulate or i > 0)
         return out
 
     def device_dense(self) -> torch.Tensor:

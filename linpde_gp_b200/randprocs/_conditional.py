@@ -145,6 +145,10 @@ class ConditionalGaussianProcess(GaussianProcess):
                 diag = rows[: l_hi - l_lo, blk.col_off + l_lo : blk.col_off + l_hi]
                 if kind == "diag":
                     backend.add_diag(diag, backend.to_device(val[l_lo:l_hi]), 1.0)
+                elif kind == "kernel":
+                    Xn = backend.points(val._x0, val.covfunc.input_size)  # pylint: disable=protected-access
+                    val.assemble_into(rows[: l_hi - l_lo, blk.col_off : blk.col_off + l_hi], X0=Xn[l_lo:l_hi], X1=Xn[:l_hi],
+                                      accumulate=True)
                 else:
                     diag.add_(backend.to_device(val[l_lo:l_hi, l_lo:l_hi]))
                     if l_lo > 0:
@@ -337,6 +341,8 @@ class ConditionalGaussianProcess(GaussianProcess):
             kind, val = noise
             if kind == "diag":
                 backend.add_diag(D, backend.to_device(val), 1.0)
+            elif kind == "kernel":
+                val.assemble_into(D, lower=True, accumulate=True)
             else:
                 D.add_(backend.to_device(val))
         if blk.n_phys != n:  # identity padding row keeps segment offsets even (16-byte aligned TMA rows)
@@ -384,6 +390,10 @@ class ConditionalGaussianProcess(GaussianProcess):
             cov = b.cov
             if isinstance(cov, linops.Scaling):
                 noise = ("diag", cov.factors)
+            elif isinstance(cov, linops.CovarianceLinearOperator) and cov._x1 is None:  # pylint: disable=protected-access
+                # b is the marginal of another GP at the observation points (uncertain right-hand side, ``b=-f(X)``):
+                # its covariance block is assembled on the device, straight into the Gram rows (accumulate mode)
+                noise = ("kernel", cov)
             elif isinstance(cov, linops.LinearOperator):
                 noise = ("dense", cov.todense())
             else:

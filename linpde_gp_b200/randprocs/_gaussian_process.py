@@ -51,9 +51,10 @@ class GaussianProcess:
         return 0
 
     def __call__(self, args) -> randvars.Normal:
-        """Finite-dimensional marginal ``Normal(mean(x), cov.matrix(x))``."""
+        """Finite-dimensional marginal ``Normal(mean(x), cov.linop(x))`` -- the covariance stays a lazy,
+        device-assembled operator, as in pn/randprocs/_gaussian_process.py:75-79."""
         x = np.asarray(args, dtype=np.double)
-        return randvars.Normal(mean=np.array(self._mean(x), copy=False).reshape(-1), cov=self._cov.matrix(x))
+        return randvars.Normal(mean=np.array(self._mean(x), copy=False).reshape(-1), cov=self._cov.linop(x))
 
     def var(self, args) -> np.ndarray:
         return self._cov(np.asarray(args, dtype=np.double), None)

@@ -59,6 +59,11 @@ class Normal:
     def shape(self):
         return self._mean.shape
 
+    def __neg__(self):
+        """``-b``: same covariance (kept lazy), negated mean -- e.g. ``b=-f_prior(X)`` for an uncertain right-hand
+        side (experiments/0003_poisson_1d_inverse_rhs.ipynb cell 19)."""
+        return Normal(-self._mean, self._cov)
+
     @property
     def dense_cov(self):
         return self._cov.todense() if isinstance(self._cov, linops.LinearOperator) else self._cov

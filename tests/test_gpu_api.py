@@ -103,7 +103,7 @@ def test_iterative_equals_batch_conditioning():
     np.testing.assert_allclose(one.std(Xt) ** 2, it["var"], rtol=1e-7, atol=1e-10)
     marg = one(Xt[:16])
     np.testing.assert_allclose(marg.mean, it["mean"][:16], rtol=1e-7, atol=1e-10)
-    np.testing.assert_allclose(marg.cov, it["cov"], rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(marg.dense_cov, it["cov"], rtol=1e-7, atol=1e-10)
 
 
 def test_medium_poisson2d_against_oracle():
@@ -257,3 +257,50 @@ def test_one_shot_with_distributed_factor_not_replicated():
     assert np.max(np.abs(post.cov.matrix(Xt[:50]) - post_seq.cov.matrix(Xt[:50]))) <= 1e-9 * sc
     with pytest.raises(NotImplementedError):
         post.condition_on_observations(np.zeros(2), X=Xt[:2] + 0.0123)
+
+
+def test_inverse_rhs_conditioning_lazy_kernel_noise():
+    """Uncertain right-hand side (experiments/0003_poisson_1d_inverse_rhs.ipynb cell 19): ``b = -f_prior(X)`` makes
+    the Gram matrix  L k_u L*(X, X) + k_f(X, X)  (_conditional.py:392-394).  The marginal's covariance stays a lazy
+    operator and is accumulated into the Gram rows on the device; result == dense-``b`` path == numpy formula built
+    from the oracle's matrices, for sequential, one-shot and distributed-layout conditioning."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.linfuncops import diffops
+    from linpde_gp_b200.randprocs import covfuncs
+    from oracle import covfuncs as ocf
+
+    rng = np.random.default_rng(3)
+    ell = 0.25
+    ku_spec = {"scale": 4.0, "base": {"kind": "tensor_product", "factors": [
+        {"kind": "matern", "input_shape": [], "nu": 2.5, "lengthscales": ell},
+        {"kind": "matern", "input_shape": [], "nu": 2.5, "lengthscales": ell}]}}
+    kf_spec = {"scale": 100.0, "base": {"kind": "expquad", "input_shape": [2], "lengthscales": [0.3, 0.4]}}
+    k_u, k_f = helpers.api_kernel(ku_spec), helpers.api_kernel(kf_spec)
+    u_prior = lg.GaussianProcess(lg.functions.Zero(input_shape=(2,)), k_u)
+    f_prior = lg.GaussianProcess(lg.functions.Constant(input_shape=(2,), value=1.5), k_f)
+    Xb = np.stack([np.linspace(0, 1, 33), np.zeros(33)], -1)
+    Xp = rng.uniform(0, 1, (301, 2))
+    Xt = rng.uniform(0, 1, (57, 2))
+    L = -1.0 * diffops.Laplacian((2,))
+    Yb, Yp = np.zeros(33), np.zeros(301)
+    b_lazy = -f_prior(Xp)
+    assert isinstance(b_lazy.cov, lg.linops.CovarianceLinearOperator)
+    b_dense = lg.randvars.Normal(b_lazy.mean, b_lazy.dense_cov)
+    posts = {}
+    for name, b in (("lazy", b_lazy), ("dense", b_dense)):
+        posts[name] = u_prior.condition_on_observations(Yb, X=Xb).condition_on_observations(Yp, X=Xp, L=L, b=b)
+    posts["oneshot"] = lg.ConditionalGaussianProcess.from_observation_batches(u_prior, [(Yb, Xb), (Yp, Xp, L, b_lazy)])
+    posts["blockrows"] = lg.ConditionalGaussianProcess.from_observation_batches(
+        u_prior, [(Yb, Xb), (Yp, Xp, L, b_lazy)], nb=128, replicate=False)
+    # numpy formula from the oracle's matrices
+    lap = [(-1.0, ("wl", np.ones(2)))]
+    G = np.block([[ocf.matrix(ku_spec, None, None, Xb), ocf.matrix(ku_spec, None, lap, Xb, Xp)],
+                  [ocf.matrix(ku_spec, lap, None, Xp, Xb), ocf.matrix(ku_spec, lap, lap, Xp) + ocf.matrix(kf_spec, None, None, Xp)]])
+    KtX = np.hstack([ocf.matrix(ku_spec, None, None, Xt, Xb), ocf.matrix(ku_spec, None, lap, Xt, Xp)])
+    y = np.concatenate([Yb, Yp - (-1.5)])  # residual: Y - (L m_u + b.mean), b.mean = -1.5
+    mean_ref = KtX @ np.linalg.solve(G, y)
+    var_ref = 4.0 - np.einsum("ij,ji->i", KtX, np.linalg.solve(G, KtX.T))
+    sc = max(np.max(np.abs(mean_ref)), 4.0)
+    for name, post in posts.items():
+        assert np.max(np.abs(post.mean(Xt) - mean_ref)) <= 1e-8 * sc, name
+        assert np.max(np.abs(post.var(Xt) - var_ref)) <= 1e-8 * sc, name
