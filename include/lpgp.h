@@ -75,6 +75,9 @@ long long lpgp_launch_count(int reset); /* kernels launched by the library so fa
  * kernels use by default; both agree to a few ulp (tests/test_gpu_kernels.py), the switch exists so that
  * the two can be compared and profiled against each other.                                               */
 #define LPGP_OPT_DIRECT_EXP 1
+/* LPGP_OPT_NO_LOOKAHEAD != 0: lpgp_potrf / lpgp_chol_append run the plain one-stream recursion instead of the
+ * two-stream right-looking pipeline with one panel of lookahead (same factor up to rounding; for A/B timing). */
+#define LPGP_OPT_NO_LOOKAHEAD 2
 int lpgp_set_option(int key, int value);
 /* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and
  * reports the flop count; timed by the caller it yields the roofline denominator of the DMMA kernels on the

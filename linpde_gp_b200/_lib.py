@@ -20,6 +20,7 @@ MAX_SEG = 64
 DIM_MATERN, DIM_EXPQUAD = 0, 1
 GRAM_FULL, GRAM_LOWER = 0, 1
 OPT_DIRECT_EXP = 1
+OPT_NO_LOOKAHEAD = 2
 
 
 class KernelDesc(ctypes.Structure):

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
   double* rdiag = a + LEAF * LDS_A;                  // [LEAF] reciprocals of the diagonal of L
   double* tbuf = rdiag + LEAF;                       // [3][32][33] scratch for the inverse
   __shared__ int s_fail;
+  __shared__ __align__(16) double scol[2 * 32];  // column broadcast buffers of the register Cholesky
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_fail = 0;
 
@@ -91,30 +93,33 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
       __syncthreads();
     }
     // ---- (2) Cholesky of the 32x32 diagonal block in the registers of warp 0 (lane = row) ----
+    // Column j: every lane publishes its (unscaled) column-j entry in shared memory, ONE __syncwarp, then all lanes
+    // read the pivot and the entries of the other rows as broadcast LDS.128 pairs -- one shared-memory round trip
+    // per column instead of 32 warp shuffles; the reciprocal square root of the pivot is computed redundantly by
+    // all lanes (MUFU.RSQ64H + Newton, no divide / square-root subroutine calls on the critical path).  The
+    // rank-1 update uses the unscaled entries: r[c] -= r_ij r_cj / pivot.
     if (warp == 0) {
       double r[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) r[c] = a[(c0 + lane) * LDS_A + c0 + c];
-      bool fail = false;
+      int fail_j = -1;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const double djj = __shfl_sync(0xffffffffu, r[j], j);
-        if (!(djj > 0.0) && !fail) {  // warp-uniform; also catches NaN
-          fail = true;
-          if (lane == 0) {
-            s_fail = 1;
-            atomicCAS(info, 0, global_off + c0 + j + 1);
-          }
-        }
-        const double d = sqrt(djj), inv = 1.0 / d;
-        const double lij = lane > j ? r[j] * inv : (lane == j ? d : r[j]);
-        r[j] = lij;
+        double* colbuf = scol + (j & 1) * 32;
+        colbuf[lane] = r[j];
+        __syncwarp();
+        const double piv = colbuf[j];
+        if (!(piv > 0.0) && fail_j < 0) fail_j = j;  // warp-uniform; also catches NaN
+        const double inv = rsqrt(piv);
+        const double t = r[j] * (inv * inv);
+        r[j] = lane == j ? piv * inv : r[j] * inv;  // L_ij (entries with lane < j are never read)
         if (lane == j) rdiag[c0 + j] = inv;
 #pragma unroll
-        for (int c = j + 1; c < 32; ++c) {
-          const double lcj = __shfl_sync(0xffffffffu, lij, c);
-          r[c] = fma(-lij, lcj, r[c]);  // only entries with lane >= c are meaningful (lower triangle)
-        }
+        for (int c = j + 1; c < 32; ++c) r[c] = fma(-t, colbuf[c], r[c]);  // meaningful for lane >= c only
+      }
+      if (fail_j >= 0 && lane == 0) {
+        s_fail = 1;
+        atomicCAS(info, 0, global_off + c0 + fail_j + 1);
       }
 #pragma unroll
       for (int c = 0; c < 32; ++c) a[(c0 + lane) * LDS_A + c0 + c] = c <= lane ? r[c] : 0.0;
@@ -379,6 +384,106 @@ int potrf_rec(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaS
   return potrf_rec(f, lv, mid, hi, info, st);
 }
 
+// ---- right-looking factorisation with ONE PANEL OF LOOKAHEAD on two streams -----------------------------------
+// The recursion above runs every kernel on one stream, so the latency-bound chain leaf -> small TRSM -> small SYRK
+// of each diagonal block (~0.3 TFLOP/s) is exposed: 1/3 of the run time at N = 16k.  Here the leaf range is cut
+// into panels of `pb` leaves; an internal high-priority *panel* stream carries the critical path of panel p+1
+// (update of block column p+1 with panel p, recursive potrf of its diagonal block, TRSM of the rows below) while
+// the caller's stream applies panel p to the block columns >= p+2 (lower-triangle DMMA SYRK, K = panel width).
+// Events order the two: ev_panel[p] = "panel p final", ev_upd[p] = "columns >= p+2 have seen panels <= p".
+struct LookaheadState {
+  cudaStream_t panel = nullptr;
+  std::vector<cudaEvent_t> ev;
+};
+std::mutex g_la_mutex;
+LookaheadState g_la[LPGP_MAX_DEVICES];
+
+int lookahead_state(int nevents, LookaheadState** out) {
+  int dev = 0;
+  LPGP_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= LPGP_MAX_DEVICES) return -1;
+  LookaheadState& la = g_la[dev];
+  if (!la.panel) {
+    int least = 0, greatest = 0;
+    LPGP_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    LPGP_CHECK(cudaStreamCreateWithPriority(&la.panel, cudaStreamNonBlocking, greatest));
+  }
+  while ((int)la.ev.size() < nevents) {
+    cudaEvent_t e;
+    LPGP_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    la.ev.push_back(e);
+  }
+  *out = &la;
+  return 0;
+}
+
+// panel width in leaves for a range of nl leaves: 512 rows up to N = 16k, 1024 at 32k, 2048 from 64k
+inline int lookahead_panel_leaves(int nl) {
+  int pb = nl / 32;
+  return pb < 4 ? 4 : (pb > 16 ? 16 : pb);
+}
+
+int potrf_lookahead(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st) {
+  const int pb = lookahead_panel_leaves(hi - lo);
+  const int P = (hi - lo + pb - 1) / pb;
+  std::lock_guard<std::mutex> guard(g_la_mutex);
+  LookaheadState* la = nullptr;
+  int rc = lookahead_state(2 * P + 1, &la);
+  if (rc) return rc;
+  cudaStream_t ps = la->panel;
+  cudaEvent_t* ev_panel = la->ev.data();
+  cudaEvent_t* ev_upd = la->ev.data() + P;
+  cudaEvent_t ev_fork = la->ev[2 * P];
+  auto leaf_lo = [&](int p) { return lo + p * pb < hi ? lo + p * pb : hi; };
+  const int64_t n_hi = lv.off[hi];
+  const int64_t ld = f->ld;
+  // factor panel p on stream s: diagonal block, then the rows below it
+  auto factor_panel = [&](int p, cudaStream_t s) -> int {
+    const int l0 = leaf_lo(p), l1 = leaf_lo(p + 1);
+    int r = potrf_rec(f, lv, l0, l1, info, s);
+    if (r) return r;
+    const int64_t r0 = lv.off[l0], r1 = lv.off[l1];
+    if (r1 < n_hi) r = trsm_rec(f, lv, l0, l1, f->L + r1 * ld + r0, n_hi - r1, ld, s);
+    return r;
+  };
+  LPGP_CHECK(cudaEventRecord(ev_fork, st));
+  LPGP_CHECK(cudaStreamWaitEvent(ps, ev_fork, 0));
+  rc = factor_panel(0, ps);
+  if (rc) return rc;
+  LPGP_CHECK(cudaEventRecord(ev_panel[0], ps));
+  for (int p = 0; p < P; ++p) {
+    const int64_t r0 = lv.off[leaf_lo(p)], r1 = lv.off[leaf_lo(p + 1)];
+    const int64_t kb = r1 - r0;
+    if (p + 1 < P) {
+      // panel stream: block column p+1 -= L[r1:, panel p] L[r1:r2, panel p]^T, then factor panel p+1
+      const int64_t r2 = lv.off[leaf_lo(p + 2)];
+      if (p >= 1) LPGP_CHECK(cudaStreamWaitEvent(ps, ev_upd[p - 1], 0));
+      const double* A = f->L + r1 * ld + r0;
+      rc = lpgp_gemm_nt(n_hi - r1, r2 - r1, kb, -1.0, A, ld, A, ld, 1.0, f->L + r1 * ld + r1, ld, 0, ps);
+      if (rc) return rc;
+      rc = factor_panel(p + 1, ps);
+      if (rc) return rc;
+      LPGP_CHECK(cudaEventRecord(ev_panel[p + 1], ps));
+      if (p + 2 < P) {
+        // caller's stream: trailing update of the block columns >= p+2 with panel p (lower tiles only)
+        LPGP_CHECK(cudaStreamWaitEvent(st, ev_panel[p], 0));
+        const double* A2 = f->L + r2 * ld + r0;
+        rc = lpgp_gemm_nt(n_hi - r2, n_hi - r2, kb, -1.0, A2, ld, A2, ld, 1.0, f->L + r2 * ld + r2, ld, 1, st);
+        if (rc) return rc;
+        LPGP_CHECK(cudaEventRecord(ev_upd[p], st));
+      }
+    }
+  }
+  LPGP_CHECK(cudaStreamWaitEvent(st, ev_panel[P - 1], 0));  // join
+  return 0;
+}
+
+// factor the leaf range [lo, hi): lookahead pipeline for ranges of at least three panels, else the recursion
+int potrf_range(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st) {
+  if (!g_lpgp_no_lookahead && hi - lo >= 3 * lookahead_panel_leaves(hi - lo)) return potrf_lookahead(f, lv, lo, hi, info, st);
+  return potrf_rec(f, lv, lo, hi, info, st);
+}
+
 int check_factor(const lpgp_factor* f) {
   if (!f || !f->L || !f->dinv) return -1;
   if (f->n < 1 || f->ld < f->n || (f->ld % 2) || ((uintptr_t)f->L % 16)) return -1;
@@ -424,7 +529,7 @@ int potrf_impl(lpgp_factor* f, void* stream, bool sync) {
   const bool dbg = getenv("LPGP_DEBUG_TIMING") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
   const long long l0 = g_lpgp_launches;
-  rc = potrf_rec(f, lv, 0, nl, info, st);
+  rc = potrf_range(f, lv, 0, nl, info, st);
   if (rc) return rc;
   if (!sync) return 0;
   const auto t1 = std::chrono::steady_clock::now();
@@ -464,7 +569,7 @@ extern "C" int lpgp_chol_append(lpgp_factor* f, void* stream) {
   if (rc) return rc;
   rc = lpgp_gemm_nt(nn, nn, np, -1.0, A21, f->ld, A21, f->ld, 1.0, f->L + np * f->ld + np, f->ld, 1, st);  // Schur
   if (rc) return rc;
-  rc = potrf_rec(f, lv, l0, nl, info, st);
+  rc = potrf_range(f, lv, l0, nl, info, st);
   if (rc) return rc;
   return finish_info(info, st);
 }

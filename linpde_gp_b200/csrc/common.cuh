@@ -12,6 +12,9 @@ extern long long g_lpgp_launches;
 #define LPGP_COUNT(n) (g_lpgp_launches += (n))
 // diagnostics switch (lpgp_set_option): 1 = evaluate Matern exponentials directly instead of the separable form
 extern int g_lpgp_no_sep;
+// 1 = factor on one stream with the plain recursion (no panel lookahead)
+extern int g_lpgp_no_lookahead;
+#define LPGP_MAX_DEVICES 32
 
 #define LPGP_CHECK_LAUNCH()                            \
   do {                                                 \

@@ -73,8 +73,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int m, int n,
-                   int k, double alpha, double beta, double* __restrict__ C, int64_t ldc, int lower, int tiles_n,
-                   int vec_ok, const int* __restrict__ col_limit, int col_base) {
+                   int k, double alpha, double beta, double* __restrict__ C, int64_t ldc, int lower, int tiles_m,
+                   int tiles_n, int vec_ok, const int* __restrict__ col_limit, int col_base) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, NCONSUMER_WARPS = Cfg::NCONSUMER_WARPS, MI = Cfg::MI, NJ = Cfg::NJ;
   constexpr int STAGE_A_BYTES = Cfg::STAGE_A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -82,18 +82,43 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
 
-  // ---- tile coordinates ----------------------------------------------------------------------------
+  // ---- tile coordinates: GROUPED rasterisation -----------------------------------------------------------
+  // CTAs are scheduled in blockIdx order, ~148 at a time.  Walking the tile grid in bands of RASTER_GM tile rows,
+  // column by column inside a band, makes one wave touch ~RASTER_GM A strips + ~148/RASTER_GM B strips instead of
+  // ~2 + tiles_n (row-major order): the k-blocks of an operand strip are then shared through L2 by the CTAs of
+  // the wave that need them, and DRAM sees each strip once per band instead of once per tile row.
   int tm, tn;
-  if (lower) {  // linear index over the lower triangle of the tile grid, row-major
+  if (lower) {
+    // lower triangle, bands of 8 tile rows: band b holds the full columns 0..8b (8 rows each) followed by the
+    // 28 tiles of the small triangle; tiles before band b: 32 b^2 + 4 b
     const long long x = blockIdx.x;
-    long long r = (long long)((sqrt(8.0 * (double)x + 1.0) - 1.0) * 0.5);
-    while (r * (r + 1) / 2 > x) --r;
-    while ((r + 1) * (r + 2) / 2 <= x) ++r;
-    tm = (int)r;
-    tn = (int)(x - r * (r + 1) / 2);
+    long long b = (long long)((sqrt(16.0 + 128.0 * (double)x) - 4.0) * (1.0 / 64.0));
+    while (32 * b * b + 4 * b > x) --b;
+    while (32 * (b + 1) * (b + 1) + 4 * (b + 1) <= x) ++b;
+    int y = (int)(x - (32 * b * b + 4 * b));
+    const int b8 = (int)b * 8;
+    if (y < 8 * (b8 + 1)) {
+      tn = y >> 3;
+      tm = b8 + (y & 7);
+    } else {
+      y -= 8 * (b8 + 1);
+      int c = 0;
+      while (y >= 7 - c) {
+        y -= 7 - c;
+        ++c;
+      }
+      tn = b8 + 1 + c;
+      tm = tn + y;
+    }
+    if (tm >= tiles_m) return;  // the last band is launched whole
   } else {
-    tm = blockIdx.x / tiles_n;
-    tn = blockIdx.x % tiles_n;
+    constexpr int RASTER_GM = 12;
+    const int per_band = RASTER_GM * tiles_n;
+    const int band = blockIdx.x / per_band, y = blockIdx.x % per_band;
+    const int first = band * RASTER_GM;
+    const int gsz = min(RASTER_GM, tiles_m - first);
+    tm = first + y % gsz;
+    tn = y / gsz;
   }
   const int row0 = tm * BM, col0 = tn * BN;
   // optional per-row-block column limit (distributed block-row layouts: the rows of one 128-row block only need
@@ -287,11 +312,12 @@ int launch(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64
   rc = make_map(&tmB, B, n, k > 0 ? k : 1, ldb, Cfg::BN);
   if (rc) return rc;
   const int64_t tiles_m = ceil_div64(m, Cfg::BM), tiles_n = ceil_div64(n, Cfg::BN);
-  const int64_t ntiles = lower ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
+  const int64_t bands = ceil_div64(tiles_m, 8);  // lower: whole bands of 8 tile rows (see the kernel)
+  const int64_t ntiles = lower ? 32 * bands * bands + 4 * bands : tiles_m * tiles_n;
   if (ntiles > INT32_MAX) return -1;
   const int vec_ok = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
   gemm_nt_kernel<Cfg><<<(unsigned)ntiles, Cfg::NTHREADS, Cfg::SMEM_BYTES, (cudaStream_t)stream>>>(
-      tmA, tmB, (int)m, (int)n, (int)k, alpha, beta, C, ldc, lower, (int)tiles_n, vec_ok, col_limit, col_base);
+      tmA, tmB, (int)m, (int)n, (int)k, alpha, beta, C, ldc, lower, (int)tiles_m, (int)tiles_n, vec_ok, col_limit, col_base);
   LPGP_CHECK_LAUNCH();
   return 0;
 }

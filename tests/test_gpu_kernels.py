@@ -178,6 +178,47 @@ def test_potrf_vs_torch(be, n):
     assert abs(f.logdet() - torch.logdet(G).item()) <= 1e-9 * max(1.0, abs(torch.logdet(G).item()))
 
 
+@pytest.mark.parametrize("sizes", [(6000,), (2000, 3210), (130, 2, 5000)])
+def test_potrf_lookahead_pipeline_matches_one_stream_recursion(be, sizes):
+    """Ranges of >= 3 panels are factored by the two-stream right-looking pipeline with one panel of lookahead
+    (cholesky.cu: potrf_lookahead); LPGP_OPT_NO_LOOKAHEAD selects the one-stream recursion.  Same factor up to
+    rounding, for lpgp_potrf and for lpgp_chol_append (ragged segments)."""
+    from linpde_gp_b200 import _lib
+
+    n = sum(sizes)
+    G = _spd(n, n)
+    Ls = []
+    for flag in (0, 1):
+        assert _lib.lib.lpgp_set_option(_lib.OPT_NO_LOOKAHEAD, flag) == 0
+        try:
+            f, off = None, 0
+            for s in sizes:
+                f = be.DeviceFactor([s]) if f is None else f.extended(s)
+                f.L[off : off + s, : off + s].copy_(G[off : off + s, : off + s])
+                f.potrf() if off == 0 else f.append_last()
+                off += s
+            torch.cuda.synchronize()
+            Ls.append(torch.tril(f.L).clone())
+        finally:
+            _lib.lib.lpgp_set_option(_lib.OPT_NO_LOOKAHEAD, 0)
+    L_ref = torch.linalg.cholesky(G)
+    sc = L_ref.abs().max().item()
+    assert (Ls[0] - L_ref).abs().max().item() <= 1e-12 * sc
+    assert (Ls[1] - L_ref).abs().max().item() <= 1e-12 * sc
+    assert (Ls[0] - Ls[1]).abs().max().item() <= 1e-13 * sc
+
+
+def test_potrf_lookahead_reports_first_failing_minor(be):
+    n = 5000
+    G = _spd(n, 3)
+    G[3300, 3300] = -1.0
+    f = be.DeviceFactor([n])
+    f.L.copy_(G)
+    with pytest.raises(np.linalg.LinAlgError) as ei:
+        f.potrf()
+    assert "3301" in str(ei.value)
+
+
 def test_potrf_not_positive_definite_raises(be):
     n = 300
     G = _spd(n, 1)

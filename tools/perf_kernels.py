@@ -38,17 +38,26 @@ if "gemm" in which:
         fl = 2.0 * m * n * k * (0.5 if low else 1.0)
         print(f"gemm_nt m={m} n={n} k={k} lower={low}: {ms:.2f} ms  {fl/ms*1e-9:.2f} TFLOP/s", flush=True)
         del A, B, C
-if "potrf" in which:
-    for n in (8192, 16384, 32768):
-        X = torch.randn(n, n, dtype=torch.float64, device="cuda")
-        G = X @ X.T / n; del X
-        G.diagonal().add_(2.0)
+if "potrf" in which or "potrf64" in which:
+    from linpde_gp_b200 import _lib
+    sizes = (8192, 16384, 32768) if "potrf" in which else ()
+    if "potrf64" in which:
+        sizes = sizes + (65536,)
+    for n in sizes:
         f = be.DeviceFactor([n])
+        # SPD test matrix built in place, block-wise (no second n x n buffer at n = 65536)
+        G = be.alloc_matrix(n, n)
+        Xs = torch.randn(n, 512, dtype=torch.float64, device="cuda")
+        torch.mm(Xs, Xs.T, out=G)  # n is a multiple of 16: G is contiguous
+        G.mul_(1.0 / 512); G.diagonal().add_(2.0); del Xs
         def run():
             f.L.copy_(G); f.potrf()
         tcopy = tm(lambda: f.L.copy_(G))
-        ms = tm(run, reps=2) - tcopy
-        print(f"potrf n={n}: {ms:.1f} ms  {n**3/3/ms*1e-9:.2f} TFLOP/s", flush=True)
+        for flag, label in ((1, "one-stream recursion"), (0, "lookahead pipeline")):
+            _lib.lib.lpgp_set_option(_lib.OPT_NO_LOOKAHEAD, flag)
+            ms = tm(run, reps=2) - tcopy
+            print(f"potrf n={n} [{label}]: {ms:.1f} ms  {n**3/3/ms*1e-9:.2f} TFLOP/s", flush=True)
+        _lib.lib.lpgp_set_option(_lib.OPT_NO_LOOKAHEAD, 0)
         if "trsm" in which:
             m = 8192
             Xr = be.alloc_matrix(m, n).normal_()
