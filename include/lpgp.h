@@ -109,6 +109,17 @@ int lpgp_add_diag(double* A, int64_t n, int64_t ld, const double* v, double scal
 /* mirror the lower triangle into the upper one (todense() of a block assembled in LOWER mode).        */
 int lpgp_symmetrize_lower(double* A, int64_t n, int64_t ld, void* stream);
 
+/* Tensor-grid structure path.  Dense assembly of a sum of Kronecker products,
+ *   out[(i1*n2 + i2)*ld + (j1*m2 + j2)] (+)= sum_t alpha[t] * A[t][i1*lda[t] + j1] * B[t][i2*ldb[t] + j2],
+ * A[t]: n1 x m1, B[t]: n2 x m2 (device, row-major).  Replaces .todense() of the lazy operators the reference
+ * builds for TensorProductGrid inputs: functools.reduce(pn.linops.Kronecker, ...) in
+ * src/linpde_gp/randprocs/covfuncs/_tensor_product.py:64-82 and the sum over operator terms of Kronecker products in
+ * .../covfuncs/linfuncops/diffops/_tensor_product.py:84-119, 140-156.  `A`, `lda`, `B`, `ldb`, `alpha` are HOST
+ * arrays of length nterms (the pointers inside A / B are device pointers).  mode / accumulate as lpgp_gram.   */
+int lpgp_kron_sum(int nterms, const double* const* A, const int64_t* lda, const double* const* B, const int64_t* ldb,
+                  const double* alpha, int64_t n1, int64_t m1, int64_t n2, int64_t m2, double* out, int64_t ld,
+                  int mode, int accumulate, void* stream);
+
 /* (2) dense FP64 linear algebra on the DMMA (FP64 tensor core) path ---------------------------------------
  * C[m x n] = beta*C + alpha * A[m x k] * B[n x k]^T  (all row-major);  lower != 0: only tiles that intersect
  * the lower triangle of the (square) C are updated (SYRK-style trailing update).  C may alias A only for

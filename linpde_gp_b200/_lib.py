@@ -78,6 +78,8 @@ def _load() -> ctypes.CDLL:
         "lpgp_gram_diag": (ci, [KD, i64, vp, dbl, vp]),
         "lpgp_add_diag": (ci, [vp, i64, i64, vp, dbl, vp]),
         "lpgp_symmetrize_lower": (ci, [vp, i64, i64, vp]),
+        "lpgp_kron_sum": (ci, [ci, ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(vp), ctypes.POINTER(i64),
+                          ctypes.POINTER(dbl), i64, i64, i64, i64, vp, i64, ci, ci, vp]),
         "lpgp_gemm_nt": (ci, [i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, ci, vp]),
         "lpgp_gemm_nt_limited": (ci, [i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, vp, i64, vp]),
         "lpgp_factor_dinv_bytes": (ctypes.c_size_t, [ctypes.POINTER(i64), ci]),
@@ -103,7 +105,7 @@ def _load() -> ctypes.CDLL:
 
 lib = _load()
 EXPORTED = (
-    "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_set_option lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower "
+    "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_set_option lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower lpgp_kron_sum "
     "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
     "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq"
 ).split()

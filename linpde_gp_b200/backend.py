@@ -107,6 +107,29 @@ def symmetrize_lower(A: torch.Tensor) -> None:
     check(lib.lpgp_symmetrize_lower(_ptr(A), A.shape[0], _ld(A), _stream()), "lpgp_symmetrize_lower")
 
 
+def kron_sum(terms, out: Optional[torch.Tensor] = None, *, lower: bool = False, accumulate: bool = False) -> torch.Tensor:
+    """out (+)= sum_t alpha_t * kron(A_t, B_t) for ``terms = [(alpha, A, B), ...]`` (device matrices, all A_t of one
+    shape and all B_t of one shape).  One multiply-add per term and entry: HBM-write bound."""
+    _require_cuda()
+    assert len(terms) >= 1
+    (n1, m1), (n2, m2) = terms[0][1].shape, terms[0][2].shape
+    assert all(A.shape == (n1, m1) and B.shape == (n2, m2) for _, A, B in terms)
+    if out is None:
+        out = alloc_matrix(n1 * n2, m1 * m2)
+    assert out.shape == (n1 * n2, m1 * m2)
+    nt = len(terms)
+    vp, i64, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double
+    A = (vp * nt)(*[t[1].data_ptr() for t in terms])
+    B = (vp * nt)(*[t[2].data_ptr() for t in terms])
+    lda = (i64 * nt)(*[_ld(t[1]) for t in terms])
+    ldb = (i64 * nt)(*[_ld(t[2]) for t in terms])
+    al = (dbl * nt)(*[float(t[0]) for t in terms])
+    rc = lib.lpgp_kron_sum(nt, A, lda, B, ldb, al, n1, m1, n2, m2, _ptr(out), _ld(out),
+                           _lib.GRAM_LOWER if lower else _lib.GRAM_FULL, int(accumulate), _stream())
+    check(rc, "lpgp_kron_sum")
+    return out
+
+
 def gemm_nt(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, alpha: float = 1.0, beta: float = 0.0,
             lower: bool = False) -> torch.Tensor:
     """C = beta*C + alpha * A @ B.T on the DMMA path."""

@@ -54,6 +54,10 @@ class LinearFunctional:
 
 class _EvaluationFunctional(LinearFunctional):
     def __init__(self, input_domain_shape, input_codomain_shape, X):
+        from .randprocs import covfuncs
+
+        # an intact TensorProductGrid is remembered: conditioning assembles its Gram blocks from Kronecker factors
+        self._grid = X if covfuncs._grid_factors(X) is not None else None  # pylint: disable=protected-access
         X = np.asarray(X, dtype=np.double)
         input_domain_shape = _as_shape(input_domain_shape)
         input_codomain_shape = _as_shape(input_codomain_shape)
@@ -69,7 +73,7 @@ class _EvaluationFunctional(LinearFunctional):
         return self._X
 
     def _as_observation(self):
-        return None, self._X
+        return None, (self._X if self._grid is None else self._grid)
 
 
 class CompositeLinearFunctional(LinearFunctional):

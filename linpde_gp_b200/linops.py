@@ -47,6 +47,66 @@ class LinearOperator:
     def todense(self, cache: bool = True) -> np.ndarray:
         return self.device_dense()[: self.shape[0], : self.shape[1]].cpu().numpy()
 
+    def assemble_into(self, out: torch.Tensor, lower: bool = False, accumulate: bool = False) -> torch.Tensor:
+        """Write (or add) the matrix into ``out`` (a view into a larger device buffer); structured operators
+        override this with their own assembly kernel."""
+        D = self.device_dense()[: self.shape[0], : self.shape[1]]
+        if accumulate:
+            out.add_(D)
+        else:
+            out.copy_(D)
+        return out
+
+    def kron_terms(self):
+        """``[(alpha, A_dev, B_dev), ...]`` with ``self == sum alpha * kron(A, B)``, or ``None``."""
+        return None
+
+    # -- arithmetic (pn/linops/_arithmetic_fallbacks.py: ScaledLinearOperator / SumLinearOperator) -------------
+    def __rmul__(self, other):
+        if np.ndim(other) == 0:
+            return ScaledLinearOperator(self, other)
+        return NotImplemented
+
+    def __neg__(self):
+        return ScaledLinearOperator(self, -1.0)
+
+    def __add__(self, other):
+        if isinstance(other, LinearOperator):
+            return SumLinearOperator(self, other)
+        return NotImplemented
+
+    def __radd__(self, other):
+        if np.ndim(other) == 0 and other == 0:  # sum([...]) / the reference's `res_zero_value=0`
+            return self
+        return NotImplemented
+
+    # -- SPD solves (pn/linops/_linear_operator.py:267-315) ------------------------------------------------
+    _factor = None
+
+    def cholesky(self, lower: bool = True) -> "CholeskyFactor":
+        if not self.is_square:
+            raise np.linalg.LinAlgError("The Cholesky decomposition is only defined for square matrices.")
+        if self.is_symmetric is False:
+            raise np.linalg.LinAlgError("The Cholesky decomposition is only defined for symmetric matrices.")
+        if self._factor is None:
+            n = self.shape[0]
+            f = backend.DeviceFactor([n + n % 2])
+            self.assemble_into(f.L[:n, :n], lower=True)
+            if n % 2:
+                f.L[n, : n + 1] = 0.0
+                f.L[n, n] = 1.0
+            try:
+                f.potrf()
+            except np.linalg.LinAlgError:
+                self.is_positive_definite = False
+                raise
+            self.is_positive_definite = True
+            self._factor = CholeskyFactor(f, n)
+        return self._factor if lower else self._factor.T
+
+    def solve(self, B):
+        return self.cholesky(True).solve_spd(B)
+
     @property
     def T(self):
         return _Transposed(self)
@@ -170,31 +230,6 @@ class CovarianceLinearOperator(LinearOperator):
             self._dense = out
         return self._dense
 
-    # -- SPD solves (pn/linops/_linear_operator.py:267-315) ------------------------------------------------
-    def cholesky(self, lower: bool = True) -> "CholeskyFactor":
-        if not self.is_square:
-            raise np.linalg.LinAlgError("The Cholesky decomposition is only defined for square matrices.")
-        if self.is_symmetric is False:
-            raise np.linalg.LinAlgError("The Cholesky decomposition is only defined for symmetric matrices.")
-        if self._factor is None:
-            n = self.shape[0]
-            f = backend.DeviceFactor([n + n % 2])
-            self.assemble_into(f.L[:n, :n], lower=True)
-            if n % 2:
-                f.L[n, : n + 1] = 0.0
-                f.L[n, n] = 1.0
-            try:
-                f.potrf()
-            except np.linalg.LinAlgError:
-                self.is_positive_definite = False
-                raise
-            self.is_positive_definite = True
-            self._factor = CholeskyFactor(f, n)
-        return self._factor if lower else self._factor.T
-
-    def solve(self, B):
-        return self.cholesky(True).solve_spd(B)
-
 
 class CholeskyFactor(LinearOperator):
     """Lower-triangular factor ``L`` of an SPD matrix, resident on the device together with its inverted
@@ -235,3 +270,141 @@ class CholeskyFactor(LinearOperator):
         t = _Transposed(self)
         t.is_upper_triangular = True
         return t
+
+
+def _aligned(A: torch.Tensor) -> torch.Tensor:
+    """``A`` itself if the DMMA GEMM can read it through TMA (even leading dimension, 16-byte aligned), else a copy."""
+    if A.dim() == 2 and A.stride(1) == 1 and A.stride(0) % 2 == 0 and A.data_ptr() % 16 == 0 and A.stride(0) >= A.shape[1]:
+        return A
+    B = backend.alloc_matrix(*A.shape)
+    B.copy_(A)
+    return B
+
+
+class ScaledLinearOperator(LinearOperator):
+    """``scalar * A`` (pn/linops/_arithmetic_fallbacks.py:26-60)."""
+
+    def __init__(self, linop: LinearOperator, scalar):
+        if np.ndim(scalar) != 0:
+            raise TypeError("`scalar` must be a scalar")
+        super().__init__(linop.shape)
+        self._linop = linop
+        self._scalar = float(scalar)
+        self.is_symmetric = linop.is_symmetric
+
+    def kron_terms(self):
+        t = self._linop.kron_terms()
+        return None if t is None else [(self._scalar * a, A, B) for a, A, B in t]
+
+    def device_dense(self):
+        t = self.kron_terms()
+        if t is not None:
+            return backend.kron_sum(t)
+        return self._scalar * self._linop.device_dense()[: self.shape[0], : self.shape[1]]
+
+    def assemble_into(self, out, lower=False, accumulate=False):
+        t = self.kron_terms()
+        if t is not None:
+            return backend.kron_sum(t, out=out, lower=lower, accumulate=accumulate)
+        return super().assemble_into(out, lower=lower, accumulate=accumulate)
+
+    def __matmul__(self, other):
+        return self._scalar * (self._linop @ other)
+
+
+class SumLinearOperator(LinearOperator):
+    """``A + B + ...`` (pn/linops/_arithmetic_fallbacks.py:63-117); nested sums are flattened."""
+
+    def __init__(self, *summands: LinearOperator):
+        flat = []
+        for s_ in summands:
+            flat.extend(s_._summands if isinstance(s_, SumLinearOperator) else [s_])
+        if not all(s_.shape == flat[0].shape for s_ in flat):
+            raise ValueError("All summands must have the same shape.")
+        super().__init__(flat[0].shape)
+        self._summands = tuple(flat)
+        if all(s_.is_symmetric for s_ in flat):
+            self.is_symmetric = True
+
+    def kron_terms(self):
+        out = []
+        for s_ in self._summands:
+            t = s_.kron_terms()
+            if t is None:
+                return None
+            out.extend(t)
+        if not all(A.shape == out[0][1].shape and B.shape == out[0][2].shape for _, A, B in out):
+            return None
+        return out
+
+    def assemble_into(self, out, lower=False, accumulate=False):
+        t = self.kron_terms()
+        if t is not None:
+            return backend.kron_sum(t, out=out, lower=lower, accumulate=accumulate)
+        for i, s_ in enumerate(self._summands):
+            s_.assemble_into(out, lower=lower, accumulate=accumulate or i > 0)
+        return out
+
+    def device_dense(self):
+        out = backend.alloc_matrix(*self.shape)
+        return self.assemble_into(out)
+
+    def __matmul__(self, other):
+        res = None
+        for s_ in self._summands:
+            v = s_ @ other
+            res = v if res is None else res + v
+        return res
+
+
+class Kronecker(LinearOperator):
+    """Kronecker product ``A (x) B`` (pn/linops/_kronecker.py:17-166) with device-resident factors.
+
+    ``todense`` / ``assemble_into`` run the Kronecker assembly kernel (``lpgp_kron_sum``, one multiply per entry,
+    HBM-write bound); ``@`` uses ``(A (x) B) vec(X) = vec(A X B^T)`` -- two DMMA GEMMs with the small factors, the
+    big matrix is never formed."""
+
+    def __init__(self, A: LinearOperator, B: LinearOperator):
+        self.A = A if isinstance(A, LinearOperator) else Matrix(A)
+        self.B = B if isinstance(B, LinearOperator) else Matrix(B)
+        super().__init__((self.A.shape[0] * self.B.shape[0], self.A.shape[1] * self.B.shape[1]))
+        if self.A.is_symmetric and self.B.is_symmetric:
+            self.is_symmetric = True
+        self._mats = None
+
+    def _factor_matrices(self):
+        if self._mats is None:  # the (small) factor matrices are assembled once
+            self._mats = (self.A.device_dense()[: self.A.shape[0], : self.A.shape[1]],
+                          self.B.device_dense()[: self.B.shape[0], : self.B.shape[1]])
+        return self._mats
+
+    def kron_terms(self):
+        A, B = self._factor_matrices()
+        return [(1.0, A, B)]
+
+    def device_dense(self):
+        return backend.kron_sum(self.kron_terms())
+
+    def assemble_into(self, out, lower=False, accumulate=False):
+        return backend.kron_sum(self.kron_terms(), out=out, lower=lower, accumulate=accumulate)
+
+    def __matmul__(self, other):
+        if isinstance(other, LinearOperator):
+            other = other.todense()
+        x = np.asarray(other, dtype=np.double)
+        vec = x.ndim == 1
+        if vec:
+            x = x[:, None]
+        if x.shape[0] != self.shape[1]:
+            raise ValueError(f"shape mismatch: {self.shape} @ {x.shape}")
+        A, B = self._factor_matrices()
+        (n1, m1), (n2, m2) = A.shape, B.shape
+        k = x.shape[1]
+        Xd = backend.to_device(np.ascontiguousarray(x.T)).reshape(k * m1, m2)  # rows (c, j1), columns j2
+        T = backend.alloc_matrix(k * m1, n2)
+        backend.gemm_nt(_aligned(Xd), _aligned(B), T, 1.0, 0.0)                # T[(c, j1), i2] = sum_j2 X B[i2, j2]
+        T2 = _aligned(T.reshape(k, m1, n2).permute(0, 2, 1).reshape(k * n2, m1))  # rows (c, i2), columns j1
+        U = backend.alloc_matrix(k * n2, n1)
+        backend.gemm_nt(T2, _aligned(A), U, 1.0, 0.0)                           # U[(c, i2), i1] = sum_j1 T A[i1, j1]
+        res = U.reshape(k, n2, n1).permute(2, 1, 0).reshape(n1 * n2, k).cpu().numpy()
+        return res[:, 0] if vec else res

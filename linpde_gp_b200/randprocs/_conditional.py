@@ -37,10 +37,31 @@ def _descs(k: covfuncs.CovarianceFunction):
     return [k.descriptor()]
 
 
+def _assemble_kronecker(k: covfuncs.CovarianceFunction, grid0, grid1, out: "torch.Tensor", lower: bool) -> bool:
+    """Tensor-grid structure path: if both point sets are intact TensorProductGrids and
+    ``k.linop`` yields a sum of Kronecker products, densify it with the Kronecker assembly kernel (one multiply-add
+    per term and entry, HBM-write bound) instead of evaluating the kernel pair by pair.  ``grid1=None`` = symmetric
+    block.  Returns False when the structure is not available (the caller then uses the pairwise Gram kernel)."""
+    if grid0 is None or (grid1 is None and not lower):  # off-diagonal blocks need BOTH grids
+        return False
+    try:
+        op = k.linop(grid0, grid1)
+    except NotImplementedError:
+        return False
+    terms = op.kron_terms()
+    if terms is None:
+        return False
+    backend.kron_sum(terms, out=out, lower=lower)
+    return True
+
+
 class _Block:
     """One observation batch: points, operator, logical / physical (even-padded) size, offset in the factor."""
 
     def __init__(self, X_host: np.ndarray, op: Optional[LinearFunctionOperator], d: int, col_off: int):
+        # intact TensorProductGrid: Gram blocks against other gridded batches are sums of Kronecker products
+        self.grid = X_host if covfuncs._grid_factors(X_host) is not None else None  # pylint: disable=protected-access
+        X_host = np.asarray(X_host, dtype=np.double)
         self.X_host = X_host
         self.op = op
         self.X = backend.points(X_host, d)
@@ -328,15 +349,17 @@ class ConditionalGaussianProcess(GaussianProcess):
             kj = k if pb.op is None else pb.op(k, argnum=1)
             kij = kj if blk.op is None else blk.op(kj, argnum=0)
             out = rows[:n, pb.col_off : pb.col_off + pb.n]
-            for i, dsc in enumerate(_descs(kij)):
-                backend.gram(dsc, blk.X, pb.X, out=out, accumulate=i > 0)
+            if not _assemble_kronecker(kij, blk.grid, pb.grid, out, lower=False):
+                for i, dsc in enumerate(_descs(kij)):
+                    backend.gram(dsc, blk.X, pb.X, out=out, accumulate=i > 0)
             if pb.n_phys != pb.n:
                 rows[:, pb.col_off + pb.n] = 0.0
         kj = k if blk.op is None else blk.op(k, argnum=1)
         kii = kj if blk.op is None else blk.op(kj, argnum=0)
         D = rows[:n, r0 : r0 + n]
-        for i, dsc in enumerate(_descs(kii)):
-            backend.gram(dsc, blk.X, None, out=D, lower=True, accumulate=i > 0)
+        if not _assemble_kronecker(kii, blk.grid, None, D, lower=True):
+            for i, dsc in enumerate(_descs(kii)):
+                backend.gram(dsc, blk.X, None, out=D, lower=True, accumulate=i > 0)
         if noise is not None:
             kind, val = noise
             if kind == "diag":

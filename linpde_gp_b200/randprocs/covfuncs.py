@@ -16,7 +16,43 @@ import numpy as np
 
 from .. import _lowering, backend
 from ..functions import _as_shape
-from ..linops import CovarianceLinearOperator
+from ..linops import CovarianceLinearOperator, Kronecker
+
+
+class TensorProductGrid(np.ndarray):
+    """Points of a tensor-product grid, ``grid[i_1, ..., i_d] = (f_1[i_1], ..., f_d[i_d])``, that remember their 1-D
+    factors (src/linpde_gp/randprocs/covfuncs/_tensor_product.py:133-152).  Tensor-product kernels evaluated on two
+    such grids give Kronecker-structured matrices; ``linop`` exploits that (see :class:`TensorProduct`)."""
+
+    def __new__(cls, *factors, indexing="ij"):
+        factors = tuple(np.asarray(f, dtype=np.double) for f in factors)
+        if not factors or any(f.ndim != 1 for f in factors):
+            raise ValueError("the factors of a TensorProductGrid must be one-dimensional arrays")
+        mesh = np.meshgrid(*factors, copy=True, sparse=False, indexing=indexing)
+        obj = np.stack(mesh, axis=-1).view(cls)
+        obj.factors = factors
+        obj.indexing = indexing
+        return obj
+
+    def __array_finalize__(self, obj):
+        # slices / arithmetic results are plain point sets: they do not inherit the factorisation
+        self.factors = None
+        self.indexing = None
+
+
+def _grid_factors(x):
+    """The 1-D factors of ``x`` if it is an intact "ij"-ordered TensorProductGrid (C-order flattening of the grid
+    equals the Kronecker ordering of the factors), else ``None``."""
+    if isinstance(x, TensorProductGrid) and getattr(x, "factors", None) is not None and x.indexing == "ij":
+        return x.factors
+    return None
+
+
+def _kron_all(ops):
+    out = ops[0]
+    for o in ops[1:]:
+        out = Kronecker(out, o)
+    return out
 
 
 class CovarianceFunction:
@@ -230,6 +266,14 @@ class TensorProduct(CovarianceFunction):
     def factors(self):
         return self._factors
 
+    def linop(self, x0, x1=None):
+        """Kronecker product of the factors' 1-D covariance matrices when both inputs are tensor-product grids
+        (src/linpde_gp/randprocs/covfuncs/_tensor_product.py:64-82), else the generic lazy covariance matrix."""
+        f0, f1 = _grid_factors(x0), (None if x1 is None else _grid_factors(x1))
+        if f0 is not None and len(f0) == len(self._factors) and (x1 is None or (f1 is not None and len(f1) == len(f0))):
+            return _kron_all([k.linop(f0[i], None if x1 is None else f1[i]) for i, k in enumerate(self._factors)])
+        return super().linop(x0, x1)
+
     def _product_form(self):
         fs, scale = [], 1.0
         for k in self._factors:
@@ -263,6 +307,13 @@ class ScaledCovarianceFunction(CovarianceFunction):
         f, t0, t1, s = self._covfunc._product_form()
         return f, t0, t1, s * float(self._scalar)
 
+    def linop(self, x0, x1=None):
+        if _grid_factors(x0) is not None:  # keep the Kronecker structure of the wrapped kernel
+            inner = self._covfunc.linop(x0, x1)
+            if inner.kron_terms() is not None:
+                return float(self._scalar) * inner
+        return super().linop(x0, x1)
+
     def __rmul__(self, other):
         if np.ndim(other) == 0:
             return ScaledCovarianceFunction(self._covfunc, scalar=np.asarray(other) * self._scalar)
@@ -294,6 +345,16 @@ class SumCovarianceFunction(CovarianceFunction):
 
     def descriptors(self):
         return [s.descriptor() for s in self._summands]
+
+    def linop(self, x0, x1=None):
+        if _grid_factors(x0) is not None:
+            parts = [s.linop(x0, x1) for s in self._summands]
+            if all(p.kron_terms() is not None for p in parts):
+                out = parts[0]
+                for p in parts[1:]:
+                    out = out + p
+                return out
+        return super().linop(x0, x1)
 
     def _evaluate(self, x0, x1, batch):
         out = None
@@ -347,8 +408,53 @@ class LinDiffOpCovarianceFunction(CovarianceFunction):
         return f, terms(self._L0), terms(self._L1), s
 
 
+class _UnivariateDerivativeFactor(CovarianceFunction):
+    """``d^a/dx^a d^b/dx'^b kappa(x, x')`` of ONE univariate factor of a tensor-product kernel: what the reference's
+    ``k_x0_x1s`` cache holds (diffops/_tensor_product.py:34-82).  Lowered to a 1-D device descriptor."""
+
+    def __init__(self, factor: CovarianceFunction, a: int, b: int):
+        super().__init__(())
+        self._factor, self._a, self._b = factor, int(a), int(b)
+
+    def _product_form(self):
+        f, t0, t1, s = self._factor._product_form()
+        if t0 is not None or t1 is not None or len(f) != 1:
+            raise NotImplementedError("TensorProduct factors must be plain univariate kernels")
+        return f, ({(self._a,): 1.0} if self._a else None), ({(self._b,): 1.0} if self._b else None), s
+
+
 class TensorProduct_LinDiffOp_LinDiffOp(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
     """diffops/_tensor_product.py:21"""
+
+    def linop(self, x0, x1=None):
+        """Sum over the operator terms of Kronecker products of 1-D derivative-kernel matrices when the inputs are
+        tensor-product grids (diffops/_tensor_product.py:84-119, 140-156), else the generic lazy matrix.
+
+        Deviation from the reference, on purpose: with ``x1`` given the reference pairs ``x0``'s factors with
+        THEMSELVES (``x1_factors = x0.factors``, diffops/_tensor_product.py:147-148, an upstream slip); here the
+        factors of ``x1`` are used, so that ``linop(x0, x1).todense() == matrix(x0, x1)`` always holds."""
+        f0, f1 = _grid_factors(x0), (None if x1 is None else _grid_factors(x1))
+        base = self._k
+        d = len(base.factors) if isinstance(base, TensorProduct) else 0
+        if d and f0 is not None and len(f0) == d and (x1 is None or (f1 is not None and len(f1) == d)):
+            ident = {(0,) * d: 1.0}
+            t0 = ident if self._L0 is None else self._L0._terms()
+            t1 = ident if self._L1 is None else self._L1._terms()
+            cache = {}
+
+            def factor_linop(i, a, b):
+                if (i, a, b) not in cache:
+                    kf = _UnivariateDerivativeFactor(base.factors[i], a, b)
+                    cache[(i, a, b)] = kf.linop(f0[i], None if x1 is None else f1[i])
+                return cache[(i, a, b)]
+
+            res = 0
+            for mi0, c0 in t0.items():
+                for mi1, c1 in t1.items():
+                    term = _kron_all([factor_linop(i, mi0[i], mi1[i]) for i in range(d)])
+                    res = res + (float(c0) * float(c1)) * term
+            return res
+        return super().linop(x0, x1)
 
 
 class ExpQuad_Identity_DirectionalDerivative(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name

@@ -158,8 +158,48 @@ def heat_problem(n_ic=5, n_bc=10, nt=15, nx=8, alpha=0.1, grid=10):
     return {"kernel": kernel, "blocks": blocks, "Xt": Xt.tolist(), "n_cov": 16}
 
 
+def _grid_block(factors, Y, L, noise_var=None):
+    """Observation batch on a tensor-product grid: ``X`` is the C-order flattening (what the reference sees after
+    ``np.asarray``), ``grid`` keeps the 1-D factors for implementations that exploit the Kronecker structure."""
+    X = np.stack(np.meshgrid(*[np.asarray(f, dtype=float) for f in factors], indexing="ij"), -1).reshape(-1, len(factors))
+    Y = np.broadcast_to(np.asarray(Y, dtype=float), (len(X),))
+    return {"X": X.tolist(), "Y": Y.tolist(), "L": L, "noise_var": noise_var, "grid": [np.asarray(f, dtype=float).tolist() for f in factors]}
+
+
+def poisson2d_grid_problem(nx=9, ny=8, n_bc_edge=10, ell=0.35, sigma2=4.0, grid=10):
+    """As :func:`poisson2d_problem`, with ALL batches on tensor-product grids (boundary edges = grids with one
+    singleton factor): every Gram block is a sum of Kronecker products."""
+    kernel = {"scale": sigma2, "base": _tp(_m(2.5, ell), _m(2.5, ell))}
+    s = np.linspace(0.0, 1.0, n_bc_edge)
+    blocks = [
+        _grid_block([s, [0.0]], 0.0, None),
+        _grid_block([[1.0], s[1:]], 0.0, None),
+        _grid_block([s[:-1], [1.0]], 0.0, None),
+        _grid_block([[0.0], s[1:-1]], 0.0, None),
+        _grid_block([np.linspace(0.0, 1.0, nx + 2)[1:-1], np.linspace(0.0, 1.0, ny + 2)[1:-1]], 2.0, _neg_lap(2)),
+    ]
+    g = np.linspace(0.0, 1.0, grid)
+    Xt = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    return {"kernel": kernel, "blocks": blocks, "Xt": Xt.tolist(), "n_cov": 16}
+
+
+def heat_grid_problem(n_ic=7, n_bc=9, nt=11, nx=6, alpha=0.1, grid=10):
+    """As :func:`heat_problem` with every batch given as a tensor-product grid."""
+    kernel = {"scale": None, "base": _tp(_m(1.5, 2.5), _m(2.5, 2.0))}
+    xs = np.linspace(-1.0, 1.0, n_ic)
+    ts = np.linspace(0.0, 5.0, n_bc)[1:]
+    ic = _grid_block([[0.0], xs], 0.0, None)
+    ic["Y"] = np.sin(np.pi * (xs + 1.0) / 2.0).tolist()
+    blocks = [ic, _grid_block([ts, [-1.0]], 0.0, None, 1e-5), _grid_block([ts, [1.0]], 0.0, None, 1e-5),
+              _grid_block([np.linspace(0.0, 5.0, nt), np.linspace(-1.0, 1.0, nx + 2)[1:-1]], 0.0, _heat(alpha))]
+    Xt = np.stack(np.meshgrid(np.linspace(0, 5, grid), np.linspace(-1, 1, grid), indexing="ij"), -1).reshape(-1, 2)
+    return {"kernel": kernel, "blocks": blocks, "Xt": Xt.tolist(), "n_cov": 16}
+
+
 def golden_problems():
     probs = {}
+    probs["poisson2d_grid_kron"] = poisson2d_grid_problem()
+    probs["heat_grid_kron"] = heat_grid_problem()
     # C1: experiments/0000_poisson_dirichlet_1d.ipynb (cells 9, 17, 21): PDE first, then boundary
     xp = np.linspace(-0.8, 0.8, 3)
     probs["poisson1d_expquad"] = {

@@ -114,6 +114,43 @@ def make_kernels():
     return worst
 
 
+def make_kron():
+    """Tensor-grid structure path: the reference's Kronecker linops on TensorProductGrids, densified and applied to a
+    fixed block of vectors.  Derivative kernels with an explicit second grid go through ``.matrix`` (the reference's
+    derivative ``linop(x0, x1)`` pairs x0's factors with themselves, diffops/_tensor_product.py:147-148)."""
+    from linpde_gp.randprocs.covfuncs import TensorProductGrid
+
+    from oracle import kron as okron
+
+    out, worst = {}, 0.0
+    specs = gcases.build_kron_cases()
+    for spec in specs:
+        kref = ref_L0kL1(spec)
+        g0 = TensorProductGrid(*[np.asarray(f) for f in spec["factors0"]])
+        g1 = None if spec["factors1"] is None else TensorProductGrid(*[np.asarray(f) for f in spec["factors1"]])
+        plain = spec["L0"] is None and spec["L1"] is None
+        if g1 is None or plain:
+            op = kref.linop(g0, g1)
+            K = np.asarray(op.todense())
+        else:
+            op = None
+            K = np.asarray(kref.matrix(np.asarray(g0), np.asarray(g1)))
+        V = np.random.default_rng(len(spec["name"])).standard_normal((K.shape[1], 3))
+        KV = np.asarray(op @ V) if op is not None else K @ V
+        o0, o1 = gcases.spec_to_oracle_op(spec["L0"]), gcases.spec_to_oracle_op(spec["L1"])
+        terms = okron.kronecker_terms(spec["kernel"], o0, o1, spec["factors0"], spec["factors1"])
+        Ko, KVo = okron.dense(terms), okron.matvec(terms, V)
+        sc = np.max(np.abs(K))
+        err = max(np.max(np.abs(K - Ko)) / sc, np.max(np.abs(KV - KVo)) / np.max(np.abs(KV)))
+        worst = max(worst, err)
+        print(f"{spec['name']:24s} linop={type(op).__name__:28s} shape={K.shape} terms={len(terms)} oracle-ref rel {err:.2e}")
+        out[spec["name"] + "__K"], out[spec["name"] + "__V"], out[spec["name"] + "__KV"] = K, V, KV
+    out["__specs__"] = np.frombuffer(json.dumps(specs).encode(), dtype=np.uint8)
+    np.savez(os.path.join(GOLDEN, "kron.npz"), **out)
+    print(f"kron.npz: {len(specs)} cases, worst oracle-vs-reference deviation {worst:.2e}")
+    return worst
+
+
 def make_gp():
     worst = 0.0
     for name, problem in ogp.golden_problems().items():
@@ -165,4 +202,5 @@ if __name__ == "__main__":
     refshim.load()
     w1 = make_kernels()
     w2 = make_gp()
-    print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}")
+    w3 = make_kron()
+    print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}, kron {w3:.2e}")

@@ -202,3 +202,27 @@ def kernel_input_shape(kernel):
     if base["kind"] == "tensor_product":
         return (len(base["factors"]),)
     return tuple(base["input_shape"])
+
+
+# ---- tensor-grid (Kronecker) structure path: SURVEY.md section 8f item 3 ------------------------------------------
+def build_kron_cases():
+    """Tensor-product kernels on TensorProductGrids (src/linpde_gp/randprocs/covfuncs/_tensor_product.py:64-82,
+    .../linfuncops/diffops/_tensor_product.py:140-156).  ``factors1=None`` -> symmetric block (``x1=None``)."""
+    g7, g5 = np.linspace(0.0, 1.0, 7).tolist(), np.linspace(-1.0, 1.0, 5).tolist()
+    h4, h6 = np.linspace(0.1, 0.9, 4).tolist(), np.linspace(-0.7, 1.3, 6).tolist()
+    tp2 = _tp(_m(2.5, 0.4), _m(2.5, 0.7))
+    tpm = _tp(_m(1.5, 0.9), _m(2.5, 0.5))
+    tp3 = _tp(_e(0.8), _m(2.5, 0.6), _m(1.5, 1.1))
+    lap2, lap3 = _wl([1.0, 1.0], -1.0), _wl([1.0, 0.5, 2.0])
+    cases = [
+        dict(name="kron_tp2_k", kernel=dict(scale=None, base=tp2), L0=None, L1=None, factors0=[g7, g5], factors1=None),
+        dict(name="kron_tp2_k_cross", kernel=dict(scale=3.0, base=tp2), L0=None, L1=None, factors0=[g7, g5], factors1=[h4, h6]),
+        dict(name="kron_tp2_kL", kernel=dict(scale=2.0, base=tp2), L0=None, L1=lap2, factors0=[g7, g5], factors1=[h4, h6]),
+        dict(name="kron_tp2_LkL", kernel=dict(scale=2.0, base=tp2), L0=lap2, L1=lap2, factors0=[g7, g5], factors1=None),
+        dict(name="kron_tp2_LkL_edge", kernel=dict(scale=2.0, base=tp2), L0=lap2, L1=None, factors0=[g7, g5], factors1=[[0.0], h6]),
+        dict(name="kron_heat_LkL", kernel=dict(scale=None, base=tpm), L0=_heat(2, 0.1), L1=_heat(2, 0.1), factors0=[g7, g5], factors1=None),
+        dict(name="kron_heat_Lk", kernel=dict(scale=None, base=tpm), L0=_heat(2, 0.2), L1=None, factors0=[h4, h6], factors1=[g7, g5]),
+        dict(name="kron_tp3_k", kernel=dict(scale=None, base=tp3), L0=None, L1=None, factors0=[h4, [0.0, 0.5, 1.5], g5], factors1=None),
+        dict(name="kron_tp3_LkL", kernel=dict(scale=1.5, base=tp3), L0=lap3, L1=lap3, factors0=[h4, [0.0, 0.5, 1.5], g5], factors1=None),
+    ]
+    return cases

@@ -154,6 +154,9 @@ def api_solve(problem):
     for blk in problem["blocks"]:
         X = np.asarray(blk["X"], dtype=float)
         Y = np.asarray(blk["Y"], dtype=float)
+        if blk.get("grid") is not None:  # gridded batch: hand the product the TensorProductGrid itself
+            X = lg.randprocs.covfuncs.TensorProductGrid(*[np.asarray(f, dtype=float) for f in blk["grid"]])
+            Y = Y.reshape(X.shape[:-1])
         b = None
         if blk.get("noise_var") is not None:
             nv = np.broadcast_to(np.asarray(blk["noise_var"], dtype=float), Y.shape).copy()

@@ -146,3 +146,23 @@ def test_product_path_has_no_cpu_fallback():
     for path in src:
         text = open(path).read()
         assert "import oracle" not in text and "from oracle" not in text, path
+
+
+def test_tensor_product_grid_host_semantics():
+    """TensorProductGrid (src/linpde_gp/randprocs/covfuncs/_tensor_product.py:133-152): meshgrid "ij" stacked on the last
+    axis; the C-order flattening enumerates points in Kronecker order; views lose the factorisation."""
+    from linpde_gp_b200.randprocs import covfuncs
+
+    xs, ys = np.array([0.0, 0.5, 1.0]), np.array([-1.0, 1.0])
+    g = covfuncs.TensorProductGrid(xs, ys)
+    assert g.shape == (3, 2, 2) and isinstance(g, np.ndarray)
+    assert len(g.factors) == 2 and np.array_equal(g.factors[0], xs)
+    flat = np.asarray(g).reshape(-1, 2)
+    np.testing.assert_array_equal(flat[:, 0], np.kron(xs, np.ones(2)))
+    np.testing.assert_array_equal(flat[:, 1], np.kron(np.ones(3), ys))
+    assert covfuncs._grid_factors(g) is g.factors
+    assert covfuncs._grid_factors(g[1:]) is None and covfuncs._grid_factors(g + 1.0) is None
+    assert covfuncs._grid_factors(flat) is None
+    assert covfuncs._grid_factors(covfuncs.TensorProductGrid(xs, ys, indexing="xy")) is None
+    with pytest.raises(ValueError):
+        covfuncs.TensorProductGrid(np.zeros((2, 2)))

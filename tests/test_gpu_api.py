@@ -304,3 +304,95 @@ def test_inverse_rhs_conditioning_lazy_kernel_noise():
     for name, post in posts.items():
         assert np.max(np.abs(post.mean(Xt) - mean_ref)) <= 1e-8 * sc, name
         assert np.max(np.abs(post.var(Xt) - var_ref)) <= 1e-8 * sc, name
+
+
+# ---- tensor-grid (Kronecker) structure path: SURVEY.md section 8f item 3 ------------------------------------------
+_KR = np.load(os.path.join(GOLDEN, "kron.npz"))
+KRON_SPECS = json.loads(bytes(_KR["__specs__"]).decode())
+
+
+@pytest.mark.parametrize("spec", KRON_SPECS, ids=[s["name"] for s in KRON_SPECS])
+def test_kronecker_linop_on_tensor_product_grids_matches_reference(spec):
+    """``k.linop(TensorProductGrid, TensorProductGrid | None)`` yields (sums of) Kronecker products whose dense form
+    (Kronecker assembly kernel) and structured product (two DMMA GEMMs per term) match the frozen outputs of the
+    reference's Kronecker linops; the same kernel evaluated pair by pair on the flattened grid agrees too."""
+    from linpde_gp_b200 import linops
+    from linpde_gp_b200.randprocs import covfuncs
+
+    k = helpers.api_L0kL1(spec)
+    g0 = covfuncs.TensorProductGrid(*[np.asarray(f) for f in spec["factors0"]])
+    g1 = None if spec["factors1"] is None else covfuncs.TensorProductGrid(*[np.asarray(f) for f in spec["factors1"]])
+    K_ref, V, KV_ref = _KR[spec["name"] + "__K"], _KR[spec["name"] + "__V"], _KR[spec["name"] + "__KV"]
+    sc = np.max(np.abs(K_ref))
+    op = k.linop(g0, g1)
+    assert op.kron_terms() is not None, "grid inputs must keep the Kronecker structure"
+    assert isinstance(op, (linops.Kronecker, linops.ScaledLinearOperator, linops.SumLinearOperator))
+    assert op.shape == K_ref.shape
+    K = op.todense()
+    assert np.max(np.abs(K - K_ref)) <= GRAM_TOL * sc
+    assert np.max(np.abs(op @ V - KV_ref)) <= 1e-11 * np.max(np.abs(KV_ref))
+    assert np.max(np.abs(op @ V[:, 0] - KV_ref[:, 0])) <= 1e-11 * np.max(np.abs(KV_ref))
+    # plain point sets (the grid flattened C-order) take the pairwise Gram kernel: same matrix
+    d = len(spec["factors0"])
+    Kp = k.matrix(np.asarray(g0).reshape(-1, d), None if g1 is None else np.asarray(g1).reshape(-1, d))
+    assert np.max(np.abs(Kp - K_ref)) <= GRAM_TOL * sc
+    if g1 is None:  # SPD solves straight from the Kronecker assembly (lower mode into the factor buffer)
+        A = K_ref + 1e-6 * sc * np.eye(len(K_ref))
+        noisy = op + linops.Matrix(1e-6 * sc * np.eye(len(K_ref)))
+        x = noisy.solve(V)
+        assert np.max(np.abs(A @ x - V)) <= 1e-7 * np.max(np.abs(V))
+
+
+@pytest.mark.parametrize("shapes", [((1, 1), (1, 1)), ((3, 5), (7, 2)), ((4, 4), (65, 65)), ((33, 17), (9, 31)), ((130, 2), (3, 129))])
+def test_kron_sum_kernel_vs_torch(shapes):
+    """lpgp_kron_sum against torch.kron: ragged shapes, odd leading dimensions, more terms than one launch takes,
+    accumulate mode and the lower-triangle mode."""
+    import torch
+
+    from linpde_gp_b200 import backend as be
+
+    (n1, m1), (n2, m2) = shapes
+    g = torch.Generator(device="cuda").manual_seed(n1 * 1000 + m2)
+    for nterms in (1, 3, 6):
+        terms = []
+        for t in range(nterms):
+            A = be.alloc_matrix(n1, m1).normal_(generator=g)
+            B = torch.randn(n2, m2 + 1, dtype=torch.float64, device="cuda", generator=g)[:, :m2]  # odd ld / unaligned rows
+            terms.append((0.5 + t, A, B))
+        ref = sum(a * torch.kron(A, B) for a, A, B in terms)
+        out = be.kron_sum(terms)
+        assert out.shape == ref.shape
+        assert (out - ref).abs().max().item() <= 1e-13 * max(ref.abs().max().item(), 1.0)
+        out2 = be.kron_sum(terms, out=out, accumulate=True)
+        assert (out2 - 2 * ref).abs().max().item() <= 1e-13 * max(ref.abs().max().item(), 1.0)
+    if n1 * n2 == m1 * m2:
+        n = n1 * n2
+        out = be.alloc_matrix(n, n).fill_(-7.0)
+        be.kron_sum(terms, out=out, lower=True)
+        low = torch.tril(out)
+        assert (low - torch.tril(ref)).abs().max().item() <= 1e-13 * max(ref.abs().max().item(), 1.0)
+        if n > 512:  # tiles strictly above the diagonal stay untouched
+            assert (out[:64, 320:] == -7.0).all()
+
+
+def test_gridded_conditioning_uses_kronecker_assembly_and_matches_pairwise():
+    """Conditioning on TensorProductGrid batches assembles the Gram blocks from Kronecker factors; the posterior is
+    the one obtained from the same points passed as plain arrays (pairwise Gram kernel) and the oracle's."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200._lib import lib
+    from oracle import gp as ogp
+
+    prob = ogp.poisson2d_grid_problem(nx=24, ny=20, n_bc_edge=30, ell=0.2, grid=14)
+    ref = ogp.solve(prob)
+    post_g, res_g = helpers.api_solve(prob)
+    assert all(b.grid is not None for b in post_g._blocks)
+    flat = dict(prob, blocks=[{k: v for k, v in b.items() if k != "grid"} for b in prob["blocks"]])
+    post_p, res_p = helpers.api_solve(flat)
+    assert all(b.grid is None for b in post_p._blocks)
+    gsc = np.max(np.abs(ref["gram"]))
+    assert np.max(np.abs(res_g["gram"] - ref["gram"])) <= GRAM_TOL * gsc
+    assert np.max(np.abs(res_g["gram"] - res_p["gram"])) <= GRAM_TOL * gsc
+    for key in ("mean", "var", "cov"):
+        sc = max(np.max(np.abs(ref[key])), np.max(np.abs(ref["var"])))
+        assert np.max(np.abs(res_g[key] - ref[key])) <= POST_TOL * sc, key
+        assert np.max(np.abs(res_g[key] - res_p[key])) <= POST_TOL * sc, key

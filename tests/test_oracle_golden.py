@@ -9,6 +9,7 @@ import pytest
 
 from oracle import covfuncs as ocf
 from oracle import gp as ogp
+from oracle import kron as okron
 from tests.golden import cases as gcases
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -96,3 +97,29 @@ def test_not_positive_definite_raises():
 
     with pytest.raises(np.linalg.LinAlgError):
         ola.cholesky_lower(np.array([[1.0, 2.0], [2.0, 1.0]]))
+
+
+# ---- tensor-grid (Kronecker) structure path -----------------------------------------------------------------------
+_KR = np.load(os.path.join(GOLDEN, "kron.npz"))
+KRON_SPECS = json.loads(bytes(_KR["__specs__"]).decode())
+
+
+@pytest.mark.parametrize("spec", KRON_SPECS, ids=[s["name"] for s in KRON_SPECS])
+def test_kronecker_linop_matches_reference(spec):
+    """Frozen outputs of the reference's Kronecker linops on TensorProductGrids (densified + applied to vectors)
+    against the restatement in oracle/kron.py -- and the Kronecker sum against the pairwise dense evaluation."""
+    o0, o1 = gcases.spec_to_oracle_op(spec["L0"]), gcases.spec_to_oracle_op(spec["L1"])
+    terms = okron.kronecker_terms(spec["kernel"], o0, o1, spec["factors0"], spec["factors1"])
+    K_ref, V, KV_ref = _KR[spec["name"] + "__K"], _KR[spec["name"] + "__V"], _KR[spec["name"] + "__KV"]
+    K = okron.dense(terms)
+    sc = np.max(np.abs(K_ref))
+    assert np.max(np.abs(K - K_ref)) <= 2e-15 * sc
+    assert np.max(np.abs(okron.matvec(terms, V) - KV_ref)) <= 1e-13 * np.max(np.abs(KV_ref))
+    d = len(spec["factors0"])
+    g0 = okron.tensor_product_grid(*spec["factors0"]).reshape(-1, d)
+    g1 = None if spec["factors1"] is None else okron.tensor_product_grid(*spec["factors1"]).reshape(-1, d)
+    assert np.max(np.abs(ocf.matrix(spec["kernel"], o0, o1, g0, g1) - K_ref)) <= 2e-15 * sc
+
+
+def test_generated_kron_case_list_is_the_frozen_one():
+    assert json.loads(json.dumps(gcases.build_kron_cases())) == KRON_SPECS

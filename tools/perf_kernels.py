@@ -75,3 +75,16 @@ if "mean" in which:
     blocks = be.ObsBlocks([d_kL], [X], [0])
     ms = tm(lambda: be.post_mean(blocks, w, Xt))
     print(f"post_mean m={m} n={n}: {ms:.2f} ms  {m*n/ms*1e-6:.1f} Gevals/s", flush=True)
+if "kron" in which:
+    # tensor-grid path: Gram block of -Laplace k -Laplace on a g1 x g2 collocation grid, 4 Kronecker terms
+    for (g1, g2) in ((128, 128), (256, 128), (256, 256)):
+        n = g1 * g2
+        terms = [(1.0 + t, be.alloc_matrix(g1, g1).normal_(), be.alloc_matrix(g2, g2).normal_()) for t in range(4)]
+        out = be.alloc_matrix(n, n)
+        ms = tm(lambda: be.kron_sum(terms, out=out))
+        print(f"kron_sum 4 terms n={n} full: {ms:.2f} ms  {n*n/ms*1e-6:.1f} Gentries/s  ({n*n*8/ms*1e-6:.0f} GB/s)", flush=True)
+        ms = tm(lambda: be.kron_sum(terms[:1], out=out))
+        print(f"kron_sum 1 term  n={n} full: {ms:.2f} ms  {n*n/ms*1e-6:.1f} Gentries/s  ({n*n*8/ms*1e-6:.0f} GB/s)", flush=True)
+        ms = tm(lambda: be.kron_sum(terms, out=out, lower=True))
+        print(f"kron_sum 4 terms n={n} lower: {ms:.2f} ms  {n*(n+1)/2/ms*1e-6:.1f} Gentries/s (lower entries)", flush=True)
+        del out, terms
