@@ -50,6 +50,82 @@ class Function:
     def _evaluate(self, x):  # pragma: no cover - abstract
         raise NotImplementedError
 
+    # -- arithmetic (pn/functions/_algebra_fallbacks.py: ScaledFunction / SumFunction) ---------------------------
+    def __rmul__(self, other):
+        if np.ndim(other) == 0:
+            return ScaledFunction(self, scalar=other)
+        return NotImplemented
+
+    def __neg__(self):
+        return -1.0 * self
+
+    def __add__(self, other):
+        if isinstance(other, Function):
+            return SumFunction(self, other)
+        return NotImplemented
+
+    def __sub__(self, other):
+        if isinstance(other, Function):
+            return SumFunction(self, -other)
+        return NotImplemented
+
+
+class ScaledFunction(Function):
+    def __init__(self, function: Function, scalar):
+        super().__init__(function.input_shape, function.output_shape)
+        self._function = function
+        self._scalar = float(scalar)
+
+    @property
+    def function(self):
+        return self._function
+
+    @property
+    def scalar(self):
+        return self._scalar
+
+    def _evaluate(self, x):
+        return self._scalar * self._function(x)
+
+
+class SumFunction(Function):
+    def __init__(self, *summands: Function):
+        first = summands[0]
+        if not all(s.input_shape == first.input_shape and s.output_shape == first.output_shape for s in summands):
+            raise ValueError("The functions must have the same input and output shapes")
+        super().__init__(first.input_shape, first.output_shape)
+        self._summands = tuple(summands)
+
+    @property
+    def summands(self):
+        return self._summands
+
+    def _evaluate(self, x):
+        out = self._summands[0](x)
+        for s in self._summands[1:]:
+            out = out + s(x)
+        return out
+
+
+class StackedFunction(Function):
+    """``x -> (f_0(x), ..., f_{n-1}(x))`` of scalar-output functions (src/linpde_gp/functions/_stacked.py): the prior
+    mean of a multi-output process."""
+
+    def __init__(self, *fns: Function):
+        if not fns:
+            raise ValueError("at least one function is needed")
+        if not all(f.input_shape == fns[0].input_shape and f.output_shape == () for f in fns):
+            raise ValueError("stacked functions must share the input shape and be scalar-valued")
+        super().__init__(fns[0].input_shape, (len(fns),))
+        self._fns = tuple(fns)
+
+    @property
+    def fns(self):
+        return self._fns
+
+    def _evaluate(self, x):
+        return np.stack([f(x) for f in self._fns], axis=-1)
+
 
 class Constant(Function):
     def __init__(self, input_shape, value):

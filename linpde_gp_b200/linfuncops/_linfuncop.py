@@ -7,7 +7,7 @@ import operator
 
 import numpy as np
 
-from ..functions import Constant, Function, Zero, _as_shape
+from ..functions import Constant, Function, ScaledFunction, StackedFunction, SumFunction, Zero, _as_shape
 
 
 class LinearFunctionOperator:
@@ -62,6 +62,10 @@ class LinearFunctionOperator:
         )
 
     def _apply_to_function(self, f):
+        if isinstance(f, ScaledFunction):  # linearity (src/linpde_gp/functions/linfuncops/_registry.py)
+            return f.scalar * self(f.function)
+        if isinstance(f, SumFunction):
+            return functools.reduce(operator.add, (self(s) for s in f.summands))
         terms = self._terms()
         order0 = sum(c for mi, c in terms.items() if sum(mi) == 0)
         if isinstance(f, Zero):
@@ -96,6 +100,14 @@ class LinearFunctionOperator:
             return SumLinearFunctionOperator(self, other)
         return NotImplemented
 
+    def __matmul__(self, other):
+        """``self @ other``: apply ``other`` first (``_linfuncop.py:131-136``, ``_arithmetic.py:142-144``)."""
+        if isinstance(other, SumLinearFunctionOperator):
+            return SumLinearFunctionOperator(*(self @ summand for summand in other.summands))
+        if isinstance(other, LinearFunctionOperator):
+            return CompositeLinearFunctionOperator(self, other)
+        return NotImplemented
+
     def __sub__(self, other):
         if isinstance(other, LinearFunctionOperator):
             return SumLinearFunctionOperator(self, -other)
@@ -120,6 +132,12 @@ class ScaledLinearFunctionOperator(LinearFunctionOperator):
 
     def _terms(self):
         return {mi: float(self._scalar) * c for mi, c in self._linfuncop._terms().items()}
+
+    def _apply_to_function(self, f):
+        try:
+            return super()._apply_to_function(f)
+        except NotImplementedError:  # no flat partial-derivative form (e.g. a SelectOutput inside): linearity
+            return float(self._scalar) * self._linfuncop(f)
 
     def __rmul__(self, other):
         if np.ndim(other) == 0:
@@ -148,8 +166,71 @@ class SumLinearFunctionOperator(LinearFunctionOperator):
                 out[mi] = out.get(mi, 0.0) + c
         return out
 
+    def _apply_to_function(self, f):
+        try:
+            return super()._apply_to_function(f)
+        except NotImplementedError:
+            return functools.reduce(operator.add, (s(f) for s in self._summands))
+
     def __repr__(self):
         return " + ".join(str(s) for s in self._summands)
+
+
+class CompositeLinearFunctionOperator(LinearFunctionOperator):
+    """``L_0 @ L_1 @ ...`` -- the rightmost operator acts first (src/linpde_gp/linfuncops/_arithmetic.py:112-139)."""
+
+    def __init__(self, *linfuncops):
+        assert all(L0.input_shapes == L1.output_shapes for L0, L1 in zip(linfuncops[:-1], linfuncops[1:]))
+        self._linfuncops = tuple(linfuncops)
+        super().__init__(input_shapes=self._linfuncops[-1].input_shapes, output_shapes=self._linfuncops[0].output_shapes)
+
+    @property
+    def linfuncops(self):
+        return self._linfuncops
+
+    def _terms(self):
+        if len(self._linfuncops) == 1:
+            return self._linfuncops[0]._terms()
+        raise NotImplementedError("a composition has no flat partial-derivative representation")
+
+    def _apply_to_function(self, f):
+        return functools.reduce(lambda h, L: L(h), reversed(self._linfuncops), f)
+
+    def __repr__(self):
+        return " @ ".join(repr(L) for L in self._linfuncops)
+
+
+class SelectOutput(LinearFunctionOperator):
+    """Picks one output of a multi-output function / process (src/linpde_gp/linfuncops/_select_output.py:9-34)."""
+
+    def __init__(self, input_shapes, idx):
+        self._idx = idx
+        in_dom, in_codom = _as_shape(input_shapes[0]), _as_shape(input_shapes[1])
+        out_codom = np.empty(in_codom, dtype=[])[idx].shape
+        super().__init__((in_dom, in_codom), output_shapes=(in_dom, out_codom))
+
+    @property
+    def idx(self):
+        return self._idx
+
+    def _terms(self):
+        raise NotImplementedError("SelectOutput is not a differential operator")
+
+    def _apply_to_function(self, f):
+        if isinstance(f, StackedFunction):  # functions/linfuncops/_registry.py:8-13
+            assert isinstance(self._idx, (int, np.integer))
+            return f.fns[self._idx]
+        if isinstance(f, ScaledFunction):
+            return f.scalar * self(f.function)
+        if isinstance(f, SumFunction):
+            return functools.reduce(operator.add, (self(s) for s in f.summands))
+        from ..functions import LambdaFunction
+
+        idx = self._idx
+        return LambdaFunction(lambda x: f(x)[..., idx], f.input_shape, self.output_codomain_shape)
+
+    def __repr__(self):
+        return f"SelectOutput(idx={self.idx})"
 
 
 class Identity(LinearFunctionOperator):

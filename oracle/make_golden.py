@@ -198,9 +198,75 @@ def run_reference_gp(problem):
     return {"w": w, "mean": mean, "var": var, "cov": cov, "gram": gram}
 
 
+def run_reference_multi_output(problem):
+    """The unmodified reference on a multi-output problem: IndependentMultiOutputCovarianceFunction prior,
+    ``L = sum_t c_t * (D_t @ SelectOutput(o_t))`` observations, ``SelectOutput(j)(posterior)`` evaluated."""
+    pn, lg = refshim.load()
+    from linpde_gp import functions, linfuncops
+    from linpde_gp.randprocs import covfuncs
+
+    ks = [ref_kernel(k) for k in problem["kernels"]]
+    shape = gcases.kernel_input_shape(problem["kernels"][0])
+    nout = len(ks)
+    prior = pn.randprocs.GaussianProcess(
+        functions.StackedFunction(*(functions.Constant(shape, m) for m in problem["means"])),
+        covfuncs.IndependentMultiOutputCovarianceFunction(*ks),
+    )
+    sel = [linfuncops.SelectOutput((shape, (nout,)), idx=j) for j in range(nout)]
+    post = prior
+    for blk in problem["blocks"]:
+        X = np.asarray(blk["X"], dtype=float)
+        Y = np.asarray(blk["Y"], dtype=float)
+        L = None
+        for o, c, op in blk["Ls"]:
+            t = sel[o] if op is None else ref_op(op, shape) @ sel[o]
+            if c != 1.0:
+                t = c * t
+            L = t if L is None else L + t
+        b = None
+        if blk.get("noise_var") is not None:
+            nv = np.asarray(blk["noise_var"], dtype=float)
+            b = pn.randvars.Normal(np.zeros_like(Y), pn.linops.Scaling(np.broadcast_to(nv, Y.shape).copy()))
+        post = post.condition_on_observations(Y, X=X, L=L, b=b)
+    Xt = np.asarray(problem["Xt"], dtype=float)
+    Xc = Xt[: problem.get("n_cov", 8)]
+    outs = [s(post) for s in sel]
+    return {
+        "w": np.asarray(post.representer_weights),
+        "gram": np.asarray(post.gram.todense()),
+        "mean": np.stack([np.asarray(o.mean(Xt)) for o in outs]),
+        "var": np.stack([np.asarray(o.cov(Xt, None)) for o in outs]),
+        "cov": np.stack([np.asarray(o.cov.matrix(Xc)) for o in outs]),
+    }
+
+
+def make_multi_output():
+    from oracle import multi_output as omo
+
+    worst = 0.0
+    for name, problem in omo.golden_problems().items():
+        res = run_reference_multi_output(problem)
+        ores = omo.solve(problem)
+        for key in ("w", "gram", "mean", "var", "cov"):
+            sc = max(np.max(np.abs(res[key])), 1e-300)
+            err = np.max(np.abs(res[key] - ores[key])) / sc
+            worst = max(worst, err)
+            print(f"mo_{name:25s} {key:5s} oracle-ref rel {err:.2e}")
+        np.savez(
+            os.path.join(GOLDEN, f"mo_{name}.npz"),
+            problem=np.frombuffer(json.dumps(problem).encode(), dtype=np.uint8),
+            **res,
+        )
+    return worst
+
+
 if __name__ == "__main__":
     refshim.load()
+    if "--multi-output-only" in sys.argv:
+        print(f"worst deviation: multi-output {make_multi_output():.2e}")
+        sys.exit(0)
     w1 = make_kernels()
     w2 = make_gp()
     w3 = make_kron()
-    print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}, kron {w3:.2e}")
+    w4 = make_multi_output()
+    print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}, kron {w3:.2e}, multi-output {w4:.2e}")
