@@ -219,7 +219,10 @@ int lpgp_post_mean(const lpgp_obs_block* blocks, int nblocks, const double* w, c
                    double* out, int accumulate, void* stream);
 
 /* K[i, col_off_b + j] = (k L_b^*)(Xt[i], X_b[j]) for all blocks, gaps zeroed: the cross-covariance rows
- * PriorPredictiveCrossCovariance._evaluate (_conditional.py:140-153) of m test points, n = factor size.      */
+ * PriorPredictiveCrossCovariance._evaluate (_conditional.py:140-153) of m test points, n = factor size.
+ * Blocks must be sorted by col_off; consecutive entries with identical (X, n, col_off) are summands of ONE kernel
+ * (sum kernels, multi-output observation operators -- crosscov/_arithmetic.py Sum wrappers) and are accumulated.
+ * nblocks = 0 clears K.                                                                                       */
 int lpgp_crosscov(const lpgp_obs_block* blocks, int nblocks, int64_t n, const double* Xt, int64_t m, double* K,
                   int64_t ldk, void* stream);
 

@@ -254,17 +254,20 @@ extern "C" int lpgp_post_mean(const lpgp_obs_block* blocks, int nblocks, const d
 // assemble the m x n cross-covariance rows of a chunk of test points into K (gaps between blocks zeroed)
 extern "C" int lpgp_crosscov(const lpgp_obs_block* blocks, int nblocks, int64_t n, const double* Xt, int64_t m, double* K,
                              int64_t ldk, void* stream) {
-  if (!blocks || nblocks < 1) return -1;
+  if (nblocks < 0 || (nblocks > 0 && !blocks)) return -1;
   if (!Xt) return -4;
   if (!K || ldk < n) return -6;
   cudaStream_t st = (cudaStream_t)stream;
   int64_t cursor = 0;
   for (int b = 0; b < nblocks; ++b) {
     const lpgp_obs_block& blk = blocks[b];
-    if (blk.col_off < cursor || blk.col_off + blk.n > n) return -1;
-    int rc = zero_cols(K, m, ldk, cursor, blk.col_off, st);
+    // consecutive entries on the SAME columns are summands of one kernel (sum kernels, multi-output observation
+    // operators): the first one writes, the others accumulate
+    const bool same = b > 0 && blk.col_off == blocks[b - 1].col_off && blk.n == blocks[b - 1].n && blk.X == blocks[b - 1].X;
+    if (!same && (blk.col_off < cursor || blk.col_off + blk.n > n)) return -1;
+    int rc = same ? 0 : zero_cols(K, m, ldk, cursor, blk.col_off, st);
     if (rc) return rc;
-    rc = lpgp_gram(blk.desc, Xt, m, blk.X, blk.n, K + blk.col_off, ldk, LPGP_GRAM_FULL, 0, 1.0, stream);
+    rc = lpgp_gram(blk.desc, Xt, m, blk.X, blk.n, K + blk.col_off, ldk, LPGP_GRAM_FULL, same ? 1 : 0, 1.0, stream);
     if (rc) return rc;
     cursor = blk.col_off + blk.n;
   }

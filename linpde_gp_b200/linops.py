@@ -408,3 +408,60 @@ class Kronecker(LinearOperator):
         backend.gemm_nt(T2, _aligned(A), U, 1.0, 0.0)                           # U[(c, i2), i1] = sum_j1 T A[i1, j1]
         res = U.reshape(k, n2, n1).permute(2, 1, 0).reshape(n1 * n2, k).cpu().numpy()
         return res[:, 0] if vec else res
+
+
+class BlockMatrix(LinearOperator):
+    """Dense block matrix ``[[A_00, A_01, ...], [A_10, ...], ...]`` of linear operators
+    (src/linpde_gp/linops/_block.py:17-80); blocks are assembled straight into their place in one device buffer."""
+
+    def __init__(self, blocks):
+        self._blocks = [list(row) for row in blocks]
+        if not self._blocks or any(len(row) != len(self._blocks[0]) for row in self._blocks):
+            raise ValueError("blocks must form a rectangular grid")
+        self._row_sizes = [row[0].shape[0] for row in self._blocks]
+        self._col_sizes = [b.shape[1] for b in self._blocks[0]]
+        for row, rs in zip(self._blocks, self._row_sizes):
+            for b, cs in zip(row, self._col_sizes):
+                if b.shape != (rs, cs):
+                    raise ValueError("inconsistent block shapes")
+        super().__init__((sum(self._row_sizes), sum(self._col_sizes)))
+
+    @property
+    def blocks(self):
+        return self._blocks
+
+    def device_dense(self):
+        out = backend.alloc_matrix(*self.shape)
+        r = 0
+        for row, rs in zip(self._blocks, self._row_sizes):
+            c = 0
+            for b, cs in zip(row, self._col_sizes):
+                b.assemble_into(out[r : r + rs, c : c + cs])
+                c += cs
+            r += rs
+        return out
+
+
+class BlockDiagonalMatrix(LinearOperator):
+    """``diag(A_0, A_1, ...)`` with possibly non-square blocks (pn/linops/_block.py ``BlockDiagonalMatrix``): the
+    covariance matrix of a process with independent outputs."""
+
+    def __init__(self, *blocks: LinearOperator):
+        self._blocks = tuple(blocks)
+        super().__init__((sum(b.shape[0] for b in blocks), sum(b.shape[1] for b in blocks)))
+        if all(b.is_symmetric for b in blocks):
+            self.is_symmetric = True
+
+    @property
+    def blocks(self):
+        return self._blocks
+
+    def device_dense(self):
+        out = backend.alloc_matrix(*self.shape)
+        out.zero_()
+        r = c = 0
+        for b in self._blocks:
+            b.assemble_into(out[r : r + b.shape[0], c : c + b.shape[1]])
+            r += b.shape[0]
+            c += b.shape[1]
+        return out

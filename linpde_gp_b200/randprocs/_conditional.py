@@ -25,7 +25,9 @@ VAR_CHUNK_BYTES = 4 << 30  # cross-covariance workspace per chunk of test points
 
 
 def _descs(k: covfuncs.CovarianceFunction):
-    """Device descriptors of a (possibly sum) kernel."""
+    """Device descriptors of a (possibly sum) kernel; the zero kernel has none."""
+    if isinstance(k, covfuncs.Zero):
+        return []
     if isinstance(k, covfuncs.SumCovarianceFunction):
         try:
             return [k.descriptor()]
@@ -35,6 +37,16 @@ def _descs(k: covfuncs.CovarianceFunction):
                 out.extend(_descs(s))
             return out
     return [k.descriptor()]
+
+
+def _gram_into(k: covfuncs.CovarianceFunction, X0, X1, out: "torch.Tensor", lower: bool = False) -> None:
+    """``out <- k(X0, X1)`` (``X1=None``: symmetric block, lower triangle when ``lower``): one pairwise-kernel launch per
+    device descriptor, accumulating from the second on; blocks of the zero kernel are cleared."""
+    descs = _descs(k)
+    if not descs:
+        out.zero_()
+    for t, dsc in enumerate(descs):
+        backend.gram(dsc, X0, X1, out=out, lower=lower, accumulate=t > 0)
 
 
 def _assemble_kronecker(k: covfuncs.CovarianceFunction, grid0, grid1, out: "torch.Tensor", lower: bool) -> bool:
@@ -156,9 +168,7 @@ class ConditionalGaussianProcess(GaussianProcess):
                 kij = kj if blk.op is None else blk.op(kj, argnum=0)
                 c_hi = pb.n if bj < bi else min(pb.n, l_hi)  # own batch: columns up to the last row's diagonal
                 if l_hi > l_lo and c_hi > 0:
-                    view = rows[: l_hi - l_lo, pb.col_off : pb.col_off + c_hi]
-                    for t, dsc in enumerate(_descs(kij)):
-                        backend.gram(dsc, Xi, pb.X[:c_hi], out=view, accumulate=t > 0)
+                    _gram_into(kij, Xi, pb.X[:c_hi], rows[: l_hi - l_lo, pb.col_off : pb.col_off + c_hi])
                 if pb.n_phys != pb.n and pb.col_off + pb.n < r_hi:
                     rows[:, pb.col_off + pb.n] = 0.0  # padding column of batch bj
             if noises[bi] is not None and l_hi > l_lo:
@@ -229,29 +239,36 @@ class ConditionalGaussianProcess(GaussianProcess):
         return backend.ObsBlocks(descs, Xs, offs)
 
     def _obs_blocks_unique(self) -> backend.ObsBlocks:
-        """One entry per observation block (sum kernels not supported for the variance workspace assembly)."""
-        descs, Xs, offs = [], [], []
-        for blk in self._blocks:
-            ds = _descs(self._k_test_obs(blk))
-            if len(ds) != 1:
-                raise NotImplementedError("posterior covariance of sum-kernels with different base factors")
-            descs.append(ds[0])
-            Xs.append(blk.X)
-            offs.append(blk.col_off)
-        return backend.ObsBlocks(descs, Xs, offs)
+        """Entries for the cross-covariance workspace ``k(x_test, X_obs)``: consecutive entries on the same columns
+        (sum kernels) are accumulated by ``lpgp_crosscov``, columns nobody covers (zero kernels) are cleared."""
+        return self._obs_blocks()
+
+    @property
+    def _is_multi_output(self) -> bool:
+        return self._prior.output_shape != ()
+
+    def _select(self, j: int) -> "ConditionalGaussianProcess":
+        from ..linfuncops import SelectOutput
+
+        return self._apply_linfuncop(SelectOutput((self._prior.input_shape, self._prior.output_shape), idx=j))
 
     # -- posterior mean / covariance -----------------------------------------------------------------------------
     class Mean(functions.Function):
         def __init__(self, post: "ConditionalGaussianProcess"):
             self._post = post
-            super().__init__(input_shape=post._prior.mean.input_shape, output_shape=())
+            super().__init__(input_shape=post._prior.mean.input_shape, output_shape=post._prior.mean.output_shape)
 
         def _evaluate(self, x: np.ndarray) -> np.ndarray:
             post = self._post
+            if post._is_multi_output:  # one matrix-free pass per output (outputs share the representer weights)
+                return np.stack([post._select(j).mean(x) for j in range(post._prior.output_shape[0])], axis=-1)
             batch = x.shape[: x.ndim - self.input_ndim]
             m_x = post._prior.mean(x)
+            blocks = post._obs_blocks()
+            if blocks.n == 0:  # no observation is correlated with this (output of the) process
+                return m_x
             Xt = backend.points(x, post._base_prior.cov.input_size)
-            upd = backend.post_mean(post._obs_blocks(), post._w, Xt)
+            upd = backend.post_mean(blocks, post._w, Xt)
             return m_x + upd.cpu().numpy().reshape(batch)
 
     class CovarianceFunction(covfuncs.CovarianceFunction):
@@ -259,14 +276,32 @@ class ConditionalGaussianProcess(GaussianProcess):
             self._post = post
             super().__init__(post._prior.cov.input_shape)
 
+        @property
+        def output_shape_0(self):
+            return self._post._prior.cov.output_shape_0
+
+        @property
+        def output_shape_1(self):
+            return self._post._prior.cov.output_shape_1
+
+        def _require_scalar(self):
+            if self._post._is_multi_output:
+                raise NotImplementedError(
+                    "posterior covariance of a multi-output process: apply `SelectOutput` to the posterior first "
+                    "(the reference's un-selected posterior covariance is not evaluable either)"
+                )
+
         def _evaluate(self, x0, x1, batch):
             post = self._post
+            self._require_scalar()
             d = self.input_size
             if x1 is None:  # pointwise variance
                 Xt = backend.points(x0, d)
                 prior_diag = _descs(post._prior.cov)
                 diag = sum(dsc.diag_value for dsc in prior_diag)
                 n = post._factor.n
+                if post._obs_blocks().n == 0:
+                    return np.full(batch, diag)
                 if getattr(post._factor, "distributed", False):
                     return post._var_distributed(Xt, diag).cpu().numpy().reshape(batch)
                 chunk = int(max(256, min(Xt.shape[0], VAR_CHUNK_BYTES // (8 * backend.round_up(n, 16)))))
@@ -287,20 +322,22 @@ class ConditionalGaussianProcess(GaussianProcess):
         def _dense(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> torch.Tensor:
             """k(x0,x1) - K_0 G^{-1} K_1^T = k(x0,x1) - (K_0 L^{-T})(K_1 L^{-T})^T  (_conditional.py:245-251)."""
             post = self._post
+            self._require_scalar()
             d = self.input_size
             X0 = backend.points(x0, d)
+            X1 = None if x1 is None else backend.points(x1, d)
+            C = backend.alloc_matrix(X0.shape[0], X0.shape[0] if X1 is None else X1.shape[0])
+            _gram_into(post._prior.cov, X0, X1, C)
             blocks = post._obs_blocks_unique()
+            if blocks.n == 0:
+                return C
             V0 = backend.crosscov(blocks, post._factor.n, X0)
             post._factor.trsm_rlt(V0)
             if x1 is None:
-                X1, V1 = None, V0
+                V1 = V0
             else:
-                X1 = backend.points(x1, d)
                 V1 = backend.crosscov(blocks, post._factor.n, X1)
                 post._factor.trsm_rlt(V1)
-            C = backend.alloc_matrix(X0.shape[0], V1.shape[0])
-            for i, dsc in enumerate(_descs(post._prior.cov)):
-                backend.gram(dsc, X0, X1, out=C, accumulate=i > 0)
             backend.gemm_nt(V0, V1, C, -1.0, 1.0)
             return C
 
@@ -350,16 +387,14 @@ class ConditionalGaussianProcess(GaussianProcess):
             kij = kj if blk.op is None else blk.op(kj, argnum=0)
             out = rows[:n, pb.col_off : pb.col_off + pb.n]
             if not _assemble_kronecker(kij, blk.grid, pb.grid, out, lower=False):
-                for i, dsc in enumerate(_descs(kij)):
-                    backend.gram(dsc, blk.X, pb.X, out=out, accumulate=i > 0)
+                _gram_into(kij, blk.X, pb.X, out)
             if pb.n_phys != pb.n:
                 rows[:, pb.col_off + pb.n] = 0.0
         kj = k if blk.op is None else blk.op(k, argnum=1)
         kii = kj if blk.op is None else blk.op(kj, argnum=0)
         D = rows[:n, r0 : r0 + n]
         if not _assemble_kronecker(kii, blk.grid, None, D, lower=True):
-            for i, dsc in enumerate(_descs(kii)):
-                backend.gram(dsc, blk.X, None, out=D, lower=True, accumulate=i > 0)
+            _gram_into(kii, blk.X, None, D, lower=True)
         if noise is not None:
             kind, val = noise
             if kind == "diag":
@@ -392,6 +427,10 @@ class ConditionalGaussianProcess(GaussianProcess):
         else:
             raise TypeError("`L` must be a `LinearFunctional`, a `LinearFunctionOperator` or `None`.")
         op, Xobs = Lf._as_observation()  # pylint: disable=protected-access
+        if prior.output_shape != () and (op is None or tuple(op.output_codomain_shape) != ()):
+            raise NotImplementedError(
+                "observations of a multi-output process must be scalar-valued: compose the operator with `SelectOutput`"
+            )
 
         if b is not None:
             b = randvars.asrandvar(b)

@@ -21,8 +21,13 @@ class GaussianProcess:
                 f"The mean and covariance functions must have the same input shapes ({mean.input_shape} and "
                 f"{cov.input_shape})."
             )
-        if mean.output_shape != ():
-            raise NotImplementedError("only scalar-output processes are on the accelerated path")
+        if mean.output_shape != cov.output_shape_0 or mean.output_shape != cov.output_shape_1:
+            raise ValueError(
+                f"The output shapes of the mean function ({mean.output_shape}) and of the covariance function "
+                f"({cov.output_shape_0}, {cov.output_shape_1}) must match."
+            )
+        if len(mean.output_shape) > 1:
+            raise NotImplementedError("processes with more than one output axis are not on the accelerated path")
         self._mean = mean
         self._cov = cov
 
@@ -44,11 +49,11 @@ class GaussianProcess:
 
     @property
     def output_shape(self):
-        return ()
+        return self._mean.output_shape
 
     @property
     def output_ndim(self):
-        return 0
+        return len(self._mean.output_shape)
 
     def __call__(self, args) -> randvars.Normal:
         """Finite-dimensional marginal ``Normal(mean(x), cov.linop(x))`` -- the covariance stays a lazy,
@@ -57,7 +62,10 @@ class GaussianProcess:
         return randvars.Normal(mean=np.array(self._mean(x), copy=False).reshape(-1), cov=self._cov.linop(x))
 
     def var(self, args) -> np.ndarray:
-        return self._cov(np.asarray(args, dtype=np.double), None)
+        v = self._cov(np.asarray(args, dtype=np.double), None)
+        if self.output_ndim:  # multi-output: the pointwise covariance is an (n, n) matrix per point
+            v = np.diagonal(v, axis1=-2, axis2=-1)
+        return v
 
     def std(self, args) -> np.ndarray:
         return np.sqrt(self.var(args))

@@ -77,9 +77,26 @@ class CovarianceFunction:
     def input_size(self):
         return int(np.prod(self._input_shape)) if self._input_shape else 1
 
-    output_shape_0 = ()
-    output_shape_1 = ()
-    output_shape = ()
+    # scalar-output unless a subclass (multi-output kernels below) overrides these
+    @property
+    def output_shape_0(self):
+        return ()
+
+    @property
+    def output_shape_1(self):
+        return ()
+
+    @property
+    def output_shape(self):
+        return self.output_shape_0
+
+    @property
+    def output_size_0(self):
+        return int(np.prod(self.output_shape_0)) if self.output_shape_0 else 1
+
+    @property
+    def output_size_1(self):
+        return int(np.prod(self.output_shape_1)) if self.output_shape_1 else 1
 
     # -- lowering ------------------------------------------------------------------------------------------
     def _product_form(self):
@@ -303,9 +320,22 @@ class ScaledCovarianceFunction(CovarianceFunction):
     def covfunc(self):
         return self._covfunc
 
+    @property
+    def output_shape_0(self):
+        return self._covfunc.output_shape_0
+
+    @property
+    def output_shape_1(self):
+        return self._covfunc.output_shape_1
+
     def _product_form(self):
         f, t0, t1, s = self._covfunc._product_form()
         return f, t0, t1, s * float(self._scalar)
+
+    def _evaluate(self, x0, x1, batch):
+        if self.output_shape_0 != () or self.output_shape_1 != ():
+            return float(self._scalar) * self._covfunc._evaluate(x0, x1, batch)
+        return super()._evaluate(x0, x1, batch)
 
     def linop(self, x0, x1=None):
         if _grid_factors(x0) is not None:  # keep the Kronecker structure of the wrapped kernel
@@ -333,12 +363,23 @@ class SumCovarianceFunction(CovarianceFunction):
             raise TypeError()
         if not all(s.input_shape == summands[0].input_shape for s in summands):
             raise ValueError("All summands must have the same input shape")
+        if not all(s.output_shape_0 == summands[0].output_shape_0 and s.output_shape_1 == summands[0].output_shape_1
+                   for s in summands):
+            raise ValueError("All summands must have the same output shapes")
         super().__init__(summands[0].input_shape)
         self._summands = tuple(summands)
 
     @property
     def summands(self):
         return self._summands
+
+    @property
+    def output_shape_0(self):
+        return self._summands[0].output_shape_0
+
+    @property
+    def output_shape_1(self):
+        return self._summands[0].output_shape_1
 
     def _product_form(self):
         raise NotImplementedError("sum of kernels with different base factors: evaluated block-wise")
@@ -497,6 +538,207 @@ class UnivariateHalfIntegerMatern_DirectionalDerivative_WeightedLaplacian(LinDif
     """diffops/_matern.py:512"""
 
 
+
+# ---------------------------------------------------------------------------------------------------------------
+# multi-output kernels (SURVEY.md section 8f item 4)
+# ---------------------------------------------------------------------------------------------------------------
+class Zero(CovarianceFunction):
+    """The zero covariance function (src/linpde_gp/randprocs/covfuncs/_zero.py): the cross-covariance between
+    independent outputs.  Contributes no device work -- blocks made of it are zero-filled."""
+
+    def __init__(self, input_shape=()):
+        super().__init__(input_shape)
+
+    def _product_form(self):
+        raise NotImplementedError("the zero kernel has no descriptor (nothing to evaluate)")
+
+    def _evaluate(self, x0, x1, batch):
+        return np.zeros(batch)
+
+    def linop(self, x0, x1=None):
+        from ..linops import Matrix
+
+        n0 = self._preprocess_linop_input(x0, 0).shape[0]
+        n1 = n0 if x1 is None else self._preprocess_linop_input(x1, 1).shape[0]
+        return Matrix(np.zeros((n0, n1)))
+
+    def __rmul__(self, other):
+        return self if np.ndim(other) == 0 else NotImplemented
+
+
+class IndependentMultiOutputCovarianceFunction(CovarianceFunction):
+    """``k(x, x')[i, j] = delta_ij k_i(x, x')`` for scalar kernels ``k_i`` on a common input space
+    (src/linpde_gp/randprocs/covfuncs/_independent_multi_output.py:11-71)."""
+
+    def __init__(self, *covfuncs):
+        if not covfuncs:
+            raise ValueError("at least one covariance function is needed")
+        for c in covfuncs:
+            if not isinstance(c, CovarianceFunction):
+                raise TypeError()
+            if c.input_shape != covfuncs[0].input_shape or c.output_shape_0 != () or c.output_shape_1 != ():
+                raise ValueError("the outputs must be scalar kernels on the same input space")
+        super().__init__(covfuncs[0].input_shape)
+        self._covfuncs = tuple(covfuncs)
+
+    @property
+    def covfuncs(self):
+        return self._covfuncs
+
+    @property
+    def output_shape_0(self):
+        return (len(self._covfuncs),)
+
+    @property
+    def output_shape_1(self):
+        return (len(self._covfuncs),)
+
+    def _product_form(self):
+        raise NotImplementedError("multi-output kernel: select an output first")
+
+    def _evaluate(self, x0, x1, batch):
+        n = len(self._covfuncs)
+        out = np.zeros(tuple(batch) + (n, n))
+        for i, c in enumerate(self._covfuncs):
+            out[..., i, i] = c._evaluate(x0, x1, batch)
+        return out
+
+    def linop(self, x0, x1=None):
+        from ..linops import BlockDiagonalMatrix
+
+        return BlockDiagonalMatrix(*(c.linop(x0, x1) for c in self._covfuncs))
+
+
+class StackCovarianceFunction(CovarianceFunction):
+    """A vector of scalar kernels read as ONE kernel with a vector-valued output on argument ``output_idx``
+    (src/linpde_gp/randprocs/covfuncs/_stack.py:15-104): what ``L(k_multi, argnum=1)`` is for a scalar-valued
+    observation operator ``L`` -- the covariance between every output of the process and the observed quantity."""
+
+    def __init__(self, covfuncs, output_idx: int = 1):
+        covfuncs = tuple(covfuncs)
+        if not covfuncs or not all(isinstance(c, CovarianceFunction) for c in covfuncs):
+            raise ValueError()
+        if any(c.input_shape != covfuncs[0].input_shape for c in covfuncs):
+            raise ValueError()
+        if any(c.output_shape_0 != () or c.output_shape_1 != () for c in covfuncs):
+            raise ValueError()
+        output_idx = int(output_idx)
+        if output_idx not in (0, 1):
+            raise ValueError()
+        super().__init__(covfuncs[0].input_shape)
+        self._covfuncs = covfuncs
+        self._output_idx = output_idx
+
+    @property
+    def covfuncs(self):
+        return self._covfuncs
+
+    @property
+    def output_idx(self):
+        return self._output_idx
+
+    @property
+    def output_shape_0(self):
+        return (len(self._covfuncs),) if self._output_idx == 0 else ()
+
+    @property
+    def output_shape_1(self):
+        return (len(self._covfuncs),) if self._output_idx == 1 else ()
+
+    def _product_form(self):
+        raise NotImplementedError("multi-output kernel: select an output first")
+
+    def _evaluate(self, x0, x1, batch):
+        return np.stack([c._evaluate(x0, x1, batch) for c in self._covfuncs], axis=-1)
+
+    def linop(self, x0, x1=None):
+        from ..linops import BlockMatrix
+
+        ops = [c.linop(x0, x1) for c in self._covfuncs]
+        return BlockMatrix([[o] for o in ops] if self._output_idx == 0 else [ops])
+
+    # sums / scalar multiples of stacks stay stacks (element-wise), so that one SelectOutput resolves them
+    def __add__(self, other):
+        if isinstance(other, StackCovarianceFunction):
+            if other.output_idx != self._output_idx or len(other.covfuncs) != len(self._covfuncs):
+                raise ValueError("stacks of different layout cannot be added")
+            return StackCovarianceFunction(
+                tuple(_add_cov(a, b) for a, b in zip(self._covfuncs, other.covfuncs)), output_idx=self._output_idx)
+        return super().__add__(other)
+
+    def __rmul__(self, other):
+        if np.ndim(other) == 0:
+            return StackCovarianceFunction(tuple(_scale_cov(other, c) for c in self._covfuncs), output_idx=self._output_idx)
+        return NotImplemented
+
+
+def _add_cov(a: CovarianceFunction, b: CovarianceFunction) -> CovarianceFunction:
+    """``a + b`` with zeros dropped and nested sums flattened."""
+    if isinstance(a, Zero):
+        return b
+    if isinstance(b, Zero):
+        return a
+    if isinstance(a, StackCovarianceFunction) or isinstance(b, StackCovarianceFunction):
+        return a + b
+    parts = []
+    for c in (a, b):
+        parts.extend(c.summands if isinstance(c, SumCovarianceFunction) else (c,))
+    return SumCovarianceFunction(*parts)
+
+
+def _scale_cov(scalar, k: CovarianceFunction) -> CovarianceFunction:
+    """``scalar * k`` distributed over sums (every summand keeps its own device descriptor)."""
+    if isinstance(k, (Zero, StackCovarianceFunction)):
+        return scalar * k
+    if isinstance(k, SumCovarianceFunction):
+        return SumCovarianceFunction(*(_scale_cov(scalar, s) for s in k.summands))
+    return scalar * k
+
+
+def _apply_multi_output(L, k: CovarianceFunction, argnum: int) -> CovarianceFunction:
+    """Operators and kernels with vector-valued (co)domains: linearity over sums / scalars / compositions, then the
+    ``SelectOutput`` and element-wise ``StackCovarianceFunction`` rules of
+    src/linpde_gp/randprocs/covfuncs/linfuncops/_registry.py:34-48, 82-120."""
+    from ..linfuncops import _linfuncop
+
+    if isinstance(L, _linfuncop.CompositeLinearFunctionOperator):
+        out = k
+        for op in reversed(L.linfuncops):
+            out = apply_linfuncop(op, out, argnum)
+        return out
+    if isinstance(L, _linfuncop.SumLinearFunctionOperator) and L.input_codomain_shape != ():
+        out = None
+        for summand in L.summands:
+            v = apply_linfuncop(summand, k, argnum)
+            out = v if out is None else _add_cov(out, v)
+        return out
+    if isinstance(L, _linfuncop.ScaledLinearFunctionOperator) and L.input_codomain_shape != ():
+        return _scale_cov(float(L.scalar), apply_linfuncop(L.linfuncop, k, argnum))
+    if isinstance(k, ScaledCovarianceFunction):
+        return _scale_cov(float(k.scalar), apply_linfuncop(L, k.covfunc, argnum))
+    if isinstance(k, SumCovarianceFunction):
+        out = None
+        for s in k.summands:
+            v = apply_linfuncop(L, s, argnum)
+            out = v if out is None else _add_cov(out, v)
+        return out
+    if isinstance(L, _linfuncop.SelectOutput):
+        if isinstance(k, IndependentMultiOutputCovarianceFunction):
+            if not isinstance(L.idx, (int, np.integer)):
+                raise NotImplementedError("SelectOutput with a non-integer index")
+            zero = Zero(k.input_shape)
+            return StackCovarianceFunction(
+                tuple(c if i == L.idx else zero for i, c in enumerate(k.covfuncs)), output_idx=1 - argnum)
+        if isinstance(k, StackCovarianceFunction) and k.output_idx == argnum:
+            return k.covfuncs[L.idx]
+        raise NotImplementedError(f"SelectOutput on argument {argnum} of {type(k).__name__}")
+    if isinstance(k, StackCovarianceFunction):
+        if (argnum == 0 and k.output_idx == 1) or (argnum == 1 and k.output_idx == 0):
+            return StackCovarianceFunction(tuple(apply_linfuncop(L, c, argnum) for c in k.covfuncs), output_idx=k.output_idx)
+        raise NotImplementedError("the operator acts on the stacked argument: select an output first")
+    raise NotImplementedError(f"{type(L).__name__} applied to {type(k).__name__}")
+
+
 def _kind_of(L):
     from ..linfuncops import diffops
 
@@ -558,6 +800,14 @@ def apply_linfuncop(L, k: CovarianceFunction, argnum: int = 0) -> CovarianceFunc
         raise ValueError("`argnum` must either be 0 or 1.")
     if tuple(L.input_domain_shape) != tuple(k.input_shape):
         raise ValueError(f"operator input domain shape {L.input_domain_shape} != kernel input shape {k.input_shape}")
+    k_out = k.output_shape_0 if argnum == 0 else k.output_shape_1
+    if tuple(L.input_codomain_shape) != tuple(k_out):
+        raise ValueError(f"operator input codomain shape {L.input_codomain_shape} != kernel output shape {k_out}")
+    if isinstance(k, Zero):
+        return k
+    if (L.input_codomain_shape != () or k.output_shape_0 != () or k.output_shape_1 != ()
+            or isinstance(L, _linfuncop.CompositeLinearFunctionOperator)):
+        return _apply_multi_output(L, k, argnum)
     if isinstance(L, _linfuncop.Identity):
         return k
     if isinstance(k, ScaledCovarianceFunction):

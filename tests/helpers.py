@@ -171,3 +171,51 @@ def api_solve(problem):
         "cov": post.cov.matrix(Xc),
         "gram": post.gram.todense(),
     }
+
+
+def api_solve_multi_output(problem, one_shot: bool = False):
+    """Run a multi-output golden problem (oracle/multi_output.py spec) through the product API: independent-output
+    prior, observation operators ``sum_t c_t * (D_t @ SelectOutput(o_t))``, posterior of every selected output."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200 import linfuncops
+    from linpde_gp_b200.randprocs import covfuncs
+    from tests.golden import cases as gcases
+
+    shape = gcases.kernel_input_shape(problem["kernels"][0])
+    nout = len(problem["kernels"])
+    prior = lg.GaussianProcess(
+        lg.functions.StackedFunction(*(lg.functions.Constant(shape, m) for m in problem["means"])),
+        covfuncs.IndependentMultiOutputCovarianceFunction(*(api_kernel(k) for k in problem["kernels"])),
+    )
+    sel = [linfuncops.SelectOutput((shape, (nout,)), idx=j) for j in range(nout)]
+    batches = []
+    for blk in problem["blocks"]:
+        X = np.asarray(blk["X"], dtype=float)
+        Y = np.asarray(blk["Y"], dtype=float)
+        L = None
+        for o, c, op in blk["Ls"]:
+            t = sel[o] if op is None else api_op(op) @ sel[o]
+            if c != 1.0:
+                t = c * t
+            L = t if L is None else L + t
+        b = None
+        if blk.get("noise_var") is not None:
+            nv = np.broadcast_to(np.asarray(blk["noise_var"], dtype=float), Y.shape).copy()
+            b = lg.randvars.Normal(np.zeros_like(Y), lg.linops.Scaling(nv))
+        batches.append((Y, X, L, b))
+    if one_shot:
+        post = lg.ConditionalGaussianProcess.from_observation_batches(prior, batches)
+    else:
+        post = prior
+        for Y, X, L, b in batches:
+            post = post.condition_on_observations(Y, X=X, L=L, b=b)
+    Xt = np.asarray(problem["Xt"], dtype=float)
+    Xc = Xt[: problem.get("n_cov", 8)]
+    outs = [s(post) for s in sel]
+    return post, {
+        "w": post.representer_weights,
+        "gram": post.gram.todense(),
+        "mean": np.stack([o.mean(Xt) for o in outs]),
+        "var": np.stack([o.cov(Xt, None) for o in outs]),
+        "cov": np.stack([o.cov.matrix(Xc) for o in outs]),
+    }

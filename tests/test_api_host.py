@@ -166,3 +166,57 @@ def test_tensor_product_grid_host_semantics():
     assert covfuncs._grid_factors(covfuncs.TensorProductGrid(xs, ys, indexing="xy")) is None
     with pytest.raises(ValueError):
         covfuncs.TensorProductGrid(np.zeros((2, 2)))
+
+
+def test_multi_output_dispatch_follows_the_reference_registry():
+    """covfuncs/linfuncops/_registry.py:34-48, 82-120 and linfuncops/_arithmetic.py:112-144 (host-side, symbolic)."""
+    from linpde_gp_b200 import functions, linfuncops
+    from linpde_gp_b200.randprocs._conditional import _descs
+
+    ku = 9.0 * covfuncs.Matern((), nu=2.5, lengthscales=0.75)
+    kv = 0.81 * covfuncs.Matern((), nu=0.5)
+    k = covfuncs.IndependentMultiOutputCovarianceFunction(ku, kv, kv)
+    assert k.output_shape_0 == (3,) and k.output_shape_1 == (3,) and k.input_shape == ()
+    su, sv, sa = (linfuncops.SelectOutput(((), (3,)), idx=i) for i in range(3))
+    assert su.output_shapes == ((), ()) and su.input_shapes == ((), (3,))
+    D = -0.5 * diffops.Laplacian(())
+    # SelectOutput on the block-diagonal kernel -> a stack with zeros off the selected output
+    st = su(k, argnum=1)
+    assert type(st) is covfuncs.StackCovarianceFunction and st.output_idx == 0 and st.output_shape_0 == (3,)
+    assert st.covfuncs[0] is ku and all(type(c) is covfuncs.Zero for c in st.covfuncs[1:])
+    assert su(k, argnum=0).output_idx == 1
+    # selecting the stacked argument picks the entry; selecting twice recovers the output's own kernel
+    assert su(st, argnum=0) is ku and type(sv(st, argnum=0)) is covfuncs.Zero
+    # composition acts right to left; sums / scalars distribute (Sum of stacks stays a stack)
+    L = D @ su - sv
+    assert type(D @ su) is linfuncops.CompositeLinearFunctionOperator
+    assert type(D @ (su + su)) is linfuncops.SumLinearFunctionOperator
+    kL = L(k, argnum=1)
+    assert type(kL) is covfuncs.StackCovarianceFunction and kL.output_idx == 0
+    assert type(kL.covfuncs[2]) is covfuncs.Zero
+    inner = kL.covfuncs[0]
+    assert float(inner.scalar) == 9.0
+    assert type(inner.covfunc) is covfuncs.UnivariateHalfIntegerMatern_Identity_WeightedLaplacian
+    LkL = L(kL, argnum=0)
+    assert type(LkL) is covfuncs.SumCovarianceFunction and len(LkL.summands) == 2 and LkL.output_shape_0 == ()
+    assert type(LkL.summands[0].covfunc) is covfuncs.UnivariateHalfIntegerMatern_WeightedLaplacian_WeightedLaplacian
+    assert len(_descs(LkL)) == 2 and _descs(sa(kL, argnum=0)) == []
+    # an operator on the stacked argument needs a SelectOutput first (validate_covfunc_transformation: ValueError)
+    with pytest.raises(ValueError):
+        D(kL, argnum=0)
+    with pytest.raises(ValueError):
+        D(k, argnum=0)  # codomain shapes differ
+    # functions: SelectOutput / linear combinations of a stacked mean
+    mean = functions.StackedFunction(functions.Constant((), 57.0), functions.Constant((), 0.3), functions.Constant((), -0.1))
+    assert mean.output_shape == (3,) and mean(np.zeros(4)).shape == (4, 3)
+    np.testing.assert_allclose(L(mean)(np.zeros(2)), [-0.3, -0.3])
+    np.testing.assert_allclose((2.0 * su - sa)(mean)(np.zeros(1)), [114.1])
+    # processes
+    prior = lg.GaussianProcess(mean, k)
+    assert prior.output_shape == (3,)
+    pu = su(prior)
+    assert pu.output_shape == () and pu.cov is ku
+    with pytest.raises(ValueError):
+        lg.GaussianProcess(functions.Constant((), 1.0), k)
+    with pytest.raises(NotImplementedError):
+        prior.condition_on_observations(np.zeros((3, 4)), X=np.zeros(4))  # vector-valued observation

@@ -399,3 +399,88 @@ def test_gridded_conditioning_uses_kronecker_assembly_and_matches_pairwise():
         sc = max(np.max(np.abs(ref[key])), np.max(np.abs(ref["var"])))
         assert np.max(np.abs(res_g[key] - ref[key])) <= POST_TOL * sc, key
         assert np.max(np.abs(res_g[key] - res_p[key])) <= POST_TOL * sc, key
+
+
+# ---- multi-output processes with independent outputs ------------------------------------------------
+MO_FILES = sorted(glob.glob(os.path.join(GOLDEN, "mo_*.npz")))
+
+
+@pytest.mark.parametrize("one_shot", [False, True], ids=["sequential", "one_shot"])
+@pytest.mark.parametrize("path", MO_FILES, ids=[os.path.basename(p)[3:-4] for p in MO_FILES])
+def test_multi_output_conditioning_matches_reference_golden(path, one_shot):
+    """IndependentMultiOutputCovarianceFunction prior, ``D @ SelectOutput(i) - SelectOutput(j)`` observations
+    (experiments/0000_cpu_stationary_1d.ipynb cells 55-82), ``SelectOutput(j)(posterior)`` mean / variance /
+    covariance against the frozen outputs of the real reference; Gram 1e-11 (reconstructed as L L^T), posterior 1e-8."""
+    g = np.load(path)
+    problem = json.loads(bytes(g["problem"]).decode())
+    post, res = helpers.api_solve_multi_output(problem, one_shot=one_shot)
+    gs = np.max(np.abs(g["gram"]))
+    assert np.max(np.abs(res["gram"] - g["gram"])) <= 1e-11 * gs
+    for key in ("mean", "var", "cov"):
+        for j in range(len(problem["kernels"])):
+            sc = max(np.max(np.abs(g[key][j])), np.max(np.abs(g["var"][j])))
+            assert np.max(np.abs(res[key][j] - g[key][j])) <= POST_TOL * sc, (key, j)
+    assert np.max(np.abs(res["w"] - g["w"])) <= 1e-6 * np.max(np.abs(g["w"]))
+    # the un-selected posterior: mean of all outputs at once, variance via the per-output posteriors
+    Xt = np.asarray(problem["Xt"], dtype=float)
+    m_all = post.mean(Xt)
+    assert m_all.shape == Xt.shape[:1] + (len(problem["kernels"]),)
+    np.testing.assert_allclose(m_all.T, res["mean"], rtol=0, atol=1e-12 * np.max(np.abs(res["mean"])))
+    with pytest.raises(NotImplementedError):
+        post.cov(Xt, None)
+
+
+def test_multi_output_prior_kernel_evaluation():
+    """tests/linpde_gp/randprocs/kernels/test_independent_multi_output.py: independence, batched shapes,
+    block-diagonal ``linop`` with non-square blocks."""
+    from linpde_gp_b200.randprocs import covfuncs
+
+    ls = np.random.default_rng(12938422).random(size=(3, 2))
+    ks = [covfuncs.TensorProduct(*(covfuncs.Matern((), nu=2.5, lengthscales=l) for l in row)) for row in ls]
+    mo = covfuncs.IndependentMultiOutputCovarianceFunction(*ks)
+    rng = np.random.default_rng(9238134)
+    x0, x1 = rng.random(size=(10, 1, 2)), rng.random(size=(1, 15, 2))
+    res = mo(x0, x1)
+    assert res.shape == (10, 15, 3, 3)
+    for i, j in np.ndindex(3, 3):
+        if i != j:
+            assert np.all(res[..., i, j] == 0.0)
+        else:
+            np.testing.assert_allclose(res[..., i, i], ks[i](x0, x1), rtol=0, atol=1e-15)
+    same = mo(x0[:, 0], x0[:, 0])
+    np.testing.assert_allclose(same[..., np.arange(3), np.arange(3)], 1.0, atol=1e-15)
+    dense = mo.linop(x0, x1).todense()
+    assert dense.shape == (30, 45)
+    for i in range(3):
+        np.testing.assert_allclose(dense[10 * i : 10 * i + 10, 15 * i : 15 * i + 15], ks[i].matrix(x0, x1), atol=1e-15)
+    assert np.count_nonzero(dense[:10, 15:]) == 0
+    st = covfuncs.StackCovarianceFunction((ks[0], covfuncs.Zero((2,)), ks[2]), output_idx=0)
+    assert st(x0, x1).shape == (10, 15, 3) and st.linop(x0, x1).shape == (30, 15)
+    np.testing.assert_allclose(st.linop(x0, x1).todense()[20:], ks[2].matrix(x0, x1), atol=1e-15)
+
+
+def test_sum_kernel_prior_posterior_covariance():
+    """Posterior covariance with a SUM prior kernel of different base factors (two descriptors per block): the
+    cross-covariance workspace accumulates consecutive entries on the same columns."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.randprocs import covfuncs
+    from oracle import covfuncs as ocf
+    from oracle import linalg as ola
+
+    rng = np.random.default_rng(5)
+    X, Xt = rng.uniform(0, 1, 40), np.linspace(0, 1, 23)
+    Y = np.sin(3 * X)
+    k = 2.0 * covfuncs.Matern((), nu=2.5, lengthscales=0.3) + 0.5 * covfuncs.ExpQuad((), lengthscales=0.2)
+    post = lg.GaussianProcess(lg.functions.Zero(()), k).condition_on_observations(
+        Y, X=X, b=lg.randvars.Normal(np.zeros(40), lg.linops.Scaling(1e-4 * np.ones(40))))
+    s1 = {"scale": 2.0, "base": {"kind": "matern", "input_shape": [], "nu": 2.5, "lengthscales": 0.3}}
+    s2 = {"scale": 0.5, "base": {"kind": "expquad", "input_shape": [], "lengthscales": 0.2}}
+    kk = lambda a, b=None: ocf.matrix(s1, None, None, a, b) + ocf.matrix(s2, None, None, a, b)
+    G = kk(X) + 1e-4 * np.eye(40)
+    Lc = ola.cholesky_lower(G)
+    Kt = kk(Xt, X)
+    mean = Kt @ ola.cho_solve_lower(Lc, Y)
+    cov = kk(Xt) - Kt @ ola.cho_solve_lower(Lc, Kt.T)
+    np.testing.assert_allclose(post.mean(Xt), mean, rtol=0, atol=POST_TOL * np.max(np.abs(mean)))
+    np.testing.assert_allclose(post.cov.matrix(Xt), cov, rtol=0, atol=POST_TOL * 2.5)
+    np.testing.assert_allclose(post.var(Xt), np.diag(cov), rtol=0, atol=POST_TOL * 2.5)

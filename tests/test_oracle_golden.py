@@ -123,3 +123,31 @@ def test_kronecker_linop_matches_reference(spec):
 
 def test_generated_kron_case_list_is_the_frozen_one():
     assert json.loads(json.dumps(gcases.build_kron_cases())) == KRON_SPECS
+
+
+# ---- multi-output processes with independent outputs ------------------------------------------------
+MO_FILES = sorted(glob.glob(os.path.join(GOLDEN, "mo_*.npz")))
+
+
+@pytest.mark.parametrize("path", MO_FILES, ids=[os.path.basename(p)[3:-4] for p in MO_FILES])
+def test_multi_output_conditioning_matches_reference(path):
+    """IndependentMultiOutputCovarianceFunction prior + ``D @ SelectOutput`` observations, run through the real
+    reference by oracle/make_golden.py (experiments/0000_cpu_stationary_1d.ipynb cells 55-82 shape)."""
+    from oracle import multi_output as omo
+
+    g = np.load(path)
+    problem = json.loads(bytes(g["problem"]).decode())
+    res = omo.solve(problem)
+    np.testing.assert_allclose(res["gram"], g["gram"], rtol=0, atol=4e-16 * np.max(np.abs(g["gram"])))
+    for key, tol in (("mean", 1e-9), ("var", 1e-8), ("cov", 1e-8)):
+        sc = np.max(np.abs(g[key]))
+        assert np.max(np.abs(res[key] - g[key])) <= tol * sc, key
+    assert len(MO_FILES) == 2
+
+
+def test_multi_output_golden_problems_are_the_frozen_ones():
+    from oracle import multi_output as omo
+
+    for name, prob in omo.golden_problems().items():
+        g = np.load(os.path.join(GOLDEN, f"mo_{name}.npz"))
+        assert json.loads(json.dumps(prob)) == json.loads(bytes(g["problem"]).decode())
