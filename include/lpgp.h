@@ -220,8 +220,9 @@ int lpgp_post_mean(const lpgp_obs_block* blocks, int nblocks, const double* w, c
 
 /* K[i, col_off_b + j] = (k L_b^*)(Xt[i], X_b[j]) for all blocks, gaps zeroed: the cross-covariance rows
  * PriorPredictiveCrossCovariance._evaluate (_conditional.py:140-153) of m test points, n = factor size.
- * Blocks must be sorted by col_off; consecutive entries with identical (X, n, col_off) are summands of ONE kernel
- * (sum kernels, multi-output observation operators -- crosscov/_arithmetic.py Sum wrappers) and are accumulated.
+ * Blocks must be sorted by col_off; consecutive entries with identical (n, col_off) are summands of ONE observation
+ * (sum kernels, multi-output observation operators, sums of evaluation functionals -- crosscov/_arithmetic.py Sum
+ * wrappers, linfunctls/_arithmetic.py:58-90) and are accumulated.
  * nblocks = 0 clears K.                                                                                       */
 int lpgp_crosscov(const lpgp_obs_block* blocks, int nblocks, int64_t n, const double* Xt, int64_t m, double* K,
                   int64_t ldk, void* stream);
@@ -236,6 +237,36 @@ int lpgp_post_var(const lpgp_obs_block* blocks, int nblocks, const lpgp_factor* 
 /* out[i] (+)= scale * sum_j A[i*ld + j]^2   (row sums of squares; building block of lpgp_post_var).    */
 int lpgp_row_sumsq(const double* A, int64_t m, int64_t n, int64_t ld, double scale, double offset, double* out,
                    void* stream);
+
+/* (4) integral observations ---------------------------------------------------
+ * Lebesgue integrals of a univariate half-integer Matern kernel, the closed forms of
+ * src/linpde_gp/randprocs/crosscov/linfunctls/integrals/_matern_lebesgue.py:14-141 and _radial_lebesgue.py:37-69
+ * (dispatch: src/linpde_gp/randprocs/covfuncs/linfunctls/_registry.py:157-193), used by the stationarity
+ * observation of experiments/0000_cpu_stationary_1d.ipynb cells 65-66, 85.  In the scaled variable
+ * v = scale * |delta| (scale = sqrt(2 nu) / lengthscale) the first / second radial antiderivatives are
+ *   H1(delta) = sign(delta)/scale * (poly1[0] - exp(-v) poly1(v)),
+ *   H2(delta) = 1/scale^2 * (exp(-v) poly2(v) - poly2[0] + poly1[0] v)
+ * with poly1 = sum_m P^(m), poly2 = P + sum_i (i+1) P^(i) (P = Matern polynomial, ascending coefficients).     */
+#define LPGP_MAX_INTEGRAL_COEF 8
+typedef struct lpgp_matern_integral_desc {
+  int32_t ncoef;     /* p + 1, 1..LPGP_MAX_INTEGRAL_COEF                                               */
+  int32_t reserved;
+  double scale;      /* sqrt(2 nu) / lengthscale                                                       */
+  double poly1[LPGP_MAX_INTEGRAL_COEF];
+  double poly2[LPGP_MAX_INTEGRAL_COEF];
+} lpgp_matern_integral_desc;
+
+/* out[i * out_stride] (+)= alpha * (w ? *w : 1) * int_a^b k(x[i], t) dt  for n points x (device, contiguous):
+ * UnivariateRadialCovarianceFunctionLebesgueIntegral._evaluate (_radial_lebesgue.py:37-45).  The stride lets the
+ * values land in a row (1) or a column (ld) of the Gram matrix / cross-covariance workspace; `w` (device scalar,
+ * may be NULL) folds a representer weight in, which is how the integral row enters the posterior mean.         */
+int lpgp_matern_integral(const lpgp_matern_integral_desc* desc, double a, double b, const double* x, int64_t n,
+                         double alpha, const double* w, double* out, int64_t out_stride, int accumulate, void* stream);
+
+/* *out (+)= alpha * int_a^b int_c^d k(s, t) dt ds:  univariate_radial_covfunc_lebesgue_integral_lebesgue_integral
+ * (_radial_lebesgue.py:54-69) with HalfIntegerMaternRadialSecondAntiderivative (_matern_lebesgue.py:60-108).   */
+int lpgp_matern_integral2(const lpgp_matern_integral_desc* desc, double a, double b, double c, double d, double alpha,
+                          double* out, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,19 @@ class ObsBlock(ctypes.Structure):
     ]
 
 
+MAX_INTEGRAL_COEF = 8
+
+
+class MaternIntegralDesc(ctypes.Structure):
+    _fields_ = [
+        ("ncoef", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("scale", ctypes.c_double),
+        ("poly1", ctypes.c_double * MAX_INTEGRAL_COEF),
+        ("poly2", ctypes.c_double * MAX_INTEGRAL_COEF),
+    ]
+
+
 def _load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -95,6 +108,8 @@ def _load() -> ctypes.CDLL:
         "lpgp_crosscov": (ci, [OB, ci, i64, vp, i64, vp, i64, vp]),
         "lpgp_post_var": (ci, [OB, ci, FP, vp, i64, dbl, vp, i64, vp, vp]),
         "lpgp_row_sumsq": (ci, [vp, i64, i64, i64, dbl, dbl, vp, vp]),
+        "lpgp_matern_integral": (ci, [ctypes.POINTER(MaternIntegralDesc), dbl, dbl, vp, i64, dbl, vp, vp, i64, ci, vp]),
+        "lpgp_matern_integral2": (ci, [ctypes.POINTER(MaternIntegralDesc), dbl, dbl, dbl, dbl, dbl, vp, ci, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -107,7 +122,7 @@ lib = _load()
 EXPORTED = (
     "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_set_option lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower lpgp_kron_sum "
     "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
-    "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq"
+    "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq lpgp_matern_integral lpgp_matern_integral2"
 ).split()
 
 

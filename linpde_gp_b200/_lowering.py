@@ -56,6 +56,49 @@ def hermite_poly(n: int):
     return tuple(out)
 
 
+def _poly_deriv(c):
+    return tuple(c[k] * k for k in range(1, len(c)))
+
+
+def _poly_add(a, b):
+    n = max(len(a), len(b))
+    a = tuple(a) + (Fraction(0),) * (n - len(a))
+    b = tuple(b) + (Fraction(0),) * (n - len(b))
+    return tuple(x + y for x, y in zip(a, b))
+
+
+@functools.lru_cache(maxsize=None)
+def matern_antiderivative_polys(p: int):
+    """Exact polynomial parts of the first / second radial antiderivative of a Matern-(p + 1/2) profile:
+    P1 = sum_{m=0}^{p} P^(m), P2 = P + sum_{i=1}^{p} (i + 1) P^(i)
+    (src/linpde_gp/randprocs/crosscov/linfunctls/integrals/_matern_lebesgue.py:22-34, 71-83)."""
+    d = matern_poly(p, 0)
+    p1 = p2 = d
+    for i in range(1, p + 1):
+        d = _poly_deriv(d)
+        p1 = _poly_add(p1, d)
+        p2 = _poly_add(p2, tuple((i + 1) * c for c in d))
+    return p1, p2
+
+
+def matern_integral_desc(nu: float, lengthscale: float) -> _lib.MaternIntegralDesc:
+    """Descriptor of ``lpgp_matern_integral`` / ``lpgp_matern_integral2`` for a univariate half-integer Matern kernel."""
+    p = nu - 0.5
+    if p != int(p) or p < 0:
+        raise NotImplementedError("closed-form Lebesgue integrals exist for half-integer Matern kernels only")
+    p = int(p)
+    if p + 1 > _lib.MAX_INTEGRAL_COEF:
+        raise NotImplementedError(f"Matern order nu={nu} exceeds the device descriptor")
+    p1, p2 = matern_antiderivative_polys(p)
+    desc = _lib.MaternIntegralDesc()
+    desc.ncoef = p + 1
+    desc.scale = float(np.sqrt(2 * nu) / float(lengthscale))
+    for i in range(p + 1):
+        desc.poly1[i] = float(p1[i])
+        desc.poly2[i] = float(p2[i])
+    return desc
+
+
 class Factor1D:
     """One stationary 1-D factor: ('matern', p, ell) or ('expquad', ell)."""
 

@@ -172,6 +172,30 @@ def row_sumsq(A: torch.Tensor, scale: float = 1.0, offset: float = 0.0) -> torch
     return out
 
 
+def matern_integral(desc: _lib.MaternIntegralDesc, a: float, b: float, x: torch.Tensor, out: torch.Tensor, *,
+                    out_stride: int = 1, alpha: float = 1.0, w: Optional[torch.Tensor] = None,
+                    accumulate: bool = False) -> torch.Tensor:
+    """out[i * out_stride] (+)= alpha * (w or 1) * int_a^b k(x[i], t) dt  (``out``: any view whose first element is
+    the first target; ``w``: one-element device tensor)."""
+    _require_cuda()
+    x = x.reshape(-1)
+    assert x.is_contiguous() and x.dtype == F64
+    rc = lib.lpgp_matern_integral(ctypes.byref(desc), float(a), float(b), _ptr(x), x.numel(), float(alpha), _ptr(w),
+                                  _ptr(out), int(out_stride), int(accumulate), _stream())
+    check(rc, "lpgp_matern_integral")
+    return out
+
+
+def matern_integral2(desc: _lib.MaternIntegralDesc, dom0, dom1, out: torch.Tensor, *, alpha: float = 1.0,
+                     accumulate: bool = False) -> torch.Tensor:
+    """out[0] (+)= alpha * int_dom0 int_dom1 k(s, t) dt ds."""
+    _require_cuda()
+    rc = lib.lpgp_matern_integral2(ctypes.byref(desc), float(dom0[0]), float(dom0[1]), float(dom1[0]), float(dom1[1]),
+                                   float(alpha), _ptr(out), int(accumulate), _stream())
+    check(rc, "lpgp_matern_integral2")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 class DeviceFactor:
     """Device-resident, appendable lower Cholesky factor (``lpgp_factor``).
@@ -270,10 +294,12 @@ class DeviceFactor:
 class ObsBlocks:
     """ctypes array of ``lpgp_obs_block`` keeping the referenced descriptors / tensors alive."""
 
-    def __init__(self, descs, Xs, col_offs):
+    def __init__(self, descs, Xs, col_offs, extras=()):
         self.descs = list(descs)
         self.Xs = list(Xs)
         self.n = len(self.descs)
+        # integral observations: (column, (a, b), [(alpha, MaternIntegralDesc), ...]) -- one closed-form column each
+        self.extras = list(extras)
         self.arr = (_lib.ObsBlock * self.n)()
         for i, (dsc, X, off) in enumerate(zip(self.descs, self.Xs, col_offs)):
             self.arr[i].desc = ctypes.pointer(dsc)
@@ -281,14 +307,31 @@ class ObsBlocks:
             self.arr[i].n = X.shape[0]
             self.arr[i].col_off = int(off)
 
+    @property
+    def empty(self) -> bool:
+        return self.n == 0 and not self.extras
+
+    def add_integral_columns(self, Xt: torch.Tensor, K: torch.Tensor) -> None:
+        """K[:, col] += sum alpha * int_a^b k(Xt, t) dt for every integral observation (after ``lpgp_crosscov``)."""
+        for col, (a, b), terms in self.extras:
+            for alpha, dsc in terms:
+                matern_integral(dsc, a, b, Xt, K[:, col:], out_stride=_ld(K), alpha=alpha, accumulate=True)
+
 
 def post_mean(blocks: ObsBlocks, w: torch.Tensor, Xt: torch.Tensor, out: Optional[torch.Tensor] = None,
               accumulate: bool = False) -> torch.Tensor:
     m = Xt.shape[0]
     if out is None:
         out = torch.empty(m, dtype=F64, device=Xt.device)
-    rc = lib.lpgp_post_mean(blocks.arr, blocks.n, _ptr(w), _ptr(Xt), m, _ptr(out), int(accumulate), _stream())
-    check(rc, "lpgp_post_mean")
+    if blocks.n == 0:
+        if not accumulate:
+            out.zero_()
+    else:
+        rc = lib.lpgp_post_mean(blocks.arr, blocks.n, _ptr(w), _ptr(Xt), m, _ptr(out), int(accumulate), _stream())
+        check(rc, "lpgp_post_mean")
+    for col, (a, b), terms in blocks.extras:  # integral observations: one closed-form column each, weight folded in
+        for alpha, dsc in terms:
+            matern_integral(dsc, a, b, Xt, out, alpha=alpha, w=w[col : col + 1], accumulate=True)
     return out
 
 
@@ -297,6 +340,7 @@ def crosscov(blocks: ObsBlocks, n: int, Xt: torch.Tensor, out: Optional[torch.Te
     if out is None:
         out = alloc_matrix(m, n)
     check(lib.lpgp_crosscov(blocks.arr, blocks.n, n, _ptr(Xt), m, _ptr(out), _ld(out), _stream()), "lpgp_crosscov")
+    blocks.add_integral_columns(Xt, out)
     return out
 
 
@@ -311,6 +355,13 @@ def post_var(blocks: ObsBlocks, factor: DeviceFactor, Xt: torch.Tensor, prior_di
     f = factor._struct()
     for i0 in range(0, m, chunk):
         mc = min(chunk, m - i0)
+        if blocks.extras:  # same three steps as lpgp_post_var, with the integral columns added in between
+            Kc = K[:mc]
+            crosscov(blocks, factor.n, Xt[i0 : i0 + mc], out=Kc)
+            factor.trsm_rlt(Kc)
+            check(lib.lpgp_row_sumsq(_ptr(Kc), mc, factor.n, _ld(K), -1.0, float(prior_diag), _ptr(out[i0:]), _stream()),
+                  "lpgp_row_sumsq")
+            continue
         rc = lib.lpgp_post_var(blocks.arr, blocks.n, ctypes.byref(f), _ptr(Xt[i0:]), mc, float(prior_diag), _ptr(K),
                                _ld(K), _ptr(out[i0:]), _stream())
         check(rc, "lpgp_post_var")

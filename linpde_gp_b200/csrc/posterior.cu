@@ -261,9 +261,9 @@ extern "C" int lpgp_crosscov(const lpgp_obs_block* blocks, int nblocks, int64_t 
   int64_t cursor = 0;
   for (int b = 0; b < nblocks; ++b) {
     const lpgp_obs_block& blk = blocks[b];
-    // consecutive entries on the SAME columns are summands of one kernel (sum kernels, multi-output observation
-    // operators): the first one writes, the others accumulate
-    const bool same = b > 0 && blk.col_off == blocks[b - 1].col_off && blk.n == blocks[b - 1].n && blk.X == blocks[b - 1].X;
+    // consecutive entries on the SAME columns are summands of one observation (sum kernels, multi-output observation
+    // operators, sums of evaluation functionals at different points): the first one writes, the others accumulate
+    const bool same = b > 0 && blk.col_off == blocks[b - 1].col_off && blk.n == blocks[b - 1].n;
     if (!same && (blk.col_off < cursor || blk.col_off + blk.n > n)) return -1;
     int rc = same ? 0 : zero_cols(K, m, ldk, cursor, blk.col_off, st);
     if (rc) return rc;

@@ -1,13 +1,21 @@
-"""Linear functionals of the hot path (``linpde_gp.linfunctls``): point evaluation composed with an operator.
+"""Linear functionals of the hot path (``linpde_gp.linfunctls``): point evaluation composed with an operator,
+Lebesgue integrals, and their arithmetic.
 
 ``_EvaluationFunctional`` (src/linpde_gp/linfunctls/_evaluation.py:10-60) evaluates a function at the points ``X``
 (output layout: codomain_shape + batch_shape); ``CompositeLinearFunctional`` (``_arithmetic.py:92-140``) is
-``linfunctl @ linop``, which is what ``LinearFunctionOperator.to_linfunctl(X)`` returns."""
+``linfunctl @ linop``, which is what ``LinearFunctionOperator.to_linfunctl(X)`` returns; ``LebesgueIntegral``
+(``_integrals.py:13-62``) integrates over an interval; ``ScaledLinearFunctional`` / ``SumLinearFunctional``
+(``_arithmetic.py:12-90``) combine them, e.g. the stationarity condition of
+experiments/0000_cpu_stationary_1d.ipynb cell 65.
+
+For the conditioning code every functional flattens into a list of ATOMS ``(coef, kind, op, payload)`` with
+``kind = "pts"`` (``coef * (op f)(X)``, payload = points) or ``"int"`` (``coef * int_a^b (op f)``, payload = (a, b));
+all atoms of one functional produce the same number of rows."""
 from __future__ import annotations
 
 import numpy as np
 
-from .functions import _as_shape
+from .functions import Constant, Function, _as_shape
 
 
 class LinearFunctional:
@@ -36,9 +44,15 @@ class LinearFunctional:
     def output_size(self):
         return int(np.prod(self._output_shape)) if self._output_shape else 1
 
-    # (operator or None, evaluation points) -- what the conditioning code needs from a functional
-    def _as_observation(self):  # pragma: no cover - abstract
-        raise NotImplementedError(f"{type(self).__name__} is not a point-evaluation observation")
+    # (operator or None, evaluation points) -- what the conditioning code needs from a point-evaluation functional
+    def _as_observation(self):
+        atoms = self._atoms()
+        if len(atoms) != 1 or atoms[0][1] != "pts" or atoms[0][0] != 1.0:
+            raise NotImplementedError(f"{type(self).__name__} is not a plain point-evaluation observation")
+        return atoms[0][2], atoms[0][3]
+
+    def _atoms(self):  # pragma: no cover - abstract
+        raise NotImplementedError(f"{type(self).__name__} cannot be used as an observation")
 
     def __call__(self, f, /, **kwargs):
         from .randprocs import _conditional, _gaussian_process
@@ -47,9 +61,54 @@ class LinearFunctional:
             return f._apply_linfunctl(self)  # pylint: disable=protected-access
         if isinstance(f, _gaussian_process.GaussianProcess):
             return _gaussian_process.apply_linfunctl_to_gp(self, f)
-        op, X = self._as_observation()
-        g = f if op is None else op(f)
-        return g(X)
+        res = None
+        for coef, kind, op, payload in self._atoms():
+            g = f if op is None else op(f)
+            v = g(payload) if kind == "pts" else _integrate_function(g, payload)
+            v = v if coef == 1.0 else coef * np.asarray(v)
+            res = v if res is None else res + v
+        return res
+
+    # -- arithmetic (src/linpde_gp/linfunctls/_linfunctl.py:74-129) ------------------------------------------------
+    __array_ufunc__ = None
+
+    def __neg__(self):
+        return -1.0 * self
+
+    def __add__(self, other):
+        if isinstance(other, LinearFunctional):
+            return SumLinearFunctional(self, other)
+        return NotImplemented
+
+    def __sub__(self, other):
+        if isinstance(other, LinearFunctional):
+            return self + (-other)
+        return NotImplemented
+
+    def __rmul__(self, other):
+        if np.ndim(other) == 0:
+            return ScaledLinearFunctional(linfunctl=self, scalar=other)
+        return NotImplemented
+
+    def __matmul__(self, other):
+        from .linfuncops import LinearFunctionOperator
+
+        if isinstance(other, LinearFunctionOperator):
+            return CompositeLinearFunctional(linop=other, linfunctl=self)
+        return NotImplemented
+
+
+def _integrate_function(g: Function, dom):
+    """``LebesgueIntegral.__call__`` on functions (_integrals.py:36-62): closed form for constants, scipy.integrate.quad
+    otherwise (the user's prior-mean function is host code; this is not on the device path)."""
+    a, b = dom
+    if isinstance(g, Constant):
+        return g.value * (b - a)
+    import scipy.integrate  # pylint: disable=import-outside-toplevel
+
+    if tuple(g.output_shape) != ():
+        raise NotImplementedError("quadrature of vector-valued functions")
+    return scipy.integrate.quad(lambda t: float(g(np.asarray(t, dtype=np.double))), a=a, b=b)[0]
 
 
 class _EvaluationFunctional(LinearFunctional):
@@ -72,13 +131,21 @@ class _EvaluationFunctional(LinearFunctional):
     def X(self):
         return self._X
 
-    def _as_observation(self):
-        return None, (self._X if self._grid is None else self._grid)
+    def _atoms(self):
+        return [(1.0, "pts", None, self._X if self._grid is None else self._grid)]
 
 
 class CompositeLinearFunctional(LinearFunctional):
-    def __init__(self, *, linop, linfunctl):
-        if tuple(linop.output_shapes[0]) != tuple(linfunctl.input_domain_shape):
+    """``linfunctl @ linop``: apply the function operator first (``_arithmetic.py:92-174``; the reference's keyword
+    for the operator is ``linfuncop``, accepted as an alias)."""
+
+    def __init__(self, *, linop=None, linfunctl, linfuncop=None):
+        if linfuncop is not None:
+            if linop is not None:
+                raise NotImplementedError("matrix @ functional compositions are not supported")
+            linop = linfuncop
+        if tuple(linop.output_shapes[0]) != tuple(linfunctl.input_domain_shape) or tuple(
+                linop.output_shapes[1]) != tuple(linfunctl.input_codomain_shape):
             raise ValueError("shape mismatch between operator output and functional input")
         super().__init__(linop.input_shapes, linfunctl.output_shape)
         self._linop = linop
@@ -89,11 +156,93 @@ class CompositeLinearFunctional(LinearFunctional):
         return self._linop
 
     @property
+    def linfuncop(self):
+        return self._linop
+
+    @property
     def linfunctl(self):
         return self._linfunctl
 
-    def _as_observation(self):
-        inner_op, X = self._linfunctl._as_observation()
-        if inner_op is not None:
-            raise NotImplementedError("nested operator compositions are not supported")
-        return self._linop, X
+    def _atoms(self):
+        # (inner.op @ linop): the function operator of this composite acts first
+        return [(c, kind, self._linop if op is None else op @ self._linop, payload)
+                for c, kind, op, payload in self._linfunctl._atoms()]  # pylint: disable=protected-access
+
+    def __matmul__(self, other):
+        from .linfuncops import LinearFunctionOperator
+
+        if isinstance(other, LinearFunctionOperator):
+            return CompositeLinearFunctional(linop=self._linop @ other, linfunctl=self._linfunctl)
+        return NotImplemented
+
+
+class ScaledLinearFunctional(LinearFunctional):
+    """``scalar * linfunctl`` (_arithmetic.py:12-55)."""
+
+    def __init__(self, linfunctl, scalar):
+        if np.ndim(scalar) != 0:
+            raise ValueError()
+        super().__init__(linfunctl.input_shapes, linfunctl.output_shape)
+        self._linfunctl = linfunctl
+        self._scalar = np.asarray(scalar, dtype=np.double)
+
+    @property
+    def linfunctl(self):
+        return self._linfunctl
+
+    @property
+    def scalar(self):
+        return self._scalar
+
+    def _atoms(self):
+        s = float(self._scalar)
+        return [(s * c, kind, op, payload) for c, kind, op, payload in self._linfunctl._atoms()]  # pylint: disable=protected-access
+
+    def __rmul__(self, other):
+        if np.ndim(other) == 0:
+            return ScaledLinearFunctional(linfunctl=self._linfunctl, scalar=np.asarray(other) * self._scalar)
+        return NotImplemented
+
+
+class SumLinearFunctional(LinearFunctional):
+    """``L_1 + ... + L_n`` (_arithmetic.py:58-90): all summands share input shapes and output shape."""
+
+    def __init__(self, *summands):
+        self._summands = tuple(summands)
+        first = self._summands[0]
+        if not all(tuple(s.input_domain_shape) == tuple(first.input_domain_shape)
+                   and tuple(s.input_codomain_shape) == tuple(first.input_codomain_shape)
+                   and tuple(s.output_shape) == tuple(first.output_shape) for s in self._summands):
+            raise ValueError("summands of a SumLinearFunctional must agree in input and output shapes")
+        super().__init__(first.input_shapes, first.output_shape)
+
+    @property
+    def summands(self):
+        return self._summands
+
+    def _atoms(self):
+        return [a for s in self._summands for a in s._atoms()]  # pylint: disable=protected-access
+
+
+class LebesgueIntegral(LinearFunctional):
+    """``f -> int_domain f(x) dx`` over an interval (src/linpde_gp/linfunctls/_integrals.py:13-62).  Closed-form
+    cross-covariances exist for univariate half-integer Matern kernels
+    (src/linpde_gp/randprocs/covfuncs/linfunctls/_registry.py:175-193); there is no quadrature fallback on the device."""
+
+    def __init__(self, input_domain, input_codomain_shape=()):
+        dom = np.asarray(input_domain, dtype=np.double)
+        if dom.shape != (2,):
+            if dom.ndim == 2 and dom.shape[1] == 2:
+                raise NotImplementedError("integrals over boxes have no closed form on the device (1-D intervals only)")
+            raise TypeError("`input_domain` must be an interval (a, b)")
+        if not dom[0] <= dom[1]:
+            raise ValueError("empty interval")
+        self._domain = (float(dom[0]), float(dom[1]))
+        super().__init__(input_shapes=((), input_codomain_shape), output_shape=input_codomain_shape)
+
+    @property
+    def domain(self):
+        return self._domain
+
+    def _atoms(self):
+        return [(1.0, "int", None, self._domain)]

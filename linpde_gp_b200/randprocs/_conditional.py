@@ -16,7 +16,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .. import backend, functions, linfunctls, linops, randvars
+from .. import _lowering, backend, functions, linfunctls, linops, randvars
 from ..linfuncops import LinearFunctionOperator
 from . import covfuncs
 from ._gaussian_process import GaussianProcess
@@ -39,14 +39,90 @@ def _descs(k: covfuncs.CovarianceFunction):
     return [k.descriptor()]
 
 
-def _gram_into(k: covfuncs.CovarianceFunction, X0, X1, out: "torch.Tensor", lower: bool = False) -> None:
-    """``out <- k(X0, X1)`` (``X1=None``: symmetric block, lower triangle when ``lower``): one pairwise-kernel launch per
-    device descriptor, accumulating from the second on; blocks of the zero kernel are cleared."""
+def _gram_into(k: covfuncs.CovarianceFunction, X0, X1, out: "torch.Tensor", lower: bool = False, *,
+               accumulate: bool = False, alpha: float = 1.0) -> None:
+    """``out (+)= alpha * k(X0, X1)`` (``X1=None``: symmetric block, lower triangle when ``lower``): one pairwise-kernel
+    launch per device descriptor, accumulating from the second on; blocks of the zero kernel are cleared."""
     descs = _descs(k)
-    if not descs:
+    if not descs and not accumulate:
         out.zero_()
     for t, dsc in enumerate(descs):
-        backend.gram(dsc, X0, X1, out=out, lower=lower, accumulate=t > 0)
+        backend.gram(dsc, X0, X1, out=out, lower=lower, accumulate=accumulate or t > 0, alpha=alpha)
+
+
+def _integral_terms(k: covfuncs.CovarianceFunction):
+    """``[(scale, nu, lengthscale), ...]`` such that ``k = sum scale * Matern_nu(lengthscale)`` on scalar inputs -- the
+    kernels whose Lebesgue integrals have closed forms (dispatch of
+    src/linpde_gp/randprocs/covfuncs/linfunctls/_registry.py:25-41, 175-193 on Scaled / Sum / Matern kernels).  The
+    reference integrates everything else numerically with scipy.integrate.quad (_covfunc_lebesgue.py:45-51); there
+    is no host fallback here."""
+    if isinstance(k, covfuncs.Zero):
+        return []
+    if isinstance(k, covfuncs.ScaledCovarianceFunction):
+        return [(float(k.scalar) * s, nu, ell) for s, nu, ell in _integral_terms(k.covfunc)]
+    if isinstance(k, covfuncs.SumCovarianceFunction):
+        return [t for summand in k.summands for t in _integral_terms(summand)]
+    if isinstance(k, covfuncs.Matern) and k.input_size == 1 and k.is_half_integer and k.output_shape_0 == () \
+            and k.output_shape_1 == ():
+        return [(1.0, k.nu, float(np.broadcast_to(k.lengthscales, (1,))[0]))]
+    raise NotImplementedError(
+        f"Lebesgue integral of {type(k).__name__}: closed forms exist for (sums of scaled) univariate half-integer "
+        "Matern kernels only; the reference's scipy.integrate.quad fallback is host code and not provided"
+    )
+
+
+class _Atom:
+    """One summand of an observation functional: ``coef * (op f)(X)`` (``kind == "pts"``) or
+    ``coef * int_a^b (op f)(t) dt`` (``kind == "int"``, one row)."""
+
+    def __init__(self, coef, kind, op, payload, d: int):
+        self.coef, self.kind, self.op = float(coef), kind, op
+        if kind == "pts":
+            self.X_host = np.asarray(payload, dtype=np.double)
+            self.X = backend.points(self.X_host, d)
+            self.n = self.X.shape[0]
+            self.dom = None
+        else:
+            if d != 1:
+                raise NotImplementedError("integral observations need a univariate input domain")
+            self.X_host = self.X = None
+            self.n = 1
+            self.dom = (float(payload[0]), float(payload[1]))
+
+    def apply(self, k, argnum: int):
+        return k if self.op is None else self.op(k, argnum=argnum)
+
+
+def _atom_cov_into(k: covfuncs.CovarianceFunction, A: _Atom, B: _Atom, out: "torch.Tensor", accumulate: bool) -> None:
+    """``out (+)= coef_A coef_B cov(atom_A f, atom_B f)`` for ``f ~ GP(., k)`` (out: n_A x n_B view of a row-major
+    device matrix)."""
+    kk = A.apply(B.apply(k, 1), 0)
+    alpha = A.coef * B.coef
+    if A.kind == "pts" and B.kind == "pts":
+        _gram_into(kk, A.X, B.X, out, accumulate=accumulate, alpha=alpha)
+        return
+    terms = _integral_terms(kk)
+    if not terms and not accumulate:
+        out.zero_()
+    ld = out.stride(0) if out.shape[0] > 1 else 1
+    for t, (scale, nu, ell) in enumerate(terms):
+        dsc = _lowering.matern_integral_desc(nu, ell)
+        acc = accumulate or t > 0
+        if A.kind == "int" and B.kind == "int":
+            backend.matern_integral2(dsc, A.dom, B.dom, out, alpha=alpha * scale, accumulate=acc)
+        elif A.kind == "int":  # one row: int_a^b k(t, X_B) dt
+            backend.matern_integral(dsc, A.dom[0], A.dom[1], B.X, out, out_stride=1, alpha=alpha * scale, accumulate=acc)
+        else:  # one column
+            backend.matern_integral(dsc, B.dom[0], B.dom[1], A.X, out, out_stride=ld, alpha=alpha * scale, accumulate=acc)
+
+
+def _block_cov_into(k, blk: "_Block", pb: "_Block", out: "torch.Tensor") -> None:
+    """``out <- cov(block, pb)`` as the sum over all atom pairs (n_blk x n_pb)."""
+    first = True
+    for A in blk.atoms:
+        for B in pb.atoms:
+            _atom_cov_into(k, A, B, out, accumulate=not first)
+            first = False
 
 
 def _assemble_kronecker(k: covfuncs.CovarianceFunction, grid0, grid1, out: "torch.Tensor", lower: bool) -> bool:
@@ -68,9 +144,26 @@ def _assemble_kronecker(k: covfuncs.CovarianceFunction, grid0, grid1, out: "torc
 
 
 class _Block:
-    """One observation batch: points, operator, logical / physical (even-padded) size, offset in the factor."""
+    """One observation batch: points, operator, logical / physical (even-padded) size, offset in the factor.
 
-    def __init__(self, X_host: np.ndarray, op: Optional[LinearFunctionOperator], d: int, col_off: int):
+    ``atoms`` (``LinearFunctional._atoms()``) generalises the batch to a SUM of point-evaluation and integral atoms
+    (``simple`` is False then and ``X`` / ``op`` are unset); plain ``L[f](X)`` batches keep the single-atom fast paths
+    (Kronecker assembly, one-shot / multi-GPU assembly)."""
+
+    def __init__(self, X_host, op: Optional[LinearFunctionOperator], d: int, col_off: int, atoms=None):
+        self.col_off = col_off
+        if atoms is not None and not (len(atoms) == 1 and atoms[0][1] == "pts" and atoms[0][0] == 1.0):
+            self.simple = False
+            self.grid = self.X_host = self.X = self.op = None
+            self.atoms = [_Atom(c, kind, aop, payload, d) for c, kind, aop, payload in atoms]
+            self.n = self.atoms[0].n
+            if any(a.n != self.n for a in self.atoms):
+                raise ValueError("all summands of an observation functional must produce the same number of rows")
+            self.n_phys = self.n + (self.n % 2)
+            return
+        if atoms is not None:
+            _, _, op, X_host = atoms[0]
+        self.simple = True
         # intact TensorProductGrid: Gram blocks against other gridded batches are sums of Kronecker products
         self.grid = X_host if covfuncs._grid_factors(X_host) is not None else None  # pylint: disable=protected-access
         X_host = np.asarray(X_host, dtype=np.double)
@@ -79,14 +172,16 @@ class _Block:
         self.X = backend.points(X_host, d)
         self.n = self.X.shape[0]
         self.n_phys = self.n + (self.n % 2)
-        self.col_off = col_off
+        atom = _Atom.__new__(_Atom)
+        atom.coef, atom.kind, atom.op, atom.X_host, atom.X, atom.n, atom.dom = 1.0, "pts", op, X_host, self.X, self.n, None
+        self.atoms = [atom]
 
 
 class ConditionalGaussianProcess(GaussianProcess):
     @classmethod
     def from_observations(cls, prior: GaussianProcess, Y, X=None, *, L=None, b=None):
-        Y, Lf, b, op, Xobs, resid, noise = cls._preprocess_observations(prior=prior, Y=Y, X=X, L=L, b=b)
-        blk = _Block(Xobs, op, prior.cov.input_size, 0)
+        Y, Lf, b, atoms, resid, noise = cls._preprocess_observations(prior=prior, Y=Y, X=X, L=L, b=b)
+        blk = _Block(None, None, prior.cov.input_size, 0, atoms=atoms)
         factor = backend.DeviceFactor([blk.n_phys])
         cls._assemble_rows(prior, [], blk, factor, noise)
         factor.potrf()
@@ -119,12 +214,16 @@ class ConditionalGaussianProcess(GaussianProcess):
                for t in batches]
         d = prior.cov.input_size
         blocks, off = [], 0
-        for (_, _, _, op, Xobs, _, _) in pre:
-            blk = _Block(Xobs, op, d, off)
+        for (_, _, _, atoms, _, _) in pre:
+            blk = _Block(None, None, d, off, atoms=atoms)
+            if not blk.simple:
+                raise NotImplementedError(
+                    "one-shot / multi-GPU conditioning takes plain `L[f](X)` batches; add functional (integral, sum) "
+                    "observations afterwards with `condition_on_observations`")
             blocks.append(blk)
             off += blk.n_phys
         n = off
-        noises = [p[6] for p in pre]
+        noises = [p[5] for p in pre]
         world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         if world > 1 or not replicate:
             ch = distributed.DistributedCholesky(n, nb=nb, group=process_group)
@@ -146,7 +245,7 @@ class ConditionalGaussianProcess(GaussianProcess):
         factor.factored_segments = 1
         y = torch.zeros(n, dtype=torch.float64, device=backend._require_cuda())  # pylint: disable=protected-access
         for blk, p in zip(blocks, pre):
-            y[blk.col_off : blk.col_off + blk.n].copy_(backend.to_device(p[5]))
+            y[blk.col_off : blk.col_off + blk.n].copy_(backend.to_device(p[4]))
         w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
         return cls(prior=prior, Ys=tuple(p[0] for p in pre), Ls=tuple(p[1] for p in pre), bs=tuple(p[2] for p in pre),
                    blocks=tuple(blocks), factor=factor, resid=y, weights=w)
@@ -223,20 +322,31 @@ class ConditionalGaussianProcess(GaussianProcess):
     def representer_weights(self) -> np.ndarray:
         return self._w.cpu().numpy()[self._logical_index]
 
-    # -- kernels between the test side and observation block j ------------------------------------------------
-    def _k_test_obs(self, blk: _Block):
-        k = self._base_prior.cov
-        kk = k if blk.op is None else blk.op(k, argnum=1)
+    # -- kernels between the test side and one atom of an observation block ----------------------------------------
+    def _k_test_obs(self, atom: _Atom):
+        kk = atom.apply(self._base_prior.cov, 1)
         return kk if self._test_op is None else self._test_op(kk, argnum=0)
 
     def _obs_blocks(self) -> backend.ObsBlocks:
-        descs, Xs, offs = [], [], []
+        """Device view of ``k(x_test, observations)``: one entry per (point atom, kernel descriptor) -- entries on the
+        same columns accumulate -- plus the integral atoms (``extras``), whose single column is the closed-form
+        ``int_a^b k(x_test, t) dt`` evaluated by ``lpgp_matern_integral``."""
+        descs, Xs, offs, extras = [], [], [], []
         for blk in self._blocks:
-            for dsc in _descs(self._k_test_obs(blk)):
-                descs.append(dsc)
-                Xs.append(blk.X)
-                offs.append(blk.col_off)
-        return backend.ObsBlocks(descs, Xs, offs)
+            for atom in blk.atoms:
+                kk = self._k_test_obs(atom)
+                if atom.kind == "int":
+                    terms = [(atom.coef * sc, _lowering.matern_integral_desc(nu, ell)) for sc, nu, ell in _integral_terms(kk)]
+                    if terms:
+                        extras.append((blk.col_off, atom.dom, terms))
+                    continue
+                if atom.coef != 1.0:
+                    kk = atom.coef * kk
+                for dsc in _descs(kk):
+                    descs.append(dsc)
+                    Xs.append(atom.X)
+                    offs.append(blk.col_off)
+        return backend.ObsBlocks(descs, Xs, offs, extras=extras)
 
     def _obs_blocks_unique(self) -> backend.ObsBlocks:
         """Entries for the cross-covariance workspace ``k(x_test, X_obs)``: consecutive entries on the same columns
@@ -265,7 +375,7 @@ class ConditionalGaussianProcess(GaussianProcess):
             batch = x.shape[: x.ndim - self.input_ndim]
             m_x = post._prior.mean(x)
             blocks = post._obs_blocks()
-            if blocks.n == 0:  # no observation is correlated with this (output of the) process
+            if blocks.empty:  # no observation is correlated with this (output of the) process
                 return m_x
             Xt = backend.points(x, post._base_prior.cov.input_size)
             upd = backend.post_mean(blocks, post._w, Xt)
@@ -300,7 +410,7 @@ class ConditionalGaussianProcess(GaussianProcess):
                 prior_diag = _descs(post._prior.cov)
                 diag = sum(dsc.diag_value for dsc in prior_diag)
                 n = post._factor.n
-                if post._obs_blocks().n == 0:
+                if post._obs_blocks().empty:
                     return np.full(batch, diag)
                 if getattr(post._factor, "distributed", False):
                     return post._var_distributed(Xt, diag).cpu().numpy().reshape(batch)
@@ -329,7 +439,7 @@ class ConditionalGaussianProcess(GaussianProcess):
             C = backend.alloc_matrix(X0.shape[0], X0.shape[0] if X1 is None else X1.shape[0])
             _gram_into(post._prior.cov, X0, X1, C)
             blocks = post._obs_blocks_unique()
-            if blocks.n == 0:
+            if blocks.empty:
                 return C
             V0 = backend.crosscov(blocks, post._factor.n, X0)
             post._factor.trsm_rlt(V0)
@@ -359,8 +469,8 @@ class ConditionalGaussianProcess(GaussianProcess):
         if self._test_op is not None:
             raise NotImplementedError("condition the original process, then apply the operator")
         prior = self._base_prior
-        Y, Lf, b, op, Xobs, resid, noise = self._preprocess_observations(prior=prior, Y=Y, X=X, L=L, b=b)
-        blk = _Block(Xobs, op, prior.cov.input_size, self._factor.n)
+        Y, Lf, b, atoms, resid, noise = self._preprocess_observations(prior=prior, Y=Y, X=X, L=L, b=b)
+        blk = _Block(None, None, prior.cov.input_size, self._factor.n, atoms=atoms)
         factor = self._factor.extended(blk.n_phys)
         self._assemble_rows(prior, self._blocks, blk, factor, noise)
         factor.append_last()
@@ -383,18 +493,24 @@ class ConditionalGaussianProcess(GaussianProcess):
         r0, n = blk.col_off, blk.n
         rows = factor.L[r0 : r0 + blk.n_phys]
         for pb in prev_blocks:
-            kj = k if pb.op is None else pb.op(k, argnum=1)
-            kij = kj if blk.op is None else blk.op(kj, argnum=0)
             out = rows[:n, pb.col_off : pb.col_off + pb.n]
-            if not _assemble_kronecker(kij, blk.grid, pb.grid, out, lower=False):
-                _gram_into(kij, blk.X, pb.X, out)
+            if blk.simple and pb.simple:
+                kj = k if pb.op is None else pb.op(k, argnum=1)
+                kij = kj if blk.op is None else blk.op(kj, argnum=0)
+                if not _assemble_kronecker(kij, blk.grid, pb.grid, out, lower=False):
+                    _gram_into(kij, blk.X, pb.X, out)
+            else:  # functional observations: sum over all pairs of atoms
+                _block_cov_into(k, blk, pb, out)
             if pb.n_phys != pb.n:
                 rows[:, pb.col_off + pb.n] = 0.0
-        kj = k if blk.op is None else blk.op(k, argnum=1)
-        kii = kj if blk.op is None else blk.op(kj, argnum=0)
         D = rows[:n, r0 : r0 + n]
-        if not _assemble_kronecker(kii, blk.grid, None, D, lower=True):
-            _gram_into(kii, blk.X, None, D, lower=True)
+        if blk.simple:
+            kj = k if blk.op is None else blk.op(k, argnum=1)
+            kii = kj if blk.op is None else blk.op(kj, argnum=0)
+            if not _assemble_kronecker(kii, blk.grid, None, D, lower=True):
+                _gram_into(kii, blk.X, None, D, lower=True)
+        else:
+            _block_cov_into(k, blk, blk, D)
         if noise is not None:
             kind, val = noise
             if kind == "diag":
@@ -426,8 +542,8 @@ class ConditionalGaussianProcess(GaussianProcess):
             )
         else:
             raise TypeError("`L` must be a `LinearFunctional`, a `LinearFunctionOperator` or `None`.")
-        op, Xobs = Lf._as_observation()  # pylint: disable=protected-access
-        if prior.output_shape != () and (op is None or tuple(op.output_codomain_shape) != ()):
+        atoms = Lf._atoms()  # pylint: disable=protected-access
+        if prior.output_shape != () and any(op is None or tuple(op.output_codomain_shape) != () for _, _, op, _ in atoms):
             raise NotImplementedError(
                 "observations of a multi-output process must be scalar-valued: compose the operator with `SelectOutput`"
             )
@@ -439,8 +555,7 @@ class ConditionalGaussianProcess(GaussianProcess):
             if tuple(b.shape) != tuple(Lf.output_shape):
                 raise ValueError(f"{b.shape=} must be equal to {Lf.output_shape}")
 
-        mean_fn = prior.mean if op is None else op(prior.mean)
-        pred_mean = np.asarray(mean_fn(Xobs), dtype=np.double).reshape(-1, order="C")
+        pred_mean = np.asarray(Lf(prior.mean), dtype=np.double).reshape(-1, order="C")
         Y = np.asarray(Y, dtype=np.double)
         if Y.shape != tuple(Lf.output_shape):
             raise ValueError(f"Expected Y to have shape {Lf.output_shape}, got shape {Y.shape}.")
@@ -460,7 +575,7 @@ class ConditionalGaussianProcess(GaussianProcess):
                 noise = ("dense", cov.todense())
             else:
                 noise = ("dense", np.asarray(cov, dtype=np.double))
-        return Y, Lf, b, op, Xobs, Y - pred_mean, noise
+        return Y, Lf, b, atoms, Y - pred_mean, noise
 
     # -- push-forwards L(posterior) (_conditional.py:432-467) --------------------------------------------------------
     def _apply_linfuncop(self, L: LinearFunctionOperator) -> "ConditionalGaussianProcess":

@@ -215,6 +215,18 @@ def run_reference_multi_output(problem):
     sel = [linfuncops.SelectOutput((shape, (nout,)), idx=j) for j in range(nout)]
     post = prior
     for blk in problem["blocks"]:
+        if "functional" in blk:  # scalar observation: sum of Lebesgue integrals and point evaluations
+            from linpde_gp import linfunctls
+
+            L = None
+            for a in blk["functional"]:
+                if a[0] == "int":
+                    t = a[2] * linfunctls.LebesgueIntegral((a[3], a[4])) @ sel[a[1]]
+                else:
+                    t = a[2] * sel[a[1]].to_linfunctl(a[3])
+                L = t if L is None else L + t
+            post = post.condition_on_observations(Y=float(blk["Y"][0]), L=L)
+            continue
         X = np.asarray(blk["X"], dtype=float)
         Y = np.asarray(blk["Y"], dtype=float)
         L = None
@@ -260,13 +272,58 @@ def make_multi_output():
     return worst
 
 
+INTEGRAL_NUS = (0.5, 1.5, 2.5, 3.5, 4.5)
+INTEGRAL_LENGTHSCALES = (0.8, 1.1, 2.1)
+INTEGRAL_DOMAINS = ((-2.2, -1.8), (-0.8, 0.5))
+INTEGRAL_DOMAIN_PAIRS = (((-2.2, -1.8), (-0.8, 0.5)), ((-1.3, 0.0), (-0.2, 0.1)), ((0.25, 0.75), (0.3, 0.6)))
+
+
+def make_integrals():
+    """Lebesgue integrals of univariate half-integer Matern kernels on the reference's own test cases
+    (tests/linpde_gp/randprocs/crosscov/linfunctls/cases/cases_integral_matern.py:11-44 and
+    tests/linpde_gp/randprocs/cov/linfunctls/cases/cases_integral_matern.py:11-48)."""
+    pn, lg = refshim.load()
+    from linpde_gp import linfunctls
+    from linpde_gp.randprocs.crosscov.linfunctls import integrals as ref_integrals
+    from oracle import integrals as oint
+
+    Lk = np.zeros((len(INTEGRAL_NUS), len(INTEGRAL_LENGTHSCALES), len(INTEGRAL_DOMAINS), 10))
+    Xs = np.zeros((len(INTEGRAL_DOMAINS), 10))
+    LkL = np.zeros((len(INTEGRAL_NUS), len(INTEGRAL_LENGTHSCALES), len(INTEGRAL_DOMAIN_PAIRS)))
+    worst = 0.0
+    for i, nu in enumerate(INTEGRAL_NUS):
+        for j, ell in enumerate(INTEGRAL_LENGTHSCALES):
+            k = pn.randprocs.covfuncs.Matern(input_shape=(), nu=nu, lengthscales=ell)
+            for d, (a, b) in enumerate(INTEGRAL_DOMAINS):
+                hw = (b - a) / 2
+                Xs[d] = np.linspace(a - hw, b + hw, 10)
+                L = linfunctls.LebesgueIntegral((a, b))
+                kL, Lk_ = L(k, argnum=1), L(k, argnum=0)
+                assert isinstance(kL, ref_integrals.UnivariateHalfIntegerMaternLebesgueIntegral)
+                Lk[i, j, d] = np.asarray(kL(Xs[d]))
+                assert np.array_equal(Lk[i, j, d], np.asarray(Lk_(Xs[d])))
+                worst = max(worst, np.max(np.abs(Lk[i, j, d] - oint.matern_lebesgue_integral(int(nu - 0.5), ell, a, b, Xs[d]))))
+            for d, (d0, d1) in enumerate(INTEGRAL_DOMAIN_PAIRS):
+                L0, L1 = linfunctls.LebesgueIntegral(d0), linfunctls.LebesgueIntegral(d1)
+                LkL[i, j, d] = float(np.asarray(L0(L1(k, argnum=1)).array if hasattr(L0(L1(k, argnum=1)), "array") else L0(L1(k, argnum=1))))
+                worst = max(worst, abs(LkL[i, j, d] - oint.matern_lebesgue_integral_lebesgue_integral(int(nu - 0.5), ell, d0, d1)))
+    np.savez(os.path.join(GOLDEN, "integrals.npz"), nus=np.array(INTEGRAL_NUS), lengthscales=np.array(INTEGRAL_LENGTHSCALES),
+             domains=np.array(INTEGRAL_DOMAINS), domain_pairs=np.array(INTEGRAL_DOMAIN_PAIRS), X=Xs, Lk=Lk, LkL=LkL)
+    print(f"integrals.npz: {Lk.size + LkL.size} values, worst oracle-vs-reference deviation {worst:.2e}")
+    return worst
+
+
 if __name__ == "__main__":
     refshim.load()
     if "--multi-output-only" in sys.argv:
         print(f"worst deviation: multi-output {make_multi_output():.2e}")
         sys.exit(0)
+    if "--integrals-only" in sys.argv:
+        print(f"worst deviation: integrals {make_integrals():.2e}, multi-output {make_multi_output():.2e}")
+        sys.exit(0)
     w1 = make_kernels()
     w2 = make_gp()
     w3 = make_kron()
     w4 = make_multi_output()
-    print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}, kron {w3:.2e}, multi-output {w4:.2e}")
+    w5 = make_integrals()
+    print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}, kron {w3:.2e}, multi-output {w4:.2e}, integrals {w5:.2e}")

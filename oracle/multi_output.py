@@ -13,9 +13,16 @@ and ``SelectOutput(j)`` of the posterior has cross-covariance ``sum_{t : o_t == 
 observation block ``b`` (experiments/0000_cpu_stationary_1d.ipynb cells 55-82: joint belief over temperature, volumetric
 and surface heat sources).
 
+Scalar FUNCTIONAL observations (second half): a block may instead carry
+``"functional": [["int", output, coef, a, b] | ["eval", output, coef, x, op | None], ...]`` -- one row that is the sum
+of Lebesgue integrals ``coef * int_a^b f_output`` (closed forms of ``oracle/integrals.py``) and point evaluations, the
+stationarity condition ``h * LebesgueIntegral(domain) @ select_q_V + h * (select_q_A.to_linfunctl(w) +
+select_q_A.to_linfunctl(0))`` of experiments/0000_cpu_stationary_1d.ipynb cells 65-66, 85.
+
 A *problem* is a JSON-able dict:
     {"kernels": [<kernel spec> per output], "means": [float per output],
-     "blocks": [{"X": ..., "Y": ..., "Ls": [[output, scalar, op | None], ...], "noise_var": ...}, ...],
+     "blocks": [{"X": ..., "Y": ..., "Ls": [[output, scalar, op | None], ...], "noise_var": ...}
+                | {"functional": [...], "Y": [y]}, ...],
      "Xt": (M, d) list, "n_cov": int}
 """
 from __future__ import annotations
@@ -24,6 +31,7 @@ import numpy as np
 
 from . import covfuncs as ocf
 from . import gp as ogp
+from . import integrals as oint
 from . import linalg as ola
 
 
@@ -47,43 +55,95 @@ def block(kernels, La, Lb, Xa, Xb=None):
     return out
 
 
+# An observation batch is a SUM OF ATOMS, every atom producing the same number of rows:
+#   ("pts", output, coef, op | None, X)      coef * (op f_output)(X)          -- point evaluations
+#   ("int", output, coef, (a, b))            coef * int_a^b f_output(t) dt    -- one row (LebesgueIntegral @ SelectOutput)
+# (src/linpde_gp/linfunctls/_arithmetic.py:12-90 Scaled / Sum functionals, :92-140 CompositeLinearFunctional).
+def _atoms_of(blk):
+    if "functional" not in blk:
+        X = np.asarray(blk["X"], dtype=np.double)
+        return [("pts", o, c, op, X) for o, c, op in _terms(blk["Ls"])]
+    atoms = []
+    for a in blk["functional"]:
+        if a[0] == "int":
+            atoms.append(("int", int(a[1]), float(a[2]), (float(a[3]), float(a[4]))))
+        else:  # ["eval", output, coef, x, op | None]
+            op = ogp._op(a[4]) if len(a) > 4 and a[4] is not None else None  # pylint: disable=protected-access
+            atoms.append(("pts", int(a[1]), float(a[2]), op, np.asarray([a[3]], dtype=np.double)))
+    return atoms
+
+
+def _rows(atoms):
+    return 1 if atoms[0][0] == "int" else len(atoms[0][4])
+
+
+def _atom_cov(kernels, A, B):
+    """cov(atom A, atom B) for independent outputs (zero across outputs)."""
+    k = kernels[A[1]]
+    cc = A[2] * B[2]
+    if A[0] == "pts" and B[0] == "pts":
+        return cc * ocf.matrix(k, A[3], B[3], A[4], B[4])
+    if A[0] == "int" and B[0] == "int":
+        return cc * np.full((1, 1), oint.integral_integral(k, A[3], B[3]))
+    pts, itg = (A, B) if A[0] == "pts" else (B, A)
+    if pts[3] is not None:
+        raise NotImplementedError("a differential operator applied to an integral cross-covariance (not in the reference either)")
+    v = cc * oint.integral_crosscov(k, itg[3], pts[4]).reshape(-1, 1)
+    return v if A[0] == "pts" else v.T
+
+
+def atoms_cov(kernels, atoms_a, atoms_b):
+    out = np.zeros((_rows(atoms_a), _rows(atoms_b)))
+    for A in atoms_a:
+        for B in atoms_b:
+            if A[1] == B[1]:
+                out = out + _atom_cov(kernels, A, B)
+    return out
+
+
+def _atom_prior_mean(means, A):
+    """L applied to the constant prior mean: order-zero parts (functions/_constant.py), integrals -> value * volume
+    (src/linpde_gp/linfunctls/_integrals.py:60-62)."""
+    if A[0] == "int":
+        return A[2] * means[A[1]] * (A[3][1] - A[3][0])
+    return A[2] * means[A[1]] if A[3] is None else 0.0
+
+
 class Posterior:
     def __init__(self, kernels, means):
         self.kernels, self.means = kernels, [float(m) for m in means]
-        self.Xs, self.Ls = [], []
+        self.blocks = []
         self.L = np.zeros((0, 0))
         self.resid = np.zeros((0,))
         self.gram = np.zeros((0, 0))
         self.w = np.zeros((0,))
 
-    def condition(self, Y, X, Ls, noise_var=None):
-        X = np.asarray(X, dtype=np.double)
-        Y = np.asarray(Y, dtype=np.double).reshape(-1)
-        T = _terms(Ls)
-        # L applied to the constant prior mean: only order-zero parts survive (functions/_constant.py)
+    def condition(self, blk):
+        atoms = _atoms_of(blk)
+        Y = np.asarray(blk["Y"], dtype=np.double).reshape(-1)
+        noise_var = blk.get("noise_var")
         pred = np.zeros_like(Y)
-        for o, c, op in T:
-            if op is None:
-                pred = pred + c * self.means[o]
-        D = block(self.kernels, T, T, X, None)
+        for A in atoms:
+            pred = pred + _atom_prior_mean(self.means, A)
+        D = atoms_cov(self.kernels, atoms, atoms)
         if noise_var is not None:
             D = D + np.diag(np.broadcast_to(np.asarray(noise_var, dtype=np.double), Y.shape))
         new = Posterior(self.kernels, self.means)
-        new.Xs, new.Ls = self.Xs + [X], self.Ls + [T]
+        new.blocks = self.blocks + [atoms]
         new.resid = np.concatenate([self.resid, Y - pred])
         if self.L.shape[0] == 0:
             new.L = ola.cholesky_lower(D)
             new.gram = D
         else:
-            C = np.concatenate([block(self.kernels, T, Lj, X, Xj) for Xj, Lj in zip(self.Xs, self.Ls)], axis=1)
+            C = np.concatenate([atoms_cov(self.kernels, atoms, prev) for prev in self.blocks], axis=1)
             new.L = ola.cholesky_append(self.L, C.T, D)
             new.gram = np.block([[self.gram, C.T], [C, D]])
         new.w = ola.cho_solve_lower(new.L, new.resid)
         return new
 
     def crosscov(self, j, Xt):
-        sel = [(j, 1.0, None)]
-        return np.concatenate([block(self.kernels, sel, Lb, Xt, Xb) for Xb, Lb in zip(self.Xs, self.Ls)], axis=1)
+        sel = [("pts", j, 1.0, None, np.asarray(Xt, dtype=np.double))]
+        return np.concatenate([atoms_cov(self.kernels, sel, b) for b in self.blocks], axis=1)
 
     def mean(self, j, Xt):
         return self.means[j] + self.crosscov(j, Xt) @ self.w
@@ -101,7 +161,7 @@ def solve(problem):
     """Posterior of every selected output: ``mean`` / ``var`` have shape (n_outputs, M), ``cov`` (n_outputs, c, c)."""
     post = Posterior(problem["kernels"], problem["means"])
     for blk in problem["blocks"]:
-        post = post.condition(blk["Y"], blk["X"], blk["Ls"], blk.get("noise_var"))
+        post = post.condition(blk)
     Xt = np.asarray(problem["Xt"], dtype=np.double)
     Xc = Xt[: problem.get("n_cov", 8)]
     nout = len(problem["kernels"])
@@ -175,5 +235,27 @@ def poisson2d_joint_problem(n_pde=60, n_bc_edge=6, n_f=12, grid=7, seed=3):
     }
 
 
+def _stationarity_block(h=0.4, width=1.0):
+    """``h * int_0^w q_V + h * (q_A(w) + q_A(0)) = 0`` (notebook cell 65)."""
+    return {"functional": [["int", 1, h, 0.0, width], ["eval", 2, h, width, None], ["eval", 2, h, 0.0, None]], "Y": [0.0]}
+
+
+def cpu_1d_stat_problem():
+    """cpu_1d plus the stationarity functional as the LAST observation (notebook cell 85); q_A is Matern-3/2 here so
+    that two different antiderivative polynomials are exercised."""
+    prob = cpu_1d_problem()
+    prob["kernels"][1] = _k(0.81, ogp._m(1.5, 0.8))  # pylint: disable=protected-access
+    prob["blocks"] = prob["blocks"] + [_stationarity_block()]
+    return prob
+
+
+def cpu_1d_stat_first_problem():
+    """Stationarity functional FIRST (notebook cell 66), then PDE and temperature observations appended to it."""
+    prob = cpu_1d_problem(n_pde=9, n_dts=4, grid=17)
+    prob["blocks"] = [_stationarity_block(h=0.25)] + prob["blocks"]
+    return prob
+
+
 def golden_problems():
-    return {"cpu_1d": cpu_1d_problem(), "poisson2d_joint": poisson2d_joint_problem()}
+    return {"cpu_1d": cpu_1d_problem(), "poisson2d_joint": poisson2d_joint_problem(),
+            "cpu_1d_stat": cpu_1d_stat_problem(), "cpu_1d_stat_first": cpu_1d_stat_first_problem()}

@@ -190,6 +190,16 @@ def api_solve_multi_output(problem, one_shot: bool = False):
     sel = [linfuncops.SelectOutput((shape, (nout,)), idx=j) for j in range(nout)]
     batches = []
     for blk in problem["blocks"]:
+        if "functional" in blk:  # scalar observation: sum of Lebesgue integrals and point evaluations (X=None)
+            L = None
+            for a in blk["functional"]:
+                if a[0] == "int":
+                    t = a[2] * lg.linfunctls.LebesgueIntegral((a[3], a[4])) @ sel[a[1]]
+                else:
+                    t = a[2] * sel[a[1]].to_linfunctl(a[3])
+                L = t if L is None else L + t
+            batches.append((float(blk["Y"][0]), None, L, None))
+            continue
         X = np.asarray(blk["X"], dtype=float)
         Y = np.asarray(blk["Y"], dtype=float)
         L = None

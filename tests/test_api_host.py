@@ -220,3 +220,69 @@ def test_multi_output_dispatch_follows_the_reference_registry():
         lg.GaussianProcess(functions.Constant((), 1.0), k)
     with pytest.raises(NotImplementedError):
         prior.condition_on_observations(np.zeros((3, 4)), X=np.zeros(4))  # vector-valued observation
+
+
+def test_linear_functional_arithmetic_and_atoms():
+    """src/linpde_gp/linfunctls/_linfunctl.py:74-129, _arithmetic.py:12-174, _integrals.py:13-62 (host-side, symbolic):
+    the stationarity functional of experiments/0000_cpu_stationary_1d.ipynb cell 65."""
+    from linpde_gp_b200 import _lowering, functions, linfuncops, linfunctls
+    from oracle import integrals as oint
+
+    sel = [linfuncops.SelectOutput(((), (3,)), idx=j) for j in range(3)]
+    integral = linfunctls.LebesgueIntegral((0.0, 1.5))
+    assert integral.domain == (0.0, 1.5) and integral.output_shape == () and integral.input_shapes == ((), ())
+    part = 0.4 * integral @ sel[1]
+    assert type(0.4 * integral) is linfunctls.ScaledLinearFunctional
+    assert type(part) is linfunctls.CompositeLinearFunctional and part.linfuncop is sel[1]
+    assert part.input_shapes == ((), (3,)) and part.output_shape == ()
+    L = part + 0.4 * (sel[2].to_linfunctl(1.5) + sel[2].to_linfunctl(0.0))
+    assert type(L) is linfunctls.SumLinearFunctional and L.output_shape == ()
+    atoms = L._atoms()
+    assert [(c, kind) for c, kind, _, _ in atoms] == [(0.4, "int"), (0.4, "pts"), (0.4, "pts")]
+    assert atoms[0][2] is sel[1] and atoms[0][3] == (0.0, 1.5) and float(atoms[1][3]) == 1.5
+    assert type(2.0 * (0.4 * integral)) is linfunctls.ScaledLinearFunctional and float((2.0 * (0.4 * integral)).scalar) == 0.8
+    assert [c for c, *_ in (-L)._atoms()] == [-0.4, -0.4, -0.4]
+    assert [c for c, *_ in (part - part)._atoms()] == [0.4, -0.4]
+    # functions: integral of a constant = value * volume; generic functions by quadrature (like the reference)
+    mean = functions.StackedFunction(functions.Constant((), 57.0), functions.Constant((), 0.3), functions.Constant((), -0.1))
+    np.testing.assert_allclose(L(mean), 0.4 * 0.3 * 1.5 + 0.4 * 2 * (-0.1), rtol=1e-15)
+    np.testing.assert_allclose(integral(functions.LambdaFunction(lambda x: np.sin(x), (), ())), 1 - np.cos(1.5), rtol=1e-12)
+    # a point-evaluation functional still exposes (operator, points); composite functionals do not
+    op, X = sel[0].to_linfunctl(np.linspace(0, 1, 4))._as_observation()
+    assert op is sel[0] and X.shape == (4,)
+    with pytest.raises(NotImplementedError):
+        L._as_observation()
+    # argument / shape errors
+    with pytest.raises(ValueError):
+        linfunctls.SumLinearFunctional(integral, sel[0].to_linfunctl(np.zeros(3)))  # output shapes differ
+    with pytest.raises(ValueError):
+        integral @ linfuncops.SelectOutput(((2,), (3,)), idx=0)  # domain shapes differ
+    with pytest.raises(TypeError):
+        linfunctls.LebesgueIntegral(3.0)
+    with pytest.raises(NotImplementedError):
+        linfunctls.LebesgueIntegral([[0.0, 1.0], [0.0, 1.0]])
+    # exact antiderivative polynomials of the device descriptor == the oracle's restatement of the reference classes
+    for p in range(6):
+        p1, p2 = _lowering.matern_antiderivative_polys(p)
+        assert p1 == oint.antiderivative_polynomial(p) and p2 == oint.second_antiderivative_polynomial(p)
+    dsc = _lowering.matern_integral_desc(2.5, 0.5)
+    assert dsc.ncoef == 3 and dsc.scale == np.sqrt(5.0) / 0.5 and dsc.poly1[0] == float(oint.antiderivative_polynomial(2)[0])
+    with pytest.raises(NotImplementedError):
+        _lowering.matern_integral_desc(1.2, 1.0)
+
+
+def test_integral_dispatch_needs_closed_form_kernels():
+    """covfuncs/linfunctls/_registry.py:157-193: Scaled / Sum / univariate half-integer Matern have closed forms; the
+    reference's scipy quadrature fallback for everything else is not provided (NotImplementedError, no CPU path)."""
+    from linpde_gp_b200.randprocs._conditional import _integral_terms
+
+    m1 = covfuncs.Matern((), nu=1.5, lengthscales=0.8)
+    m2 = covfuncs.Matern((), nu=0.5, lengthscales=2.0)
+    assert _integral_terms(3.0 * m1 + 0.5 * (2.0 * m2)) == [(3.0, 1.5, 0.8), (1.0, 0.5, 2.0)]
+    assert _integral_terms(covfuncs.Zero(())) == []
+    with pytest.raises(NotImplementedError):
+        _integral_terms(covfuncs.ExpQuad((), lengthscales=1.0))
+    with pytest.raises(NotImplementedError):
+        _integral_terms(diffops.Laplacian(())(m1, argnum=1))
+    with pytest.raises(NotImplementedError):
+        _integral_terms(covfuncs.Matern((), nu=1.2))

@@ -142,7 +142,7 @@ def test_multi_output_conditioning_matches_reference(path):
     for key, tol in (("mean", 1e-9), ("var", 1e-8), ("cov", 1e-8)):
         sc = np.max(np.abs(g[key]))
         assert np.max(np.abs(res[key] - g[key])) <= tol * sc, key
-    assert len(MO_FILES) == 2
+    assert len(MO_FILES) == 4
 
 
 def test_multi_output_golden_problems_are_the_frozen_ones():
@@ -151,3 +151,42 @@ def test_multi_output_golden_problems_are_the_frozen_ones():
     for name, prob in omo.golden_problems().items():
         g = np.load(os.path.join(GOLDEN, f"mo_{name}.npz"))
         assert json.loads(json.dumps(prob)) == json.loads(bytes(g["problem"]).decode())
+
+
+# ---- Lebesgue integrals of univariate half-integer Matern kernels (second half) ----------------------
+_I = np.load(os.path.join(GOLDEN, "integrals.npz"))
+
+
+def test_matern_lebesgue_integrals_match_reference():
+    """The reference's own cases (tests/linpde_gp/randprocs/{crosscov,cov}/linfunctls/cases/cases_integral_matern.py):
+    closed-form ``int_a^b k(x, t) dt`` at 10 points around the domain and ``int int k`` for three domain pairs, frozen
+    outputs of the real ``UnivariateHalfIntegerMaternLebesgueIntegral``."""
+    from oracle import integrals as oint
+
+    for i, nu in enumerate(_I["nus"]):
+        for j, ell in enumerate(_I["lengthscales"]):
+            for d, (a, b) in enumerate(_I["domains"]):
+                v = oint.matern_lebesgue_integral(int(nu - 0.5), ell, a, b, _I["X"][d])
+                np.testing.assert_allclose(v, _I["Lk"][i, j, d], rtol=0, atol=1e-15)
+            for d, (d0, d1) in enumerate(_I["domain_pairs"]):
+                v = oint.matern_lebesgue_integral_lebesgue_integral(int(nu - 0.5), ell, tuple(d0), tuple(d1))
+                assert abs(v - _I["LkL"][i, j, d]) <= 1e-15
+
+
+def test_matern_lebesgue_integrals_match_quadrature():
+    """The check the reference's tests make (test_Lk_kL.py / test_LkL.py): closed form == scipy.integrate.quad of the
+    kernel (its generic fallback, _covfunc_lebesgue.py:45-51, 56-71)."""
+    import scipy.integrate
+
+    from oracle import covfuncs as ocf
+    from oracle import integrals as oint
+
+    for nu, ell in ((0.5, 0.8), (2.5, 1.1), (4.5, 2.1)):
+        k = {"scale": None, "base": {"kind": "matern", "input_shape": [], "nu": nu, "lengthscales": ell}}
+        kf = lambda s, t: float(ocf.evaluate(k, None, None, np.asarray(s), np.asarray(t)))  # noqa: E731
+        (a, b), (c, d) = (-1.3, 0.0), (-0.2, 0.1)
+        for x in (-2.0, -0.7, 0.0, 0.4):
+            q = scipy.integrate.quad(lambda t: kf(x, t), a, b, points=[x] if a < x < b else None)[0]
+            assert abs(oint.matern_lebesgue_integral(int(nu - 0.5), ell, a, b, x) - q) <= 1e-9
+        q2 = scipy.integrate.dblquad(lambda t, s: kf(s, t), a, b, c, d, epsabs=1e-10)[0]
+        assert abs(oint.matern_lebesgue_integral_lebesgue_integral(int(nu - 0.5), ell, (a, b), (c, d)) - q2) <= 1e-7
