@@ -108,13 +108,27 @@ __global__ void __launch_bounds__(NTHREADS)
 }
 
 // ---- all-Matern product kernels: separable exponentials (see kernel_eval.cuh) -----------------------------------
-// 128 x 128 tile per CTA.  After the TMA stage-in, thread i turns point i of the tile (128 row + 128 column points)
-// into its record (x, a, b) per dimension -- 2 exp per point and dimension, i.e. 4 exp per thread for d = 2 against
-// 64 matrix entries per thread -- and the entry loop is exp-free: ~16 FP64-pipe operations per entry (2-D
-// Matern-5/2, any operator pair of even orders) instead of ~40, which puts the kernel at the HBM-write bound.
+// 128 x 256 tile per CTA.  After the TMA stage-in, thread i turns point i of the tile (128 row + 256 column points)
+// into its record -- 2 exp per point and dimension, i.e. ~6 exp per thread for d = 2 against 128 matrix entries per
+// thread -- and the entry loop is exp-free.
+//
+// Records hold the PRODUCTS of the per-dimension factors for every sign pattern of (y - x):
+//   pattern bit d = [y_d < x_d];   A_pat(y) = prod_d (bit_d ? b_d(y) : a_d(y)),   B_pat(x) = alpha prod_d (bit_d ? a_d(x) : b_d(x))
+//   =>  alpha exp(-sum_d s_d |y_d - x_d|) = A_pat(y) * B_pat(x)            (ONE multiplication per entry, any d)
+// so that an entry costs 14 FP64-pipe operations for d = 2 (2 subtractions, 2 scalings, 8 Horner DFMAs, 2 products)
+// and the pattern is two shifts and an add on the integer pipe; both operands are fetched from shared memory by
+// computed address (row side: 2^d adjacent words of the warp-uniform row record -> multicast; column side:
+// [parity][pattern][column pair] layout -> bank = lane, conflict-free), no selects.  Full tiles of plain stores run a
+// check-free loop with a running output pointer; edge tiles / accumulation use the same evaluator with guards.
 constexpr int TMS = 128;
 constexpr int TNS = 256;
 constexpr int SEP_ROWS_PER_THREAD = TMS / (NTHREADS / (TNS / 2));  // 64
+
+template <int D>
+struct SepRec {
+  static constexpr int NPAT = 1 << D;
+  static constexpr int YREC = (D + NPAT + 1) / 2 * 2;  // doubles per row record (coords, A[pat]); even -> 16-byte aligned
+};
 
 // direct evaluation of one entry, kept out of line so that the (rare) fallback path does not inflate the
 // register allocation of the separable hot loop
@@ -127,8 +141,25 @@ __device__ __noinline__ double eval_pair_outofline(const EvalParams<D, NB, ODD>&
   return eval_pair<D, NB, ODD>(p, y.v, x.v);
 }
 
-// resident CTAs per SM the register allocation is tuned for: 3 (<= 80 registers) while the coefficient tensor is
-// small enough not to spill, else 2 or 1
+// one entry from the pattern-product records: yrec = row record in shared memory, xc = my column's coordinates
+// (registers), bcol = &sB[parity][0][column pair] (stride TNS/2 doubles between patterns)
+template <int D, int NB, bool ODD, typename P>
+__device__ __forceinline__ double eval_entry_pat(const P& p, const double* __restrict__ yrec, const double* yc,
+                                                 const double* xc, const double* __restrict__ bcol) {
+  double v[D], u[D];
+  unsigned pat = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double delta = yc[d] - xc[d];
+    u[d] = delta * p.scale[d];
+    v[d] = fabs(u[d]);
+    pat |= ((unsigned)__double2hiint(delta) >> 31) << d;  // sign bit only (delta = -0 picks exp(0) either way)
+  }
+  const double E = yrec[D + pat] * bcol[pat * (TNS / 2)];
+  return NestedHorner<D, NB, ODD, 0>::run(p, v, u, 0) * E;
+}
+
+// resident CTAs per SM the register allocation is tuned for
 template <int D, int NB, bool ODD>
 constexpr int sep_min_blocks() {
   return EvalParams<D, NB, ODD>::NCOEF <= 25 ? 3 : (EvalParams<D, NB, ODD>::NCOEF <= 64 ? 2 : 1);
@@ -139,14 +170,16 @@ __global__ void __launch_bounds__(NTHREADS, sep_min_blocks<D, NB, ODD>())
     gram_sep_kernel(const __grid_constant__ EvalParams<D, NB, ODD> p, const double* __restrict__ X0, int64_t n0,
                     const double* __restrict__ X1, int64_t n1, double* __restrict__ out, int64_t ld, int mode,
                     int accumulate, double alpha, int vec_ok) {
+  constexpr int NPAT = SepRec<D>::NPAT;
+  constexpr int YREC = SepRec<D>::YREC;
   const int64_t row0 = (int64_t)blockIdx.y * TMS;
   const int64_t col0 = (int64_t)blockIdx.x * TNS;
   if (mode == LPGP_GRAM_LOWER && col0 > row0 + (TMS - 1)) return;  // tile strictly above the diagonal
 
   __shared__ __align__(16) double sx0[TMS * D];
   __shared__ __align__(16) double sx1[TNS * D];
-  __shared__ __align__(16) double sp0[TMS * 3 * D];
-  __shared__ __align__(16) double sp1[TNS * 3 * D];
+  __shared__ __align__(16) double sy[TMS * YREC];             // row records: coords, A[pat]
+  __shared__ __align__(16) double sB[2 * NPAT * (TNS / 2)];   // column products: [parity][pat][column pair]
   __shared__ __align__(8) uint64_t bar;
 
   const int rows = (int)min((int64_t)TMS, n0 - row0);
@@ -172,86 +205,105 @@ __global__ void __launch_bounds__(NTHREADS, sep_min_blocks<D, NB, ODD>())
     __syncthreads();
   }
 
-  // point records relative to the tile's first row point
+  // point records relative to the tile's first row point; products over dimensions stay finite while
+  // sum_d |t_d| < LPGP_SEP_MAX_T, guaranteed by |t_d| < LPGP_SEP_MAX_T / D
   bool ok = true;
-  for (int i = threadIdx.x; i < rows + cols; i += NTHREADS) {
-    const bool isrow = i < rows;
-    const int q = isrow ? i : i - rows;
+  for (int i = threadIdx.x; i < TMS + TNS; i += NTHREADS) {
+    const bool isrow = i < TMS;
+    const int q = isrow ? i : i - TMS;
+    const bool live = isrow ? q < rows : q < cols;
     const double* src = isrow ? sx0 + q * D : sx1 + q * D;
-    double* dst = isrow ? sp0 + q * 3 * D : sp1 + q * 3 * D;
+    double a[D], b[D], x[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) ok = sep_point(src[d], sx0[d], p.scale[d], dst + 3 * d) && ok;
+    for (int d = 0; d < D; ++d) {
+      double rec[3];
+      x[d] = live ? src[d] : sx0[d];
+      ok = (sep_point(x[d], sx0[d], p.scale[d], rec) && fabs(rec[0] - sx0[d]) * p.scale[d] * D < LPGP_SEP_MAX_T) && ok;
+      a[d] = rec[1];
+      b[d] = rec[2];
+    }
+#pragma unroll
+    for (int pat = 0; pat < NPAT; ++pat) {
+      double prod = isrow ? 1.0 : alpha;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const bool bit = (pat >> d) & 1;
+        prod *= isrow ? (bit ? b[d] : a[d]) : (bit ? a[d] : b[d]);
+      }
+      if (isrow)
+        sy[q * YREC + D + pat] = prod;
+      else
+        sB[((q & 1) * NPAT + pat) * (TNS / 2) + (q >> 1)] = prod;
+    }
+    if (isrow) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) sy[q * YREC + d] = x[d];
+    }
   }
   const bool sep = !__syncthreads_or(!ok);  // block-uniform; also publishes the records
 
-  const int cpair = (threadIdx.x % (TNS / 2)) * 2;
+  const int tcol = threadIdx.x % (TNS / 2);  // my column pair
+  const int cpair = tcol * 2;
   const int rgrp = threadIdx.x / (TNS / 2);  // 0..1
   const bool c0_ok = cpair < cols, c1_ok = cpair + 1 < cols;
-  double xa[3 * D], xb[3 * D];
+  double xa[D], xb[D];
 #pragma unroll
-  for (int i = 0; i < 3 * D; ++i) {
-    xa[i] = c0_ok ? sp1[cpair * 3 * D + i] : 1.0;
-    xb[i] = c1_ok ? sp1[(cpair + 1) * 3 * D + i] : 1.0;
+  for (int d = 0; d < D; ++d) {
+    xa[d] = c0_ok ? sx1[cpair * D + d] : sx0[d];
+    xb[d] = c1_ok ? sx1[(cpair + 1) * D + d] : sx0[d];
   }
-  if (sep) {  // fold alpha into the first exponential factor of my two columns
-    xa[1] *= alpha;
-    xa[2] *= alpha;
-    xb[1] *= alpha;
-    xb[2] *= alpha;
+  const double* ba = sB + tcol;
+  const double* bb = sB + NPAT * (TNS / 2) + tcol;
+  double* optr = out + (row0 + rgrp * SEP_ROWS_PER_THREAD) * ld + col0 + cpair;
+  const double* yrec = sy + rgrp * SEP_ROWS_PER_THREAD * YREC;
+
+  if (sep && rows == TMS && cols == TNS && vec_ok && !accumulate) {
+    // full tile, plain 16-byte stores: no guards, running pointers
+#pragma unroll 2
+    for (int r = 0; r < SEP_ROWS_PER_THREAD; ++r) {
+      double yc[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) yc[d] = yrec[d];
+      const double v0 = eval_entry_pat<D, NB, ODD>(p, yrec, yc, xa, ba);
+      const double v1 = eval_entry_pat<D, NB, ODD>(p, yrec, yc, xb, bb);
+      *reinterpret_cast<double2*>(optr) = make_double2(v0, v1);
+      optr += ld;
+      yrec += YREC;
+    }
+    return;
   }
-  double* obase = out + (row0 + rgrp * SEP_ROWS_PER_THREAD) * ld + col0 + cpair;
 
 #pragma unroll 1
-  for (int r = 0; r < SEP_ROWS_PER_THREAD; r += 2) {
-    const int lr = rgrp * SEP_ROWS_PER_THREAD + r;
-    if (lr >= rows) break;
-    const bool r1_ok = lr + 1 < rows;
-    const double* y0 = sp0 + lr * 3 * D;
-    const double* y1 = r1_ok ? y0 + 3 * D : y0;
-    double v00, v01, v10, v11;
+  for (int r = 0; r < SEP_ROWS_PER_THREAD; ++r, optr += ld, yrec += YREC) {
+    if (rgrp * SEP_ROWS_PER_THREAD + r >= rows) break;
+    double yc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) yc[d] = yrec[d];
+    double v0, v1;
     if (sep) {
-      v00 = eval_pair_sep<D, NB, ODD>(p, y0, xa);
-      v01 = eval_pair_sep<D, NB, ODD>(p, y0, xb);
-      v10 = eval_pair_sep<D, NB, ODD>(p, y1, xa);
-      v11 = eval_pair_sep<D, NB, ODD>(p, y1, xb);
+      v0 = eval_entry_pat<D, NB, ODD>(p, yrec, yc, xa, ba);
+      v1 = eval_entry_pat<D, NB, ODD>(p, yrec, yc, xb, bb);
     } else {
-      Coords<D> z0, z1, ca, cb;
+      Coords<D> z, ca, cb;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        z0.v[d] = y0[3 * d];
-        z1.v[d] = y1[3 * d];
-        ca.v[d] = xa[3 * d];
-        cb.v[d] = xb[3 * d];
+        z.v[d] = yc[d];
+        ca.v[d] = xa[d];
+        cb.v[d] = xb[d];
       }
-      v00 = alpha * eval_pair_outofline<D, NB, ODD>(p, z0, ca);
-      v01 = alpha * eval_pair_outofline<D, NB, ODD>(p, z0, cb);
-      v10 = alpha * eval_pair_outofline<D, NB, ODD>(p, z1, ca);
-      v11 = alpha * eval_pair_outofline<D, NB, ODD>(p, z1, cb);
+      v0 = alpha * eval_pair_outofline<D, NB, ODD>(p, z, ca);
+      v1 = alpha * eval_pair_outofline<D, NB, ODD>(p, z, cb);
     }
-    double* o0 = obase + (int64_t)r * ld;
-    double* o1 = o0 + ld;
     if (vec_ok && c1_ok) {
       if (accumulate) {
-        double2 a = *reinterpret_cast<double2*>(o0);
-        v00 += a.x;
-        v01 += a.y;
-        if (r1_ok) {
-          double2 b = *reinterpret_cast<double2*>(o1);
-          v10 += b.x;
-          v11 += b.y;
-        }
+        const double2 a = *reinterpret_cast<double2*>(optr);
+        v0 += a.x;
+        v1 += a.y;
       }
-      *reinterpret_cast<double2*>(o0) = make_double2(v00, v01);
-      if (r1_ok) *reinterpret_cast<double2*>(o1) = make_double2(v10, v11);
+      *reinterpret_cast<double2*>(optr) = make_double2(v0, v1);
     } else {
-      if (c0_ok) {
-        o0[0] = accumulate ? o0[0] + v00 : v00;
-        if (r1_ok) o1[0] = accumulate ? o1[0] + v10 : v10;
-      }
-      if (c1_ok) {
-        o0[1] = accumulate ? o0[1] + v01 : v01;
-        if (r1_ok) o1[1] = accumulate ? o1[1] + v11 : v11;
-      }
+      if (c0_ok) optr[0] = accumulate ? optr[0] + v0 : v0;
+      if (c1_ok) optr[1] = accumulate ? optr[1] + v1 : v1;
     }
   }
 }
