@@ -530,11 +530,11 @@ def run_b200(args):
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 # dram__bytes_read+write of ONE representative launch (8192 x 8192 x 2048, beta = 1) from the committed
-                # ncu --set full capture (profiles/ncu_kernels_r01c.md); its algorithmic bytes are 1.34e9 (A + B once,
-                # C read + written) -- the excess is B re-streamed per wave of row-major tiles, at 0.7 TB/s far from
-                # the HBM bound of this tensor-bound kernel
-                "traffic": 5.528e9,
-                "traffic_launch": "gemm_nt_kernel 8192x8192x2048 beta=1: 5.00 GB read + 0.53 GB written (algorithmic 1.34 GB)",
+                # ncu --set full capture (profiles/ncu_kernels_r01d.md, banded tile rasterisation; 5.53e9 before it);
+                # its algorithmic bytes are 1.34e9 (A + B once, C read + written) -- the excess is B re-streamed
+                # once per band of tile rows, at 0.35 TB/s far from the HBM bound of this tensor-bound kernel
+                "traffic": 2.786e9,
+                "traffic_launch": "gemm_nt_kernel 8192x8192x2048 beta=1: 2.26 GB read + 0.53 GB written (algorithmic 1.34 GB)",
                 "kernel": "gemm_nt_kernel (DMMA m8n8k4.f64) inside lpgp_potrf/lpgp_chol_append + lpgp_post_var",
                 "peak_source": "FP64 tensor-pipe issue rate measured live (lpgp_dmma_peak_probe); MEASURED_PEAKS.json "
                                "holds no FP64 figure",

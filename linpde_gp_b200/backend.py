@@ -274,6 +274,13 @@ class DeviceFactor:
         check(lib.lpgp_trsm_rlt(ctypes.byref(f), nlead, _ptr(X), X.shape[0], _ld(X), _stream()), "lpgp_trsm_rlt")
         return X
 
+    def trsv(self, b: torch.Tensor, trans: bool = False) -> torch.Tensor:
+        """b <- L^{-1} b (``trans``: L^{-T} b) in place; one contiguous right-hand side of length n."""
+        assert b.numel() == self.n and b.is_contiguous()
+        f = self._struct()
+        check(lib.lpgp_trsv(ctypes.byref(f), int(trans), _ptr(b), _stream()), "lpgp_trsv")
+        return b
+
     def potrs(self, B: torch.Tensor) -> torch.Tensor:
         """Rows of B <- G^{-1} rows of B, in place."""
         if B.dim() == 1:

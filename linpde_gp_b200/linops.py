@@ -104,11 +104,48 @@ class LinearOperator:
             self._factor = CholeskyFactor(f, n)
         return self._factor if lower else self._factor.T
 
+    def _adopt_factor(self, fac: "CholeskyFactor") -> None:
+        self._factor = fac
+        self.is_positive_definite = True
+
     def solve(self, B):
+        """``A^{-1} B`` (pn/linops/_linear_operator.py:221-315): triangular operators substitute, symmetric ones go
+        through the cached Cholesky factor.  There is no LU kernel on this path (the reference's last-resort branch
+        :311-315): an operator flagged non-symmetric raises ``LinAlgError`` from ``cholesky``."""
+        if self.is_lower_triangular or self.is_upper_triangular:
+            return self._triangular_solve(B)
         return self.cholesky(True).solve_spd(B)
+
+    def _triangular_solve(self, B):
+        raise NotImplementedError(f"{type(self).__name__} has no triangular solve")
+
+    def inv(self) -> "LinearOperator":
+        """Lazy inverse (pn/linops/_linear_operator.py:1009-1028, 1474-1521): ``inv() @ B`` is ``solve(B)``."""
+        if not self.is_square:
+            raise np.linalg.LinAlgError("Only square operators can be inverted.")
+        return _InverseLinearOperator(self)
+
+    def logabsdet(self) -> float:
+        if self.is_lower_triangular or self.is_upper_triangular:
+            d = torch.diagonal(self.device_dense()[: self.shape[0], : self.shape[1]])
+            return float(torch.log(torch.abs(d)).sum().item())
+        return self.cholesky(True).factor.logdet()
+
+    def det(self) -> float:
+        if self.is_lower_triangular or self.is_upper_triangular:
+            d = torch.diagonal(self.device_dense()[: self.shape[0], : self.shape[1]])
+            return float(torch.prod(d).item())
+        return float(np.exp(self.logabsdet()))
+
+    def trace(self) -> float:
+        if not self.is_square:
+            raise ValueError("The trace is only defined for square operators.")
+        return float(torch.diagonal(self.device_dense()[: self.shape[0], : self.shape[1]]).sum().item())
 
     @property
     def T(self):
+        if self.is_symmetric:
+            return self
         return _Transposed(self)
 
     def __matmul__(self, other):
@@ -138,13 +175,76 @@ class _Transposed(LinearOperator):
         super().__init__((op.shape[1], op.shape[0]))
         self._op = op
         self.is_symmetric = op.is_symmetric
+        self.is_positive_definite = op.is_positive_definite
+        self.is_lower_triangular = op.is_upper_triangular
+        self.is_upper_triangular = op.is_lower_triangular
 
     @property
     def T(self):
         return self._op
 
     def device_dense(self):
-        return self._op.device_dense().T.contiguous()
+        return self._op.device_dense()[: self._op.shape[0], : self._op.shape[1]].T.contiguous()
+
+    def _triangular_solve(self, B):
+        return self._op._triangular_solve(B, trans=True)  # pylint: disable=protected-access
+
+
+class _InverseLinearOperator(LinearOperator):
+    """``A^{-1}`` applied by solving with ``A`` (pn/linops/_linear_operator.py:1474-1521)."""
+
+    def __init__(self, op: LinearOperator):
+        super().__init__(op.shape)
+        self._op = op
+        self.is_symmetric = op.is_symmetric
+        self.is_positive_definite = op.is_positive_definite
+        self.is_lower_triangular = op.is_lower_triangular
+        self.is_upper_triangular = op.is_upper_triangular
+
+    def inv(self):
+        return self._op
+
+    @property
+    def T(self):
+        return self if self.is_symmetric else _InverseLinearOperator(self._op.T)
+
+    def __matmul__(self, other):
+        if isinstance(other, LinearOperator):
+            other = other.todense()
+        return self._op.solve(other)
+
+    def solve(self, B):
+        return self._op @ B
+
+    def todense(self, cache: bool = True) -> np.ndarray:
+        return self._op.solve(np.eye(self.shape[0]))
+
+    def device_dense(self):
+        return backend.to_device(self.todense())
+
+    def det(self):
+        return 1.0 / self._op.det()
+
+    def logabsdet(self):
+        return -self._op.logabsdet()
+
+
+def aslinop(A) -> LinearOperator:
+    """``pn.linops.aslinop``: linear operators pass through, arrays become device-resident ``Matrix`` objects."""
+    return A if isinstance(A, LinearOperator) else Matrix(np.atleast_2d(np.asarray(A, dtype=np.double)))
+
+
+def _rows_of(B, n):
+    """Right-hand sides ``(n,)``, ``(n, k)`` or ``(..., n, k)`` as an array of rows ``(nrhs, n)`` + the inverse map."""
+    B = np.asarray(B, dtype=np.double)
+    if B.ndim == 1:
+        if B.shape[0] != n:
+            raise ValueError("`b` has the wrong length")
+        return B[None, :], (lambda res: res[0])
+    if B.shape[-2] != n:
+        raise ValueError("`b` must be a vector or a (stack of) matrices.")
+    rows = np.moveaxis(B, -2, -1).reshape(-1, n)
+    return rows, (lambda res: np.moveaxis(res.reshape(B.shape[:-2] + (B.shape[-1], n)), -1, -2))
 
 
 class Matrix(LinearOperator):
@@ -181,6 +281,52 @@ class Scaling(LinearOperator):
 
     def todense(self, cache=True):
         return np.diag(self.factors)
+
+
+class Identity(Scaling):
+    """``pn.linops.Identity``."""
+
+    def __init__(self, shape):
+        n = int(shape[0]) if np.ndim(shape) else int(shape)
+        if np.ndim(shape) and int(shape[0]) != int(shape[-1]):
+            raise ValueError("Identity must be square")
+        super().__init__(np.ones(n))
+        self.is_positive_definite = True
+        self.is_lower_triangular = self.is_upper_triangular = True
+
+    def _triangular_solve(self, B, trans: bool = False):
+        return np.array(B, dtype=np.double)
+
+
+class Zero(LinearOperator):
+    """``pn.linops.Zero``: the all-zero block of a block-diagonal / block-triangular matrix."""
+
+    def __init__(self, shape):
+        super().__init__(shape)
+        if self.is_square:
+            self.is_symmetric = True
+
+    @property
+    def T(self):
+        return Zero((self.shape[1], self.shape[0]))
+
+    def device_dense(self):
+        out = backend.alloc_matrix(*self.shape)
+        return out.zero_()
+
+    def assemble_into(self, out, lower=False, accumulate=False):
+        return out if accumulate else out.zero_()
+
+    def todense(self, cache=True):
+        return np.zeros(self.shape)
+
+    def __matmul__(self, other):
+        if isinstance(other, LinearOperator):
+            other = other.todense()
+        x = np.asarray(other, dtype=np.double)
+        if x.shape[0 if x.ndim == 1 else -2] != self.shape[1]:
+            raise ValueError(f"shape mismatch: {self.shape} @ {x.shape}")
+        return np.zeros((self.shape[0],) if x.ndim == 1 else x.shape[:-2] + (self.shape[0], x.shape[-1]))
 
 
 class CovarianceLinearOperator(LinearOperator):
@@ -233,43 +379,65 @@ class CovarianceLinearOperator(LinearOperator):
 
 class CholeskyFactor(LinearOperator):
     """Lower-triangular factor ``L`` of an SPD matrix, resident on the device together with its inverted
-    diagonal blocks.  ``solve_spd`` solves with ``L L^T``."""
+    diagonal blocks.  ``solve_spd`` solves with ``L L^T``; ``solve`` / ``inv() @`` substitute with ``L`` itself and
+    ``.T.solve`` with ``L^T`` (scipy ``solve_triangular``, pn/linops/_linear_operator.py:296-299).
 
-    def __init__(self, factor: backend.DeviceFactor, n: int):
-        super().__init__((n, n))
+    ``index`` maps the logical rows to the rows of the device factor: bordered factors pad every observation batch
+    to an even size with an identity row, so the logical matrix is a sub-matrix of the physical one."""
+
+    def __init__(self, factor: backend.DeviceFactor, n=None, index=None):
+        if index is None:
+            index = np.arange(int(n))
+        index = np.asarray(index, dtype=np.int64)
+        super().__init__((len(index), len(index)))
         self.factor = factor
+        self.index = index
         self.is_lower_triangular = True
+
+    def _dev_index(self):
+        return torch.as_tensor(self.index, device=self.factor.L.device)
 
     def device_dense(self):
         n = self.shape[0]
-        return torch.tril(self.factor.L[:n, :n])
+        if n == self.factor.n or np.array_equal(self.index, np.arange(n)):
+            return torch.tril(self.factor.L[:n, :n])
+        idx = self._dev_index()
+        return torch.tril(self.factor.L)[idx][:, idx].contiguous()
+
+    def _scatter(self, rows: np.ndarray) -> torch.Tensor:
+        dev = backend.alloc_matrix(rows.shape[0], self.factor.n)
+        dev.zero_()
+        dev[:, self._dev_index()] = backend.to_device(np.ascontiguousarray(rows))
+        return dev
 
     def solve_spd(self, B):
         """``(L L^T)^{-1} B`` for a vector, a matrix of column right-hand sides or a stack (..., n, k)."""
-        B = np.asarray(B, dtype=np.double)
-        n, nphys = self.shape[0], self.factor.n
-        if B.ndim == 1:
-            if B.shape[0] != n:
-                raise ValueError("`b` has the wrong length")
-            rows = B[None, :]
-        elif B.ndim >= 2:
-            if B.shape[-2] != n:
-                raise ValueError("`b` must be a vector or a (stack of) matrices.")
-            rows = np.moveaxis(B, -2, -1).reshape(-1, n)
-        dev = backend.alloc_matrix(rows.shape[0], nphys)
-        dev.zero_()
-        dev[:, :n].copy_(backend.to_device(np.ascontiguousarray(rows)))
+        rows, back = _rows_of(B, self.shape[0])
+        dev = self._scatter(rows)
         self.factor.potrs(dev)  # forward + backward substitution per right-hand side
-        res = dev[:, :n].cpu().numpy()
-        if B.ndim == 1:
-            return res[0]
-        return np.moveaxis(res.reshape(B.shape[:-2] + (B.shape[-1], n)), -1, -2)
+        return back(dev[:, self._dev_index()].cpu().numpy())
+
+    def _triangular_solve(self, B, trans: bool = False):
+        """``L^{-1} B`` (``trans``: ``L^{-T} B``).  The padding rows of the physical factor are identity rows, so
+        substituting with the physical factor on zero-padded right-hand sides gives the logical solution."""
+        rows, back = _rows_of(B, self.shape[0])
+        dev = self._scatter(rows)
+        if not trans:
+            self.factor.trsm_rlt(dev)  # rows <- rows L^{-T}, i.e. L^{-1} b for every right-hand side b
+        else:
+            for r in range(dev.shape[0]):
+                self.factor.trsv(dev[r], trans=True)
+        return back(dev[:, self._dev_index()].cpu().numpy())
+
+    def logabsdet(self) -> float:
+        return 0.5 * self.factor.logdet()
+
+    def det(self) -> float:
+        return float(np.exp(self.logabsdet()))
 
     @property
     def T(self):
-        t = _Transposed(self)
-        t.is_upper_triangular = True
-        return t
+        return _Transposed(self)
 
 
 def _aligned(A: torch.Tensor) -> torch.Tensor:
@@ -415,7 +583,7 @@ class BlockMatrix(LinearOperator):
     (src/linpde_gp/linops/_block.py:17-80); blocks are assembled straight into their place in one device buffer."""
 
     def __init__(self, blocks):
-        self._blocks = [list(row) for row in blocks]
+        self._blocks = [[aslinop(b) for b in row] for row in blocks]
         if not self._blocks or any(len(row) != len(self._blocks[0]) for row in self._blocks):
             raise ValueError("blocks must form a rectangular grid")
         self._row_sizes = [row[0].shape[0] for row in self._blocks]
@@ -429,6 +597,10 @@ class BlockMatrix(LinearOperator):
     @property
     def blocks(self):
         return self._blocks
+
+    @property
+    def T(self):
+        return BlockMatrix([[self._blocks[i][j].T for i in range(len(self._blocks))] for j in range(len(self._blocks[0]))])
 
     def device_dense(self):
         out = backend.alloc_matrix(*self.shape)
@@ -465,3 +637,253 @@ class BlockDiagonalMatrix(LinearOperator):
             r += b.shape[0]
             c += b.shape[1]
         return out
+
+
+class ConcatenatedLinearOperator(LinearOperator):
+    """Operators stacked along ``axis`` 0 (rows) or 1 (columns) (src/linpde_gp/linops/_concatenated.py:8-72)."""
+
+    def __init__(self, linops, axis: int):
+        linops = tuple(aslinop(op) for op in linops)
+        if len(linops) < 1:
+            raise ValueError("At least one linear operator must be given.")
+        if axis not in [0, 1, -1, -2]:
+            raise ValueError(f"axis is {axis}, expected one of 0, 1, -1, -2.")
+        if axis < 0:
+            axis += 2
+        other = 1 - axis
+        if not all(op.shape[other] == linops[0].shape[other] for op in linops):
+            raise ValueError("All operators must agree along the axis that is not concatenated.")
+        shape = [0, 0]
+        shape[axis] = sum(op.shape[axis] for op in linops)
+        shape[other] = linops[0].shape[other]
+        super().__init__(shape)
+        self._linops = linops
+        self._axis = axis
+
+    @property
+    def linops(self):
+        return self._linops
+
+    @property
+    def axis(self) -> int:
+        return self._axis
+
+    @property
+    def T(self):
+        return ConcatenatedLinearOperator(tuple(op.T for op in self._linops), 1 - self._axis)
+
+    def device_dense(self):
+        out = backend.alloc_matrix(*self.shape)
+        o = 0
+        for op in self._linops:
+            n = op.shape[self._axis]
+            op.assemble_into(out[o : o + n, :] if self._axis == 0 else out[:, o : o + n])
+            o += n
+        return out
+
+
+class BlockMatrix2x2(LinearOperator):
+    """``[[A, B], [C, D]]`` (src/linpde_gp/linops/_block.py:84-292) with the reference's four structures:
+
+    * block diagonal (``B = C = None``);
+    * symmetric positive definite (``is_spd=True``, exactly one of ``B``/``C`` given, the other one is its transpose):
+      the bordered factor ``[[L_A, 0], [(L_A^{-1} B)^T, chol(S)]]``, ``S = D - (L_A^{-1}B)^T (L_A^{-1}B)`` (:191-242),
+      is produced on the device by ``lpgp_chol_append`` -- A's cached factor is copied into a factor with one more
+      segment, the new rows ``[C | D]`` are written behind it and TRSM + SYRK + POTRF run on those rows only;
+    * block lower / upper triangular (triangular ``A``, ``D`` and ``B`` resp. ``C`` missing): block substitution
+      (:251-266);
+    * general (both ``B`` and ``C`` given, no structure): dense products only -- there is no LU on the device path.
+    """
+
+    def __init__(self, A, B, C, D, is_spd: bool = False):
+        self._A, self._D = aslinop(A), aslinop(D)
+        nA, mA = self._A.shape
+        nD, mD = self._D.shape
+        super().__init__((nA + nD, mA + mD))
+        self.is_block_diagonal = False
+        if B is None and C is None:
+            self._B, self._C = Zero((nA, mD)), Zero((nD, mA))
+            self.is_block_diagonal = True
+            if self._A.is_symmetric and self._D.is_symmetric:
+                self.is_symmetric = True
+                if is_spd or (self._A.is_positive_definite and self._D.is_positive_definite):
+                    self.is_positive_definite = True
+            if self._A.is_lower_triangular and self._D.is_lower_triangular:
+                self.is_lower_triangular = True
+            if self._A.is_upper_triangular and self._D.is_upper_triangular:
+                self.is_upper_triangular = True
+        elif is_spd:
+            if (B is None) == (C is None):
+                raise ValueError("exactly one of B and C must be given for an SPD block matrix")
+            if not (self._A.is_symmetric and self._D.is_symmetric):
+                raise ValueError("A and D must be flagged symmetric")
+            if self._A.is_positive_definite is False:
+                raise ValueError("A must be positive definite")
+            if C is None:
+                self._B = aslinop(B)
+                self._C = self._B.T
+            else:
+                self._C = aslinop(C)
+                self._B = self._C.T
+            self.is_symmetric = True
+            self.is_positive_definite = True
+        elif self._A.is_lower_triangular and self._D.is_lower_triangular and B is None:
+            self._C = aslinop(C)
+            self._B = Zero((nA, mD))
+            self.is_lower_triangular = True
+        elif self._A.is_upper_triangular and self._D.is_upper_triangular and C is None:
+            self._B = aslinop(B)
+            self._C = Zero((nD, mA))
+            self.is_upper_triangular = True
+        else:
+            if B is None or C is None:
+                raise ValueError("B and C must both be given unless the matrix is block diagonal, SPD or block triangular")
+            self._B, self._C = aslinop(B), aslinop(C)
+        if self._B.shape != (nA, mD) or self._C.shape != (nD, mA):
+            raise ValueError("inconsistent block shapes")
+        self._schur = None
+        self._L_A_inv_B = None
+
+    A = property(lambda self: self._A)
+    B = property(lambda self: self._B)
+    C = property(lambda self: self._C)
+    D = property(lambda self: self._D)
+
+    def _split(self, x: np.ndarray, axis: int = -2):
+        return np.split(x, [self._A.shape[1]], axis=axis)
+
+    @property
+    def T(self):
+        if self.is_symmetric:
+            return self
+        return BlockMatrix2x2(self._A.T, None if self.is_upper_triangular or self.is_block_diagonal else self._C.T,
+                              None if self.is_lower_triangular or self.is_block_diagonal else self._B.T, self._D.T)
+
+    def device_dense(self):
+        out = backend.alloc_matrix(*self.shape)
+        nA, mA = self._A.shape
+        self._A.assemble_into(out[:nA, :mA])
+        self._B.assemble_into(out[:nA, mA:])
+        self._C.assemble_into(out[nA:, :mA])
+        self._D.assemble_into(out[nA:, mA:])
+        return out
+
+    # -- SPD: bordered Cholesky on the device ------------------------------------------------------------------------
+    def _require_spd(self):
+        if not (self.is_symmetric and self.is_positive_definite):
+            raise ValueError("This quantity can only be computed for SPD matrices.")
+
+    def cholesky(self, lower: bool = True):
+        if not (self.is_symmetric and self.is_positive_definite is not False):
+            return super().cholesky(lower)
+        if self._factor is None:
+            fa = self._A.cholesky(True)  # cached on A: conditioning on a new batch reuses the old factor
+            nA, nD = self._A.shape[0], self._D.shape[0]
+            pA, pD = fa.factor.n, nD + nD % 2
+            new = fa.factor.extended(pD)
+            rows = new.L[pA : pA + pD]
+            rows.zero_()
+            Cd = self._C.device_dense()[:nD, :nA]
+            rows[:nD].index_copy_(1, fa._dev_index(), Cd.contiguous())  # pylint: disable=protected-access
+            self._D.assemble_into(rows[:nD, pA : pA + nD], lower=True)
+            if nD % 2:
+                rows[nD, pA + nD] = 1.0
+            try:
+                new.append_last()
+            except np.linalg.LinAlgError:
+                self.is_positive_definite = False
+                raise
+            self._factor = CholeskyFactor(new, index=np.concatenate([fa.index, pA + np.arange(nD)]))
+        return self._factor if lower else self._factor.T
+
+    @property
+    def L_A_inv_B(self) -> LinearOperator:
+        """``L_A^{-1} B`` (:203-207): the transposed off-diagonal block of the bordered factor."""
+        self._require_spd()
+        if self._L_A_inv_B is None:
+            fac = self.cholesky(True)
+            nA = self._A.shape[0]
+            idx = fac._dev_index()  # pylint: disable=protected-access
+            L21 = fac.factor.L[idx[nA:]][:, idx[:nA]]
+            dev = backend.alloc_matrix(nA, self._D.shape[0])
+            dev.copy_(L21.T)
+            self._L_A_inv_B = _Device(dev)
+        return self._L_A_inv_B
+
+    @property
+    def schur(self) -> LinearOperator:
+        """Schur complement ``D - C A^{-1} B`` (:191-201)."""
+        if self._schur is None:
+            if self.is_symmetric and self.is_positive_definite:
+                X = self.L_A_inv_B.device_dense()  # (nA, nD)
+                Xt = backend.alloc_matrix(X.shape[1], X.shape[0])
+                Xt.copy_(X.T)
+                S = backend.alloc_matrix(*self._D.shape)
+                self._D.assemble_into(S)
+                backend.gemm_nt(Xt, Xt, S, -1.0, 1.0)
+            else:
+                AinvB = self._A.solve(self._B.todense())
+                S = backend.to_device(self._D.todense() - self._C @ AinvB)
+            self._schur = _Device(S)
+            self._schur.is_symmetric = self.is_symmetric
+            self._schur.is_positive_definite = self.is_positive_definite
+        return self._schur
+
+    def schur_update(self, A_inv_u: np.ndarray, v: np.ndarray) -> np.ndarray:
+        """Solution of ``[[A, B], [C, D]] [x; y] = [u; v]`` from ``A^{-1} u`` (:226-231)."""
+        A_inv_u, v = np.asarray(A_inv_u, dtype=np.double), np.asarray(v, dtype=np.double)
+        if self.is_block_diagonal:
+            return np.concatenate((A_inv_u, self._D.solve(v)))
+        y = self.schur.solve(v - self._C @ A_inv_u)
+        x = A_inv_u - self._A.solve(self._B @ y)
+        return np.concatenate((x, y))
+
+    def solve(self, B):
+        B = np.asarray(B, dtype=np.double)
+        if B.shape[0 if B.ndim == 1 else -2] != self.shape[0]:
+            raise ValueError("`b` must be a vector or a (stack of) matrices.")
+        axis = 0 if B.ndim == 1 else -2
+        b0, b1 = np.split(B, [self._A.shape[0]], axis=axis)
+        if self.is_block_diagonal:
+            return np.concatenate((self._A.solve(b0), self._D.solve(b1)), axis=axis)
+        if self.is_symmetric:
+            return self.cholesky(True).solve_spd(B)
+        if self.is_lower_triangular:
+            y0 = self._A.solve(b0)
+            y1 = self._D.solve(b1 - self._C @ y0)
+            return np.concatenate((y0, y1), axis=axis)
+        if self.is_upper_triangular:
+            y1 = self._D.solve(b1)
+            y0 = self._A.solve(b0 - self._B @ y1)
+            return np.concatenate((y0, y1), axis=axis)
+        raise NotImplementedError("general (unstructured) block systems need an LU factorisation, which the device path "
+                                  "does not provide")
+
+    def _triangular_solve(self, B, trans: bool = False):
+        return (self.T if trans else self).solve(B)
+
+    def trace(self) -> float:
+        return self._A.trace() + self._D.trace()
+
+    def logabsdet(self) -> float:
+        if self.is_block_diagonal or self.is_lower_triangular or self.is_upper_triangular:
+            return self._A.logabsdet() + self._D.logabsdet()
+        if self.is_symmetric and self.is_positive_definite:
+            return self.cholesky(True).factor.logdet()
+        raise NotImplementedError("determinant of an unstructured block matrix")
+
+    def det(self) -> float:
+        if self.is_block_diagonal or self.is_lower_triangular or self.is_upper_triangular:
+            return self._A.det() * self._D.det()
+        return float(np.exp(self.logabsdet()))
+
+
+class _Device(LinearOperator):
+    """A matrix that already lives on the device."""
+
+    def __init__(self, dev: torch.Tensor):
+        super().__init__(dev.shape)
+        self._dev = dev
+
+    def device_dense(self):
+        return self._dev
