@@ -78,6 +78,13 @@ long long lpgp_launch_count(int reset); /* kernels launched by the library so fa
 /* LPGP_OPT_NO_LOOKAHEAD != 0: lpgp_potrf / lpgp_chol_append run the plain one-stream recursion instead of the
  * two-stream right-looking pipeline with one panel of lookahead (same factor up to rounding; for A/B timing). */
 #define LPGP_OPT_NO_LOOKAHEAD 2
+/* LPGP_OPT_TRSM_REFINE: residual correction in the leaf step of the blocked triangular solves.  The leaf step
+ * multiplies with the explicit inverse of a 128 x 128 diagonal block, which leaves a residual of order
+ * cond(L_kk) eps; one correction step (two more 128-wide GEMMs) restores the O(eps) residual of LAPACK's dtrsm.
+ * 0 = never, 1 = inside factorisations only (lpgp_potrf, lpgp_chol_append, lpgp_trsm_rlt_refined; DEFAULT -- there the
+ * residual perturbs the Gram matrix itself and decides whether a nearly singular matrix still factors, as it does
+ * with the reference's dpotrf), 2 = also in lpgp_trsm_rlt.                                                  */
+#define LPGP_OPT_TRSM_REFINE 3
 int lpgp_set_option(int key, int value);
 /* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and
  * reports the flop count; timed by the caller it yields the roofline denominator of the DMMA kernels on the
@@ -182,6 +189,11 @@ int lpgp_chol_append(lpgp_factor* f, void* stream);
  * k(x_test, X_obs).  `nlead` restricts the solve to the leading nlead columns/rows of the factor (must be a
  * segment boundary; pass f->n for the whole factor).                                                       */
 int lpgp_trsm_rlt(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int64_t ldx, void* stream);
+/* Same solve with the residual-corrected leaf step (LPGP_OPT_TRSM_REFINE >= 1): the panel solve
+ * A21 <- A21 L11^{-T} of a blocked factorisation driven from the host side (multi-GPU block-row Cholesky), where
+ * backward stability matters (scipy.linalg.cholesky, pn/linops/_linear_operator.py:860-865).  Allocates an
+ * m x 128 workspace on `stream` (cudaMallocAsync / cudaFreeAsync).                                           */
+int lpgp_trsm_rlt_refined(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int64_t ldx, void* stream);
 
 /* B[r, :] <- G^{-1} B[r, :] for nrhs right-hand sides stored as rows of B (nrhs x n): forward and backward
  * substitution = scipy.linalg.cho_solve of pn/linops/_linear_operator.py:303-307.                          */

@@ -21,6 +21,7 @@ DIM_MATERN, DIM_EXPQUAD = 0, 1
 GRAM_FULL, GRAM_LOWER = 0, 1
 OPT_DIRECT_EXP = 1
 OPT_NO_LOOKAHEAD = 2
+OPT_TRSM_REFINE = 3
 
 
 class KernelDesc(ctypes.Structure):
@@ -100,6 +101,7 @@ def _load() -> ctypes.CDLL:
         "lpgp_potrf_async": (ci, [FP, vp]),
         "lpgp_chol_append": (ci, [FP, vp]),
         "lpgp_trsm_rlt": (ci, [FP, i64, vp, i64, i64, vp]),
+        "lpgp_trsm_rlt_refined": (ci, [FP, i64, vp, i64, i64, vp]),
         "lpgp_potrs": (ci, [FP, vp, i64, i64, vp]),
         "lpgp_trsv": (ci, [FP, ci, vp, vp]),
         "lpgp_gemv": (ci, [ci, i64, i64, dbl, vp, i64, vp, vp, vp]),
@@ -121,7 +123,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTED = (
     "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_set_option lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower lpgp_kron_sum "
-    "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
+    "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_trsm_rlt_refined lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
     "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq lpgp_matern_integral lpgp_matern_integral2"
 ).split()
 

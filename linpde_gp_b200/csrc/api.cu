@@ -15,6 +15,7 @@ extern "C" const char* lpgp_error_string(int code) {
 long long g_lpgp_launches = 0;
 int g_lpgp_no_sep = 0;
 int g_lpgp_no_lookahead = 0;
+int g_lpgp_trsm_refine = 1;
 
 extern "C" int lpgp_set_option(int key, int value) {
   if (key == LPGP_OPT_DIRECT_EXP) {
@@ -23,6 +24,11 @@ extern "C" int lpgp_set_option(int key, int value) {
   }
   if (key == LPGP_OPT_NO_LOOKAHEAD) {
     g_lpgp_no_lookahead = value != 0;
+    return 0;
+  }
+  if (key == LPGP_OPT_TRSM_REFINE) {
+    if (value < 0 || value > 2) return -2;
+    g_lpgp_trsm_refine = value;
     return 0;
   }
   return -1;

@@ -141,10 +141,11 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     __syncthreads();
   }
 
-  // write L back (coalesced rows)
+  // write L back (coalesced rows); the strict upper triangle of the block is cleared so that the block can be used as
+  // a plain GEMM operand (residual of the refined panel solve, trsm_rec)
   for (int idx = tid; idx < nb * nb; idx += DIAG_THREADS) {
     const int i = idx / nb, j = idx % nb;
-    if (j <= i) A[(int64_t)i * ld + j] = a[i * LDS_A + j];
+    A[(int64_t)i * ld + j] = (j <= i) ? a[i * LDS_A + j] : 0.0;
   }
 
   // ---- inverse, step 1: W_bb = L_bb^{-1} for the four diagonal blocks (warp b, lane = column) ----
@@ -344,25 +345,64 @@ inline int* info_ptr(const lpgp_factor* f, int nleaves) {
 
 int g_diag_attr_set = 0;
 
-// X[m x (off[hi]-off[lo])] <- X * L[lo:hi, lo:hi]^{-T}; X points at column off[lo] of the right-hand-side rows
-int trsm_rec(const lpgp_factor* f, const Leaves& lv, int lo, int hi, double* X, int64_t m, int64_t ldx, cudaStream_t st) {
+// X[m x (off[hi]-off[lo])] <- X * L[lo:hi, lo:hi]^{-T}; X points at column off[lo] of the right-hand-side rows.
+//
+// Leaf step.  Multiplying with the explicit inverse W = L_kk^{-1} is fast (one GEMM) but not backward stable: the
+// residual  B - X L_kk^T  is of order cond(L_kk) eps |B| instead of eps |B|.  That is harmless when the result is the
+// final answer (posterior variance: the forward error is cond(L) eps either way), but inside a FACTORISATION the
+// residual is a perturbation of the Gram matrix itself -- at cond(G) ~ 1e12 it reaches 1e-12 |G| and the blocked
+// factorisation reports "not positive definite" for matrices LAPACK's dpotrf (the reference,
+// pn/linops/_linear_operator.py:860-865) still factors.  With a workspace T (m x 128) the leaf step therefore does one
+// step of residual correction,
+//     T = B W^T;   B <- B - T L_kk^T (residual);   T += B W^T;   X = T,
+// which brings the residual back to O(eps) (tests/test_gpu_kernels.py::test_potrf_backward_error_ill_conditioned).
+// The two extra GEMMs are m x 128 x 128: N^2 * 256 extra flops per factorisation (1.2 % at N = 64k).
+int trsm_rec(const lpgp_factor* f, const Leaves& lv, int lo, int hi, double* X, int64_t m, int64_t ldx, cudaStream_t st,
+             double* T = nullptr) {
   const int64_t c0 = lv.off[lo];
   if (hi - lo == 1) {
     const int nb = (int)(lv.off[hi] - c0);
-    // in place: one tile column (nb <= 128), every CTA reads all of its own rows before writing them
-    return lpgp_gemm_nt(m, nb, nb, 1.0, X, ldx, dinv_block(f, lo), LEAF, 0.0, X, ldx, 0, st);
+    const double* W = dinv_block(f, lo);
+    if (T == nullptr)  // in place: one tile column (nb <= 128), every CTA reads all of its own rows before writing them
+      return lpgp_gemm_nt(m, nb, nb, 1.0, X, ldx, W, LEAF, 0.0, X, ldx, 0, st);
+    const double* Lkk = f->L + c0 * f->ld + c0;  // strict upper triangle cleared by the leaf kernel
+    int rc = lpgp_gemm_nt(m, nb, nb, 1.0, X, ldx, W, LEAF, 0.0, T, LEAF, 0, st);
+    if (rc) return rc;
+    rc = lpgp_gemm_nt(m, nb, nb, -1.0, T, LEAF, Lkk, f->ld, 1.0, X, ldx, 0, st);
+    if (rc) return rc;
+    rc = lpgp_gemm_nt(m, nb, nb, 1.0, X, ldx, W, LEAF, 1.0, T, LEAF, 0, st);
+    if (rc) return rc;
+    LPGP_CHECK(cudaMemcpy2DAsync(X, (size_t)ldx * 8, T, (size_t)LEAF * 8, (size_t)nb * 8, (size_t)m,
+                                 cudaMemcpyDeviceToDevice, st));
+    return 0;
   }
   const int mid = lo + (hi - lo) / 2;
   const int64_t c1 = lv.off[mid], c2 = lv.off[hi];
-  int rc = trsm_rec(f, lv, lo, mid, X, m, ldx, st);
+  int rc = trsm_rec(f, lv, lo, mid, X, m, ldx, st, T);
   if (rc) return rc;
   // X2 -= X1 * L21^T,  L21 = L[c1:c2, c0:c1]
   rc = lpgp_gemm_nt(m, c2 - c1, c1 - c0, -1.0, X, ldx, f->L + c1 * f->ld + c0, f->ld, 1.0, X + (c1 - c0), ldx, 0, st);
   if (rc) return rc;
-  return trsm_rec(f, lv, mid, hi, X + (c1 - c0), m, ldx, st);
+  return trsm_rec(f, lv, mid, hi, X + (c1 - c0), m, ldx, st, T);
 }
 
-int potrf_rec(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st) {
+// refinement workspace of a factorisation over n rows: stream-ordered allocation (no hidden persistent state; safe
+// for concurrent callers on distinct streams)
+struct TrsmWork {
+  double* T = nullptr;
+  cudaStream_t st = nullptr;
+  int acquire(int64_t rows, cudaStream_t s) {
+    st = s;
+    if (g_lpgp_trsm_refine == 0 || rows <= 0) return 0;
+    LPGP_CHECK(cudaMallocAsync((void**)&T, (size_t)rows * LEAF * sizeof(double), st));
+    return 0;
+  }
+  ~TrsmWork() {
+    if (T) cudaFreeAsync(T, st);
+  }
+};
+
+int potrf_rec(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st, double* T) {
   const int64_t c0 = lv.off[lo];
   double* A = f->L + c0 * f->ld + c0;
   if (hi - lo == 1) {
@@ -373,15 +413,15 @@ int potrf_rec(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaS
   }
   const int mid = lo + (hi - lo) / 2;
   const int64_t c1 = lv.off[mid], c2 = lv.off[hi];
-  int rc = potrf_rec(f, lv, lo, mid, info, st);
+  int rc = potrf_rec(f, lv, lo, mid, info, st, T);
   if (rc) return rc;
   double* A21 = f->L + c1 * f->ld + c0;
-  rc = trsm_rec(f, lv, lo, mid, A21, c2 - c1, f->ld, st);
+  rc = trsm_rec(f, lv, lo, mid, A21, c2 - c1, f->ld, st, T);
   if (rc) return rc;
   double* A22 = f->L + c1 * f->ld + c1;
   rc = lpgp_gemm_nt(c2 - c1, c2 - c1, c1 - c0, -1.0, A21, f->ld, A21, f->ld, 1.0, A22, f->ld, 1, st);
   if (rc) return rc;
-  return potrf_rec(f, lv, mid, hi, info, st);
+  return potrf_rec(f, lv, mid, hi, info, st, T);
 }
 
 // ---- right-looking factorisation with ONE PANEL OF LOOKAHEAD on two streams -----------------------------------
@@ -423,7 +463,7 @@ inline int lookahead_panel_leaves(int nl) {
   return pb < 4 ? 4 : (pb > 16 ? 16 : pb);
 }
 
-int potrf_lookahead(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st) {
+int potrf_lookahead(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st, double* T) {
   const int pb = lookahead_panel_leaves(hi - lo);
   const int P = (hi - lo + pb - 1) / pb;
   std::lock_guard<std::mutex> guard(g_la_mutex);
@@ -440,10 +480,10 @@ int potrf_lookahead(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info,
   // factor panel p on stream s: diagonal block, then the rows below it
   auto factor_panel = [&](int p, cudaStream_t s) -> int {
     const int l0 = leaf_lo(p), l1 = leaf_lo(p + 1);
-    int r = potrf_rec(f, lv, l0, l1, info, s);
+    int r = potrf_rec(f, lv, l0, l1, info, s, T);
     if (r) return r;
     const int64_t r0 = lv.off[l0], r1 = lv.off[l1];
-    if (r1 < n_hi) r = trsm_rec(f, lv, l0, l1, f->L + r1 * ld + r0, n_hi - r1, ld, s);
+    if (r1 < n_hi) r = trsm_rec(f, lv, l0, l1, f->L + r1 * ld + r0, n_hi - r1, ld, s, T);
     return r;
   };
   LPGP_CHECK(cudaEventRecord(ev_fork, st));
@@ -479,9 +519,12 @@ int potrf_lookahead(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info,
 }
 
 // factor the leaf range [lo, hi): lookahead pipeline for ranges of at least three panels, else the recursion
-int potrf_range(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st) {
-  if (!g_lpgp_no_lookahead && hi - lo >= 3 * lookahead_panel_leaves(hi - lo)) return potrf_lookahead(f, lv, lo, hi, info, st);
-  return potrf_rec(f, lv, lo, hi, info, st);
+// (T: refinement workspace of trsm_rec with at least off[hi] - off[lo] rows, or nullptr; all uses of T are ordered:
+// inside the lookahead pipeline only the panel stream solves, after the fork and before the join)
+int potrf_range(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st, double* T) {
+  if (!g_lpgp_no_lookahead && hi - lo >= 3 * lookahead_panel_leaves(hi - lo))
+    return potrf_lookahead(f, lv, lo, hi, info, st, T);
+  return potrf_rec(f, lv, lo, hi, info, st, T);
 }
 
 int check_factor(const lpgp_factor* f) {
@@ -529,7 +572,10 @@ int potrf_impl(lpgp_factor* f, void* stream, bool sync) {
   const bool dbg = getenv("LPGP_DEBUG_TIMING") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
   const long long l0 = g_lpgp_launches;
-  rc = potrf_range(f, lv, 0, nl, info, st);
+  TrsmWork work;
+  rc = work.acquire(f->n, st);
+  if (rc) return rc;
+  rc = potrf_range(f, lv, 0, nl, info, st, work.T);
   if (rc) return rc;
   if (!sync) return 0;
   const auto t1 = std::chrono::steady_clock::now();
@@ -565,16 +611,20 @@ extern "C" int lpgp_chol_append(lpgp_factor* f, void* stream) {
   set_int_kernel<<<1, 1, 0, st>>>(info, 0);
   LPGP_CHECK_LAUNCH();
   double* A21 = f->L + np * f->ld;
-  rc = trsm_rec(f, lv, 0, l0, A21, nn, f->ld, st);  // L21 = B^T L11^{-T}
+  TrsmWork work;
+  rc = work.acquire(nn, st);
+  if (rc) return rc;
+  rc = trsm_rec(f, lv, 0, l0, A21, nn, f->ld, st, work.T);  // L21 = B^T L11^{-T}
   if (rc) return rc;
   rc = lpgp_gemm_nt(nn, nn, np, -1.0, A21, f->ld, A21, f->ld, 1.0, f->L + np * f->ld + np, f->ld, 1, st);  // Schur
   if (rc) return rc;
-  rc = potrf_range(f, lv, l0, nl, info, st);
+  rc = potrf_range(f, lv, l0, nl, info, st, work.T);
   if (rc) return rc;
   return finish_info(info, st);
 }
 
-extern "C" int lpgp_trsm_rlt(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int64_t ldx, void* stream) {
+namespace {
+int trsm_rlt_impl(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int64_t ldx, void* stream, bool refine) {
   if (check_factor(f)) return -1;
   if (!X || ldx < nlead || (ldx % 2) || ((uintptr_t)X % 16)) return -3;
   if (m < 0) return -4;
@@ -585,7 +635,21 @@ extern "C" int lpgp_trsm_rlt(const lpgp_factor* f, int64_t nlead, double* X, int
   for (int s = 1; s <= f->nseg; ++s)
     if (f->seg_off[s] == nlead) hi = lv.seg_first[s];
   if (hi < 0) return -2;
-  return trsm_rec(f, lv, 0, hi, X, m, ldx, (cudaStream_t)stream);
+  TrsmWork work;
+  if (refine) {
+    const int rc = work.acquire(m, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return trsm_rec(f, lv, 0, hi, X, m, ldx, (cudaStream_t)stream, work.T);
+}
+}  // namespace
+
+extern "C" int lpgp_trsm_rlt(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int64_t ldx, void* stream) {
+  return trsm_rlt_impl(f, nlead, X, m, ldx, stream, g_lpgp_trsm_refine >= 2);
+}
+
+extern "C" int lpgp_trsm_rlt_refined(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int64_t ldx, void* stream) {
+  return trsm_rlt_impl(f, nlead, X, m, ldx, stream, g_lpgp_trsm_refine >= 1);
 }
 
 namespace {

@@ -14,6 +14,8 @@ extern long long g_lpgp_launches;
 extern int g_lpgp_no_sep;
 // 1 = factor on one stream with the plain recursion (no panel lookahead)
 extern int g_lpgp_no_lookahead;
+// residual-corrected leaf step of the panel solves: 0 = never, 1 = inside factorisations (default), 2 = everywhere
+extern int g_lpgp_trsm_refine;
 #define LPGP_MAX_DEVICES 32
 
 #define LPGP_CHECK_LAUNCH()                            \

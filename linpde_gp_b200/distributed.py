@@ -127,13 +127,15 @@ class DeviceOps:
         self._lib.check(rc, "lpgp_potrf_async")
         info_out.copy_(dinv[-8:].view(torch.int32)[:1])
 
-    def trsm_block(self, Lkk: torch.Tensor, dinv: torch.Tensor, X: torch.Tensor) -> None:
-        """X <- X Lkk^{-T} in place."""
+    def trsm_block(self, Lkk: torch.Tensor, dinv: torch.Tensor, X: torch.Tensor, refine: bool = False) -> None:
+        """X <- X Lkk^{-T} in place; ``refine``: the residual-corrected panel solve of a factorisation
+        (``lpgp_trsm_rlt_refined``, backward stable like LAPACK's dtrsm)."""
         if X.shape[0] == 0:
             return
         f = self._factor_struct(Lkk, dinv)
-        rc = self._lib.lib.lpgp_trsm_rlt(ctypes.byref(f), Lkk.shape[0], ctypes.c_void_p(X.data_ptr()), X.shape[0],
-                                         self.be._ld(X), self.be._stream())  # pylint: disable=protected-access
+        fn = self._lib.lib.lpgp_trsm_rlt_refined if refine else self._lib.lib.lpgp_trsm_rlt
+        rc = fn(ctypes.byref(f), Lkk.shape[0], ctypes.c_void_p(X.data_ptr()), X.shape[0],
+                self.be._ld(X), self.be._stream())  # pylint: disable=protected-access
         self._lib.check(rc, "lpgp_trsm_rlt")
 
     def trsv_block(self, Lkk: torch.Tensor, dinv: torch.Tensor, b: torch.Tensor, trans: bool) -> None:
@@ -252,7 +254,7 @@ class DistributedCholesky:
                 r_lo = first * nb
                 m_loc = lay.rows_after(rank, k)
                 X = self.A_loc[r_lo : r_lo + m_loc, k0:k1]
-                ops.trsm_block(Lkk, Wk, X)
+                ops.trsm_block(Lkk, Wk, X, refine=True)
                 # (3) all-gather the panel pieces; slot (r, j) = j-th block below k of rank r.  Global block
                 #     k+1+t sits in slot ((k+1+t) % P, t // P): rotating the rank axis and swapping it with the
                 #     slot axis puts the panel into global row order.

@@ -48,7 +48,7 @@ class HostOps:
             W[l] = torch.eye(LEAF, dtype=torch.float64)
             W[l, : hi - lo, : hi - lo] = torch.linalg.inv(L[lo:hi, lo:hi])
 
-    def trsm_block(self, Lkk, dinv, X):
+    def trsm_block(self, Lkk, dinv, X, refine=False):
         if X.shape[0] == 0:
             return
         X.copy_(torch.linalg.solve_triangular(torch.tril(Lkk), X.T.contiguous(), upper=False).T)
