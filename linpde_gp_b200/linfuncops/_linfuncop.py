@@ -47,10 +47,12 @@ class LinearFunctionOperator:
 
     # -- application --------------------------------------------------------------------------------------
     def __call__(self, f, /, **kwargs):
-        from ..randprocs import _conditional, _gaussian_process, covfuncs
+        from ..randprocs import _conditional, _gaussian_process, covfuncs, crosscov
 
         if isinstance(f, covfuncs.CovarianceFunction):
             return covfuncs.apply_linfuncop(self, f, argnum=kwargs.get("argnum", 0))
+        if isinstance(f, crosscov.ProcessVectorCrossCovariance):  # acts on the free argument (crosscov/linfuncops.py:18-87)
+            return f._apply_linfuncop(self)  # pylint: disable=protected-access
         if isinstance(f, _conditional.ConditionalGaussianProcess):
             return f._apply_linfuncop(self)  # pylint: disable=protected-access
         if isinstance(f, _gaussian_process.GaussianProcess):

@@ -55,8 +55,19 @@ class LinearFunctional:
         raise NotImplementedError(f"{type(self).__name__} cannot be used as an observation")
 
     def __call__(self, f, /, **kwargs):
-        from .randprocs import _conditional, _gaussian_process
+        from .randprocs import _conditional, _gaussian_process, covfuncs, crosscov
 
+        if isinstance(f, covfuncs.CovarianceFunction):
+            # L(k, argnum=1) = Cov(f(.), L[f]); argnum=0: the same object indexed the other way round (`reverse`)
+            # (src/linpde_gp/randprocs/covfuncs/linfunctls/_registry.py, crosscov/linfunctls/_evaluation.py:21-328)
+            argnum = kwargs.get("argnum", 0)
+            if argnum not in (0, 1):
+                raise ValueError("`argnum` must either be 0 or 1.")
+            if isinstance(f, covfuncs.Zero):
+                return crosscov.Zero(f.input_shape, f.output_shape_0, self.output_shape, reverse=(argnum == 0))
+            return crosscov._FunctionalCrossCovariance(f, self, reverse=(argnum == 0))  # pylint: disable=protected-access
+        if isinstance(f, crosscov.ProcessVectorCrossCovariance):
+            return crosscov.apply_linfunctl(self, f)
         if isinstance(f, _conditional.ConditionalGaussianProcess):
             return f._apply_linfunctl(self)  # pylint: disable=protected-access
         if isinstance(f, _gaussian_process.GaussianProcess):

@@ -77,6 +77,119 @@ class Normal:
         return np.sqrt(self.var)
 
 
+class Covariance:
+    """Covariance between two random variables of shapes ``shape0`` and ``shape1``
+    (src/linpde_gp/randvars/_covariance.py:13-134): simultaneously an array of shape ``shape0 + shape1`` and a
+    ``(size0, size1)`` matrix / linear operator over the C-order flattened variables."""
+
+    def __init__(self, shape0, shape1):
+        self._shape0 = tuple(int(s) for s in np.atleast_1d(shape0)) if np.ndim(shape0) or shape0 != () else ()
+        self._shape1 = tuple(int(s) for s in np.atleast_1d(shape1)) if np.ndim(shape1) or shape1 != () else ()
+
+    shape0 = property(lambda self: self._shape0)
+    shape1 = property(lambda self: self._shape1)
+    ndim0 = property(lambda self: len(self._shape0))
+    ndim1 = property(lambda self: len(self._shape1))
+    size0 = property(lambda self: int(np.prod(self._shape0)) if self._shape0 else 1)
+    size1 = property(lambda self: int(np.prod(self._shape1)) if self._shape1 else 1)
+
+    @property
+    def array(self) -> np.ndarray:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    @property
+    def linop(self):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    @property
+    def matrix(self) -> np.ndarray:
+        return self.linop.todense()
+
+    def flatten0(self, event0) -> np.ndarray:
+        event0 = np.asarray(event0)
+        if event0.shape != self._shape0:
+            raise ValueError(f"The shape of the event must be the same as `shape0`, but {event0.shape} != {self._shape0}.")
+        return event0.reshape(-1)
+
+    def flatten1(self, event1) -> np.ndarray:
+        event1 = np.asarray(event1)
+        if event1.shape != self._shape1:
+            raise ValueError(f"The shape of the event must be the same as `shape1`, but {event1.shape} != {self._shape1}.")
+        return event1.reshape(-1)
+
+    def unflatten0(self, vec0) -> np.ndarray:
+        return np.asarray(vec0).reshape(self._shape0)
+
+    def unflatten1(self, vec1) -> np.ndarray:
+        return np.asarray(vec1).reshape(self._shape1)
+
+    @property
+    def T(self) -> "Covariance":
+        return LinearOperatorCovariance(self.linop.T, shape0=self._shape1, shape1=self._shape0)
+
+    def __neg__(self):
+        return -1.0 * self
+
+    def __rmul__(self, other):
+        if np.ndim(other) == 0:
+            return LinearOperatorCovariance(float(other) * self.linop, shape0=self._shape0, shape1=self._shape1)
+        return NotImplemented
+
+    def __add__(self, other):
+        if isinstance(other, Covariance):
+            if other.shape0 != self._shape0 or other.shape1 != self._shape1:
+                raise ValueError("shape mismatch")
+            return LinearOperatorCovariance(self.linop + other.linop, shape0=self._shape0, shape1=self._shape1)
+        return NotImplemented
+
+
+class ArrayCovariance(Covariance):
+    """Covariance given as a host array of shape ``shape0 + shape1`` (_covariance.py:137-194)."""
+
+    def __init__(self, cov_array, shape0, shape1):
+        super().__init__(shape0, shape1)
+        self._array = np.asarray(cov_array, dtype=np.double)
+        if self._array.shape != self.shape0 + self.shape1:
+            raise ValueError(f"`cov_array` must have shape {self.shape0 + self.shape1}, got {self._array.shape}")
+        self._linop = None
+
+    @classmethod
+    def from_scalar(cls, cov):
+        return cls(np.asarray(cov, dtype=np.double).reshape(()), (), ())
+
+    @property
+    def array(self):
+        return self._array
+
+    @property
+    def matrix(self):
+        return self._array.reshape(self.size0, self.size1)
+
+    @property
+    def linop(self):
+        if self._linop is None:
+            self._linop = linops.Matrix(self.matrix)
+        return self._linop
+
+
+class LinearOperatorCovariance(Covariance):
+    """Covariance given as a (lazy, device-resident) ``(size0, size1)`` linear operator (_covariance.py:197-230)."""
+
+    def __init__(self, cov_linop, shape0, shape1):
+        super().__init__(shape0, shape1)
+        if tuple(cov_linop.shape) != (self.size0, self.size1):
+            raise ValueError(f"`cov_linop` must have shape {(self.size0, self.size1)}, got {tuple(cov_linop.shape)}")
+        self._linop = cov_linop
+
+    @property
+    def linop(self):
+        return self._linop
+
+    @property
+    def array(self):
+        return self.matrix.reshape(self.shape0 + self.shape1)
+
+
 def asrandvar(b):
     if isinstance(b, (Normal, Constant)):
         return b

@@ -53,11 +53,14 @@ if "potrf" in which or "potrf64" in which:
         def run():
             f.L.copy_(G); f.potrf()
         tcopy = tm(lambda: f.L.copy_(G))
-        for flag, label in ((1, "one-stream recursion"), (0, "lookahead pipeline")):
+        for flag, refine, label in ((1, 1, "one-stream recursion"), (0, 0, "lookahead pipeline, unrefined panel solves"),
+                                    (0, 1, "lookahead pipeline")):
             _lib.lib.lpgp_set_option(_lib.OPT_NO_LOOKAHEAD, flag)
+            _lib.lib.lpgp_set_option(_lib.OPT_TRSM_REFINE, refine)
             ms = tm(run, reps=2) - tcopy
             print(f"potrf n={n} [{label}]: {ms:.1f} ms  {n**3/3/ms*1e-9:.2f} TFLOP/s", flush=True)
         _lib.lib.lpgp_set_option(_lib.OPT_NO_LOOKAHEAD, 0)
+        _lib.lib.lpgp_set_option(_lib.OPT_TRSM_REFINE, 1)
         if "trsm" in which:
             m = 8192
             Xr = be.alloc_matrix(m, n).normal_()
