@@ -146,6 +146,32 @@ class _EvaluationFunctional(LinearFunctional):
         return [(1.0, "pts", None, self._X if self._grid is None else self._grid)]
 
 
+class DiracFunctional(LinearFunctional):
+    """Point evaluation with output layout ``batch_shape + codomain_shape`` (src/linpde_gp/linfunctls/_dirac.py:10-45;
+    ``_EvaluationFunctional`` orders its output ``codomain_shape + batch_shape``).  For scalar-valued functions the
+    two coincide; vector-valued processes are observed through ``_EvaluationFunctional`` / ``SelectOutput``."""
+
+    def __init__(self, input_domain_shape, input_codomain_shape, X):
+        X = np.asarray(X, dtype=np.double)
+        input_domain_shape = _as_shape(input_domain_shape)
+        input_codomain_shape = _as_shape(input_codomain_shape)
+        nd = len(input_domain_shape)
+        if X.shape[X.ndim - nd:] != input_domain_shape:
+            raise ValueError(f"trailing shape of X {X.shape} must equal the input domain shape {input_domain_shape}")
+        self._X = X
+        self._X_batch_shape = X.shape[: X.ndim - nd]
+        super().__init__((input_domain_shape, input_codomain_shape), self._X_batch_shape + input_codomain_shape)
+
+    X = property(lambda self: self._X)
+    X_batch_shape = property(lambda self: self._X_batch_shape)
+    X_batch_ndim = property(lambda self: len(self._X_batch_shape))
+
+    def _atoms(self):
+        if self._input_codomain_shape != ():
+            raise NotImplementedError("DiracFunctional observations of vector-valued processes")
+        return [(1.0, "pts", None, self._X)]
+
+
 class CompositeLinearFunctional(LinearFunctional):
     """``linfunctl @ linop``: apply the function operator first (``_arithmetic.py:92-174``; the reference's keyword
     for the operator is ``linfuncop``, accepted as an alias)."""
