@@ -79,11 +79,12 @@ long long lpgp_launch_count(int reset); /* kernels launched by the library so fa
  * two-stream right-looking pipeline with one panel of lookahead (same factor up to rounding; for A/B timing). */
 #define LPGP_OPT_NO_LOOKAHEAD 2
 /* LPGP_OPT_TRSM_REFINE: residual correction in the leaf step of the blocked triangular solves.  The leaf step
- * multiplies with the explicit inverse of a 128 x 128 diagonal block, which leaves a residual of order
- * cond(L_kk) eps; one correction step (two more 128-wide GEMMs) restores the O(eps) residual of LAPACK's dtrsm.
- * 0 = never, 1 = inside factorisations only (lpgp_potrf, lpgp_chol_append, lpgp_trsm_rlt_refined; DEFAULT -- there the
- * residual perturbs the Gram matrix itself and decides whether a nearly singular matrix still factors, as it does
- * with the reference's dpotrf), 2 = also in lpgp_trsm_rlt.                                                  */
+ * multiplies with the explicit inverse of a 128 x 128 diagonal block L_kk, which leaves a residual of order
+ * kappa(L_kk) eps; one correction step (two more 128-wide GEMMs) restores the O(eps) residual of LAPACK's dtrsm.
+ * 0 = never; 1 = inside factorisations (lpgp_potrf, lpgp_chol_append, lpgp_trsm_rlt_refined), for the leaves
+ * whose kappa_inf(L_kk) > 256 -- decided on the device, the extra kernels exit immediately otherwise (DEFAULT: there
+ * the residual perturbs the Gram matrix itself and decides whether a nearly singular matrix still factors, as it
+ * does with the reference's dpotrf); 2 = as 1, also in lpgp_trsm_rlt; 3 = as 2 for every leaf (A/B tests).     */
 #define LPGP_OPT_TRSM_REFINE 3
 int lpgp_set_option(int key, int value);
 /* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and

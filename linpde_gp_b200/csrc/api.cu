@@ -27,7 +27,7 @@ extern "C" int lpgp_set_option(int key, int value) {
     return 0;
   }
   if (key == LPGP_OPT_TRSM_REFINE) {
-    if (value < 0 || value > 2) return -2;
+    if (value < 0 || value > 3) return -2;
     g_lpgp_trsm_refine = value;
     return 0;
   }

@@ -52,15 +52,20 @@ __device__ __forceinline__ void solve_lower32(double (&x)[32], const double* __r
 }
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
-    potrf_leaf_kernel(double* __restrict__ A, int64_t ld, int nb, double* __restrict__ W, int* info, int global_off) {
+    potrf_leaf_kernel(double* __restrict__ A, int64_t ld, int nb, double* __restrict__ W, int* info, int global_off,
+                      int* __restrict__ refine_flag, double kappa_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* a = reinterpret_cast<double*>(smem_raw);  // [LEAF][LDS_A]
   double* rdiag = a + LEAF * LDS_A;                  // [LEAF] reciprocals of the diagonal of L
   double* tbuf = rdiag + LEAF;                       // [3][32][33] scratch for the inverse
   __shared__ int s_fail;
+  __shared__ double s_norm[2];  // max row sums of |L| and |W|: kappa_inf(L) = s_norm[0] * s_norm[1]
   __shared__ __align__(16) double scol[2 * 32];  // column broadcast buffers of the register Cholesky
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_fail = 0;
+  if (tid == 0) {
+    s_fail = 0;
+    s_norm[0] = s_norm[1] = 0.0;
+  }
 
   // load the lower triangle (identity padding beyond nb, zeros above the diagonal)
   for (int idx = tid; idx < LEAF * LEAF; idx += DIAG_THREADS) {
@@ -147,6 +152,11 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     const int i = idx / nb, j = idx % nb;
     A[(int64_t)i * ld + j] = (j <= i) ? a[i * LDS_A + j] : 0.0;
   }
+  if (refine_flag != nullptr && tid < LEAF) {  // ||L||_inf (row stride LDS_A = 129: conflict-free across rows)
+    double rs = 0.0;
+    for (int j = 0; j <= tid; ++j) rs += fabs(a[tid * LDS_A + j]);
+    atomicMax(reinterpret_cast<unsigned long long*>(&s_norm[0]), (unsigned long long)__double_as_longlong(rs));
+  }
 
   // ---- inverse, step 1: W_bb = L_bb^{-1} for the four diagonal blocks (warp b, lane = column) ----
   if (warp < LEAF / 32) {
@@ -209,6 +219,54 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
   for (int idx = tid; idx < LEAF * LEAF; idx += DIAG_THREADS) {
     const int i = idx / LEAF, j = idx % LEAF;
     W[idx] = (j <= i) ? a[i * LDS_A + j] : 0.0;
+  }
+  if (refine_flag != nullptr) {  // ||W||_inf and the verdict: refine the panel solves with this block iff kappa is large
+    if (tid < LEAF) {
+      double rs = 0.0;
+      for (int j = 0; j <= tid; ++j) rs += fabs(a[tid * LDS_A + j]);
+      atomicMax(reinterpret_cast<unsigned long long*>(&s_norm[1]), (unsigned long long)__double_as_longlong(rs));
+    }
+    __syncthreads();
+    if (tid == 0) *refine_flag = (s_norm[0] * s_norm[1] > kappa_max) ? 1 : 0;
+  }
+}
+
+// the same verdict for leaves factored by an earlier call (appending to a cached factor, panel solves against a
+// separately factored diagonal block): one CTA per leaf reads L_kk and W = L_kk^{-1} from global memory
+__global__ void __launch_bounds__(LEAF) leaf_cond_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ dinv,
+                                                         int64_t seg_begin, int64_t seg_end, int leaf0,
+                                                         int* __restrict__ flags, double kappa_max) {
+  __shared__ double s_norm[2];
+  const int leaf = leaf0 + blockIdx.x, i = threadIdx.x;  // leaves of one segment: 128 rows each, the last one ragged
+  const int64_t c0 = seg_begin + (int64_t)blockIdx.x * LEAF;
+  const int nb = (int)(seg_end - c0 < LEAF ? seg_end - c0 : LEAF);
+  if (i == 0) s_norm[0] = s_norm[1] = 0.0;
+  __syncthreads();
+  double rl = 0.0, rw = 0.0;
+  if (i < nb) {
+    const double* lrow = L + (c0 + i) * ld + c0;
+    const double* wrow = dinv + (size_t)leaf * LEAF * LEAF + (size_t)i * LEAF;
+    for (int j = 0; j <= i; ++j) {
+      rl += fabs(lrow[j]);
+      rw += fabs(wrow[j]);
+    }
+  }
+  atomicMax(reinterpret_cast<unsigned long long*>(&s_norm[0]), (unsigned long long)__double_as_longlong(rl));
+  atomicMax(reinterpret_cast<unsigned long long*>(&s_norm[1]), (unsigned long long)__double_as_longlong(rw));
+  __syncthreads();
+  if (i == 0) flags[leaf] = (s_norm[0] * s_norm[1] > kappa_max) ? 1 : 0;
+}
+
+// T[m x nb] (row stride LEAF) <- X[m x nb] (row stride ldx) if *flag != 0  (nb even, both 16-byte aligned)
+__global__ void __launch_bounds__(256) copy_if_kernel(double* __restrict__ T, const double* __restrict__ X, int64_t ldx,
+                                                      int64_t m, int nb, const int* __restrict__ flag) {
+  if (*flag == 0) return;
+  const int half = nb >> 1;
+  const int64_t total = m * half;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / half;
+    const int c = (int)(idx % half) * 2;
+    *reinterpret_cast<double2*>(T + r * LEAF + c) = *reinterpret_cast<const double2*>(X + r * ldx + c);
   }
 }
 
@@ -348,80 +406,103 @@ int g_diag_attr_set = 0;
 // X[m x (off[hi]-off[lo])] <- X * L[lo:hi, lo:hi]^{-T}; X points at column off[lo] of the right-hand-side rows.
 //
 // Leaf step.  Multiplying with the explicit inverse W = L_kk^{-1} is fast (one GEMM) but not backward stable: the
-// residual  B - X L_kk^T  is of order cond(L_kk) eps |B| instead of eps |B|.  That is harmless when the result is the
-// final answer (posterior variance: the forward error is cond(L) eps either way), but inside a FACTORISATION the
+// residual  B - X L_kk^T  is of order kappa(L_kk) eps |B| instead of eps |B|.  That is harmless when the result is the
+// final answer (posterior variance: the forward error is kappa(L) eps either way), but inside a FACTORISATION the
 // residual is a perturbation of the Gram matrix itself -- at cond(G) ~ 1e12 it reaches 1e-12 |G| and the blocked
 // factorisation reports "not positive definite" for matrices LAPACK's dpotrf (the reference,
-// pn/linops/_linear_operator.py:860-865) still factors.  With a workspace T (m x 128) the leaf step therefore does one
-// step of residual correction,
-//     T = B W^T;   B <- B - T L_kk^T (residual);   T += B W^T;   X = T,
+// pn/linops/_linear_operator.py:860-865) still factors.  With a workspace the leaf step therefore does one step of
+// residual correction for every leaf whose kappa_inf(L_kk) exceeds REFINE_KAPPA (the verdict is taken on the device
+// by the leaf kernel, the host enqueues the same launches either way and the three extra kernels exit at once when
+// the flag is clear):
+//     T = B;   X = B W^T;   T <- T - X L_kk^T (residual);   X += T W^T,
 // which brings the residual back to O(eps) (tests/test_gpu_kernels.py::test_potrf_backward_error_ill_conditioned).
-// The two extra GEMMs are m x 128 x 128: N^2 * 256 extra flops per factorisation (1.2 % at N = 64k).
+// The two extra GEMMs are m x 128 x 128: at most N^2 * 256 extra flops per factorisation (1.2 % at N = 64k).
+constexpr double REFINE_KAPPA = 256.0;  // unrefined residual <= ~kappa eps ~ 3e-14 |B| below this
+
+struct RefineWs {
+  double* T = nullptr;   // m_max x LEAF doubles
+  int* flags = nullptr;  // one verdict per leaf of the factor
+  double kappa() const { return g_lpgp_trsm_refine >= 3 ? -1.0 : REFINE_KAPPA; }  // option 3: refine every leaf
+};
+
 int trsm_rec(const lpgp_factor* f, const Leaves& lv, int lo, int hi, double* X, int64_t m, int64_t ldx, cudaStream_t st,
-             double* T = nullptr) {
+             RefineWs ws = RefineWs()) {
   const int64_t c0 = lv.off[lo];
   if (hi - lo == 1) {
     const int nb = (int)(lv.off[hi] - c0);
     const double* W = dinv_block(f, lo);
-    if (T == nullptr)  // in place: one tile column (nb <= 128), every CTA reads all of its own rows before writing them
-      return lpgp_gemm_nt(m, nb, nb, 1.0, X, ldx, W, LEAF, 0.0, X, ldx, 0, st);
+    if (ws.T != nullptr) {
+      const int64_t pairs = m * (nb / 2);
+      const int grid = (int)(pairs < 256 * 1184 ? ceil_div64(pairs, 256) : 1184);
+      copy_if_kernel<<<grid, 256, 0, st>>>(ws.T, X, ldx, m, nb, ws.flags + lo);
+      LPGP_CHECK_LAUNCH();
+    }
+    // in place: one tile column (nb <= 128), every CTA reads all of its own rows before writing them
+    int rc = lpgp_gemm_nt(m, nb, nb, 1.0, X, ldx, W, LEAF, 0.0, X, ldx, 0, st);
+    if (rc || ws.T == nullptr) return rc;
     const double* Lkk = f->L + c0 * f->ld + c0;  // strict upper triangle cleared by the leaf kernel
-    int rc = lpgp_gemm_nt(m, nb, nb, 1.0, X, ldx, W, LEAF, 0.0, T, LEAF, 0, st);
+    rc = lpgp_gemm_nt_flagged(m, nb, nb, -1.0, X, ldx, Lkk, f->ld, 1.0, ws.T, LEAF, ws.flags + lo, st);
     if (rc) return rc;
-    rc = lpgp_gemm_nt(m, nb, nb, -1.0, T, LEAF, Lkk, f->ld, 1.0, X, ldx, 0, st);
-    if (rc) return rc;
-    rc = lpgp_gemm_nt(m, nb, nb, 1.0, X, ldx, W, LEAF, 1.0, T, LEAF, 0, st);
-    if (rc) return rc;
-    LPGP_CHECK(cudaMemcpy2DAsync(X, (size_t)ldx * 8, T, (size_t)LEAF * 8, (size_t)nb * 8, (size_t)m,
-                                 cudaMemcpyDeviceToDevice, st));
-    return 0;
+    return lpgp_gemm_nt_flagged(m, nb, nb, 1.0, ws.T, LEAF, W, LEAF, 1.0, X, ldx, ws.flags + lo, st);
   }
   const int mid = lo + (hi - lo) / 2;
   const int64_t c1 = lv.off[mid], c2 = lv.off[hi];
-  int rc = trsm_rec(f, lv, lo, mid, X, m, ldx, st, T);
+  int rc = trsm_rec(f, lv, lo, mid, X, m, ldx, st, ws);
   if (rc) return rc;
   // X2 -= X1 * L21^T,  L21 = L[c1:c2, c0:c1]
   rc = lpgp_gemm_nt(m, c2 - c1, c1 - c0, -1.0, X, ldx, f->L + c1 * f->ld + c0, f->ld, 1.0, X + (c1 - c0), ldx, 0, st);
   if (rc) return rc;
-  return trsm_rec(f, lv, mid, hi, X + (c1 - c0), m, ldx, st, T);
+  return trsm_rec(f, lv, mid, hi, X + (c1 - c0), m, ldx, st, ws);
 }
 
-// refinement workspace of a factorisation over n rows: stream-ordered allocation (no hidden persistent state; safe
-// for concurrent callers on distinct streams)
+// refinement workspace of one call: stream-ordered allocation (no hidden persistent state; safe for concurrent
+// callers on distinct streams).  `nleaves` flags, the first `known` of which belong to leaves factored EARLIER and
+// are computed here from the stored blocks; the leaf kernel fills in the rest as it factors them.
 struct TrsmWork {
-  double* T = nullptr;
+  RefineWs ws;
+  void* buf = nullptr;
   cudaStream_t st = nullptr;
-  int acquire(int64_t rows, cudaStream_t s) {
+  int acquire(const lpgp_factor* f, const Leaves& lv, int64_t rows, int known, cudaStream_t s) {
     st = s;
     if (g_lpgp_trsm_refine == 0 || rows <= 0) return 0;
-    LPGP_CHECK(cudaMallocAsync((void**)&T, (size_t)rows * LEAF * sizeof(double), st));
+    const int nl = (int)lv.off.size() - 1;
+    const size_t t_bytes = (size_t)rows * LEAF * sizeof(double);
+    LPGP_CHECK(cudaMallocAsync(&buf, t_bytes + (size_t)nl * sizeof(int), st));
+    ws.T = (double*)buf;
+    ws.flags = (int*)((char*)buf + t_bytes);
+    for (size_t sg = 0; sg + 1 < lv.seg_first.size() && lv.seg_first[sg] < known; ++sg) {  // one launch per old segment
+      const int l0 = lv.seg_first[sg], l1 = lv.seg_first[sg + 1] < known ? lv.seg_first[sg + 1] : known;
+      leaf_cond_kernel<<<l1 - l0, LEAF, 0, st>>>(f->L, f->ld, f->dinv, lv.off[l0], lv.off[l1], l0, ws.flags, ws.kappa());
+      LPGP_CHECK_LAUNCH();
+    }
     return 0;
   }
   ~TrsmWork() {
-    if (T) cudaFreeAsync(T, st);
+    if (buf) cudaFreeAsync(buf, st);
   }
 };
 
-int potrf_rec(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st, double* T) {
+int potrf_rec(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st, RefineWs ws) {
   const int64_t c0 = lv.off[lo];
   double* A = f->L + c0 * f->ld + c0;
   if (hi - lo == 1) {
     const int nb = (int)(lv.off[hi] - c0);
-    potrf_leaf_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(A, f->ld, nb, dinv_block(f, lo), info, (int)c0);
+    potrf_leaf_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(A, f->ld, nb, dinv_block(f, lo), info, (int)c0,
+                                                          ws.flags ? ws.flags + lo : nullptr, ws.kappa());
     LPGP_CHECK_LAUNCH();
     return 0;
   }
   const int mid = lo + (hi - lo) / 2;
   const int64_t c1 = lv.off[mid], c2 = lv.off[hi];
-  int rc = potrf_rec(f, lv, lo, mid, info, st, T);
+  int rc = potrf_rec(f, lv, lo, mid, info, st, ws);
   if (rc) return rc;
   double* A21 = f->L + c1 * f->ld + c0;
-  rc = trsm_rec(f, lv, lo, mid, A21, c2 - c1, f->ld, st, T);
+  rc = trsm_rec(f, lv, lo, mid, A21, c2 - c1, f->ld, st, ws);
   if (rc) return rc;
   double* A22 = f->L + c1 * f->ld + c1;
   rc = lpgp_gemm_nt(c2 - c1, c2 - c1, c1 - c0, -1.0, A21, f->ld, A21, f->ld, 1.0, A22, f->ld, 1, st);
   if (rc) return rc;
-  return potrf_rec(f, lv, mid, hi, info, st, T);
+  return potrf_rec(f, lv, mid, hi, info, st, ws);
 }
 
 // ---- right-looking factorisation with ONE PANEL OF LOOKAHEAD on two streams -----------------------------------
@@ -463,7 +544,7 @@ inline int lookahead_panel_leaves(int nl) {
   return pb < 4 ? 4 : (pb > 16 ? 16 : pb);
 }
 
-int potrf_lookahead(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st, double* T) {
+int potrf_lookahead(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st, RefineWs ws) {
   const int pb = lookahead_panel_leaves(hi - lo);
   const int P = (hi - lo + pb - 1) / pb;
   std::lock_guard<std::mutex> guard(g_la_mutex);
@@ -480,10 +561,10 @@ int potrf_lookahead(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info,
   // factor panel p on stream s: diagonal block, then the rows below it
   auto factor_panel = [&](int p, cudaStream_t s) -> int {
     const int l0 = leaf_lo(p), l1 = leaf_lo(p + 1);
-    int r = potrf_rec(f, lv, l0, l1, info, s, T);
+    int r = potrf_rec(f, lv, l0, l1, info, s, ws);
     if (r) return r;
     const int64_t r0 = lv.off[l0], r1 = lv.off[l1];
-    if (r1 < n_hi) r = trsm_rec(f, lv, l0, l1, f->L + r1 * ld + r0, n_hi - r1, ld, s, T);
+    if (r1 < n_hi) r = trsm_rec(f, lv, l0, l1, f->L + r1 * ld + r0, n_hi - r1, ld, s, ws);
     return r;
   };
   LPGP_CHECK(cudaEventRecord(ev_fork, st));
@@ -519,12 +600,12 @@ int potrf_lookahead(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info,
 }
 
 // factor the leaf range [lo, hi): lookahead pipeline for ranges of at least three panels, else the recursion
-// (T: refinement workspace of trsm_rec with at least off[hi] - off[lo] rows, or nullptr; all uses of T are ordered:
-// inside the lookahead pipeline only the panel stream solves, after the fork and before the join)
-int potrf_range(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st, double* T) {
+// (ws: refinement workspace of trsm_rec with at least off[hi] - off[lo] rows, or empty; all uses of ws.T are
+// ordered: inside the lookahead pipeline only the panel stream solves, after the fork and before the join)
+int potrf_range(lpgp_factor* f, const Leaves& lv, int lo, int hi, int* info, cudaStream_t st, RefineWs ws) {
   if (!g_lpgp_no_lookahead && hi - lo >= 3 * lookahead_panel_leaves(hi - lo))
-    return potrf_lookahead(f, lv, lo, hi, info, st, T);
-  return potrf_rec(f, lv, lo, hi, info, st, T);
+    return potrf_lookahead(f, lv, lo, hi, info, st, ws);
+  return potrf_rec(f, lv, lo, hi, info, st, ws);
 }
 
 int check_factor(const lpgp_factor* f) {
@@ -573,9 +654,9 @@ int potrf_impl(lpgp_factor* f, void* stream, bool sync) {
   const auto t0 = std::chrono::steady_clock::now();
   const long long l0 = g_lpgp_launches;
   TrsmWork work;
-  rc = work.acquire(f->n, st);
+  rc = work.acquire(f, lv, f->n, 0, st);
   if (rc) return rc;
-  rc = potrf_range(f, lv, 0, nl, info, st, work.T);
+  rc = potrf_range(f, lv, 0, nl, info, st, work.ws);
   if (rc) return rc;
   if (!sync) return 0;
   const auto t1 = std::chrono::steady_clock::now();
@@ -612,13 +693,13 @@ extern "C" int lpgp_chol_append(lpgp_factor* f, void* stream) {
   LPGP_CHECK_LAUNCH();
   double* A21 = f->L + np * f->ld;
   TrsmWork work;
-  rc = work.acquire(nn, st);
+  rc = work.acquire(f, lv, nn, l0, st);
   if (rc) return rc;
-  rc = trsm_rec(f, lv, 0, l0, A21, nn, f->ld, st, work.T);  // L21 = B^T L11^{-T}
+  rc = trsm_rec(f, lv, 0, l0, A21, nn, f->ld, st, work.ws);  // L21 = B^T L11^{-T}
   if (rc) return rc;
   rc = lpgp_gemm_nt(nn, nn, np, -1.0, A21, f->ld, A21, f->ld, 1.0, f->L + np * f->ld + np, f->ld, 1, st);  // Schur
   if (rc) return rc;
-  rc = potrf_range(f, lv, l0, nl, info, st, work.T);
+  rc = potrf_range(f, lv, l0, nl, info, st, work.ws);
   if (rc) return rc;
   return finish_info(info, st);
 }
@@ -637,10 +718,10 @@ int trsm_rlt_impl(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int
   if (hi < 0) return -2;
   TrsmWork work;
   if (refine) {
-    const int rc = work.acquire(m, (cudaStream_t)stream);
+    const int rc = work.acquire(f, lv, m, hi, (cudaStream_t)stream);
     if (rc) return rc;
   }
-  return trsm_rec(f, lv, 0, hi, X, m, ldx, (cudaStream_t)stream, work.T);
+  return trsm_rec(f, lv, 0, hi, X, m, ldx, (cudaStream_t)stream, work.ws);
 }
 }  // namespace
 

@@ -14,7 +14,8 @@ extern long long g_lpgp_launches;
 extern int g_lpgp_no_sep;
 // 1 = factor on one stream with the plain recursion (no panel lookahead)
 extern int g_lpgp_no_lookahead;
-// residual-corrected leaf step of the panel solves: 0 = never, 1 = inside factorisations (default), 2 = everywhere
+// residual-corrected leaf step of the panel solves: 0 = never, 1 = inside factorisations, where kappa(L_kk) asks for
+// it (default), 2 = also in lpgp_trsm_rlt, 3 = as 1 but for every leaf regardless of its condition number
 extern int g_lpgp_trsm_refine;
 #define LPGP_MAX_DEVICES 32
 
@@ -30,6 +31,10 @@ extern int g_lpgp_trsm_refine;
     cudaError_t e__ = (call);                          \
     if (e__ != cudaSuccess) return LPGP_CUDA_ERR(e__); \
   } while (0)
+
+// library-internal: lpgp_gemm_nt gated by a device-side flag (gemm_dmma.cu)
+int lpgp_gemm_nt_flagged(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
+                         int64_t ldb, double beta, double* C, int64_t ldc, const int* flag, void* stream);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

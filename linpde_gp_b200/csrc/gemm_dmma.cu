@@ -123,7 +123,9 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   const int row0 = tm * BM, col0 = tn * BN;
   // optional per-row-block column limit (distributed block-row layouts: the rows of one 128-row block only need
   // the columns up to their own diagonal block); the predicate is block-uniform
-  if (col_limit != nullptr && col0 + col_base >= col_limit[row0 >> 7]) return;
+  // (col_base < 0: col_limit[0] is a device-side on/off switch for the whole launch -- the conditional residual
+  // correction of the panel solves, cholesky.cu)
+  if (col_limit != nullptr && (col_base < 0 ? col_limit[0] == 0 : col0 + col_base >= col_limit[row0 >> 7])) return;
   const int nk = (k + BK - 1) / BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -352,6 +354,20 @@ extern "C" int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const
   return (use_small ? launch<SmallTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower, stream, nullptr, 0);
 }
 
+
+// lpgp_gemm_nt that does nothing when the device-side int *flag is 0 (library-internal; C must not alias A)
+int lpgp_gemm_nt_flagged(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
+                         int64_t ldb, double beta, double* C, int64_t ldc, const int* flag, void* stream) {
+  if (m <= 0 || n <= 0) return 0;
+  if (!A || lda < k || (lda % 2) || ((uintptr_t)A % 16)) return -6;
+  if (!B || ldb < k || (ldb % 2) || ((uintptr_t)B % 16)) return -8;
+  if (!C || ldc < n || (const double*)C == A || !flag) return -11;
+  if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return -1;
+  std::call_once(g_once, init_once);
+  if (g_init_rc) return g_init_rc;
+  const bool use_small = ceil_div64(m, 128) * ceil_div64(n, 128) < 96;
+  return (use_small ? launch<SmallTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, flag, -1);
+}
 
 // C[m x n] = beta*C + alpha*A*B^T restricted, for every block of 128 rows, to the columns j with
 // col_base + j < col_limit[row/128] (device array of ceil(m/128) ints; col_base = position of C's first column in

@@ -219,7 +219,8 @@ def _matern52_gram(n, ell, seed, noise=0.0):
                                                (3000, 0.02, 1e-11, (3000,)), (2600, 0.03, 1e-11, (1000, 1600))])
 def test_potrf_backward_error_ill_conditioned(be, n, ell, noise, sizes):
     """Backward stability of the blocked factorisation on nearly singular Gram matrices (cond 1e11 .. 1e13): with
-    the residual-corrected panel solves (LPGP_OPT_TRSM_REFINE = 1, the default) ``|L L^T - G| <= 1e-14 |G|`` like
+    the residual-corrected panel solves (LPGP_OPT_TRSM_REFINE = 1, the default: gated per leaf by kappa_inf(L_kk) on the
+    device; 3: every leaf) ``|L L^T - G| <= 1e-14 |G|`` like
     LAPACK's dpotrf -- the reference's factorisation, pn/linops/_linear_operator.py:860-865 -- whereas multiplying with
     the inverted diagonal blocks alone (option 0) leaves a residual of order cond(L_kk) eps."""
     from linpde_gp_b200 import _lib
@@ -228,7 +229,7 @@ def test_potrf_backward_error_ill_conditioned(be, n, ell, noise, sizes):
     G = torch.as_tensor(Gh, device="cuda")
     sc = float(np.abs(Gh).max())
     errs = {}
-    for mode in (1, 0):
+    for mode in (1, 3, 0):
         assert _lib.lib.lpgp_set_option(_lib.OPT_TRSM_REFINE, mode) == 0
         try:
             f, off = None, 0
@@ -245,9 +246,10 @@ def test_potrf_backward_error_ill_conditioned(be, n, ell, noise, sizes):
             _lib.lib.lpgp_set_option(_lib.OPT_TRSM_REFINE, 1)
     L_ref = torch.linalg.cholesky(G)
     err_ref = (L_ref @ L_ref.T - G).abs().max().item() / sc
-    assert errs[1] <= max(1e-14, 8 * err_ref), (errs, err_ref)
+    assert errs[1] <= max(1e-14, 8 * err_ref), (errs, err_ref)  # default: leaves with kappa_inf(L_kk) > 256 refined
+    assert errs[3] <= max(1e-14, 8 * err_ref), (errs, err_ref)  # every leaf refined
     assert errs[1] <= errs[0]
-    assert _lib.lib.lpgp_set_option(_lib.OPT_TRSM_REFINE, 3) != 0  # invalid value is rejected
+    assert _lib.lib.lpgp_set_option(_lib.OPT_TRSM_REFINE, 4) != 0  # invalid value is rejected
 
 
 def test_potrf_factors_nearly_singular_matrix_like_lapack(be):

@@ -54,7 +54,7 @@ if "potrf" in which or "potrf64" in which:
             f.L.copy_(G); f.potrf()
         tcopy = tm(lambda: f.L.copy_(G))
         for flag, refine, label in ((1, 1, "one-stream recursion"), (0, 0, "lookahead pipeline, unrefined panel solves"),
-                                    (0, 1, "lookahead pipeline")):
+                                    (0, 3, "lookahead pipeline, every leaf refined"), (0, 1, "lookahead pipeline")):
             _lib.lib.lpgp_set_option(_lib.OPT_NO_LOOKAHEAD, flag)
             _lib.lib.lpgp_set_option(_lib.OPT_TRSM_REFINE, refine)
             ms = tm(run, reps=2) - tcopy
