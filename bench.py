@@ -543,7 +543,7 @@ def run_b200(args):
             "cpu_baseline": ({"value": cpu_est, "unit": "s", "cores": cores, "threads": threads, "kind": "port",
                               **cpu_detail} if cpu_est is not None else None),
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -575,10 +575,27 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
+
+
+_STDOUT_FD = None
+
+
+def emit(line: str) -> None:
+    """The ONE JSON line goes to the real stdout; everything else written to fd 1 by this process or by libraries
+    (NCCL prints its version banner there when the box sets NCCL_DEBUG) has been redirected to stderr by main()."""
+    sys.stdout.flush()
+    if _STDOUT_FD is None:
+        print(line, flush=True)
+    else:
+        os.write(_STDOUT_FD, (line + "\n").encode())
 
 
 def main():
+    global _STDOUT_FD  # pylint: disable=global-statement
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1)
