@@ -568,3 +568,56 @@ def test_sum_kernel_prior_posterior_covariance():
     np.testing.assert_allclose(post.mean(Xt), mean, rtol=0, atol=POST_TOL * np.max(np.abs(mean)))
     np.testing.assert_allclose(post.cov.matrix(Xt), cov, rtol=0, atol=POST_TOL * 2.5)
     np.testing.assert_allclose(post.var(Xt), np.diag(cov), rtol=0, atol=POST_TOL * 2.5)
+
+
+def test_heat_ibvp_analytic_solution_within_two_sigma():
+    """The reference's end-to-end test, tests/linpde_gp/problems/test_heat.py:56-99, restated: 1-D heat equation on
+    t in [0, 5], x in [-1, 1], alpha = 0.1, initial values 1 sin(w1 (x+1)) + 2 sin(w2 (x+1)) (TruncatedSineSeries
+    [1, 2], w_n = n pi / 2), prior Matern-3/2(t; 2.5) x Matern-5/2(x; 2.0); N_ic = 5 (inset 1e-6), N_bc = 2 x 50 with
+    noise 1e-5, N_pde = 100 x 20 uniform grid.  Same assertions and tolerances as the reference: observations are
+    reproduced to atol 3e-2 and the analytic solution (problems/pde/_heat.py:96-131) lies within mean +- 2 std
+    (slack 3e-2) on a 50 x 50 grid."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.linfuncops import diffops
+    from linpde_gp_b200.randprocs import covfuncs
+
+    t0, T, lo, hi, alpha = 0.0, 5.0, -1.0, 1.0, 0.1
+    coeffs = np.array([1.0, 2.0])
+    omega = np.arange(1, 3) * np.pi / (hi - lo)
+
+    def solution(tx):
+        t, x = tx[..., :1], tx[..., 1:]
+        return np.sum(coeffs * np.sin(omega * (x - lo)) * np.exp(alpha * omega**2 * (t0 - t)), axis=-1)
+
+    def grid(ts, xs):
+        return np.stack(np.meshgrid(ts, xs, indexing="ij"), axis=-1)
+
+    def noise(X):
+        n = int(np.prod(X.shape[:-1]))
+        return lg.randvars.Normal(np.zeros(X.shape[:-1]), np.diag(1e-5 * np.ones(n)))
+
+    def assert_observations_match(X, Y, gp, tol=3e-2):
+        assert np.allclose(gp.mean(X), Y, rtol=0.0, atol=tol)
+
+    prior = lg.GaussianProcess(
+        lg.functions.Zero(input_shape=(2,)),
+        1.0**2 * covfuncs.TensorProduct(covfuncs.Matern((), nu=1.5, lengthscales=2.5),
+                                        covfuncs.Matern((), nu=2.5, lengthscales=2.0)))
+    X_ic = grid(np.array([t0]), np.linspace(lo + 1e-6, hi - 1e-6, 5))[0]
+    Y_ic = solution(X_ic)
+    u = prior.condition_on_observations(Y_ic, X_ic)
+    assert_observations_match(X_ic, Y_ic, u)
+    for xb in (lo, hi):
+        X_bc = grid(np.linspace(t0, T, 50), np.array([xb]))[:, 0]
+        Y_bc = np.zeros(50)
+        u = u.condition_on_observations(Y_bc, X=X_bc, b=noise(X_bc))
+        assert_observations_match(X_bc, Y_bc, u)
+    X_pde = grid(np.linspace(t0, T, 100), np.linspace(lo, hi, 20))
+    u = u.condition_on_observations(np.zeros((100, 20)), X=X_pde, L=diffops.HeatOperator((2,), alpha=alpha))
+    X_test = grid(np.linspace(t0, T, 50), np.linspace(lo, hi, 50))
+    Y_test = solution(X_test)
+    mean, std = u.mean(X_test), np.nan_to_num(u.std(X_test))
+    assert mean.shape == (50, 50) and std.shape == (50, 50)
+    assert np.min(mean + 2 * std - Y_test) > -3e-2
+    assert np.min(Y_test - (mean - 2 * std)) > -3e-2
+    assert np.max(np.abs(mean - Y_test)) < 0.1  # and the mean itself is a decent solution of the IBVP
