@@ -285,54 +285,236 @@ __global__ void __launch_bounds__(256) logdet_kernel(const double* L, int64_t n,
   if (threadIdx.x == 0) *out = red[0];
 }
 
-// ---- single right-hand-side substitution kernels (representer weights) ----------------------------------------
-// y_J = W_JJ b_J   (forward)   /   x_J = W_JJ^T y_J   (backward); one CTA of 128 threads, in place on b
-__global__ void __launch_bounds__(LEAF) leaf_apply_kernel(const double* __restrict__ W, double* __restrict__ b, int nb,
-                                                          int transpose) {
-  __shared__ double sb[LEAF];
-  const int t = threadIdx.x;
-  sb[t] = t < nb ? b[t] : 0.0;
-  __syncthreads();
-  double s = 0.0;
-  if (transpose) {  // s = sum_r W[r][t] sb[r]  (coalesced over t)
-    for (int r = t; r < nb; ++r) s = fma(W[r * LEAF + t], sb[r], s);
-  } else {  // s = sum_c W[t][c] sb[c]; read W transposed-coalesced through the other index
-    for (int c = 0; c <= t && c < nb; ++c) s = fma(W[t * LEAF + c], sb[c], s);
-  }
-  if (t < nb) b[t] = s;
+// ---- single right-hand-side substitution (representer weights): ONE launch per leaf, in place --------------------
+// Forward (L y = b), right-looking: the launch of leaf l holds y_l in b[c0:c1) and subtracts L[i, c0:c1) y_l from every
+// row i >= c1.  CTA 0 owns the rows of the NEXT leaf: it finishes them in shared memory and applies the inverted
+// diagonal block, y_{l+1} = W_{l+1} b_{l+1}, so that the next launch starts with its solution block ready -- the
+// sequential chain is one kernel per leaf (it was leaf kernel + update kernel, each poorly parallel).  All other CTAs
+// stream the column panel below (one warp per row, 1 KB coalesced row segments).  Backward (L^T x = y) mirrors it on
+// the row panel L[c0:c1, 0:c0) (contiguous rows): CTA 0 owns the columns of the PREVIOUS leaf and applies W^T.
+// Both directions overwrite the vector block by block, no workspace.  HBM-bound: the factor is read once per pass.
+
+// read-only global load that ptxas keeps where it is written: batches of these stay clustered, i.e. all in flight
+// together (ptxas otherwise software-pipelines a load/FMA chain with ~6 loads in flight to save registers, which
+// leaves these latency-bound kernels at a fraction of the memory-level parallelism they need)
+__device__ __forceinline__ double ldg_keep(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
 }
 
-// forward:  b[i] -= sum_{c<nb} L[i, c0+c] * y[c]  for rows i in [r0, n)   (one warp per row, coalesced row reads)
-__global__ void __launch_bounds__(256)
-    fwd_update_kernel(const double* __restrict__ L, int64_t ld, int64_t c0, int nb, int64_t r0, int64_t n,
-                      double* __restrict__ b) {
-  __shared__ double sy[LEAF];
-  if (threadIdx.x < LEAF) sy[threadIdx.x] = threadIdx.x < nb ? b[c0 + threadIdx.x] : 0.0;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t i = r0 + (int64_t)blockIdx.x * 8 + warp; i < n; i += (int64_t)gridDim.x * 8) {
-    const double* row = L + i * ld + c0;
-    double s = 0.0;
-    for (int c = lane; c < nb; c += 32) s = fma(row[c], sy[c], s);
+// 128 KB inverted leaf = 1024 lines of 128 bytes: 4 L2 prefetches per thread of a 256-thread CTA
+__device__ __forceinline__ void prefetch_leaf(const double* __restrict__ W) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) b[i] -= s;
+  for (int q = 0; q < 4; ++q)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(W) + (size_t)(threadIdx.x + 256 * q) * 128));
+}
+
+// out[t] = sum_c W[t][c] x[c] (trans = 0) or sum_r W[r][t] x[r] (trans = 1) for t < LEAF, 256 threads.  W is the
+// 128 x 128 inverted leaf (zero above the diagonal, identity beyond the leaf's size), x lives in shared memory (zero
+// beyond the leaf's size), `red` is 256 doubles of shared scratch.
+__device__ __forceinline__ void leaf_matvec(const double* __restrict__ W, const double* sx, double* out, double* red,
+                                            int trans) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (!trans) {  // warp w: rows 16 w .. 16 w + 15, coalesced 256-byte row segments + shuffle reduction; all 64
+                 // loads of a lane are independent and issued before the first reduction (latency-bound chain)
+    double acc[16], wv[16][4];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const double* row = W + (warp * 16 + r) * LEAF + lane;
+      const double w0 = ldg_keep(row), w1 = ldg_keep(row + 32), w2 = ldg_keep(row + 64), w3 = ldg_keep(row + 96);
+      wv[r][0] = w0, wv[r][1] = w1, wv[r][2] = w2, wv[r][3] = w3;
+    }
+    __syncthreads();  // scheduling fence: ptxas keeps all 64 loads above it, i.e. in flight together
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double v = wv[r][0] * sx[lane];
+      v = fma(wv[r][1], sx[lane + 32], v);
+      v = fma(wv[r][2], sx[lane + 64], v);
+      acc[r] = fma(wv[r][3], sx[lane + 96], v);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double v = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) out[warp * 16 + r] = v;
+    }
+    __syncthreads();
+  } else {  // thread (h, t): rows 64 h .. 64 h + 63 of column t (coalesced over t), two partial sums per column
+    const int t = tid & (LEAF - 1), h = tid >> 7;
+    const double* col = W + (64 * h) * LEAF + t;
+    const double* xs = sx + 64 * h;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ldg_keep(col + (16 * q + j) * LEAF);
+      __syncthreads();  // scheduling fence (see above)
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        s0 = fma(v[j + 0], xs[16 * q + j + 0], s0);
+        s1 = fma(v[j + 1], xs[16 * q + j + 1], s1);
+        s2 = fma(v[j + 2], xs[16 * q + j + 2], s2);
+        s3 = fma(v[j + 3], xs[16 * q + j + 3], s3);
+      }
+    }
+    red[tid] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < LEAF) out[tid] = red[tid] + red[tid + LEAF];
+    __syncthreads();
   }
 }
 
-// backward: b[c] -= sum_{r<nb} L[r0+r, c] * x[r]  for columns c in [0, r0)   (one thread per column, coalesced)
-__global__ void __launch_bounds__(256)
-    bwd_update_kernel(const double* __restrict__ L, int64_t ld, int64_t r0, int nb, double* __restrict__ b) {
-  __shared__ double sx[LEAF];
-  if (threadIdx.x < LEAF) sx[threadIdx.x] = threadIdx.x < nb ? b[r0 + threadIdx.x] : 0.0;
+// first block of a pass: b[0:nb) <- W b (forward, leaf 0) or W^T b (backward, last leaf); one CTA
+__global__ void __launch_bounds__(256) subst_first_kernel(const double* __restrict__ W, double* __restrict__ b, int nb, int trans) {
+  __shared__ double sx[LEAF], so[LEAF], red[256];
+  const int tid = threadIdx.x;
+  if (tid < LEAF) sx[tid] = tid < nb ? b[tid] : 0.0;
   __syncthreads();
-  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (c >= r0) return;
-  double s = 0.0;
-  const double* col = L + r0 * ld + c;
-#pragma unroll 4
-  for (int r = 0; r < nb; ++r) s = fma(col[(int64_t)r * ld], sx[r], s);
-  b[c] -= s;
+  leaf_matvec(W, sx, so, red, trans);
+  if (tid < nb) b[tid] = so[tid];
+}
+
+// forward step of leaf [c0, c0 + nb): y_l = b[c0:c0+nb) is final.  Rows [c1, c1 + nb_next) (next leaf, W_next) belong to
+// CTA 0, rows >= c1 + nb_next to the other CTAs (grid-stride, one warp per row).  c1 = c0 + nb.
+__global__ void __launch_bounds__(256)
+    fwd_step_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ W_next, int64_t c0, int nb, int nb_next,
+                    int64_t n, double* __restrict__ b) {
+  __shared__ double sy[LEAF], sb[LEAF], so[LEAF], red[256];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t c1 = c0 + nb;
+  if (blockIdx.x == 0) prefetch_leaf(W_next);  // needed at the end of CTA 0's chain: pull it towards L2 now
+  if (tid < LEAF) {
+    sy[tid] = tid < nb ? b[c0 + tid] : 0.0;
+    sb[tid] = 0.0;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    // 16 rows per warp, every load issued before the first reduction
+    double acc[16], lv4[16][4];
+    const int clast0 = nb - 1, rlast = nb_next - 1;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {  // unconditional, clamped (sy is zero beyond nb; clamped rows are discarded)
+      const int r = warp + 8 * k;
+      const double* row = L + (c1 + (r < rlast ? r : rlast)) * ld + c0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane + 32 * j;
+        lv4[k][j] = ldg_keep(row + (c < clast0 ? c : clast0));
+      }
+    }
+    __syncthreads();  // scheduling fence
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double v = lv4[k][0] * sy[lane];
+      v = fma(lv4[k][1], sy[lane + 32], v);
+      v = fma(lv4[k][2], sy[lane + 64], v);
+      acc[k] = fma(lv4[k][3], sy[lane + 96], v);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int r = warp + 8 * k;
+      double v = acc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && r < nb_next) sb[r] = b[c1 + r] - v;
+    }
+    __syncthreads();
+    leaf_matvec(W_next, sb, so, red, 0);
+    if (tid < nb_next) b[c1 + tid] = so[tid];
+    return;
+  }
+  // other CTAs: 4 rows per warp and sweep, 16 unconditional loads in flight per lane (column index clamped into the
+  // leaf -- sy is zero beyond its size -- and row index clamped to the last row, whose result is discarded)
+  const int clast = nb - 1;
+  const int64_t stride = (int64_t)(gridDim.x - 1) * 32;
+  for (int64_t base = c1 + nb_next + (int64_t)(blockIdx.x - 1) * 32; base < n; base += stride) {  // CTA-uniform trip count
+    const int64_t i0 = base + warp * 4;
+    double v[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = i0 + k < n ? i0 + k : n - 1;
+      const double* row = L + i * ld + c0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane + 32 * j;
+        v[k][j] = ldg_keep(row + (c < clast ? c : clast));
+      }
+    }
+    __syncthreads();  // scheduling fence
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double acc = v[k][0] * sy[lane];
+      acc = fma(v[k][1], sy[lane + 32], acc);
+      acc = fma(v[k][2], sy[lane + 64], acc);
+      acc = fma(v[k][3], sy[lane + 96], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0 && i0 + k < n) b[i0 + k] -= acc;
+    }
+  }
+}
+
+// backward step of leaf [c0, c0 + nb): x_l = b[c0:c0+nb) is final.  b[c] -= sum_r L[c0 + r, c] x_l[r] for c < c0: the
+// columns [c0 - nb_prev, c0) (previous leaf, W_prev) belong to CTA 0, which then applies W_prev^T; CTA j >= 1 owns the
+// 128 columns ending at c0 - nb_prev - 128 (j - 1).  Thread (h, t): rows 64 h .. of column t, coalesced over t.
+__global__ void __launch_bounds__(256)
+    bwd_step_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ W_prev, int64_t c0, int nb, int nb_prev,
+                    double* __restrict__ b) {
+  __shared__ double sx[LEAF], sv[LEAF], so[LEAF], red[256];
+  const int tid = threadIdx.x, t = tid & (LEAF - 1), h = tid >> 7;
+  if (blockIdx.x == 0) prefetch_leaf(W_prev);
+  if (tid < LEAF) sx[tid] = tid < nb ? b[c0 + tid] : 0.0;
+  __syncthreads();
+  const int64_t cprev = c0 - nb_prev;
+  int64_t col0;
+  int ncols;
+  if (blockIdx.x == 0) {
+    col0 = cprev;
+    ncols = nb_prev;
+  } else {
+    const int64_t hi = cprev - (int64_t)(blockIdx.x - 1) * LEAF;  // exclusive upper end of this CTA's columns
+    col0 = hi - LEAF > 0 ? hi - LEAF : 0;
+    ncols = (int)(hi - col0);
+  }
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  {
+    // 4 batches of 16 UNCONDITIONAL loads (all in flight together; the barrier after each batch is a scheduling
+    // fence): rows beyond the leaf's size are clamped to its last row -- finite values of L -- and multiplied by
+    // the zeros sx holds there; threads beyond the CTA's columns re-read its last column and are discarded below
+    const double* col = L + c0 * ld + col0 + (t < ncols ? t : ncols - 1);
+    const int last = nb - 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int r = 64 * h + 16 * q + j;
+        v[j] = ldg_keep(col + (int64_t)(r < last ? r : last) * ld);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const int r = 64 * h + 16 * q + j;
+        s0 = fma(v[j + 0], sx[r + 0], s0);
+        s1 = fma(v[j + 1], sx[r + 1], s1);
+        s2 = fma(v[j + 2], sx[r + 2], s2);
+        s3 = fma(v[j + 3], sx[r + 3], s3);
+      }
+    }
+  }
+  red[tid] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (blockIdx.x != 0) {
+    if (tid < ncols) b[col0 + tid] -= red[tid] + red[tid + LEAF];
+    return;
+  }
+  if (tid < LEAF) sv[tid] = tid < ncols ? b[col0 + tid] - (red[tid] + red[tid + LEAF]) : 0.0;
+  __syncthreads();
+  leaf_matvec(W_prev, sv, so, red, 1);
+  if (tid < ncols) b[col0 + tid] = so[tid];
 }
 
 // ---- general matrix-vector products (building blocks of the multi-GPU triangular solves) ----------------------
@@ -738,24 +920,24 @@ namespace {
 int trsv_impl(const lpgp_factor* f, const Leaves& lv, int trans, double* b, cudaStream_t st) {
   const int nl = (int)lv.off.size() - 1;
   const int64_t n = f->n;
-  if (!trans) {
-    for (int l = 0; l < nl; ++l) {  // forward: L y = b
-      const int64_t c0 = lv.off[l], c1 = lv.off[l + 1];
-      leaf_apply_kernel<<<1, LEAF, 0, st>>>(dinv_block(f, l), b + c0, (int)(c1 - c0), 0);
+  auto size_of = [&](int l) { return (int)(lv.off[l + 1] - lv.off[l]); };
+  if (!trans) {  // forward: L y = b
+    subst_first_kernel<<<1, 256, 0, st>>>(dinv_block(f, 0), b, size_of(0), 0);
+    LPGP_COUNT(1);
+    for (int l = 0; l + 1 < nl; ++l) {
+      const int64_t rest = n - lv.off[l + 2];  // rows below the next leaf
+      const unsigned grid = 1u + (unsigned)(rest <= 0 ? 0 : (ceil_div64(rest, 32) < 1184 ? ceil_div64(rest, 32) : 1184));
+      fwd_step_kernel<<<grid, 256, 0, st>>>(f->L, f->ld, dinv_block(f, l + 1), lv.off[l], size_of(l), size_of(l + 1), n, b);
       LPGP_COUNT(1);
-      if (c1 < n) {
-        LPGP_COUNT(1);
-        const int64_t rows = n - c1;
-        const unsigned grid = (unsigned)(rows / 8 + 1 < 1184 ? rows / 8 + 1 : 1184);
-        fwd_update_kernel<<<grid, 256, 0, st>>>(f->L, f->ld, c0, (int)(c1 - c0), c1, n, b);
-      }
     }
-  } else {
-    for (int l = nl - 1; l >= 0; --l) {  // backward: L^T x = y
-      const int64_t c0 = lv.off[l], c1 = lv.off[l + 1];
-      leaf_apply_kernel<<<1, LEAF, 0, st>>>(dinv_block(f, l), b + c0, (int)(c1 - c0), 1);
-      LPGP_COUNT(c0 > 0 ? 2 : 1);
-      if (c0 > 0) bwd_update_kernel<<<(unsigned)ceil_div64(c0, 256), 256, 0, st>>>(f->L, f->ld, c0, (int)(c1 - c0), b);
+  } else {  // backward: L^T x = y
+    subst_first_kernel<<<1, 256, 0, st>>>(dinv_block(f, nl - 1), b + lv.off[nl - 1], size_of(nl - 1), 1);
+    LPGP_COUNT(1);
+    for (int l = nl - 1; l >= 1; --l) {
+      const int64_t before = lv.off[l - 1];  // columns left of the previous leaf
+      const unsigned grid = 1u + (unsigned)ceil_div64(before, LEAF);
+      bwd_step_kernel<<<grid, 256, 0, st>>>(f->L, f->ld, dinv_block(f, l - 1), lv.off[l], size_of(l), size_of(l - 1), b);
+      LPGP_COUNT(1);
     }
   }
   LPGP_COUNT(-1);  // the check below counts one launch itself

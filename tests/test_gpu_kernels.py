@@ -379,7 +379,24 @@ def test_gemv_vs_torch(be, m, n):
     assert (w - (w0 + 1.5 * (A.T @ z))).abs().max().item() <= 1e-12 * max(1.0, (A.abs().T @ z.abs()).max().item())
 
 
-@pytest.mark.parametrize("n", [2, 128, 300, 1664])
+@pytest.mark.parametrize("sizes", [(130,), (200, 72, 300), (2, 4, 6, 130), (12000,), (5000, 2, 7002)])
+def test_potrs_residual_single_rhs(be, sizes):
+    """Fused single-RHS substitution (one launch per leaf, in place): ``G x = b`` residual over ragged segments and
+    sizes beyond the grid cap of the update CTAs (n > 9472)."""
+    n = sum(sizes)
+    G = _spd(n, n)
+    f, off = None, 0
+    for s in sizes:
+        f = be.DeviceFactor([s]) if f is None else f.extended(s)
+        f.L[off : off + s, : off + s].copy_(G[off : off + s, : off + s])
+        f.potrf() if off == 0 else f.append_last()
+        off += s
+    b = torch.randn(2, n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(n))
+    x = f.potrs(b.clone())
+    assert (x @ G - b).abs().max().item() <= 1e-11 * max(1.0, (x.abs() @ G.abs()).max().item())
+
+
+@pytest.mark.parametrize("n", [2, 128, 300, 1664, 11000])
 def test_trsv_forward_backward_vs_torch(be, n):
     import ctypes
 
