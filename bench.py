@@ -271,7 +271,7 @@ class DeviceSolve:
         offs = np.concatenate([[0], np.cumsum(sizes)[:-1]])
         blocks = be.ObsBlocks(descs, blocksX, offs)
         mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
-        chunk = int(max(256, min(self.Xt.shape[0], (4 << 30) // (8 * be.round_up(factor.n, 16)))))
+        chunk = be.var_chunk_rows(factor.n, self.Xt.shape[0])
         var = self._timed("var", lambda: be.post_var(blocks, factor, self.Xt, self.d_k.diag_value, chunk=chunk))
         return mean, var
 
@@ -321,7 +321,7 @@ class DeviceSolve:
             del ch
             w = self._timed("solve", lambda: factor.potrs(self.y.clone().reshape(1, -1)).reshape(-1))
             mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
-            chunk = int(max(256, min(self.Xt.shape[0], (4 << 30) // (8 * be.round_up(factor.n, 16)))))
+            chunk = be.var_chunk_rows(factor.n, self.Xt.shape[0])
             var = self._timed("var", lambda: be.post_var(blocks, factor, self.Xt, self.d_k.diag_value, chunk=chunk))
         else:  # the factor stays distributed: owner-computes solve, block rows of L streamed for the variance
             self._timed("factor", ch.factor)

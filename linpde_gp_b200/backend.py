@@ -351,6 +351,17 @@ def crosscov(blocks: ObsBlocks, n: int, Xt: torch.Tensor, out: Optional[torch.Te
     return out
 
 
+def var_chunk_rows(n: int, m: int, max_bytes: int = 16 << 30) -> int:
+    """Test points per chunk of the posterior-variance solve: the cross-covariance workspace (chunk x n doubles) takes
+    up to a quarter of the free device memory, at most ``max_bytes``.  Larger chunks make the 128-wide leaf steps and
+    the small GEMMs near the leaves of the blocked TRSM proportionally cheaper (m = 8192 -> 32768 rows at N = 64k)."""
+    free, _ = torch.cuda.mem_get_info()
+    budget = max(256 << 20, min(int(max_bytes), free // 4))
+    rows = budget // (8 * round_up(max(int(n), 1), 16))
+    rows = (rows // 128) * 128 if rows >= 128 else rows
+    return int(max(1, min(int(m), max(rows, 256))))
+
+
 def post_var(blocks: ObsBlocks, factor: DeviceFactor, Xt: torch.Tensor, prior_diag: float, chunk: int = 8192,
              out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pointwise posterior variance, test points processed in chunks of ``chunk`` rows."""

@@ -67,12 +67,25 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     s_norm[0] = s_norm[1] = 0.0;
   }
 
-  // load the lower triangle (identity padding beyond nb, zeros above the diagonal)
-  for (int idx = tid; idx < LEAF * LEAF; idx += DIAG_THREADS) {
-    const int i = idx / LEAF, j = idx % LEAF;
-    double v = (i == j) ? 1.0 : 0.0;
-    if (i < nb && j <= i) v = A[(int64_t)i * ld + j];
-    a[i * LDS_A + j] = v;
+  // load the lower triangle (identity padding beyond nb, zeros above the diagonal): 4 batches of 16 unconditional
+  // loads per thread (addresses clamped into the block, unwanted values replaced afterwards); the barrier after
+  // each batch keeps ptxas from serialising the loads -- one CTA pulling 128 KB is latency-bound otherwise
+  for (int q = 0; q < 4; ++q) {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + (16 * q + u) * DIAG_THREADS;
+      const int i = idx / LEAF, j = idx % LEAF;
+      const int ic = i < nb ? i : nb - 1, jc = j <= ic ? j : ic;
+      v[u] = A[(int64_t)ic * ld + jc];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + (16 * q + u) * DIAG_THREADS;
+      const int i = idx / LEAF, j = idx % LEAF;
+      a[i * LDS_A + j] = (i < nb && j <= i) ? v[u] : ((i == j) ? 1.0 : 0.0);
+    }
   }
   __syncthreads();
 

@@ -21,7 +21,7 @@ from ..linfuncops import LinearFunctionOperator
 from . import covfuncs
 from ._gaussian_process import GaussianProcess
 
-VAR_CHUNK_BYTES = 4 << 30  # cross-covariance workspace per chunk of test points
+VAR_CHUNK_BYTES = 16 << 30  # upper bound of the cross-covariance workspace per chunk of test points (and <= free / 4)
 
 
 def _descs(k: covfuncs.CovarianceFunction):
@@ -414,7 +414,7 @@ class ConditionalGaussianProcess(GaussianProcess):
                     return np.full(batch, diag)
                 if getattr(post._factor, "distributed", False):
                     return post._var_distributed(Xt, diag).cpu().numpy().reshape(batch)
-                chunk = int(max(256, min(Xt.shape[0], VAR_CHUNK_BYTES // (8 * backend.round_up(n, 16)))))
+                chunk = backend.var_chunk_rows(n, Xt.shape[0], max_bytes=VAR_CHUNK_BYTES)
                 var = backend.post_var(post._obs_blocks_unique(), post._factor, Xt, diag, chunk=chunk)
                 return var.cpu().numpy().reshape(batch)
             nd = self.input_ndim
@@ -462,7 +462,7 @@ class ConditionalGaussianProcess(GaussianProcess):
 
     def _var_distributed(self, Xt: "torch.Tensor", prior_diag: float) -> "torch.Tensor":
         """Pointwise variance of THIS rank's test points with a distributed factor (collective)."""
-        return self._factor.post_var(self._obs_blocks_unique(), Xt, prior_diag, min_chunk_bytes=VAR_CHUNK_BYTES)
+        return self._factor.post_var(self._obs_blocks_unique(), Xt, prior_diag, min_chunk_bytes=4 << 30)
 
     # -- adding observations ----------------------------------------------------------------------------------
     def condition_on_observations(self, Y, X=None, *, L=None, b=None):
