@@ -307,9 +307,11 @@ __global__ void __launch_bounds__(256) logdet_kernel(const double* L, int64_t n,
 // the row panel L[c0:c1, 0:c0) (contiguous rows): CTA 0 owns the columns of the PREVIOUS leaf and applies W^T.
 // Both directions overwrite the vector block by block, no workspace.  HBM-bound: the factor is read once per pass.
 
-// read-only global load that ptxas keeps where it is written: batches of these stay clustered, i.e. all in flight
-// together (ptxas otherwise software-pipelines a load/FMA chain with ~6 loads in flight to save registers, which
-// leaves these latency-bound kernels at a fraction of the memory-level parallelism they need)
+// read-only global load (ld.global.nc).  These kernels are latency-bound: they need a BATCH of independent loads in
+// flight per thread, but ptxas software-pipelines a load/FMA chain with ~6 loads in flight to save registers (neither
+// register arrays nor volatile asm change that, measured: 27.5 ms per N = 64k solve).  What does work is a
+// __syncthreads() between a batch of loads and its uses: memory operations do not cross the barrier, so all loads of
+// a batch are issued before the first FMA that needs them (13.9 ms).
 __device__ __forceinline__ double ldg_keep(const double* p) {
   double v;
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
