@@ -313,8 +313,91 @@ def make_integrals():
     return worst
 
 
+# ----------------------------------------------------------------------------------------
+def make_seams():
+    """Objects of the reference's Python seams evaluated by the REAL reference (tests/golden/seams.npz):
+
+    * process-vector cross-covariances ``linfunctl(k, argnum)`` -- ``pv(x)`` for both ``argnum`` (crosscov/_pv_crosscov.py,
+      crosscov/linfunctls/_evaluation.py:21-328) and the ``Covariance`` of two functionals ``L0(L1(k, argnum=1))``
+      (:11-18; randvars/_covariance.py);
+    * ``BlockMatrix2x2`` quantities (linops/_block.py:191-292): bordered Cholesky factor, Schur complement, ``L_A_inv_B``,
+      ``schur_update``, solve, determinant, for a 2 + 1 nest of ExpQuad blocks (test_symmetric_block.py) and a Matern
+      Gram matrix cut at 129 of 200."""
+    pn, lg = refshim.load()
+    from linpde_gp import linfunctls
+    from linpde_gp.linops import BlockMatrix2x2
+
+    rng = np.random.default_rng(20240)
+    out = {"X": rng.uniform(0, 1, (37, 2)), "Xt": rng.uniform(0, 1, (5, 4, 2)), "X0": rng.uniform(0, 1, (3, 6, 2))}
+    worst = 0.0
+    for kname, kspec in gcases.SEAM_KERNELS.items():
+        k = ref_kernel(kspec)
+        for oname, ospec in gcases.SEAM_OPS.items():
+            L = ref_op(ospec, (2,))
+            fctl = (linfunctls._EvaluationFunctional((2,), (), out["X"]) if L is None  # pylint: disable=protected-access
+                    else L.to_linfunctl(out["X"]))
+            # (argnum=0 cannot be generated: the reference's CovarianceFunction_Evaluation_Identity reads a
+            # non-existent `covfunc.output_shape`, crosscov/linfunctls/_evaluation.py:185, and raises AttributeError)
+            pv1 = fctl(k, argnum=1)
+            assert not pv1.reverse
+            v1 = np.asarray(pv1(out["Xt"]))
+            assert v1.shape == (5, 4, 37)
+            out[f"pv__{kname}__{oname}__argnum1"] = v1
+            out[f"pvlinop__{kname}__{oname}__argnum1"] = np.asarray(pv1.evaluate_linop(out["Xt"]).todense())
+            o_op = gcases.spec_to_oracle_op(ospec)
+            Ko = ocf.matrix(kspec, None, o_op, out["Xt"].reshape(-1, 2), out["X"])
+            worst = max(worst, np.max(np.abs(v1.reshape(20, 37) - Ko)) / np.max(np.abs(Ko)))
+            f0 = linfunctls._EvaluationFunctional((2,), (), out["X0"])  # pylint: disable=protected-access
+            cov = f0(pv1)
+            assert cov.shape0 == (3, 6) and cov.shape1 == (37,)
+            out[f"cov__{kname}__{oname}"] = np.asarray(cov.array)
+            out[f"covmat__{kname}__{oname}"] = np.asarray(cov.matrix)
+
+    def spd(M):
+        op = pn.linops.Matrix(M)
+        op.is_symmetric = True
+        op.is_positive_definite = True
+        return op
+
+    def block_case(name, K, cuts):
+        """nested BlockMatrix2x2 over the index cuts (e.g. (2, 3) -> ((2 + 1) ...)), quantities of the outermost block"""
+        A = spd(K[: cuts[0], : cuts[0]])
+        lo = cuts[0]
+        for hi in list(cuts[1:]) + [len(K)]:
+            sbm = BlockMatrix2x2(A, pn.linops.Matrix(K[:lo, lo:hi]), None, spd(K[lo:hi, lo:hi]), is_spd=True)
+            A, lo_prev, lo = sbm, lo, hi
+        r = np.random.default_rng(len(K))
+        u, v, B = r.standard_normal(lo_prev), r.standard_normal(len(K) - lo_prev), r.standard_normal((len(K), 3))
+        out[f"blk__{name}__K"] = K
+        out[f"blk__{name}__cuts"] = np.asarray(cuts)
+        out[f"blk__{name}__chol"] = np.asarray(sbm.cholesky(True).todense())
+        out[f"blk__{name}__schur"] = np.asarray(sbm.schur.todense())
+        out[f"blk__{name}__LAinvB"] = np.asarray(sbm.L_A_inv_B.todense())
+        out[f"blk__{name}__u"], out[f"blk__{name}__v"], out[f"blk__{name}__B"] = u, v, B
+        out[f"blk__{name}__schur_update"] = np.asarray(sbm.schur_update(sbm.A.inv() @ u, v))
+        out[f"blk__{name}__solve"] = np.asarray(sbm.solve(B))
+        out[f"blk__{name}__inv_u"] = np.asarray(sbm.inv() @ np.concatenate([u, v]))
+        out[f"blk__{name}__det"] = np.asarray(sbm.det())  # (underflows to 0 for the 200 x 200 case, as in the reference)
+        return float(np.max(np.abs(out[f"blk__{name}__chol"] - np.linalg.cholesky(K))))
+
+    x5 = np.arange(1.0, 6.0)
+    e1 = block_case("expquad_nested5", np.exp(-0.5 * (x5[:, None] - x5[None, :]) ** 2), (2, 4))
+    x3 = np.arange(1.0, 4.0)
+    e2 = block_case("expquad3", np.exp(-0.5 * (x3[:, None] - x3[None, :]) ** 2), (2,))
+    xs = np.sort(np.random.default_rng(7).uniform(0, 4, 200))
+    r_ = np.abs(xs[:, None] - xs[None, :]) * (np.sqrt(5.0) / 0.5)
+    e3 = block_case("matern200", (1 + r_ + r_ * r_ / 3) * np.exp(-r_) + 1e-6 * np.eye(200), (129,))
+    np.savez(os.path.join(GOLDEN, "seams.npz"), **out)
+    print(f"seams.npz: {len(out)} arrays, worst crosscov oracle-vs-reference deviation {worst:.2e}, "
+          f"block Cholesky vs numpy {max(e1, e2, e3):.2e}")
+    return worst
+
+
 if __name__ == "__main__":
     refshim.load()
+    if "--seams-only" in sys.argv:
+        print(f"worst deviation: seams {make_seams():.2e}")
+        sys.exit(0)
     if "--multi-output-only" in sys.argv:
         print(f"worst deviation: multi-output {make_multi_output():.2e}")
         sys.exit(0)
@@ -326,4 +409,6 @@ if __name__ == "__main__":
     w3 = make_kron()
     w4 = make_multi_output()
     w5 = make_integrals()
-    print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}, kron {w3:.2e}, multi-output {w4:.2e}, integrals {w5:.2e}")
+    w6 = make_seams()
+    print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}, kron {w3:.2e}, multi-output {w4:.2e}, integrals {w5:.2e}, "
+          f"seams {w6:.2e}")

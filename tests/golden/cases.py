@@ -226,3 +226,13 @@ def build_kron_cases():
         dict(name="kron_tp3_LkL", kernel=dict(scale=1.5, base=tp3), L0=lap3, L1=lap3, factors0=[h4, [0.0, 0.5, 1.5], g5], factors1=None),
     ]
     return cases
+
+
+# kernels / operators of the seam goldens (tests/golden/seams.npz, oracle/make_golden.py::make_seams)
+SEAM_KERNELS = {
+    "matern_tp": {"scale": 2.5, "base": {"kind": "tensor_product", "factors": [
+        {"kind": "matern", "nu": 2.5, "lengthscales": 0.6, "input_shape": []},
+        {"kind": "matern", "nu": 3.5, "lengthscales": 0.9, "input_shape": []}]}},
+    "expquad": {"scale": 1.7, "base": {"kind": "expquad", "lengthscales": [0.7, 1.1], "input_shape": [2]}},
+}
+SEAM_OPS = {"id": None, "neglap": [(-1.0, ("wl", [1.0, 1.0]))], "dd": [(1.0, ("dd", [0.3, -1.2]))]}

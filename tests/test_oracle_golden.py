@@ -190,3 +190,29 @@ def test_matern_lebesgue_integrals_match_quadrature():
             assert abs(oint.matern_lebesgue_integral(int(nu - 0.5), ell, a, b, x) - q) <= 1e-9
         q2 = scipy.integrate.dblquad(lambda t, s: kf(s, t), a, b, c, d, epsabs=1e-10)[0]
         assert abs(oint.matern_lebesgue_integral_lebesgue_integral(int(nu - 0.5), ell, (a, b), (c, d)) - q2) <= 1e-7
+
+
+def test_oracle_crosscov_matches_reference_seam_goldens():
+    """tests/golden/seams.npz (real reference: ``linfunctl(k, argnum=1)(x)``, ``evaluate_linop``, ``L0(L1(k, 1))``) against the
+    oracle's ``matrix``: process-vector cross-covariances are the (M, N) matrices ``(k L*)(x, X)`` in the layouts
+    batch + (N,) / (M, N) / shape0 + shape1 (crosscov/_pv_crosscov.py:60-161)."""
+    g = np.load(os.path.join(GOLDEN, "seams.npz"))
+    X, Xt, X0 = g["X"], g["Xt"], g["X0"]
+    for kname, kspec in gcases.SEAM_KERNELS.items():
+        for oname, ospec in gcases.SEAM_OPS.items():
+            o_op = gcases.spec_to_oracle_op(ospec)
+            K = ocf.matrix(kspec, None, o_op, Xt.reshape(-1, 2), X)
+            sc = np.max(np.abs(K))
+            assert np.max(np.abs(g[f"pv__{kname}__{oname}__argnum1"] - K.reshape(5, 4, 37))) <= 1e-14 * sc
+            assert np.max(np.abs(g[f"pvlinop__{kname}__{oname}__argnum1"] - K)) <= 1e-14 * sc
+            C = ocf.matrix(kspec, None, o_op, X0.reshape(-1, 2), X)
+            assert np.max(np.abs(g[f"cov__{kname}__{oname}"] - C.reshape(3, 6, 37))) <= 1e-14 * np.max(np.abs(C))
+            assert np.max(np.abs(g[f"covmat__{kname}__{oname}"] - C)) <= 1e-14 * np.max(np.abs(C))
+    # the reference's bordered block factor is the Cholesky factor of the whole matrix (oracle/linalg.py restates it)
+    for name in ("expquad3", "expquad_nested5", "matern200"):
+        K = g[f"blk__{name}__K"]
+        L = g[f"blk__{name}__chol"]
+        assert np.max(np.abs(L @ L.T - K)) <= 1e-12 * np.max(np.abs(K))
+        x = g[f"blk__{name}__schur_update"]
+        rhs = np.concatenate([g[f"blk__{name}__u"], g[f"blk__{name}__v"]])
+        assert np.max(np.abs(K @ x - rhs)) <= 1e-6 * np.max(np.abs(rhs))
