@@ -33,12 +33,44 @@ struct Status {
 // W: 128 x 128 row-major block receiving L^{-1} (lower, zero elsewhere; identity-padded beyond nb).
 //
 // The block lives in shared memory and is processed in 32-wide panels (left-looking):
-//   panel update (all 8 warps, broadcast + conflict-free LDS)  ->  32x32 diagonal Cholesky in the REGISTERS of
-//   one warp (lane = row, column scaling / rank-1 updates through warp shuffles)  ->  row-wise forward
-//   substitution of the rows below (one thread per row, the 32 unknowns in registers).
+//   panel update (DMMA from shared memory, one 8 x 32 strip per warp)  ->  32x32 diagonal Cholesky in the REGISTERS of
+//   one warp (lane = row, column broadcast through shared memory, rsqrt pivots)  ->  row-wise forward substitution of
+//   the rows below (one thread per row, the 32 unknowns in registers).
 // The inverse is built block-wise: the four 32x32 diagonal blocks are inverted by four warps in parallel (each
-// lane solves L x = e_lane in registers), the off-diagonal blocks follow from W_ij = -W_ii sum_k L_ik W_kj with
-// 2x2 register tiles.  ~20 us instead of ~235 us for the scalar version it replaces (profiles/ncu_kernels_r01.md).
+// lane solves L x = e_lane in registers), the off-diagonal blocks follow from W_ij = -W_ii sum_k L_ik W_kj as DMMA
+// block products.  Phase times measured with clock64 (cycles at 1.965 GHz, before -> after moving the two GEMM-like
+// phases from scalar DFMAs with 2x2 register tiles, which were shared-memory-pipe bound, to DMMA): load 7.4k, panel
+// updates 28.6k -> ~3k, register Cholesky 4 x 6.8k, rows below 6.9k, write-back + norms 9.8k -> ~4k, diagonal
+// inverses 5.7k, off-diagonal inverse blocks 34.6k -> ~5k, store 4k; kernel 77.7 -> 62.8 us under ncu (it was 235 us
+// as a scalar loop nest, profiles/ncu_kernels_r01.md).  What remains is the pivot chain of the register Cholesky
+// (212 cycles per column) and the cold 128 KB load through one SM.
+
+// FP64 tensor-core helpers for the small products inside the leaf (shared-memory operands).  The leaf's rank-k panel
+// updates and the block products of the inverse are GEMMs with 32-wide blocks; with scalar DFMAs and 2x2 register
+// tiles they were bound by the shared-memory pipe (one LDS per FMA: 28.6k + 34.6k of the kernel's 124k cycles,
+// measured with clock64).  One DMMA.8x8x4 does the work of 8 warp-wide DFMAs on 2 operand loads.
+__device__ __forceinline__ void leaf_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// One warp:  C[8 x 32] += (NEG ? -1 : 1) * A[8 x K] B[K x 32]  with  A(i, k) = pa[i * sai + k],  B(k, j) = pb[k * sbk + j * sbj],
+// K a multiple of 4.  Lane (g, t) = (lane / 4, lane % 4) holds C(g, 8 nj + 2 t) and C(g, 8 nj + 2 t + 1) in acc[nj].
+template <bool NEG>
+__device__ __forceinline__ void warp_mma_8x32(double (&acc)[4][2], const double* pa, int sai, const double* pb, int sbk, int sbj,
+                                              int K) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const double* ap = pa + g * sai + t;
+  const double* bp = pb + t * sbk + g * sbj;
+#pragma unroll 2
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    double av = ap[k0];
+    if (NEG) av = -av;
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj) leaf_dmma(acc[nj][0], acc[nj][1], av, bp[k0 * sbk + nj * 8 * sbj]);
+  }
+}
 
 // solve L y = b for one 32-vector held in registers; L is a 32x32 lower block in shared memory (row stride LDS_A),
 // rdiag its reciprocal diagonal.  All threads of a warp read the same L entries (broadcast).
@@ -91,23 +123,25 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
 
   for (int kb = 0; kb < LEAF / 32; ++kb) {
     const int c0 = kb * 32;
-    // ---- (1) panel update: a[i][c0+lane] -= sum_{k<c0} a[i][k] a[c0+lane][k] for the rows i >= c0 of this warp ----
+    // ---- (1) panel update: a[i][c0+j] -= sum_{k<c0} a[i][k] a[c0+j][k] for the rows i >= c0: DMMA, one 8-row strip
+    //      (8 x 32 outputs) per warp and round; inputs are columns < c0, outputs columns >= c0: no hazards ----
     if (kb > 0) {
-      constexpr int RMAX = 12;  // (128 - 32) / 8 rows per warp at most
-      double acc[RMAX];
+      const int g = lane >> 2, t = lane & 3;
+      for (int task = warp; task < (LEAF - c0) / 8; task += DIAG_THREADS / 32) {
+        double* crow = a + (c0 + task * 8 + g) * LDS_A + c0 + 2 * t;
+        double acc[4][2];
 #pragma unroll
-      for (int r = 0; r < RMAX; ++r) acc[r] = 0.0;
-      const int nr = (LEAF - c0) / 8;
-      const double* crow = a + (c0 + lane) * LDS_A;
-      for (int k = 0; k < c0; ++k) {
-        const double bc = crow[k];
+        for (int nj = 0; nj < 4; ++nj) {
+          acc[nj][0] = crow[nj * 8];
+          acc[nj][1] = crow[nj * 8 + 1];
+        }
+        warp_mma_8x32<true>(acc, a + (c0 + task * 8) * LDS_A, LDS_A, a + c0 * LDS_A, 1, LDS_A, c0);
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-          if (r < nr) acc[r] = fma(a[(c0 + warp + 8 * r) * LDS_A + k], bc, acc[r]);
+        for (int nj = 0; nj < 4; ++nj) {
+          crow[nj * 8] = acc[nj][0];
+          crow[nj * 8 + 1] = acc[nj][1];
+        }
       }
-#pragma unroll
-      for (int r = 0; r < RMAX; ++r)
-        if (r < nr) a[(c0 + warp + 8 * r) * LDS_A + c0 + lane] -= acc[r];
       __syncthreads();
     }
     // ---- (2) Cholesky of the 32x32 diagonal block in the registers of warp 0 (lane = row) ----
@@ -161,9 +195,9 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
 
   // write L back (coalesced rows); the strict upper triangle of the block is cleared so that the block can be used as
   // a plain GEMM operand (residual of the refined panel solve, trsm_rec)
-  for (int idx = tid; idx < nb * nb; idx += DIAG_THREADS) {
-    const int i = idx / nb, j = idx % nb;
-    A[(int64_t)i * ld + j] = (j <= i) ? a[i * LDS_A + j] : 0.0;
+  for (int idx = tid; idx < LEAF * LEAF; idx += DIAG_THREADS) {
+    const int i = idx / LEAF, j = idx % LEAF;
+    if (i < nb && j < nb) A[(int64_t)i * ld + j] = (j <= i) ? a[i * LDS_A + j] : 0.0;
   }
   if (refine_flag != nullptr && tid < LEAF) {  // ||L||_inf (row stride LDS_A = 129: conflict-free across rows)
     double rs = 0.0;
@@ -183,51 +217,43 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     for (int i = 0; i < 32; ++i) a[(c0 + i) * LDS_A + c0 + lane] = x[i];  // column `lane` of W_bb (zeros above the diagonal)
   }
   __syncthreads();
-  // ---- inverse, step 2: block rows i = 1..3:  T_j = sum_{k=j}^{i-1} L_ik W_kj,  W_ij = -W_ii T_j ----
-  const int tr = (tid >> 4) * 2, tc = (tid & 15) * 2;  // 2x2 register tile of a 32x32 block
-  for (int bi = 1; bi < LEAF / 32; ++bi) {
-    double t[3][2][2];
+  // ---- inverse, step 2: block rows i = 1..3:  T_j = sum_{k=j}^{i-1} L_ik W_kj,  W_ij = -W_ii T_j  (DMMA; one task =
+  //      8-row strip of one 32 x 32 block; stage a reads L_i* and finished W blocks, stage b overwrites L_i*) ----
+  {
+    const int g = lane >> 2, t = lane & 3;
+    for (int bi = 1; bi < LEAF / 32; ++bi) {
+      for (int task = warp; task < bi * 4; task += DIAG_THREADS / 32) {
+        const int bj = task >> 2, s8 = (task & 3) * 8;
+        double acc[4][2];
 #pragma unroll
-    for (int bj = 0; bj < 3; ++bj) {
-      t[bj][0][0] = t[bj][0][1] = t[bj][1][0] = t[bj][1][1] = 0.0;
-      if (bj < bi) {
-        for (int k = bj * 32; k < bi * 32; ++k) {  // L_ik (row block bi) times W_kj (column block bj)
-          const double l0 = a[(bi * 32 + tr) * LDS_A + k], l1 = a[(bi * 32 + tr + 1) * LDS_A + k];
-          const double w0 = a[k * LDS_A + bj * 32 + tc], w1 = a[k * LDS_A + bj * 32 + tc + 1];
-          t[bj][0][0] = fma(l0, w0, t[bj][0][0]);
-          t[bj][0][1] = fma(l0, w1, t[bj][0][1]);
-          t[bj][1][0] = fma(l1, w0, t[bj][1][0]);
-          t[bj][1][1] = fma(l1, w1, t[bj][1][1]);
-        }
-        double* tb = tbuf + bj * 32 * 33;
-        tb[tr * 33 + tc] = t[bj][0][0];
-        tb[tr * 33 + tc + 1] = t[bj][0][1];
-        tb[(tr + 1) * 33 + tc] = t[bj][1][0];
-        tb[(tr + 1) * 33 + tc + 1] = t[bj][1][1];
-      }
-    }
-    __syncthreads();
+        for (int nj = 0; nj < 4; ++nj) acc[nj][0] = acc[nj][1] = 0.0;
+        // A(i, k) = L[32 bi + s8 + i][32 bj + k],  B(k, j) = W[32 bj + k][32 bj + j],  K = 32 (bi - bj)
+        warp_mma_8x32<false>(acc, a + (bi * 32 + s8) * LDS_A + bj * 32, LDS_A, a + (bj * 32) * LDS_A + bj * 32, LDS_A, 1,
+                             (bi - bj) * 32);
+        double* trow = tbuf + bj * 32 * 33 + (s8 + g) * 33 + 2 * t;
 #pragma unroll
-    for (int bj = 0; bj < 3; ++bj) {
-      if (bj < bi) {
-        const double* tb = tbuf + bj * 32 * 33;
-        double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-        for (int k = 0; k < 32; ++k) {  // W_ii (lower) times T_j
-          const double w0 = a[(bi * 32 + tr) * LDS_A + bi * 32 + k], w1 = a[(bi * 32 + tr + 1) * LDS_A + bi * 32 + k];
-          const double u0 = tb[k * 33 + tc], u1 = tb[k * 33 + tc + 1];
-          s00 = fma(w0, u0, s00);
-          s01 = fma(w0, u1, s01);
-          s10 = fma(w1, u0, s10);
-          s11 = fma(w1, u1, s11);
+        for (int nj = 0; nj < 4; ++nj) {
+          trow[nj * 8] = acc[nj][0];
+          trow[nj * 8 + 1] = acc[nj][1];
         }
-        double* dst = a + (bi * 32 + tr) * LDS_A + bj * 32 + tc;
-        dst[0] = -s00;
-        dst[1] = -s01;
-        dst[LDS_A] = -s10;
-        dst[LDS_A + 1] = -s11;
       }
+      __syncthreads();
+      for (int task = warp; task < bi * 4; task += DIAG_THREADS / 32) {
+        const int bj = task >> 2, s8 = (task & 3) * 8;
+        double acc[4][2];
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) acc[nj][0] = acc[nj][1] = 0.0;
+        // A(r, m) = W_ii[s8 + r][m],  B(m, j) = T_j[m][j],  K = 32
+        warp_mma_8x32<true>(acc, a + (bi * 32 + s8) * LDS_A + bi * 32, LDS_A, tbuf + bj * 32 * 33, 33, 1, 32);
+        double* wrow = a + (bi * 32 + s8 + g) * LDS_A + bj * 32 + 2 * t;
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) {
+          wrow[nj * 8] = acc[nj][0];
+          wrow[nj * 8 + 1] = acc[nj][1];
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   for (int idx = tid; idx < LEAF * LEAF; idx += DIAG_THREADS) {
     const int i = idx / LEAF, j = idx % LEAF;
