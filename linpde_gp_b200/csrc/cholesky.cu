@@ -690,6 +690,21 @@ struct TrsmWork {
     if (g_lpgp_trsm_refine == 0 || rows <= 0) return 0;
     const int nl = (int)lv.off.size() - 1;
     const size_t t_bytes = (size_t)rows * LEAF * sizeof(double);
+    {
+      // keep up to 1 GiB cached in the device's default pool: with the default threshold (0) the workspace would go
+      // back to the driver at every stream synchronisation and be re-created by the next call (one per conditioning
+      // step, one per panel of the multi-GPU factorisation)
+      static std::once_flag once[LPGP_MAX_DEVICES];
+      int dev = 0;
+      LPGP_CHECK(cudaGetDevice(&dev));
+      if (dev >= 0 && dev < LPGP_MAX_DEVICES)
+        std::call_once(once[dev], [dev]() {
+          cudaMemPool_t pool;
+          uint64_t keep = 1ull << 30;
+          if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        });
+    }
     LPGP_CHECK(cudaMallocAsync(&buf, t_bytes + (size_t)nl * sizeof(int), st));
     ws.T = (double*)buf;
     ws.flags = (int*)((char*)buf + t_bytes);
