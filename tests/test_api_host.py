@@ -286,3 +286,56 @@ def test_integral_dispatch_needs_closed_form_kernels():
         _integral_terms(diffops.Laplacian(())(m1, argnum=1))
     with pytest.raises(NotImplementedError):
         _integral_terms(covfuncs.Matern((), nu=1.2))
+
+
+def test_covariance_containers_host_semantics():
+    """``randvars.ArrayCovariance`` / ``Covariance`` shape bookkeeping (src/linpde_gp/randvars/_covariance.py:13-194): array
+    <-> matrix views over C-order flattened variables, flatten / unflatten with shape errors."""
+    from linpde_gp_b200 import randvars
+
+    arr = np.arange(2 * 3 * 4, dtype=float).reshape(2, 3, 4)
+    cov = randvars.ArrayCovariance(arr, shape0=(2, 3), shape1=(4,))
+    assert cov.shape0 == (2, 3) and cov.shape1 == (4,) and cov.ndim0 == 2 and cov.ndim1 == 1
+    assert cov.size0 == 6 and cov.size1 == 4
+    np.testing.assert_array_equal(cov.array, arr)
+    np.testing.assert_array_equal(cov.matrix, arr.reshape(6, 4))
+    assert cov.flatten0(np.zeros((2, 3))).shape == (6,) and cov.flatten1(np.zeros(4)).shape == (4,)
+    assert cov.unflatten0(np.zeros(6)).shape == (2, 3) and cov.unflatten1(np.zeros(4)).shape == (4,)
+    with pytest.raises(ValueError):
+        cov.flatten0(np.zeros((3, 2)))
+    with pytest.raises(ValueError):
+        cov.flatten1(np.zeros(5))
+    with pytest.raises(ValueError):
+        randvars.ArrayCovariance(arr, shape0=(2, 3), shape1=(5,))
+    s = randvars.ArrayCovariance.from_scalar(2.5)
+    assert s.shape0 == () and s.shape1 == () and s.size0 == 1 and s.matrix.shape == (1, 1) and float(s.array) == 2.5
+
+
+def test_dirac_and_functional_dispatch_host_semantics():
+    """``DiracFunctional`` shapes (src/linpde_gp/linfunctls/_dirac.py:10-45: output = batch + codomain) and the argument
+    checks of ``linfunctl(k, argnum)`` (covfuncs/linfunctls/_registry.py) that run before any device work."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.randprocs import covfuncs, crosscov
+
+    X = np.linspace(0, 1, 12).reshape(3, 4)
+    d = lg.linfunctls.DiracFunctional((), (), X)
+    assert d.output_shape == (3, 4) and d.X_batch_shape == (3, 4) and d.X_batch_ndim == 2
+    assert d.input_domain_shape == () and d.input_codomain_shape == ()
+    np.testing.assert_array_equal(d(lg.functions.Constant((), 2.0)), np.full((3, 4), 2.0))
+    with pytest.raises(ValueError):
+        lg.linfunctls.DiracFunctional((2,), (), np.zeros((5, 3)))
+    d2 = lg.linfunctls.DiracFunctional((2,), (), np.zeros((5, 2)))
+    assert d2.output_shape == (5,)
+    k = covfuncs.Matern((), nu=1.5, lengthscales=1.0)
+    with pytest.raises(ValueError):
+        d(k, argnum=2)
+    z = d(covfuncs.Zero(()), argnum=1)  # the zero kernel needs no device work to be pushed through a functional
+    assert isinstance(z, crosscov.Zero) and z.randvar_shape == (3, 4) and not z.reverse and z.randproc_input_shape == ()
+    assert d(covfuncs.Zero(()), argnum=0).reverse
+    assert isinstance(-z, crosscov.ScaledProcessVectorCrossCovariance) and (2.0 * z).scalar == 2.0
+    assert isinstance(z + z, crosscov.SumProcessVectorCrossCovariance) and len((z + z + z).summands) == 3
+    pv2 = lg.linfunctls.DiracFunctional((2,), (), np.zeros((5, 2)))(covfuncs.Zero((2,)), argnum=1)
+    with pytest.raises(ValueError):
+        pv2(np.zeros((4, 3)))  # trailing shape must equal the input shape of the process (checked before device work)
+    with pytest.raises(ValueError):
+        pv2.evaluate_linop(np.zeros((4, 3)))
