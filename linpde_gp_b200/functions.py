@@ -155,3 +155,147 @@ class LambdaFunction(Function):
 
     def _evaluate(self, x):
         return np.asarray(self._fn(x), dtype=np.double)
+
+
+# -- univariate polynomials (src/linpde_gp/functions/_polynomial.py:17-238) -----------------------------------------------
+class Monomial(Function):
+    """``x -> x^degree`` on scalar inputs."""
+
+    def __init__(self, degree: int):
+        super().__init__(input_shape=(), output_shape=())
+        degree = int(degree)
+        if degree < 0:
+            raise ValueError("The degree of the monomial must be non-negative.")
+        self._degree = degree
+
+    @property
+    def degree(self) -> int:
+        return self._degree
+
+    def _evaluate(self, x):
+        return x**self._degree
+
+
+class Polynomial(Function):
+    """``x -> sum_i coeffs[i] x^i`` (ascending coefficients) on scalar inputs, evaluated by Horner's rule
+    (_polynomial.py:39-96).  ``differentiate`` / ``integrate`` are exact on the coefficients; differential operators
+    and ``LebesgueIntegral`` apply to polynomials in closed form (``LinearFunctionOperator._apply_to_function``,
+    ``linfunctls._integrate_function``), so that polynomial prior means and right-hand sides stay on the closed-form
+    path (the reference differentiates them through its JAX fallback)."""
+
+    def __init__(self, coeffs):
+        super().__init__(input_shape=(), output_shape=())
+        coeffs = tuple(float(c) for c in coeffs)
+        self._coeffs = coeffs if len(coeffs) >= 1 else (0.0,)
+
+    @property
+    def coefficients(self) -> tuple:
+        return self._coeffs
+
+    @property
+    def degree(self) -> int:
+        return len(self._coeffs) - 1
+
+    def __repr__(self) -> str:
+        return " + ".join(str(c) if k == 0 else f"{c} x^{k}" for k, c in enumerate(self._coeffs) if c != 0.0) or "0"
+
+    def _evaluate(self, x):
+        res = np.full_like(x, self._coeffs[-1], dtype=np.double)
+        for c in self._coeffs[-2::-1]:
+            res = res * x + c
+        return res
+
+    def _new(self, coeffs):
+        return Polynomial(coeffs)
+
+    def differentiate(self):
+        return self._new(tuple(c * k for k, c in enumerate(self._coeffs[1:], start=1)))
+
+    def integrate(self):
+        return self._new((0 * self._coeffs[0],) + tuple(c / (i + 1) for i, c in enumerate(self._coeffs)))
+
+    def __neg__(self):
+        return self._new(tuple(-c for c in self._coeffs))
+
+    def _combine(self, other, sign):
+        import itertools  # pylint: disable=import-outside-toplevel
+
+        both_rational = isinstance(self, RationalPolynomial) and isinstance(other, RationalPolynomial)
+        if both_rational:  # exact
+            a, b, zero = self._coeffs, other._coeffs, 0 * self._coeffs[0]  # pylint: disable=protected-access
+        else:
+            a, b, zero = self.coefficients, other.coefficients, 0.0
+        coeffs = tuple(c0 + sign * c1 for c0, c1 in itertools.zip_longest(a, b, fillvalue=zero))
+        return RationalPolynomial(coeffs) if both_rational else Polynomial(coeffs)
+
+    def __add__(self, other):
+        if isinstance(other, Polynomial):
+            return self._combine(other, 1)
+        if isinstance(other, Constant) and other.input_shape == () and other.output_shape == ():
+            return Polynomial((float(self._coeffs[0]) + float(other.value),) + tuple(float(c) for c in self._coeffs[1:]))
+        return super().__add__(other)
+
+    def __sub__(self, other):
+        if isinstance(other, Polynomial):
+            return self._combine(other, -1)
+        return super().__sub__(other)
+
+    def __rmul__(self, other):
+        if np.ndim(other) == 0 and not isinstance(other, Function):
+            return Polynomial(tuple(float(other) * float(c) for c in self._coeffs))
+        return super().__rmul__(other)
+
+    def __floordiv__(self, other):
+        if not isinstance(other, Monomial):
+            return NotImplemented
+        if not 0 <= other.degree <= self.degree:
+            raise ValueError("The degree of the monomial is larger than the degree of the polynomial")
+        if any(c != 0 for c in self._coeffs[: other.degree]):
+            raise ValueError(f"The first {other.degree} of the polynomial are not all zeros")
+        return self._new(self._coeffs[other.degree:])
+
+
+class RationalPolynomial(Polynomial):
+    """Polynomial with exact ``fractions.Fraction`` coefficients (_polynomial.py:166-238): the derivative polynomials
+    of half-integer Matern kernels are kept exact until they are folded into the device descriptor."""
+
+    def __init__(self, coeffs):
+        from fractions import Fraction  # pylint: disable=import-outside-toplevel
+
+        coeffs = tuple(Fraction(c) for c in coeffs)
+        if len(coeffs) < 1:
+            coeffs = (Fraction(0),)
+        Function.__init__(self, input_shape=(), output_shape=())
+        self._coeffs = coeffs
+
+    @property
+    def rational_coefficients(self) -> tuple:
+        return self._coeffs
+
+    @property
+    def coefficients(self) -> tuple:
+        return tuple(float(c) for c in self._coeffs)
+
+    def _new(self, coeffs):
+        return RationalPolynomial(coeffs)
+
+    def _evaluate(self, x):
+        cs = self.coefficients
+        res = np.full_like(x, cs[-1], dtype=np.double)
+        for c in cs[-2::-1]:
+            res = res * x + c
+        return res
+
+    def __repr__(self) -> str:
+        if all(c == 0 for c in self._coeffs):
+            return "0"
+        return " ".join(
+            str(c) if k == 0 else "".join(["+" if c > 0 else "-", f" {abs(c)}" if abs(c) != 1 else "", f" x^{k}"])
+            for k, c in enumerate(self._coeffs) if c != 0)
+
+    def __rmul__(self, other):
+        from fractions import Fraction  # pylint: disable=import-outside-toplevel
+
+        if isinstance(other, (int, Fraction)) and not isinstance(other, bool):
+            return RationalPolynomial(tuple(Fraction(other) * c for c in self._coeffs))
+        return super().__rmul__(other)

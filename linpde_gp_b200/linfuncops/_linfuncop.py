@@ -7,7 +7,7 @@ import operator
 
 import numpy as np
 
-from ..functions import Constant, Function, ScaledFunction, StackedFunction, SumFunction, Zero, _as_shape
+from ..functions import Constant, Function, Polynomial, ScaledFunction, StackedFunction, SumFunction, Zero, _as_shape
 
 
 class LinearFunctionOperator:
@@ -73,8 +73,21 @@ class LinearFunctionOperator:
         if isinstance(f, Zero):
             return Zero(self.output_domain_shape, self.output_codomain_shape)
         if isinstance(f, Constant):
+            if order0 == 0:  # pure derivative operator: Zero, as linfuncops/diffops/_functions.py:8-19
+                return Zero(self.output_domain_shape, self.output_codomain_shape)
             return Constant(self.output_domain_shape, order0 * f.value)
-        raise NotImplementedError("only Zero / Constant functions can be differentiated in closed form")
+        if isinstance(f, Polynomial) and self.input_domain_shape == () and self.input_codomain_shape == ():
+            # univariate polynomial: sum_n c_n d^n/dx^n on the coefficients (exact for RationalPolynomial)
+            res = None
+            for mi, c in terms.items():
+                g = f
+                for _ in range(sum(mi)):
+                    g = g.differentiate()
+                g = Polynomial(tuple(float(c) * cc for cc in g.coefficients))
+                res = g if res is None else res + g
+            return res if res is not None else Zero((), ())
+        raise NotImplementedError("only Zero / Constant / univariate Polynomial functions can be differentiated in "
+                                  "closed form")
 
     def to_linfunctl(self, X):
         """``_EvaluationFunctional(X) @ self`` (``_linfuncop.py:93-105``)."""

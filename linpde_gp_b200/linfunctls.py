@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .functions import Constant, Function, _as_shape
+from .functions import Constant, Function, Polynomial, _as_shape
 
 
 class LinearFunctional:
@@ -115,6 +115,9 @@ def _integrate_function(g: Function, dom):
     a, b = dom
     if isinstance(g, Constant):
         return g.value * (b - a)
+    if isinstance(g, Polynomial):  # src/linpde_gp/functions/_linfunctls.py:9-13
+        G = g.integrate()
+        return G(np.asarray(b, dtype=np.double)) - G(np.asarray(a, dtype=np.double))
     import scipy.integrate  # pylint: disable=import-outside-toplevel
 
     if tuple(g.output_shape) != ():

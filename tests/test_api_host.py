@@ -339,3 +339,58 @@ def test_dirac_and_functional_dispatch_host_semantics():
         pv2(np.zeros((4, 3)))  # trailing shape must equal the input shape of the process (checked before device work)
     with pytest.raises(ValueError):
         pv2.evaluate_linop(np.zeros((4, 3)))
+
+
+def test_polynomial_functions_and_closed_form_operators():
+    """``functions.Monomial / Polynomial / RationalPolynomial`` (src/linpde_gp/functions/_polynomial.py:17-238): Horner
+    evaluation, exact calculus on the coefficients, arithmetic, ``//`` by a monomial; differential operators and
+    ``LebesgueIntegral`` (functions/_linfunctls.py:9-13) apply to them in closed form."""
+    from fractions import Fraction
+
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.functions import Constant, Monomial, Polynomial, RationalPolynomial
+    from linpde_gp_b200.linfuncops import diffops
+
+    x = np.linspace(-2, 2, 9).reshape(3, 3)
+    p = Polynomial([1.0, -2.0, 0.0, 3.0])
+    assert p.degree == 3 and p.coefficients == (1.0, -2.0, 0.0, 3.0) and p.input_shape == () and p.output_shape == ()
+    np.testing.assert_allclose(p(x), 1 - 2 * x + 3 * x**3)
+    np.testing.assert_allclose(Monomial(4)(x), x**4)
+    assert p.differentiate().coefficients == (-2.0, 0.0, 9.0)
+    assert p.integrate().coefficients == (0.0, 1.0, -1.0, 0.0, 0.75)
+    assert (-p).coefficients == (-1.0, 2.0, -0.0, -3.0)
+    assert (p + Polynomial([1.0, 1.0])).coefficients == (2.0, -1.0, 0.0, 3.0)
+    assert (p - Polynomial([0.0, 0.0, 0.0, 3.0, 1.0])).coefficients == (1.0, -2.0, 0.0, 0.0, -1.0)
+    assert (p + Constant((), 2.0)).coefficients == (3.0, -2.0, 0.0, 3.0)
+    assert (0.5 * p).coefficients == (0.5, -1.0, 0.0, 1.5)
+    assert (Polynomial([0.0, 0.0, 2.0, 5.0]) // Monomial(2)).coefficients == (2.0, 5.0)
+    with pytest.raises(ValueError):
+        p // Monomial(1)  # constant coefficient is not zero
+    with pytest.raises(ValueError):
+        p // Monomial(5)
+    assert Polynomial([]).coefficients == (0.0,)
+    with pytest.raises(ValueError):
+        Monomial(-1)
+
+    # the exact Matern-5/2 polynomial P_0 = 1 + r + r^2/3 and its derivative table entries (SURVEY 8a a5)
+    q = RationalPolynomial([1, 1, Fraction(1, 3)])
+    assert q.rational_coefficients == (Fraction(1), Fraction(1), Fraction(1, 3))
+    assert q.differentiate().rational_coefficients == (Fraction(1), Fraction(2, 3))
+    assert q.integrate().rational_coefficients == (Fraction(0), Fraction(1), Fraction(1, 2), Fraction(1, 9))
+    assert isinstance(q - q.differentiate(), RationalPolynomial)
+    assert (q - q.differentiate()).rational_coefficients == (Fraction(0), Fraction(1, 3), Fraction(1, 3))
+    assert (3 * q).rational_coefficients == (Fraction(3), Fraction(3), Fraction(1))
+    assert repr(q) == "1 + x^1 + 1/3 x^2" and repr(RationalPolynomial([0])) == "0"
+    assert not isinstance(q + p, RationalPolynomial) and (q + p).coefficients[0] == 2.0
+    np.testing.assert_allclose(q(x), 1 + x + x**2 / 3)
+
+    # operators in closed form: L = -d^2/dx^2 + 2 d/dx on p
+    L = -1.0 * diffops.Laplacian(()) + 2.0 * diffops.Derivative(1)
+    Lp = L(p)
+    np.testing.assert_allclose(Lp(x), -(18 * x) + 2 * (-2 + 9 * x**2))
+    assert isinstance(diffops.Laplacian(())(Constant((), 3.0)), lg.functions.Zero)
+    # prior-mean integrals: int_a^b p
+    I = lg.linfunctls.LebesgueIntegral((-1.0, 2.0))
+    P = p.integrate()
+    assert abs(I(p) - (P(np.asarray(2.0)) - P(np.asarray(-1.0)))) < 1e-14
+    assert abs(I(Constant((), 2.0)) - 6.0) < 1e-14

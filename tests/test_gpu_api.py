@@ -621,3 +621,34 @@ def test_heat_ibvp_analytic_solution_within_two_sigma():
     assert np.min(mean + 2 * std - Y_test) > -3e-2
     assert np.min(Y_test - (mean - 2 * std)) > -3e-2
     assert np.max(np.abs(mean - Y_test)) < 0.1  # and the mean itself is a decent solution of the IBVP
+
+
+def test_polynomial_prior_mean_is_pushed_through_operators_in_closed_form():
+    """A polynomial prior mean m: conditioning f = m + g on ``L f (X) = Y`` equals conditioning the zero-mean g on
+    ``Y - (L m)(X)`` and adding m back (_conditional.py:193-197, 296-399) -- ``L m`` by exact coefficient calculus
+    (functions/_polynomial.py:88-96) instead of the reference's JAX fallback.  1e-10 relative."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.functions import Polynomial
+    from linpde_gp_b200.linfuncops import diffops
+    from linpde_gp_b200.randprocs import covfuncs
+
+    m = Polynomial([0.5, -1.0, 0.25, 2.0])
+    k = 1.5 * covfuncs.Matern((), nu=2.5, lengthscales=0.7)
+    L = -1.0 * diffops.Laplacian(())
+    X_pde, X_bc = np.linspace(-0.8, 0.8, 17), np.array([-1.0, 1.0])
+    Y_pde, Y_bc = np.pi**2 * np.sin(np.pi * X_pde), np.zeros(2)
+    xs = np.linspace(-1, 1, 41)
+
+    post = lg.GaussianProcess(m, k).condition_on_observations(Y_bc, X=X_bc).condition_on_observations(Y_pde, X=X_pde, L=L)
+    Lm = L(m)
+    np.testing.assert_allclose(Lm(X_pde), -(0.5 + 12.0 * X_pde), rtol=1e-14)
+    post0 = (lg.GaussianProcess(lg.functions.Zero(()), k)
+             .condition_on_observations(Y_bc - m(X_bc), X=X_bc)
+             .condition_on_observations(Y_pde - Lm(X_pde), X=X_pde, L=L))
+    sc = np.max(np.abs(post.mean(xs)))
+    assert np.max(np.abs(post.mean(xs) - (m(xs) + post0.mean(xs)))) <= 1e-10 * sc
+    assert np.max(np.abs(post.var(xs) - post0.var(xs))) <= 1e-10 * 1.5
+    assert np.max(np.abs(post.mean(X_bc) - Y_bc)) <= 1e-8 * sc
+    # the push-forward L(posterior) carries the mean too
+    res = L(post).mean(X_pde)
+    assert np.max(np.abs(res - Y_pde)) <= 1e-7 * np.max(np.abs(Y_pde))
