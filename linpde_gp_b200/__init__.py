@@ -8,7 +8,7 @@ kernels in ``liblpgp.so`` (C ABI, ``include/lpgp.h``) reached through ctypes; to
 There is no CPU fallback: importing this package without the built library fails.
 """
 from . import _lib  # noqa: F401  (fails loudly if liblpgp.so is missing)
-from . import backend, functions, linfuncops, linfunctls, linops, randprocs, randvars
+from . import backend, domains, functions, linfuncops, linfunctls, linops, problems, randprocs, randvars
 from .randprocs import ConditionalGaussianProcess, GaussianProcess
 
 __version__ = "0.1.0"

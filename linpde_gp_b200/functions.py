@@ -299,3 +299,33 @@ class RationalPolynomial(Polynomial):
         if isinstance(other, (int, Fraction)) and not isinstance(other, bool):
             return RationalPolynomial(tuple(Fraction(other) * c for c in self._coeffs))
         return super().__rmul__(other)
+
+
+class TruncatedSineSeries(Function):
+    """``x -> sum_n c_n sin(n pi (x - l) / (r - l))`` on an interval ``[l, r]`` (src/linpde_gp/functions/_fourier.py:12-63):
+    the initial values of the heat-equation problems."""
+
+    def __init__(self, domain, coefficients):
+        from . import domains  # pylint: disable=import-outside-toplevel
+
+        domain = domains.asdomain(domain)
+        if not isinstance(domain, domains.Interval):
+            raise TypeError("`domain` must be an `Interval`")
+        self._domain = domain
+        super().__init__(domain.shape, ())
+        coefficients = np.asarray(coefficients, dtype=np.double)
+        if coefficients.ndim != 1:
+            raise ValueError("`coefficients` must be one-dimensional")
+        self._coefficients = coefficients
+
+    domain = property(lambda self: self._domain)
+    coefficients = property(lambda self: self._coefficients)
+
+    @property
+    def half_angular_frequencies(self) -> np.ndarray:
+        l, r = self._domain
+        return np.pi * np.arange(1, self._coefficients.shape[-1] + 1) / (r - l)
+
+    def _evaluate(self, x):
+        l, _ = self._domain
+        return np.sum(self._coefficients * np.sin(self.half_angular_frequencies * (x[..., None] - l)), axis=-1)

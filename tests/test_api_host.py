@@ -394,3 +394,94 @@ def test_polynomial_functions_and_closed_form_operators():
     P = p.integrate()
     assert abs(I(p) - (P(np.asarray(2.0)) - P(np.asarray(-1.0)))) < 1e-14
     assert abs(I(Constant((), 2.0)) - 6.0) < 1e-14
+
+
+def test_domains_host_semantics():
+    """``linpde_gp.domains`` (src/linpde_gp/domains/*.py): intervals, points, boxes, Cartesian products, boundaries,
+    uniform grids (a box's grid is a TensorProductGrid, _box.py:81-114) and ``asdomain`` conversions."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200 import domains
+    from linpde_gp_b200.randprocs.covfuncs import TensorProductGrid
+
+    iv = domains.asdomain([-1.0, 1.0])
+    assert isinstance(iv, domains.Interval) and iv.shape == () and tuple(iv) == (-1.0, 1.0) and len(iv) == 2
+    assert iv[0] == -1.0 and iv[-1] == 1.0 and iv.volume == 2.0 and 0.3 in iv and 1.5 not in iv and np.zeros(2) not in iv
+    assert iv == domains.Interval(-1, 1) and iv != domains.Interval(-1, 2)
+    lo, hi = iv.boundary
+    assert isinstance(lo, domains.Point) and float(lo) == -1.0 and float(hi) == 1.0 and lo.boundary == (lo,) and lo.volume == 0.0
+    np.testing.assert_allclose(iv.uniform_grid(5, inset=0.1), np.linspace(-0.9, 0.9, 5))
+    with pytest.raises(ValueError):
+        domains.Interval(1.0, 0.0)
+    with pytest.raises(ValueError):
+        domains.asdomain([1.0, 2.0, 3.0])
+
+    box = domains.asdomain([np.array([0.0, -1.0]), np.array([1.0, 1.0])])
+    assert isinstance(box, domains.Box) and box.shape == (2,) and len(box) == 2 and box.volume == 2.0
+    np.testing.assert_array_equal(box.bounds, [[0.0, 1.0], [-1.0, 1.0]])
+    assert np.array([0.5, 0.0]) in box and np.array([1.5, 0.0]) not in box and box[1] == domains.Interval(-1, 1)
+    assert box == domains.Box(np.array([[0.0, 1.0], [-1.0, 1.0]])) and isinstance(box[0:1], domains.Box)
+    grid = box.uniform_grid((3, 5), inset=(0.0, 0.5))
+    assert isinstance(grid, TensorProductGrid) and grid.shape == (3, 5, 2)
+    np.testing.assert_allclose(grid.factors[0], [0.0, 0.5, 1.0])
+    np.testing.assert_allclose(grid.factors[1], np.linspace(-0.5, 0.5, 5))
+    assert box.uniform_grid(4).shape == (4, 4, 2)
+    parts = box.boundary
+    assert len(parts) == 4 and all(isinstance(p, domains.CartesianProduct) and p.shape == (2,) for p in parts)
+    assert isinstance(parts[0][0], domains.Point) and float(parts[0][0]) == 0.0 and parts[0][1] == domains.Interval(-1, 1)
+    edge = parts[3].uniform_grid(7)  # y = 1 edge: one point along the collapsed axis
+    assert edge.shape == (7, 1, 2) and np.all(np.asarray(edge)[..., 1] == 1.0)
+    with pytest.raises(ValueError):
+        domains.Box(np.array([[1.0, 0.0]]))
+    with pytest.raises(TypeError):
+        domains.Box(np.array([[0, 1]]))
+    cp = domains.CartesianProduct(domains.Interval(0.0, 5.0), iv)
+    assert cp.shape == (2,) and cp.volume == 10.0 and cp.uniform_grid((4, 3)).shape == (4, 3, 2) and len(cp.boundary) == 4
+    assert lg.domains.Point(np.array([1.0, 2.0])).shape == (2,)
+
+
+def test_pde_problem_definitions():
+    """``linpde_gp.problems.pde`` (src/linpde_gp/problems/pde/*.py): Poisson / heat Dirichlet problems, their operators,
+    boundary conditions and analytic solutions."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200 import domains
+    from linpde_gp_b200.linfuncops import diffops
+    from linpde_gp_b200.problems import pde
+
+    iv = domains.asdomain([-1.0, 1.0])
+    bvp = pde.PoissonEquationDirichletProblem(iv, rhs=lg.functions.Constant((), 2.0), boundary_values=(0.0, 1.0), alpha=1.0)
+    assert isinstance(bvp.pde.diffop, diffops.ScaledLinearDifferentialOperator) and bvp.domain == iv
+    assert bvp.pde.diffop._terms() == {(2,): -1.0}
+    X_bc, Y_bc = pde.get_1d_dirichlet_boundary_observations(bvp.boundary_conditions)
+    np.testing.assert_array_equal(X_bc, [-1.0, 1.0])
+    np.testing.assert_array_equal(Y_bc, [0.0, 1.0])
+    xs = np.linspace(-1, 1, 11)
+    u = bvp.solution(xs)
+    h = 1e-4  # -u'' = 2 by central differences, boundary values reproduced
+    np.testing.assert_allclose(-(bvp.solution(xs[1:-1] + h) - 2 * u[1:-1] + bvp.solution(xs[1:-1] - h)) / h**2, 2.0, rtol=1e-6)
+    assert u[0] == 0.0 and abs(u[-1] - 1.0) < 1e-15
+    sq = domains.asdomain([np.zeros(2), np.ones(2)])
+    bvp2 = pde.PoissonEquationDirichletProblem(sq, rhs=lg.functions.Constant((2,), 2.0))
+    assert len(bvp2.boundary_conditions) == 4 and bvp2.solution is None
+    assert all(isinstance(bc.values, lg.functions.Zero) and bc.operator.input_domain_shape == (2,) for bc in bvp2.boundary_conditions)
+    with pytest.raises(ValueError):
+        pde.LinearPDE(iv, diffops.Laplacian((2,)))
+
+    ibvp = pde.HeatEquationDirichletProblem(t0=0.0, T=5.0, spatial_domain=iv, alpha=0.1,
+                                            initial_values=lg.functions.TruncatedSineSeries(iv, coefficients=[1.0, 2.0]))
+    assert isinstance(ibvp.pde.diffop, diffops.HeatOperator) and ibvp.pde.diffop.alpha == 0.1
+    assert ibvp.t0 == 0.0 and ibvp.T == 5.0 and ibvp.spatial_domain == iv and ibvp.temporal_domain == domains.Interval(0, 5)
+    X_ic = ibvp.initial_domain.uniform_grid(5, inset=1e-6)
+    assert X_ic.shape == (1, 5, 2) and np.all(np.asarray(X_ic)[..., 0] == 0.0)
+    Y_ic = ibvp.initial_condition.values(np.asarray(X_ic)[..., 1])
+    np.testing.assert_allclose(ibvp.solution(np.asarray(X_ic)), Y_ic, rtol=1e-13, atol=1e-15)  # u(t0, x) = initial values
+    for bc in ibvp.boundary_conditions:
+        Xb = bc.boundary.uniform_grid(50)
+        assert Xb.shape == (50, 1, 2) and np.all(bc.values(np.asarray(Xb)) == 0.0)
+        assert np.max(np.abs(ibvp.solution(np.asarray(Xb)))) < 1e-14  # zero Dirichlet values
+    # the analytic solution solves the PDE: u_t - alpha u_xx = 0 by finite differences at interior points
+    tx = np.asarray(ibvp.domain.uniform_grid((6, 7), inset=(0.5, 0.3)))
+    e_t, e_x, h = np.array([1.0, 0.0]), np.array([0.0, 1.0]), 1e-4
+    u_t = (ibvp.solution(tx + h * e_t) - ibvp.solution(tx - h * e_t)) / (2 * h)
+    u_xx = (ibvp.solution(tx + h * e_x) - 2 * ibvp.solution(tx) + ibvp.solution(tx - h * e_x)) / h**2
+    assert np.max(np.abs(u_t - 0.1 * u_xx)) < 1e-5
+    assert isinstance(pde.HeatEquationDirichletProblem(0.0, iv, T=1.0).solution, lg.functions.Zero)

@@ -652,3 +652,82 @@ def test_polynomial_prior_mean_is_pushed_through_operators_in_closed_form():
     # the push-forward L(posterior) carries the mean too
     res = L(post).mean(X_pde)
     assert np.max(np.abs(res - Y_pde)) <= 1e-7 * np.max(np.abs(Y_pde))
+
+
+def test_reference_heat_test_verbatim_through_problem_classes():
+    """tests/linpde_gp/problems/test_heat.py:9-99 of the reference with only the package name changed: problem
+    definition through ``problems.pde.HeatEquationDirichletProblem``, grids through ``domains`` (TensorProductGrids, so
+    the PDE batch takes the Kronecker assembly path), same assertions and tolerances."""
+    import linpde_gp_b200 as linpde_gp
+
+    spatial_domain = linpde_gp.domains.asdomain([-1.0, 1.0])
+    ibvp = linpde_gp.problems.pde.HeatEquationDirichletProblem(
+        t0=0.0, T=5.0, spatial_domain=spatial_domain, alpha=0.1,
+        initial_values=linpde_gp.functions.TruncatedSineSeries(spatial_domain, coefficients=[1.0, 2.0]))
+
+    def assert_observations_match(obs, gp, tol=3e-2):
+        X_obs, Y_obs = obs
+        assert np.allclose(gp.mean(X_obs), Y_obs, rtol=0.0, atol=tol)
+
+    def assert_within_uncertainty_region(obs, gp):
+        X_obs, Y_obs = obs
+        vals_gp, std_gp = gp.mean(X_obs), np.nan_to_num(gp.std(X_obs))
+        assert np.min(vals_gp + 2 * std_gp - Y_obs) > -3e-2
+        assert np.min(Y_obs - (vals_gp - 2 * std_gp)) > -3e-2
+
+    def get_noise(X):
+        num_entries = int(np.prod(X.shape[:-1]))
+        return linpde_gp.randvars.Normal(np.zeros(X.shape[:-1]), np.diag(1e-5 * np.ones(num_entries)))
+
+    u_prior = linpde_gp.GaussianProcess(
+        mean=linpde_gp.functions.Zero(input_shape=(2,)),
+        cov=1.0**2 * linpde_gp.randprocs.covfuncs.TensorProduct(
+            linpde_gp.randprocs.covfuncs.Matern((), nu=1.5, lengthscales=2.5),
+            linpde_gp.randprocs.covfuncs.Matern((), nu=2.5, lengthscales=2.0)))
+
+    X_ic = ibvp.initial_domain.uniform_grid(5, inset=1e-6)
+    Y_ic = ibvp.initial_condition.values(X_ic[..., 1])
+    u_ic = u_prior.condition_on_observations(Y_ic, X_ic)
+    assert_observations_match((X_ic, Y_ic), u_ic)
+    u_ic_bc = u_ic
+    for bc in ibvp.boundary_conditions:
+        X_bc = bc.boundary.uniform_grid(50)
+        Y_bc = bc.values(X_bc)
+        u_ic_bc = u_ic_bc.condition_on_observations(Y_bc, X=X_bc, b=get_noise(X_bc))
+        assert_observations_match((X_bc, Y_bc), u_ic_bc)
+    X_pde = ibvp.domain.uniform_grid((100, 20))
+    Y_pde = ibvp.pde.rhs(X_pde)
+    u_ic_bc_pde = u_ic_bc.condition_on_observations(Y_pde, X=X_pde, L=ibvp.pde.diffop)
+    X_test = ibvp.domain.uniform_grid((50, 50))
+    Y_test = ibvp.solution(X_test)
+    assert_within_uncertainty_region((X_test, Y_test), u_ic_bc_pde)
+
+
+@pytest.mark.parametrize("prior_kind", ["expquad", "matern"])
+def test_experiment_0000_poisson_dirichlet_1d_flow(prior_kind):
+    """BASELINE.json configs[0] (experiments/0000_poisson_dirichlet_1d.ipynb): 1-D Poisson problem on [-1, 1] with constant
+    right-hand side through ``problems.pde.PoissonEquationDirichletProblem``, boundary observations from
+    ``get_1d_dirichlet_boundary_observations``, 100 collocation points; the posterior mean must agree with the analytic
+    solution within 2 std (+1e-6) and to 1e-3 absolutely, and the PDE residual posterior must vanish at the collocation points."""
+    import linpde_gp_b200 as linpde_gp
+    from linpde_gp_b200.randprocs import covfuncs
+
+    domain = linpde_gp.domains.asdomain([-1.0, 1.0])
+    bvp = linpde_gp.problems.pde.PoissonEquationDirichletProblem(
+        domain, rhs=linpde_gp.functions.Constant(input_shape=(), value=2.0), boundary_values=(0.0, 0.0))
+    cov = 2.0**2 * (covfuncs.ExpQuad((), lengthscales=1.0) if prior_kind == "expquad"
+                    else covfuncs.Matern((), nu=2.5, lengthscales=1.0))
+    u_prior = linpde_gp.GaussianProcess(linpde_gp.functions.Zero(input_shape=()), cov)
+    X_bc, Y_bc = linpde_gp.problems.pde.get_1d_dirichlet_boundary_observations(bvp.boundary_conditions)
+    u_bc = u_prior.condition_on_observations(Y_bc, X=X_bc)
+    n_pde = 100 if prior_kind == "matern" else 12  # (the ExpQuad Gram matrix of 100 points is numerically singular)
+    X_pde = domain.uniform_grid(n_pde, inset=0.2)
+    u_post = u_bc.condition_on_observations(bvp.pde.rhs(X_pde), X=X_pde, L=bvp.pde.diffop)
+    xs = domain.uniform_grid(100)
+    mean, std = u_post.mean(xs), np.nan_to_num(u_post.std(xs))
+    truth = bvp.solution(xs)
+    assert np.max(np.abs(mean - truth)) <= 1e-3
+    assert np.all(np.abs(mean - truth) <= 2 * std + 1e-6)
+    residual = bvp.pde.diffop(u_post)
+    assert np.max(np.abs(residual.mean(X_pde) - 2.0)) <= 1e-6
+    assert np.max(np.abs(u_post.mean(X_bc))) <= 1e-8
