@@ -733,3 +733,44 @@ def test_experiment_0000_poisson_dirichlet_1d_flow(prior_kind):
     residual = bvp.pde.diffop(u_post)
     assert np.max(np.abs(residual.mean(X_pde) - 2.0)) <= 1e-6
     assert np.max(np.abs(u_post.mean(X_bc))) <= 1e-8
+
+
+def test_experiment_0001_poisson_dirichlet_2d_flow():
+    """The paper's 2-D Poisson example (experiments/0001_poisson_dirichlet_2d.ipynb; BASELINE.json configs[1] at notebook
+    size): -Laplace u = 2 on [-1, 1]^2 with zero Dirichlet values, product Matern-5/2 prior, 4 x 20 boundary points and a
+    20 x 20 collocation grid from ``domains`` (TensorProductGrids -> Kronecker assembly).  Checked against the classical
+    series solution of the torsion problem, u = 1 - x^2 - 32/pi^3 sum_n (-1)^n/(2n+1)^3 cosh(k_n y)/cosh(k_n) cos(k_n x),
+    k_n = (2n+1) pi/2: inside mean +- 2 std (+1e-3) on a 40 x 40 grid, and the posterior PDE residual reproduces the
+    right-hand side at the collocation points."""
+    import linpde_gp_b200 as linpde_gp
+    from linpde_gp_b200.randprocs import covfuncs
+
+    def torsion(tx, terms=60):
+        x, y = tx[..., 0], tx[..., 1]
+        n = np.arange(terms)
+        kn = (2 * n + 1) * np.pi / 2
+        s = np.sum(((-1.0) ** n / (2 * n + 1) ** 3) * np.cosh(kn * y[..., None]) / np.cosh(kn) * np.cos(kn * x[..., None]), axis=-1)
+        return 1 - x**2 - 32 / np.pi**3 * s
+
+    domain = linpde_gp.domains.asdomain([np.array([-1.0, -1.0]), np.array([1.0, 1.0])])
+    bvp = linpde_gp.problems.pde.PoissonEquationDirichletProblem(domain, rhs=linpde_gp.functions.Constant((2,), 2.0))
+    u = linpde_gp.GaussianProcess(
+        linpde_gp.functions.Zero(input_shape=(2,)),
+        2.0**2 * covfuncs.TensorProduct(covfuncs.Matern((), nu=2.5, lengthscales=1.0),
+                                        covfuncs.Matern((), nu=2.5, lengthscales=1.0)))
+    for bc in bvp.boundary_conditions:
+        X_bc = bc.boundary.uniform_grid(20, inset=0.02)  # (without the inset the four corners are observed twice: singular)
+        u = u.condition_on_observations(bc.values(X_bc), X=X_bc)
+    X_pde = domain.uniform_grid((20, 20), inset=0.05)
+    u = u.condition_on_observations(bvp.pde.rhs(X_pde), X=X_pde, L=bvp.pde.diffop)
+    X_test = domain.uniform_grid((40, 40))
+    truth = torsion(np.asarray(X_test))
+    mean, std = u.mean(X_test), np.nan_to_num(u.std(X_test))
+    assert mean.shape == (40, 40)
+    # numpy evaluation of the same posterior (cond(G) = 1.1e9): max error 0.144 (at the unobserved corners), always
+    # 2.4e-3 inside the 2-std band
+    assert np.max(np.abs(mean - truth)) <= 0.2
+    assert np.all(np.abs(mean - truth) <= 2 * std + 1e-3)
+    res = bvp.pde.diffop(u).mean(X_pde)
+    assert np.max(np.abs(res - 2.0)) <= 1e-5
+    assert np.max(np.abs(mean - mean.T)) <= 1e-5 and np.max(np.abs(mean - mean[::-1, :])) <= 1e-5  # symmetries of the problem
