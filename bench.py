@@ -7,11 +7,15 @@ One *step* = one full pass of the hot path over one synthetic problem (BASELINE.
   assemble all Gram blocks -> bordered FP64 Cholesky -> representer weights -> posterior mean AND pointwise
   variance on the 512 x 512 test grid.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--npde ..] [--nbc-edge ..] [--grid ..]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--budget-s S] [--impl b200|reference] [--npde ..] [--nbc-edge ..]
 
-`value`      device-timed seconds per solve with all inputs already resident in HBM (CUDA events, max over ranks);
-`e2e`        the same solve through the public Python API with HOST numpy buffers (pinned H2D of the points /
-             right-hand sides and D2H of mean + variance inside the timed region);
+ONE timed loop: every step goes through the public Python API with HOST numpy buffers (pinned H2D of the points /
+right-hand sides and D2H of mean + variance inside the timed region).  --steps / --warmup are CAPS under the wall
+budget --budget-s (default 540 s, env LPGP_BENCH_BUDGET_S): at least 1 warm-up and min(3, K) timed steps always run,
+the executed counts are reported as `steps` / `warmup` next to `steps_requested` / `warmup_requested`.
+`e2e`        wall clock per step of that loop (max over ranks);
+`value`      CUDA-event time of the device phases of the SAME steps (assembly, factorisation, solves, mean, variance;
+             host<->device copies and host gaps excluded, i.e. inputs resident in HBM), max over ranks;
 `roofline`   the DMMA GEMM kernel (Cholesky trailing updates + posterior-variance triangular solve) against the
              FP64 tensor-pipe issue rate measured live on the box (lpgp_dmma_peak_probe);
 `cpu_baseline` the oracle (numpy/scipy restatement of the reference) timed on the box's host cores on a bounded
@@ -38,6 +42,13 @@ sys.path.insert(0, ROOT)
 
 SIGMA2 = 4.0
 NU = 2.5
+T_START = time.perf_counter()
+# DRAM traffic of the dominant kernel: taken from a committed ncu capture, never measured inside a bench run
+GEMM_TRAFFIC = {
+    "bytes": 2.786e9,
+    "source": "profiles/ncu_kernels_r01d.md (ncu --set full, one launch; not measured in this run)",
+    "launch": "gemm_nt_kernel 8192x8192x2048 beta=1: 2.26 GB read + 0.53 GB written (algorithmic 1.34 GB)",
+}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -205,141 +216,13 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# B200 arm
+# B200 arm: ONE timed loop, every step through the public API with host buffers
 # ----------------------------------------------------------------------------------------------------------------
-class DeviceSolve:
-    """The hot path driven at the device-buffer level (inputs resident in HBM): this is what `value` times."""
-
-    def __init__(self, prob, rank: int, world: int):
-        import torch
-
-        import linpde_gp_b200 as lg
-        from linpde_gp_b200 import backend
-        from linpde_gp_b200._lowering import Factor1D, lower
-
-        self.torch, self.be = torch, backend
-        fac = [Factor1D("matern", prob["ell"], nu=NU), Factor1D("matern", prob["ell"], nu=NU)]
-        lap = {(2, 0): -1.0, (0, 2): -1.0}
-        self.d_k = lower(fac, None, None, SIGMA2)
-        self.d_kL = lower(fac, None, lap, SIGMA2)   # test/boundary side x PDE side
-        self.d_Lk = lower(fac, lap, None, SIGMA2)   # PDE rows x boundary columns
-        self.d_LkL = lower(fac, lap, lap, SIGMA2)
-        self.edges = [backend.to_device(e) for e in prob["edges"]]
-        self.Xp = backend.to_device(prob["X_pde"])
-        self.y = torch.cat([backend.to_device(y) for y in prob["Y_bc"]] + [backend.to_device(prob["Y_pde"])])
-        Xt = prob["Xt"]
-        from linpde_gp_b200 import parallel
-
-        lo, hi = parallel.shard_bounds(len(Xt), rank, world)
-        self.Xt = backend.to_device(Xt[lo:hi])
-        self.N, self.M = prob["N"], prob["M"]
-        self.t = {}
-        self.distributed = world > 1
-
-    def _timed(self, name, fn):
-        torch = self.torch
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = fn()
-        e1.record()
-        self.t.setdefault(name, []).append((e0, e1))
-        return out
-
-    def step(self):
-        be = self.be
-        sizes = [e.shape[0] for e in self.edges] + [self.Xp.shape[0]]
-        blocksX = self.edges + [self.Xp]
-        factor = None
-        off = 0
-        for i, (X, n) in enumerate(zip(blocksX, sizes)):
-            is_pde = i == len(sizes) - 1
-            factor = be.DeviceFactor([n]) if factor is None else factor.extended(n)
-
-            def assemble():
-                rows = factor.L[off : off + n]
-                c = 0
-                for Xj, nj in zip(blocksX[:i], sizes[:i]):
-                    be.gram(self.d_Lk if is_pde else self.d_k, X, Xj, out=rows[:, c : c + nj])
-                    c += nj
-                be.gram(self.d_LkL if is_pde else self.d_k, X, None, out=rows[:, off : off + n], lower=True)
-
-            self._timed("assemble", assemble)
-            self._timed("factor", factor.potrf if i == 0 else factor.append_last)
-            off += n
-        w = self._timed("solve", lambda: factor.potrs(self.y.clone().reshape(1, -1)).reshape(-1))
-        descs = [self.d_k] * len(self.edges) + [self.d_kL]
-        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]])
-        blocks = be.ObsBlocks(descs, blocksX, offs)
-        mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
-        chunk = be.var_chunk_rows(factor.n, self.Xt.shape[0])
-        var = self._timed("var", lambda: be.post_var(blocks, factor, self.Xt, self.d_k.diag_value, chunk=chunk))
-        return mean, var
-
-    # -- multi-GPU step: block-row cyclic assembly + distributed Cholesky, replicated factor, sharded test grid --
-    def _desc_for(self, bi: int, bj: int):
-        last = len(self.edges)
-        if bi == last:
-            return self.d_LkL if bj == last else self.d_Lk
-        return self.d_k
-
-    def _assemble_block_rows(self, out, g0: int, g1: int, blocksX, offs, sizes):
-        """rows g0..g1 of the lower triangle of the block-structured Gram matrix -> out[:, :g1]"""
-        be = self.be
-        for bi, (Xi, oi, ni) in enumerate(zip(blocksX, offs, sizes)):
-            r_lo, r_hi = max(g0, oi), min(g1, oi + ni)
-            if r_lo >= r_hi:
-                continue
-            rows = out[r_lo - g0 : r_hi - g0]
-            Xr = Xi[r_lo - oi : r_hi - oi]
-            for bj in range(bi + 1):
-                oj, nj = offs[bj], sizes[bj]
-                c_hi = nj if bj < bi else r_hi - oi
-                be.gram(self._desc_for(bi, bj), Xr, blocksX[bj][:c_hi], out=rows[:, oj : oj + c_hi])
-
-    def step_distributed(self, nb: int, replicate: bool = True):
-        from linpde_gp_b200 import distributed
-
-        be, torch = self.be, self.torch
-        sizes = [e.shape[0] for e in self.edges] + [self.Xp.shape[0]]
-        blocksX = self.edges + [self.Xp]
-        offs = [int(o) for o in np.concatenate([[0], np.cumsum(sizes)[:-1]])]
-        n = int(sum(sizes))
-        ch = distributed.DistributedCholesky(n, nb=nb)
-
-        def assemble():
-            for i in ch.layout.local_blocks(ch.rank):
-                g0, g1 = ch.layout.block_bounds(i)
-                self._assemble_block_rows(ch.local_block_rows(i), g0, g1, blocksX, offs, sizes)
-
-        self._timed("assemble", assemble)
-        descs = [self.d_k] * len(self.edges) + [self.d_kL]
-        blocks = be.ObsBlocks(descs, blocksX, offs)
-        if replicate:
-            factor = be.DeviceFactor([n])
-            self._timed("factor", lambda: ch.factor(factor.L))  # every rank ends up with the whole factor
-            factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
-            del ch
-            w = self._timed("solve", lambda: factor.potrs(self.y.clone().reshape(1, -1)).reshape(-1))
-            mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
-            chunk = be.var_chunk_rows(factor.n, self.Xt.shape[0])
-            var = self._timed("var", lambda: be.post_var(blocks, factor, self.Xt, self.d_k.diag_value, chunk=chunk))
-        else:  # the factor stays distributed: owner-computes solve, block rows of L streamed for the variance
-            self._timed("factor", ch.factor)
-            fac = distributed.DistributedFactor(ch)
-            w = self._timed("solve", lambda: ch.solve(self.y))
-            mean = self._timed("mean", lambda: be.post_mean(blocks, w, self.Xt))
-            var = self._timed("var", lambda: fac.post_var(blocks, self.Xt, self.d_k.diag_value))
-        return mean, var
-
-    def phase_ms(self, last_k: int):
-        self.torch.cuda.synchronize()
-        per = lambda k: 5 if (k in ("assemble", "factor") and not self.distributed) else 1
-        return {k: sum(e0.elapsed_time(e1) for e0, e1 in v[-last_k * per(k):]) / last_k for k, v in self.t.items()}
-
-
 def api_solve(prob, rank: int, world: int, nb: int = 1024, replicate: bool = True):
-    """The same solve through the public reference-style API with host (numpy) buffers -> `e2e`."""
+    """One step = the whole solve through the public reference-style API with host (numpy) buffers: conditioning on the
+    4 boundary batches and the PDE batch, then mean and pointwise variance of this rank's shard of the test grid."""
     import linpde_gp_b200 as lg
+    from linpde_gp_b200 import parallel
     from linpde_gp_b200.linfuncops import diffops
     from linpde_gp_b200.randprocs import covfuncs
 
@@ -354,8 +237,6 @@ def api_solve(prob, rank: int, world: int, nb: int = 1024, replicate: bool = Tru
         for Xb, Yb in zip(prob["edges"], prob["Y_bc"]):
             post = post.condition_on_observations(Yb, X=Xb)
         post = post.condition_on_observations(prob["Y_pde"], X=prob["X_pde"], L=lap)
-    from linpde_gp_b200 import parallel
-
     lo, hi = parallel.shard_bounds(prob["M"], rank, world)
     Xt = prob["Xt"][lo:hi]
     return post.mean(Xt), post.var(Xt)
@@ -382,6 +263,48 @@ def dmma_peak_tflops(torch, backend):
     return best
 
 
+def gram_kernel_alone(torch, backend, prob):
+    """The assembly kernel on its own (one L k L* block of 16,384 x N_pde entries written to HBM), best of 4."""
+    from linpde_gp_b200._lowering import Factor1D, lower
+
+    fac = [Factor1D("matern", prob["ell"], nu=NU), Factor1D("matern", prob["ell"], nu=NU)]
+    lap = {(2, 0): -1.0, (0, 2): -1.0}
+    d_LkL = lower(fac, lap, lap, SIGMA2)
+    Xp = backend.to_device(prob["X_pde"])
+    nrow = min(16384, Xp.shape[0])
+    blk = backend.alloc_matrix(nrow, Xp.shape[0])
+    best = 1e30
+    for _ in range(4):
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        backend.gram(d_LkL, Xp[:nrow], Xp, out=blk)
+        g1.record()
+        torch.cuda.synchronize()
+        best = min(best, g0.elapsed_time(g1))
+    ent = nrow * Xp.shape[0] / (best * 1e-3)
+    out = {"entries_per_s": ent, "hbm_write_gbps": ent * 8e-9, "block": [int(nrow), int(Xp.shape[0])],
+           "kernel": "gram_sep_kernel<2,3,false> (L k L*, product Matern-5/2)"}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm = json.load(open(peaks_path)).get("hbm_gbs") if os.path.exists(peaks_path) else None
+    out["hbm_peak_gbps"] = hbm if hbm else 6650.0
+    out["hbm_peak_source"] = "MEASURED_PEAKS.json" if hbm else "fallback (B200_PROFILING.md: 6.65 TB/s)"
+    out["frac_of_hbm_peak"] = out["hbm_write_gbps"] / out["hbm_peak_gbps"]
+    return out
+
+
+def plan_steps(steps_req: int, warmup_req: int, t_step: float, remaining: float):
+    """(extra warm-up steps after the first, timed steps) that fit `remaining` seconds at `t_step` seconds per step:
+    --steps / --warmup are caps; at least 1 warm-up (already done) and min(3, --steps) timed steps always run, and up
+    to 3 warm-ups in total are kept as long as 3 timed steps still fit."""
+    fit = int(max(0.0, remaining) / max(t_step, 1e-6))
+    k_min = max(1, min(3, steps_req))
+    w_extra = max(0, min(warmup_req - 1, fit - k_min))
+    if fit - w_extra < steps_req:  # budget-bound: keep at most 3 warm-ups in total
+        w_extra = max(0, min(w_extra, 2, fit - k_min))
+    k = max(k_min, min(steps_req, fit - w_extra))
+    return w_extra, k
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -395,114 +318,93 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")  # panel broadcasts / all-gathers are the critical path
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from linpde_gp_b200 import backend
+    from linpde_gp_b200 import backend, parallel
     from linpde_gp_b200._lib import lib
 
     prob = make_problem(args.npde, args.nbc_edge, args.grid)
     N, M = prob["N"], prob["M"]
     if args.nb <= 0:
         args.nb = 1024 if world <= 2 else 512
+    # the replicated n x n factor, this rank's block rows and the variance workspace must fit next to each other
+    if args.replicate == "auto":
+        replicate = (N * N * 8) * (1.0 + 1.0 / world) + (8 << 30) < 0.5 * torch.cuda.get_device_properties(local).total_memory
+    else:
+        replicate = args.replicate == "yes"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    from linpde_gp_b200 import parallel
+    def max_over_ranks(*vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
 
-    def gather(mean, var):
-        """the path's only exchange step: all-gather the sharded result rows (NCCL)"""
+    def step():
+        """the whole solve through the public API + the path's only exchange step (all-gather of the result rows)"""
+        mean, var = api_solve(prob, rank, world, args.nb, replicate)
         if world == 1:
             return mean, var
-        if not hasattr(mean, "cpu"):
-            mean, var = backend.to_device(mean), backend.to_device(var)
-        return parallel.gather_concat(mean, M), parallel.gather_concat(var, M)
+        return (parallel.gather_concat(backend.to_device(mean), M).cpu().numpy(),
+                parallel.gather_concat(backend.to_device(var), M).cpu().numpy())
 
+    # ---- before the GPU loop: bounded CPU baseline (N = 1 only), roofline denominators ----
+    cpu_est, cpu_detail = (cpu_sample(prob, budget_s=args.cpu_budget_s) if (world == 1 and rank == 0) else (None, {}))
     peak = dmma_peak_tflops(torch, backend) if rank == 0 else None
-    ds = DeviceSolve(prob, rank, world)
-    # the replicated n x n factor, this rank's block rows and the variance workspace must fit next to each other
-    if args.replicate == "auto":
-        replicate = (N * N * 8) * (1.0 + 1.0 / world) + (8 << 30) < 0.5 * torch.cuda.get_device_properties(local).total_memory
-    else:
-        replicate = args.replicate == "yes"
-    step = ds.step if world == 1 else (lambda: ds.step_distributed(args.nb, replicate))
-    for _ in range(args.warmup):
-        m, v = step()
-        gather(m, v)
+    gram_kernel = gram_kernel_alone(torch, backend, prob) if rank == 0 else None
+
+    # ---- first warm-up step doubles as the estimate of the step time the plan is made from ----
+    barrier()
+    t0 = time.perf_counter()
+    step()
+    barrier()
+    t_first, elapsed = max_over_ranks(time.perf_counter() - t0, time.perf_counter() - T_START)
+    w_extra, k_steps = plan_steps(args.steps, args.warmup, t_first, args.budget_s - elapsed - 15.0)
+    for _ in range(w_extra):
+        step()
+
+    # ---- the timed loop: wall clock around it -> e2e, CUDA-event phase timers inside it -> device-only value ----
     barrier()
     lib.lpgp_launch_count(1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        m, v = step()
-        gm, gv = gather(m, v)
-    e1.record()
-    barrier()
-    launches = lib.lpgp_launch_count(0)
-    ms_dev = e0.elapsed_time(e1) / args.steps
-    phases = ds.phase_ms(args.steps)
-    # the assembly kernel on its own (one L k L* block of 16,384 x N_pde entries, written to HBM), best of 3
-    gram_kernel = None
-    if rank == 0:
-        nrow = min(16384, ds.Xp.shape[0])
-        blk = backend.alloc_matrix(nrow, ds.Xp.shape[0])
-        best = 1e30
-        for _ in range(4):
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            backend.gram(ds.d_LkL, ds.Xp[:nrow], ds.Xp, out=blk)
-            g1.record()
-            torch.cuda.synchronize()
-            best = min(best, g0.elapsed_time(g1))
-        ent = nrow * ds.Xp.shape[0] / (best * 1e-3)
-        gram_kernel = {"entries_per_s": ent, "hbm_write_gbps": ent * 8e-9, "block": [int(nrow), int(ds.Xp.shape[0])],
-                       "kernel": "gram_sep_kernel<2,3,false> (L k L*, product Matern-5/2)"}
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        hbm = json.load(open(peaks_path)).get("hbm_gbs") if os.path.exists(peaks_path) else None
-        gram_kernel["hbm_peak_gbps"] = hbm if hbm else 6650.0
-        gram_kernel["hbm_peak_source"] = "MEASURED_PEAKS.json" if hbm else "fallback (B200_PROFILING.md: 6.65 TB/s)"
-        gram_kernel["frac_of_hbm_peak"] = gram_kernel["hbm_write_gbps"] / gram_kernel["hbm_peak_gbps"]
-        del blk
-    del ds
-    torch.cuda.empty_cache()
-
-    # ---- e2e through the public API, host buffers (pinned H2D + D2H inside the timed region) ----
-    barrier()
+    timer = backend.PhaseTimer()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        em, ev = api_solve(prob, rank, world, args.nb, replicate)
-        gem, gev = gather(em, ev)
-    torch.cuda.synchronize()
-    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    with timer:
+        for _ in range(k_steps):
+            gm, gv = step()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = lib.lpgp_launch_count(0)
     clocks = sampler.stop() if rank == 0 else None
-    times = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = (float(x) for x in times.cpu())
+    phases = {k: v / k_steps for k, v in timer.totals_ms().items()}
+    ms_dev, ms_e2e = max_over_ranks(sum(phases.values()), wall * 1e3 / k_steps)
+    names = ("extend", "assemble", "factor", "solve", "mean", "var")
+    ph = max_over_ranks(*[phases.get(k, 0.0) for k in names])
+    phases = dict(zip(names, ph))
 
     if rank == 0:
-        tonp = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
-        gm, gv, gem, gev = tonp(gm), tonp(gv), tonp(gem), tonp(gev)
-        agree = float(max(np.max(np.abs(gm - gem)), np.max(np.abs(gv - gev))))
         m_shard = parallel.shard_bounds(M, 0, world)[1]
         flops_tensor = N**3 / 3.0 / world + float(m_shard) * N * N  # per rank: Cholesky share + variance TRSM
         t_tensor = (phases["factor"] + phases["var"]) * 1e-3
         achieved = flops_tensor / t_tensor * 1e-12
         h2d = sum(e.nbytes for e in prob["edges"]) + sum(y.nbytes for y in prob["Y_bc"]) + prob["X_pde"].nbytes \
             + prob["Y_pde"].nbytes + prob["Xt"].nbytes * 2 // world
-        # the CPU baseline is reported by the single-GPU run only (rank 0 at N = 1)
-        cpu_est, cpu_detail = cpu_sample(prob, budget_s=20.0) if world == 1 else (None, {})
         threads, cores = host_threads()
+        prior_var = SIGMA2
         out = {
             "metric": "s per GP-PDE solve (2D Poisson N=64k)",
             "value": ms_dev * 1e-3,
             "unit": "s",
             "n_gpus": world,
-            "steps": args.steps,
-            "warmup": args.warmup,
+            "steps": k_steps,
+            "warmup": 1 + w_extra,
+            "steps_requested": args.steps,
+            "warmup_requested": args.warmup,
+            "budget_s": args.budget_s,
             "ms_per_step": ms_dev,
             "higher_is_better": False,
             "scaling": "strong",
@@ -517,6 +419,9 @@ def run_b200(args):
                                 f"exchange), factor {'replicated' if replicate else 'left distributed (block rows streamed for the variance)'}, "
                                 "test grid sharded") if world > 1 else "single GPU",
                 "l2": f"working set {N * N * 8 / 1e9:.1f} GB Gram >> 126 MB L2 (no flush needed)",
+                "timing": "ONE loop: every step goes through the public API with host numpy buffers; `e2e` = wall clock per "
+                          "step of that loop (H2D + D2H inside), `value` = CUDA-event time of the device phases of the same "
+                          "steps (copies and host gaps excluded); --steps/--warmup are caps under --budget-s",
             },
             "phases_ms": phases,
             "gram_entries_per_s": (N * (N + 1) / 2 + 0.0) / (phases["assemble"] * 1e-3),  # whole assembly phase
@@ -524,17 +429,19 @@ def run_b200(args):
             "cholesky_tflops": N**3 / 3.0 / (phases["factor"] * 1e-3) * 1e-12,  # aggregate over all ranks
             "variance_trsm_tflops": float(m_shard) * N * N / (phases["var"] * 1e-3) * 1e-12,
             "e2e": {"value": ms_e2e * 1e-3, "unit": "s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(2 * 8 * M // world), "api_vs_device_max_abs_diff": agree},
+                    "d2h_bytes_per_step": int(2 * 8 * M // world)},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "checks": {"mean_finite": bool(np.all(np.isfinite(gm))), "var_min": float(np.min(gv)), "var_max": float(np.max(gv)),
+                       "var_within_prior": bool(np.min(gv) >= -1e-8 * prior_var and np.max(gv) <= prior_var * (1 + 1e-12))},
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # dram__bytes_read+write of ONE representative launch (8192 x 8192 x 2048, beta = 1) from the committed
-                # ncu --set full capture (profiles/ncu_kernels_r01d.md, banded tile rasterisation; 5.53e9 before it);
-                # its algorithmic bytes are 1.34e9 (A + B once, C read + written) -- the excess is B re-streamed
-                # once per band of tile rows, at 0.35 TB/s far from the HBM bound of this tensor-bound kernel
-                "traffic": 2.786e9,
-                "traffic_launch": "gemm_nt_kernel 8192x8192x2048 beta=1: 2.26 GB read + 0.53 GB written (algorithmic 1.34 GB)",
+                # NOT measured in this run: dram__bytes_read+write of ONE representative launch (8192 x 8192 x 2048,
+                # beta = 1) from the committed ncu --set full capture named in `traffic_source`; its algorithmic
+                # bytes are 1.34e9 (A + B once, C read + written)
+                "traffic": GEMM_TRAFFIC["bytes"],
+                "traffic_source": GEMM_TRAFFIC["source"],
+                "traffic_launch": GEMM_TRAFFIC["launch"],
                 "kernel": "gemm_nt_kernel (DMMA m8n8k4.f64) inside lpgp_potrf/lpgp_chol_append + lpgp_post_var",
                 "peak_source": "FP64 tensor-pipe issue rate measured live (lpgp_dmma_peak_probe); MEASURED_PEAKS.json "
                                "holds no FP64 figure",
@@ -558,16 +465,19 @@ def run_reference(args):
     vals, detail = [], None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, detail = cpu_sample(prob, budget_s=20.0)
+        v, detail = cpu_sample(prob, budget_s=args.cpu_budget_s)
         vals.append(v)
+        if time.perf_counter() - T_START > args.budget_s - 1.5 * args.cpu_budget_s and len(vals) >= min(3, args.steps):
+            break  # --steps is a cap under --budget-s, like the B200 arm
     wall = time.perf_counter() - t0
     threads, cores = host_threads()
     val = float(np.mean(vals))
     out = {
         "impl": "reference",
         "metric": "s per GP-PDE solve (2D Poisson N=64k)",
-        "value": val, "unit": "s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(args.steps, 1), "higher_is_better": False,
+        "value": val, "unit": "s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(vals),
+        "warmup": min(args.warmup, 1), "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": wall * 1e3 / max(len(vals), 1), "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"2D Poisson Dirichlet synthetic N={prob['N']}, mean+variance on {args.grid}x{args.grid} grid "
                                "(BASELINE.json configs[3]); bounded sample extrapolated to the full solve"},
@@ -598,12 +508,16 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--npde", type=int, default=63488)
     ap.add_argument("--nbc-edge", type=int, default=512)
     ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--budget-s", type=float, default=float(os.environ.get("LPGP_BENCH_BUDGET_S", "540")),
+                    help="wall-clock budget of the whole run in seconds (env LPGP_BENCH_BUDGET_S); --steps / --warmup "
+                         "are caps: at least 1 warm-up and min(3, --steps) timed steps always run")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="seconds of host work per CPU-baseline sample")
     ap.add_argument("--replicate", default="auto", choices=["auto", "yes", "no"],
                     help="N > 1 GPU: replicate the factor on every rank (auto: if it fits) or keep it distributed")
     ap.add_argument("--nb", type=int, default=0,

@@ -6,6 +6,7 @@ device and raise otherwise.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from typing import Optional, Sequence
 
@@ -32,6 +33,58 @@ def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
 
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CUDA-event phase timers (the reference has no tracing; this is the build's).  The host code
+# of the path brackets its device phases with ``phase(name)``; nothing is recorded (and nothing costs anything)
+# unless a ``PhaseTimer`` is active.  Events are recorded on torch's current stream -- the stream every C-ABI call
+# of this module is enqueued on (the library's internal lookahead stream is forked from and joined back into it).
+class PhaseTimer:
+    """``with PhaseTimer() as t: ...; t.totals_ms()`` -> device milliseconds per phase name (one host
+    synchronisation, when the totals are read)."""
+
+    def __init__(self):
+        self._spans = {}
+        self._prev = None
+
+    def __enter__(self):
+        global _ACTIVE_TIMER  # pylint: disable=global-statement
+        self._prev, _ACTIVE_TIMER = _ACTIVE_TIMER, self
+        return self
+
+    def __exit__(self, *exc):
+        global _ACTIVE_TIMER  # pylint: disable=global-statement
+        _ACTIVE_TIMER = self._prev
+        return False
+
+    def add(self, name: str, e0, e1) -> None:
+        self._spans.setdefault(name, []).append((e0, e1))
+
+    def totals_ms(self) -> dict:
+        torch.cuda.synchronize()
+        return {k: float(sum(e0.elapsed_time(e1) for e0, e1 in v)) for k, v in self._spans.items()}
+
+    def reset(self) -> None:
+        self._spans = {}
+
+
+_ACTIVE_TIMER: Optional[PhaseTimer] = None
+
+
+@contextlib.contextmanager
+def phase(name: str):
+    t = _ACTIVE_TIMER
+    if t is None:
+        yield
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    try:
+        yield
+    finally:
+        e1.record()
+        t.add(name, e0, e1)
 
 
 def round_up(n: int, m: int) -> int:
@@ -197,16 +250,45 @@ def matern_integral2(desc: _lib.MaternIntegralDesc, dom0, dom1, out: torch.Tenso
 
 
 # ------------------------------------------------------------------------------------------------------------
+# growth policy of appendable factors: a fresh allocation leaves room for `fraction` * n (at least `min_rows`) more
+# rows, provided the padded square stays below `max_free_fraction` of the free device memory
+FACTOR_RESERVE = {"fraction": 0.125, "min_rows": 1024, "max_free_fraction": 0.35}
+_LOWER_COPY_ROWS = 2048
+
+
+class _FactorStorage:
+    """One device allocation shared by a chain of factors that extend each other: ``L`` (cap x cap, row-major,
+    padded leading dimension) and ``dinv`` (inverted leaf blocks + status area).  ``claimed`` is the number of rows
+    handed out so far: only the factor whose ``n == claimed`` (the tip of the chain) may grow in place.  Rows and
+    leaf blocks below a factor's own extent are never written again once factored, so every older factor (and the
+    posterior object holding it) stays valid -- the versioned extent of SURVEY.md Appendix B."""
+
+    def __init__(self, rows: int, leaves: int, reserve_rows: Optional[int]):
+        dev = _require_cuda()
+        if reserve_rows is None:
+            reserve_rows = max(int(FACTOR_RESERVE["min_rows"]), int(rows * FACTOR_RESERVE["fraction"]))
+            free, _ = torch.cuda.mem_get_info()
+            if 8.0 * float(round_up(rows + reserve_rows, 16)) ** 2 > FACTOR_RESERVE["max_free_fraction"] * free:
+                reserve_rows = 0
+        self.cap_rows = rows + max(0, int(reserve_rows))
+        # every later segment may end in one partial leaf
+        self.cap_leaves = leaves + (self.cap_rows - rows + _lib.LEAF - 1) // _lib.LEAF + (_lib.MAX_SEG if reserve_rows else 0)
+        self.L = alloc_matrix(self.cap_rows, self.cap_rows)
+        self.dinv = torch.empty(self.cap_leaves * _lib.LEAF * _lib.LEAF + 8, dtype=F64, device=dev)
+        self.claimed = rows
+
+
 class DeviceFactor:
     """Device-resident, appendable lower Cholesky factor (``lpgp_factor``).
 
-    ``seg_sizes`` are the (even) physical sizes of the observation batches.  The object owns ``L`` (n x n,
-    row-major, padded leading dimension) and ``dinv`` (inverted 128x128 diagonal blocks).  Appending never
+    ``seg_sizes`` are the (even) physical sizes of the observation batches.  ``L`` is the n x n view (row-major,
+    padded leading dimension) of the storage, ``dinv`` the inverted 128x128 diagonal blocks.  Appending never
     mutates an existing factor: :meth:`extended` returns a new object (the reference's conditioning API is
-    functional)."""
+    functional) that SHARES the storage when the reserved capacity suffices -- no allocation,
+    no copy -- and otherwise moves the lower triangle (only) into a larger allocation."""
 
-    def __init__(self, seg_sizes: Sequence[int]):
-        dev = _require_cuda()
+    def __init__(self, seg_sizes: Sequence[int], reserve_rows: Optional[int] = None, _storage: Optional[_FactorStorage] = None):
+        _require_cuda()
         seg_sizes = [int(s) for s in seg_sizes]
         if any(s <= 0 or s % 2 for s in seg_sizes):
             raise ValueError("segment sizes must be positive and even (pad odd batches)")
@@ -216,18 +298,34 @@ class DeviceFactor:
         for s in seg_sizes:
             self.seg_off.append(self.seg_off[-1] + s)
         self.n = self.seg_off[-1]
-        self.L = alloc_matrix(self.n, self.n)
-        arr = (ctypes.c_int64 * len(self.seg_off))(*self.seg_off)
-        nbytes = lib.lpgp_factor_dinv_bytes(arr, len(seg_sizes))
-        if nbytes == 0:
-            raise ValueError("invalid segment layout")
-        self.dinv = torch.empty(round_up(nbytes, 8) // 8, dtype=F64, device=dev)
         self.nleaves = sum((s + _lib.LEAF - 1) // _lib.LEAF for s in seg_sizes)
+        arr = (ctypes.c_int64 * len(self.seg_off))(*self.seg_off)
+        if lib.lpgp_factor_dinv_bytes(arr, len(seg_sizes)) == 0:
+            raise ValueError("invalid segment layout")
+        self._storage = _FactorStorage(self.n, self.nleaves, reserve_rows) if _storage is None else _storage
+        assert self.n <= self._storage.cap_rows and self.nleaves <= self._storage.cap_leaves
+        self.L = self._storage.L[: self.n, : self.n]
+        self.dinv = self._storage.dinv
         self.factored_segments = 0
+        self._claimed_from = None  # extent of the factor this one grew from in place (rolled back when it dies unused)
+
+    def __del__(self):
+        # an in-place extension that dies while still the tip of its storage (a failed or discarded conditioning step)
+        # hands its rows back, so that the factor it grew from can grow in place again
+        try:
+            st = self._storage
+            if self._claimed_from is not None and st.claimed == self.n:
+                st.claimed = self._claimed_from
+        except Exception:  # pylint: disable=broad-except  (interpreter shutdown)
+            pass
 
     @property
     def ld(self) -> int:
-        return _ld(self.L)
+        return _ld(self._storage.L)
+
+    @property
+    def capacity(self) -> int:
+        return self._storage.cap_rows
 
     def _struct(self, nseg: Optional[int] = None) -> _lib.Factor:
         nseg = len(self.seg_off) - 1 if nseg is None else nseg
@@ -246,6 +344,8 @@ class DeviceFactor:
 
     def potrf(self) -> None:
         """Factor everything from scratch (all segments as one matrix)."""
+        if self._storage.claimed != self.n:
+            raise RuntimeError("this factor has been extended in place: its rows are shared and immutable")
         f = self._struct()
         check(lib.lpgp_potrf(ctypes.byref(f), _stream()), "lpgp_potrf")
         self.factored_segments = len(self.seg_off) - 1
@@ -256,13 +356,26 @@ class DeviceFactor:
         check(lib.lpgp_chol_append(ctypes.byref(f), _stream()), "lpgp_chol_append")
         self.factored_segments = len(self.seg_off) - 1
 
-    def extended(self, new_size: int) -> "DeviceFactor":
-        """New factor object with one more (unfactored) segment; the existing factor is copied."""
-        sizes = [self.seg_off[i + 1] - self.seg_off[i] for i in range(len(self.seg_off) - 1)]
-        new = DeviceFactor(sizes + [int(new_size)])
-        new.L[: self.n, : self.n].copy_(self.L)
-        nold = self.nleaves * _lib.LEAF * _lib.LEAF  # all leaf blocks, without the status area
-        new.dinv[:nold].copy_(self.dinv[:nold])
+    def extended(self, new_size: int, reserve_rows: Optional[int] = None) -> "DeviceFactor":
+        """New factor object with one more (unfactored) segment.  In place when this factor is the tip of its
+        storage and the capacity suffices; else the lower triangle and the leaf inverses move to a new allocation."""
+        new_size = int(new_size)
+        sizes = [self.seg_off[i + 1] - self.seg_off[i] for i in range(len(self.seg_off) - 1)] + [new_size]
+        st = self._storage
+        n_new = self.n + new_size
+        leaves_new = self.nleaves + (new_size + _lib.LEAF - 1) // _lib.LEAF
+        if (new_size > 0 and new_size % 2 == 0 and st.claimed == self.n and n_new <= st.cap_rows
+                and leaves_new <= st.cap_leaves and len(sizes) <= _lib.MAX_SEG):
+            st.claimed = n_new
+            new = DeviceFactor(sizes, _storage=st)
+            new._claimed_from = self.n  # pylint: disable=protected-access
+        else:
+            new = DeviceFactor(sizes, reserve_rows=reserve_rows)
+            for r0 in range(0, self.n, _LOWER_COPY_ROWS):  # lower triangle only, in row slabs
+                r1 = min(self.n, r0 + _LOWER_COPY_ROWS)
+                new.L[r0:r1, :r1].copy_(self.L[r0:r1, :r1])
+            nold = self.nleaves * _lib.LEAF * _lib.LEAF  # all leaf blocks, without the status area
+            new.dinv[:nold].copy_(self.dinv[:nold])
         new.factored_segments = self.factored_segments
         return new
 

@@ -12,7 +12,7 @@ extern "C" const char* lpgp_error_string(int code) {
   return "invalid argument";
 }
 
-long long g_lpgp_launches = 0;
+std::atomic<long long> g_lpgp_launches{0};
 int g_lpgp_no_sep = 0;
 int g_lpgp_no_lookahead = 0;
 int g_lpgp_trsm_refine = 1;
@@ -35,9 +35,7 @@ extern "C" int lpgp_set_option(int key, int value) {
 }
 
 extern "C" long long lpgp_launch_count(int reset) {
-  const long long v = g_lpgp_launches;
-  if (reset) g_lpgp_launches = 0;
-  return v;
+  return reset ? g_lpgp_launches.exchange(0) : g_lpgp_launches.load();
 }
 
 // ---- FP64 tensor-pipe issue-rate probe: the roofline denominator of the DMMA kernels, measured on the box ----

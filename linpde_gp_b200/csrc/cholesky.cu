@@ -624,7 +624,7 @@ inline int* info_ptr(const lpgp_factor* f, int nleaves) {
   return reinterpret_cast<int*>(f->dinv + (size_t)nleaves * LEAF * LEAF);
 }
 
-int g_diag_attr_set = 0;
+std::atomic<int> g_diag_attr_set[LPGP_MAX_DEVICES];  // per device: the opt-in shared-memory size is a per-device attribute
 
 // X[m x (off[hi]-off[lo])] <- X * L[lo:hi, lo:hi]^{-T}; X points at column off[lo] of the right-hand-side rows.
 //
@@ -854,9 +854,12 @@ int check_factor(const lpgp_factor* f) {
 }
 
 int ensure_attrs() {
-  if (!g_diag_attr_set) {
+  int dev = 0;
+  LPGP_CHECK(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < LPGP_MAX_DEVICES;
+  if (!tracked || !g_diag_attr_set[dev].load(std::memory_order_acquire)) {
     LPGP_CHECK(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-    g_diag_attr_set = 1;
+    if (tracked) g_diag_attr_set[dev].store(1, std::memory_order_release);
   }
   return 0;
 }
@@ -890,7 +893,7 @@ int potrf_impl(lpgp_factor* f, void* stream, bool sync) {
   LPGP_CHECK_LAUNCH();
   const bool dbg = getenv("LPGP_DEBUG_TIMING") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
-  const long long l0 = g_lpgp_launches;
+  const long long l0 = g_lpgp_launches.load();
   TrsmWork work;
   rc = work.acquire(f, lv, f->n, 0, st);
   if (rc) return rc;
@@ -902,7 +905,7 @@ int potrf_impl(lpgp_factor* f, void* stream, bool sync) {
   if (dbg) {
     const auto t2 = std::chrono::steady_clock::now();
     fprintf(stderr, "[lpgp_potrf] n=%lld launches=%lld host enqueue %.3f ms, until sync %.3f ms\n", (long long)f->n,
-            g_lpgp_launches - l0, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+            g_lpgp_launches.load() - l0, std::chrono::duration<double, std::milli>(t1 - t0).count(),
             std::chrono::duration<double, std::milli>(t2 - t0).count());
   }
   return rc;

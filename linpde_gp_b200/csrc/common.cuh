@@ -3,13 +3,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/lpgp.h"
 
 #define LPGP_CUDA_ERR(e) (-(1000 + (int)(e)))
 
 // every kernel launch of the library is counted (bench.py reports the number as `gpu_launches`)
-extern long long g_lpgp_launches;
-#define LPGP_COUNT(n) (g_lpgp_launches += (n))
+extern std::atomic<long long> g_lpgp_launches;
+#define LPGP_COUNT(n) (g_lpgp_launches.fetch_add((n), std::memory_order_relaxed))
 // diagnostics switch (lpgp_set_option): 1 = evaluate Matern exponentials directly instead of the separable form
 extern int g_lpgp_no_sep;
 // 1 = factor on one stream with the plain recursion (no panel lookahead)

@@ -283,12 +283,20 @@ void init_once() {
     return;
   }
   g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
-  e = cudaFuncSetAttribute(gemm_nt_kernel<BigTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigTile::SMEM_BYTES);
-  if (e != cudaSuccess) g_init_rc = LPGP_CUDA_ERR(e);
-  e = cudaFuncSetAttribute(gemm_nt_kernel<SmallTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallTile::SMEM_BYTES);
-  if (e != cudaSuccess) g_init_rc = LPGP_CUDA_ERR(e);
-  e = cudaFuncSetAttribute(gemm_nt_kernel<StripTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripTile::SMEM_BYTES);
-  if (e != cudaSuccess) g_init_rc = LPGP_CUDA_ERR(e);
+}
+
+// the opt-in dynamic shared-memory size is a PER-DEVICE function attribute: set it once on every device used
+std::atomic<int> g_attr_set[LPGP_MAX_DEVICES];
+int ensure_device_attrs() {
+  int dev = 0;
+  LPGP_CHECK(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < LPGP_MAX_DEVICES;
+  if (tracked && g_attr_set[dev].load(std::memory_order_acquire)) return 0;
+  LPGP_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<BigTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigTile::SMEM_BYTES));
+  LPGP_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<SmallTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallTile::SMEM_BYTES));
+  LPGP_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<StripTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripTile::SMEM_BYTES));
+  if (tracked) g_attr_set[dev].store(1, std::memory_order_release);
+  return 0;
 }
 
 // row-major (rows x cols, ld) FP64 matrix -> 2-D tensor map with box (BK cols) x (box_rows rows)
@@ -339,6 +347,7 @@ extern "C" int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const
   if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return -1;
   std::call_once(g_once, init_once);
   if (g_init_rc) return g_init_rc;
+  if (const int arc = ensure_device_attrs()) return arc;
   if (k == 0) {
     // pure scaling of C; reuse the kernel with an empty contraction (nk = 0)
   }
@@ -365,6 +374,7 @@ int lpgp_gemm_nt_flagged(int64_t m, int64_t n, int64_t k, double alpha, const do
   if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return -1;
   std::call_once(g_once, init_once);
   if (g_init_rc) return g_init_rc;
+  if (const int arc = ensure_device_attrs()) return arc;
   const bool use_small = ceil_div64(m, 128) * ceil_div64(n, 128) < 96;
   return (use_small ? launch<SmallTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, flag, -1);
 }
@@ -388,5 +398,6 @@ extern "C" int lpgp_gemm_nt_limited(int64_t m, int64_t n, int64_t k, double alph
   if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return -1;
   std::call_once(g_once, init_once);
   if (g_init_rc) return g_init_rc;
+  if (const int arc = ensure_device_attrs()) return arc;
   return launch<BigTile>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, col_limit, (int)col_base);
 }

@@ -86,8 +86,10 @@ class LinearOperator:
     def cholesky(self, lower: bool = True) -> "CholeskyFactor":
         if not self.is_square:
             raise np.linalg.LinAlgError("The Cholesky decomposition is only defined for square matrices.")
-        if self.is_symmetric is False:
+        if not self.is_symmetric:  # None (unknown) raises as well, like pn/linops/_linear_operator.py:823-826
             raise np.linalg.LinAlgError("The Cholesky decomposition is only defined for symmetric matrices.")
+        if self.is_positive_definite is False:
+            raise np.linalg.LinAlgError("The linear operator is not positive definite.")
         if self._factor is None:
             n = self.shape[0]
             f = backend.DeviceFactor([n + n % 2])
@@ -111,9 +113,14 @@ class LinearOperator:
     def solve(self, B):
         """``A^{-1} B`` (pn/linops/_linear_operator.py:221-315): triangular operators substitute, symmetric ones go
         through the cached Cholesky factor.  There is no LU kernel on this path (the reference's last-resort branch
-        :311-315): an operator flagged non-symmetric raises ``LinAlgError`` from ``cholesky``."""
+        :311-315): an operator that is not flagged symmetric (``is_symmetric`` None or False) is refused instead of
+        being factored from its lower triangle."""
         if self.is_lower_triangular or self.is_upper_triangular:
             return self._triangular_solve(B)
+        if not self.is_symmetric:
+            raise NotImplementedError(
+                "solve() of an operator that is not flagged symmetric needs an LU factorisation, which the device path "
+                "does not provide; set `is_symmetric = True` if the matrix is symmetric positive definite")
         return self.cholesky(True).solve_spd(B)
 
     def _triangular_solve(self, B):
@@ -357,14 +364,9 @@ class CovarianceLinearOperator(LinearOperator):
         X0 = backend.points(self._x0, d) if X0 is None else X0
         if self._x1 is not None and X1 is None:
             X1 = backend.points(self._x1, d)
-        k = self._covfunc
-        if isinstance(k, covfuncs.SumCovarianceFunction):
-            try:
-                descs = [k.descriptor()]
-            except NotImplementedError:
-                descs = k.descriptors()
-        else:
-            descs = [k.descriptor()]
+        descs = covfuncs.device_descriptors(self._covfunc)  # scalars distributed over sums, zero summands dropped
+        if not descs and not accumulate:
+            out.zero_()
         for i, desc in enumerate(descs):
             backend.gram(desc, X0, X1, out=out, lower=lower, accumulate=accumulate or i > 0)
         return out
@@ -825,8 +827,10 @@ class BlockMatrix2x2(LinearOperator):
                 AinvB = self._A.solve(self._B.todense())
                 S = backend.to_device(self._D.todense() - self._C @ AinvB)
             self._schur = _Device(S)
-            self._schur.is_symmetric = self.is_symmetric
-            self._schur.is_positive_definite = self.is_positive_definite
+            # the Schur complement of a symmetric (positive definite) matrix is symmetric (positive definite); in
+            # every other case it is NOT flagged symmetric, so that solves with it are refused rather than wrong
+            self._schur.is_symmetric = bool(self.is_symmetric)
+            self._schur.is_positive_definite = True if (self.is_symmetric and self.is_positive_definite) else None
         return self._schur
 
     def schur_update(self, A_inv_u: np.ndarray, v: np.ndarray) -> np.ndarray:

@@ -25,18 +25,10 @@ VAR_CHUNK_BYTES = 16 << 30  # upper bound of the cross-covariance workspace per 
 
 
 def _descs(k: covfuncs.CovarianceFunction):
-    """Device descriptors of a (possibly sum) kernel; the zero kernel has none."""
-    if isinstance(k, covfuncs.Zero):
-        return []
-    if isinstance(k, covfuncs.SumCovarianceFunction):
-        try:
-            return [k.descriptor()]
-        except NotImplementedError:
-            out = []
-            for s in k.summands:
-                out.extend(_descs(s))
-            return out
-    return [k.descriptor()]
+    """Device descriptors of a (possibly scaled sum of) kernel(s), one per summand without a common product form; the
+    zero kernel has none.  Scalars distribute over sums (``sigma^2 * (k1 + k2)``, what ``apply_linfuncop`` and
+    ``atom.coef * kk`` produce for sum priors -- pn/randprocs/covfuncs/_arithmetic_fallbacks.py:21-118)."""
+    return covfuncs.device_descriptors(k)
 
 
 def _gram_into(k: covfuncs.CovarianceFunction, X0, X1, out: "torch.Tensor", lower: bool = False, *,
@@ -177,17 +169,107 @@ class _Block:
         self.atoms = [atom]
 
 
+class _PosteriorState:
+    """Everything a conditioned process needs to evaluate itself: prior, observation blocks, the device-resident
+    factor, residuals and representer weights.  ``ConditionalGaussianProcess``, its ``Mean`` and its
+    ``CovarianceFunction`` all point HERE and the state points back at none of them, so the object graph has no
+    reference cycle: the device buffers (34 GB at N = 64k) are released by reference counting the moment the last
+    posterior object using them goes away, not at some later pass of the cyclic garbage collector (which used to
+    leave several dead factors resident between conditioning steps)."""
+
+    def __init__(self, *, prior, base_prior, Ys, Ls, bs, blocks, factor, resid, weights, test_op):
+        self._prior = prior
+        self._base_prior = base_prior  # the process the observations refer to
+        self._Ys = tuple(Ys)
+        self._Ls = tuple(Ls)
+        self._bs = tuple(bs)
+        self._blocks = tuple(blocks)
+        self._factor = factor
+        self._resid = resid
+        self._w = weights
+        self._test_op = test_op
+        self._gram_op = None
+
+    # -- state ---------------------------------------------------------------------------------------------
+    @property
+    def _logical_index(self) -> np.ndarray:
+        return np.concatenate([np.arange(b.col_off, b.col_off + b.n) for b in self._blocks])
+
+    @property
+    def gram(self) -> "GramFactorOperator":
+        if getattr(self._factor, "distributed", False):
+            raise NotImplementedError("the Gram factor is distributed over several GPUs (replicate=False)")
+        if self._gram_op is None:
+            self._gram_op = GramFactorOperator(self._factor, self._logical_index)
+        return self._gram_op
+
+    # -- kernels between the test side and one atom of an observation block ----------------------------------------
+    def _k_test_obs(self, atom: _Atom):
+        kk = atom.apply(self._base_prior.cov, 1)
+        return kk if self._test_op is None else self._test_op(kk, argnum=0)
+
+    def _obs_blocks(self) -> backend.ObsBlocks:
+        """Device view of ``k(x_test, observations)``: one entry per (point atom, kernel descriptor) -- entries on the
+        same columns accumulate -- plus the integral atoms (``extras``), whose single column is the closed-form
+        ``int_a^b k(x_test, t) dt`` evaluated by ``lpgp_matern_integral``."""
+        descs, Xs, offs, extras = [], [], [], []
+        for blk in self._blocks:
+            for atom in blk.atoms:
+                kk = self._k_test_obs(atom)
+                if atom.kind == "int":
+                    terms = [(atom.coef * sc, _lowering.matern_integral_desc(nu, ell)) for sc, nu, ell in _integral_terms(kk)]
+                    if terms:
+                        extras.append((blk.col_off, atom.dom, terms))
+                    continue
+                if atom.coef != 1.0:
+                    kk = atom.coef * kk
+                for dsc in _descs(kk):
+                    descs.append(dsc)
+                    Xs.append(atom.X)
+                    offs.append(blk.col_off)
+        return backend.ObsBlocks(descs, Xs, offs, extras=extras)
+
+    def _obs_blocks_unique(self) -> backend.ObsBlocks:
+        """Entries for the cross-covariance workspace ``k(x_test, X_obs)``: consecutive entries on the same columns
+        (sum kernels) are accumulated by ``lpgp_crosscov``, columns nobody covers (zero kernels) are cleared."""
+        return self._obs_blocks()
+
+    @property
+    def _is_multi_output(self) -> bool:
+        return self._prior.output_shape != ()
+
+    def _select(self, j: int) -> "ConditionalGaussianProcess":
+        from ..linfuncops import SelectOutput
+
+        return self._apply_linfuncop(SelectOutput((self._prior.input_shape, self._prior.output_shape), idx=j))
+
+    def _apply_linfuncop(self, L: LinearFunctionOperator) -> "ConditionalGaussianProcess":
+        if self._test_op is not None:
+            raise NotImplementedError("composition of two operators on a conditioned process")
+        return ConditionalGaussianProcess(
+            prior=L(self._prior), Ys=self._Ys, Ls=self._Ls, bs=self._bs, blocks=self._blocks, factor=self._factor,
+            resid=self._resid, weights=self._w, test_op=L, base_prior=self._base_prior,
+        )
+
+    def _var_distributed(self, Xt: "torch.Tensor", prior_diag: float) -> "torch.Tensor":
+        """Pointwise variance of THIS rank's test points with a distributed factor (collective)."""
+        return self._factor.post_var(self._obs_blocks_unique(), Xt, prior_diag, min_chunk_bytes=4 << 30)
+
+
 class ConditionalGaussianProcess(GaussianProcess):
     @classmethod
     def from_observations(cls, prior: GaussianProcess, Y, X=None, *, L=None, b=None):
         Y, Lf, b, atoms, resid, noise = cls._preprocess_observations(prior=prior, Y=Y, X=X, L=L, b=b)
         blk = _Block(None, None, prior.cov.input_size, 0, atoms=atoms)
         factor = backend.DeviceFactor([blk.n_phys])
-        cls._assemble_rows(prior, [], blk, factor, noise)
-        factor.potrf()
+        with backend.phase("assemble"):
+            cls._assemble_rows(prior, [], blk, factor, noise)
+        with backend.phase("factor"):
+            factor.potrf()
         y = torch.zeros(factor.n, dtype=torch.float64, device=factor.L.device)
         y[: blk.n].copy_(backend.to_device(resid))
-        w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
+        with backend.phase("solve"):
+            w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
         return cls(prior=prior, Ys=(Y,), Ls=(Lf,), bs=(b,), blocks=(blk,), factor=factor, resid=y, weights=w)
 
     @classmethod
@@ -227,26 +309,31 @@ class ConditionalGaussianProcess(GaussianProcess):
         world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         if world > 1 or not replicate:
             ch = distributed.DistributedCholesky(n, nb=nb, group=process_group)
-            for i in ch.layout.local_blocks(ch.rank):
-                g0, g1 = ch.layout.block_bounds(i)
-                cls._assemble_range(prior, blocks, noises, ch.local_block_rows(i), g0, g1)
-            if replicate:
-                factor = backend.DeviceFactor([n])
-                ch.factor(factor.L)  # the gathered panels are the block columns of L: replicated on the fly
-                factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
-                del ch
-            else:
-                ch.factor()
-                factor = distributed.DistributedFactor(ch)
+            with backend.phase("assemble"):
+                for i in ch.layout.local_blocks(ch.rank):
+                    g0, g1 = ch.layout.block_bounds(i)
+                    cls._assemble_range(prior, blocks, noises, ch.local_block_rows(i), g0, g1)
+            with backend.phase("factor"):
+                if replicate:
+                    factor = backend.DeviceFactor([n], reserve_rows=0)
+                    ch.factor(factor.L)  # the gathered panels are the block columns of L: replicated on the fly
+                    factor.dinv[: ch.dinv.numel() - 8].copy_(ch.dinv[:-8])
+                    del ch
+                else:
+                    ch.factor()
+                    factor = distributed.DistributedFactor(ch)
         else:
             factor = backend.DeviceFactor([n])
-            cls._assemble_range(prior, blocks, noises, factor.L, 0, n)
-            factor.potrf()
+            with backend.phase("assemble"):
+                cls._assemble_range(prior, blocks, noises, factor.L, 0, n)
+            with backend.phase("factor"):
+                factor.potrf()
         factor.factored_segments = 1
         y = torch.zeros(n, dtype=torch.float64, device=backend._require_cuda())  # pylint: disable=protected-access
         for blk, p in zip(blocks, pre):
             y[blk.col_off : blk.col_off + blk.n].copy_(backend.to_device(p[4]))
-        w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
+        with backend.phase("solve"):
+            w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
         return cls(prior=prior, Ys=tuple(p[0] for p in pre), Ls=tuple(p[1] for p in pre), bs=tuple(p[2] for p in pre),
                    blocks=tuple(blocks), factor=factor, resid=y, weights=w)
 
@@ -289,82 +376,47 @@ class ConditionalGaussianProcess(GaussianProcess):
                 pr[blk.col_off + blk.n] = 1.0
 
     def __init__(self, *, prior, Ys, Ls, bs, blocks, factor, resid, weights, test_op=None, base_prior=None):
-        self._prior = prior
-        self._base_prior = prior if base_prior is None else base_prior  # the process the observations refer to
-        self._Ys = tuple(Ys)
-        self._Ls = tuple(Ls)
-        self._bs = tuple(bs)
-        self._blocks = tuple(blocks)
-        self._factor = factor
-        self._resid = resid
-        self._w = weights
-        self._test_op = test_op
-        self._gram_op = None
+        self._state = _PosteriorState(prior=prior, base_prior=prior if base_prior is None else base_prior, Ys=Ys, Ls=Ls,
+                                      bs=bs, blocks=blocks, factor=factor, resid=resid, weights=weights, test_op=test_op)
         super().__init__(
-            mean=ConditionalGaussianProcess.Mean(self),
-            cov=ConditionalGaussianProcess.CovarianceFunction(self),
+            mean=ConditionalGaussianProcess.Mean(self._state),
+            cov=ConditionalGaussianProcess.CovarianceFunction(self._state),
         )
 
-    # -- state ---------------------------------------------------------------------------------------------
-    @property
-    def _logical_index(self) -> np.ndarray:
-        return np.concatenate([np.arange(b.col_off, b.col_off + b.n) for b in self._blocks])
+    # -- state (lives in ``_PosteriorState``; see there why) ------------------------------------------------------
+    _prior = property(lambda self: self._state._prior)
+    _base_prior = property(lambda self: self._state._base_prior)
+    _Ys = property(lambda self: self._state._Ys)
+    _Ls = property(lambda self: self._state._Ls)
+    _bs = property(lambda self: self._state._bs)
+    _blocks = property(lambda self: self._state._blocks)
+    _factor = property(lambda self: self._state._factor)
+    _resid = property(lambda self: self._state._resid)
+    _w = property(lambda self: self._state._w)
+    _test_op = property(lambda self: self._state._test_op)
+    _logical_index = property(lambda self: self._state._logical_index)
+    _is_multi_output = property(lambda self: self._state._is_multi_output)
 
     @property
     def gram(self) -> "GramFactorOperator":
-        if getattr(self._factor, "distributed", False):
-            raise NotImplementedError("the Gram factor is distributed over several GPUs (replicate=False)")
-        if self._gram_op is None:
-            self._gram_op = GramFactorOperator(self._factor, self._logical_index)
-        return self._gram_op
+        return self._state.gram
 
     @property
     def representer_weights(self) -> np.ndarray:
         return self._w.cpu().numpy()[self._logical_index]
 
-    # -- kernels between the test side and one atom of an observation block ----------------------------------------
-    def _k_test_obs(self, atom: _Atom):
-        kk = atom.apply(self._base_prior.cov, 1)
-        return kk if self._test_op is None else self._test_op(kk, argnum=0)
-
     def _obs_blocks(self) -> backend.ObsBlocks:
-        """Device view of ``k(x_test, observations)``: one entry per (point atom, kernel descriptor) -- entries on the
-        same columns accumulate -- plus the integral atoms (``extras``), whose single column is the closed-form
-        ``int_a^b k(x_test, t) dt`` evaluated by ``lpgp_matern_integral``."""
-        descs, Xs, offs, extras = [], [], [], []
-        for blk in self._blocks:
-            for atom in blk.atoms:
-                kk = self._k_test_obs(atom)
-                if atom.kind == "int":
-                    terms = [(atom.coef * sc, _lowering.matern_integral_desc(nu, ell)) for sc, nu, ell in _integral_terms(kk)]
-                    if terms:
-                        extras.append((blk.col_off, atom.dom, terms))
-                    continue
-                if atom.coef != 1.0:
-                    kk = atom.coef * kk
-                for dsc in _descs(kk):
-                    descs.append(dsc)
-                    Xs.append(atom.X)
-                    offs.append(blk.col_off)
-        return backend.ObsBlocks(descs, Xs, offs, extras=extras)
+        return self._state._obs_blocks()
 
     def _obs_blocks_unique(self) -> backend.ObsBlocks:
-        """Entries for the cross-covariance workspace ``k(x_test, X_obs)``: consecutive entries on the same columns
-        (sum kernels) are accumulated by ``lpgp_crosscov``, columns nobody covers (zero kernels) are cleared."""
-        return self._obs_blocks()
-
-    @property
-    def _is_multi_output(self) -> bool:
-        return self._prior.output_shape != ()
+        return self._state._obs_blocks_unique()
 
     def _select(self, j: int) -> "ConditionalGaussianProcess":
-        from ..linfuncops import SelectOutput
-
-        return self._apply_linfuncop(SelectOutput((self._prior.input_shape, self._prior.output_shape), idx=j))
+        return self._state._select(j)
 
     # -- posterior mean / covariance -----------------------------------------------------------------------------
     class Mean(functions.Function):
-        def __init__(self, post: "ConditionalGaussianProcess"):
+        def __init__(self, post: "_PosteriorState"):
             self._post = post
             super().__init__(input_shape=post._prior.mean.input_shape, output_shape=post._prior.mean.output_shape)
 
@@ -378,11 +430,12 @@ class ConditionalGaussianProcess(GaussianProcess):
             if blocks.empty:  # no observation is correlated with this (output of the) process
                 return m_x
             Xt = backend.points(x, post._base_prior.cov.input_size)
-            upd = backend.post_mean(blocks, post._w, Xt)
+            with backend.phase("mean"):
+                upd = backend.post_mean(blocks, post._w, Xt)
             return m_x + upd.cpu().numpy().reshape(batch)
 
     class CovarianceFunction(covfuncs.CovarianceFunction):
-        def __init__(self, post: "ConditionalGaussianProcess"):
+        def __init__(self, post: "_PosteriorState"):
             self._post = post
             super().__init__(post._prior.cov.input_shape)
 
@@ -413,9 +466,12 @@ class ConditionalGaussianProcess(GaussianProcess):
                 if post._obs_blocks().empty:
                     return np.full(batch, diag)
                 if getattr(post._factor, "distributed", False):
-                    return post._var_distributed(Xt, diag).cpu().numpy().reshape(batch)
+                    with backend.phase("var"):
+                        var = post._var_distributed(Xt, diag)
+                    return var.cpu().numpy().reshape(batch)
                 chunk = backend.var_chunk_rows(n, Xt.shape[0], max_bytes=VAR_CHUNK_BYTES)
-                var = backend.post_var(post._obs_blocks_unique(), post._factor, Xt, diag, chunk=chunk)
+                with backend.phase("var"):
+                    var = backend.post_var(post._obs_blocks_unique(), post._factor, Xt, diag, chunk=chunk)
                 return var.cpu().numpy().reshape(batch)
             nd = self.input_ndim
             b0, b1 = x0.shape[: x0.ndim - nd], x1.shape[: x1.ndim - nd]
@@ -460,10 +516,6 @@ class ConditionalGaussianProcess(GaussianProcess):
                 op.is_symmetric = True
             return op
 
-    def _var_distributed(self, Xt: "torch.Tensor", prior_diag: float) -> "torch.Tensor":
-        """Pointwise variance of THIS rank's test points with a distributed factor (collective)."""
-        return self._factor.post_var(self._obs_blocks_unique(), Xt, prior_diag, min_chunk_bytes=4 << 30)
-
     # -- adding observations ----------------------------------------------------------------------------------
     def condition_on_observations(self, Y, X=None, *, L=None, b=None):
         if self._test_op is not None:
@@ -471,16 +523,20 @@ class ConditionalGaussianProcess(GaussianProcess):
         prior = self._base_prior
         Y, Lf, b, atoms, resid, noise = self._preprocess_observations(prior=prior, Y=Y, X=X, L=L, b=b)
         blk = _Block(None, None, prior.cov.input_size, self._factor.n, atoms=atoms)
-        factor = self._factor.extended(blk.n_phys)
-        self._assemble_rows(prior, self._blocks, blk, factor, noise)
-        factor.append_last()
+        with backend.phase("extend"):
+            factor = self._factor.extended(blk.n_phys)
+        with backend.phase("assemble"):
+            self._assemble_rows(prior, self._blocks, blk, factor, noise)
+        with backend.phase("factor"):
+            factor.append_last()
         y = torch.zeros(factor.n, dtype=torch.float64, device=factor.L.device)
         y[: self._factor.n].copy_(self._resid)
         y[blk.col_off : blk.col_off + blk.n].copy_(backend.to_device(resid))
         # representer weights of the extended system.  The reference updates them with the Schur-complement
         # formulas of BlockMatrix2x2.schur_update (_block.py:226-231); solving with the extended factor is the same
         # linear system and costs the same O(N^2).
-        w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
+        with backend.phase("solve"):
+            w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
         return ConditionalGaussianProcess(
             prior=prior, Ys=self._Ys + (Y,), Ls=self._Ls + (Lf,), bs=self._bs + (b,),
             blocks=self._blocks + (blk,), factor=factor, resid=y, weights=w,
@@ -579,12 +635,7 @@ class ConditionalGaussianProcess(GaussianProcess):
 
     # -- push-forwards L(posterior) (_conditional.py:432-467) --------------------------------------------------------
     def _apply_linfuncop(self, L: LinearFunctionOperator) -> "ConditionalGaussianProcess":
-        if self._test_op is not None:
-            raise NotImplementedError("composition of two operators on a conditioned process")
-        return ConditionalGaussianProcess(
-            prior=L(self._prior), Ys=self._Ys, Ls=self._Ls, bs=self._bs, blocks=self._blocks, factor=self._factor,
-            resid=self._resid, weights=self._w, test_op=L, base_prior=self._base_prior,
-        )
+        return self._state._apply_linfuncop(L)
 
     def _apply_linfunctl(self, Lf) -> randvars.Normal:
         op, X = Lf._as_observation()  # pylint: disable=protected-access

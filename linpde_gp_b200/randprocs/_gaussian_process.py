@@ -59,7 +59,7 @@ class GaussianProcess:
         """Finite-dimensional marginal ``Normal(mean(x), cov.linop(x))`` -- the covariance stays a lazy,
         device-assembled operator, as in pn/randprocs/_gaussian_process.py:75-79."""
         x = np.asarray(args, dtype=np.double)
-        return randvars.Normal(mean=np.array(self._mean(x), copy=False).reshape(-1), cov=self._cov.linop(x))
+        return randvars.Normal(mean=np.asarray(self._mean(x), dtype=np.double).reshape(-1), cov=self._cov.linop(x))
 
     def var(self, args) -> np.ndarray:
         v = self._cov(np.asarray(args, dtype=np.double), None)

@@ -385,7 +385,7 @@ class SumCovarianceFunction(CovarianceFunction):
         raise NotImplementedError("sum of kernels with different base factors: evaluated block-wise")
 
     def descriptors(self):
-        return [s.descriptor() for s in self._summands]
+        return device_descriptors(self)
 
     def linop(self, x0, x1=None):
         if _grid_factors(x0) is not None:
@@ -737,6 +737,24 @@ def _apply_multi_output(L, k: CovarianceFunction, argnum: int) -> CovarianceFunc
             return StackCovarianceFunction(tuple(apply_linfuncop(L, c, argnum) for c in k.covfuncs), output_idx=k.output_idx)
         raise NotImplementedError("the operator acts on the stacked argument: select an output first")
     raise NotImplementedError(f"{type(L).__name__} applied to {type(k).__name__}")
+
+
+def device_descriptors(k: CovarianceFunction):
+    """Device descriptors whose values add up to ``k``: one for a kernel with a product form, else one per summand,
+    with outer scalars distributed over sums and ``Zero`` summands dropped."""
+    if isinstance(k, Zero):
+        return []
+    if isinstance(k, SumCovarianceFunction):
+        out = []
+        for s in k.summands:
+            out.extend(device_descriptors(s))
+        return out
+    if isinstance(k, ScaledCovarianceFunction) and isinstance(k.covfunc, (SumCovarianceFunction, Zero, ScaledCovarianceFunction)):
+        inner = k.covfunc
+        if isinstance(inner, ScaledCovarianceFunction):
+            return device_descriptors(ScaledCovarianceFunction(inner.covfunc, scalar=float(k.scalar) * float(inner.scalar)))
+        return device_descriptors(_scale_cov(float(k.scalar), inner))
+    return [k.descriptor()]
 
 
 def _kind_of(L):

@@ -191,8 +191,8 @@ class LinearOperatorCovariance(Covariance):
 
 
 def asrandvar(b):
+    """``pn.randvars.asrandvar``: random variables pass through, anything array-like (lists, ndarrays, numpy
+    scalars -- which do have a ``.mean`` METHOD) becomes a ``Constant``."""
     if isinstance(b, (Normal, Constant)):
         return b
-    if np.ndim(b) >= 0 and not hasattr(b, "mean"):
-        return Constant(b)
-    return b
+    return Constant(np.asarray(b, dtype=np.double))

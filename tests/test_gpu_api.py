@@ -6,6 +6,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from tests import helpers
 from tests.golden import cases as gcases
@@ -341,7 +342,7 @@ def test_kronecker_linop_on_tensor_product_grids_matches_reference(spec):
     # Matern-3/2 factor does not exist in the mean-square sense: kron_tp3_LkL is a formula check only, its matrix is
     # indefinite in the reference as well.)
     if A is not None and np.min(np.linalg.eigvalsh(A)) > 0:
-        noisy = op + linops.Matrix(1e-6 * sc * np.eye(len(K_ref)))
+        noisy = op + linops.Scaling(np.full(len(K_ref), 1e-6 * sc))  # flagged symmetric, like pn.linops.Scaling
         x = noisy.solve(V)
         assert np.max(np.abs(A @ x - V)) <= 1e-7 * np.max(np.abs(V))
 
@@ -774,3 +775,92 @@ def test_experiment_0001_poisson_dirichlet_2d_flow():
     res = bvp.pde.diffop(u).mean(X_pde)
     assert np.max(np.abs(res - 2.0)) <= 1e-5
     assert np.max(np.abs(mean - mean.T)) <= 1e-5 and np.max(np.abs(mean - mean[::-1, :])) <= 1e-5  # symmetries of the problem
+
+
+# ---- appendable factor: capacity reserve, versioned extent, no reference cycles -----------------
+def _poisson_prior_and_batches(n_bc=64, n_pde=600, seed=11):
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.linfuncops import diffops
+    from linpde_gp_b200.randprocs import covfuncs
+
+    rng = np.random.default_rng(seed)
+    ell = 0.25
+    k = 4.0 * covfuncs.TensorProduct(covfuncs.Matern((), nu=2.5, lengthscales=ell), covfuncs.Matern((), nu=2.5, lengthscales=ell))
+    prior = lg.GaussianProcess(lg.functions.Zero(input_shape=(2,)), k)
+    s = np.linspace(0, 1, n_bc, endpoint=False)
+    Xb = np.stack([s, np.zeros_like(s)], -1)
+    Xp = rng.uniform(0.05, 0.95, (n_pde, 2))
+    Xq = rng.uniform(0.05, 0.95, (130, 2))
+    lap = -1.0 * diffops.Laplacian((2,))
+    return prior, (np.zeros(n_bc), Xb, None), (np.full(n_pde, 2.0), Xp, lap), (np.sin(Xq[:, 0]), Xq, None)
+
+
+def test_append_in_place_shares_storage_and_keeps_old_posterior_valid():
+    """extended() allocates and copies nothing while the reserved capacity suffices; the posterior conditioned on fewer
+    batches keeps evaluating to the same numbers after its factor buffer has grown in place."""
+    prior, b0, b1, b2 = _poisson_prior_and_batches()
+    Xt = np.random.default_rng(0).uniform(0, 1, (200, 2))
+    p0 = prior.condition_on_observations(b0[0], X=b0[1])
+    p1 = p0.condition_on_observations(b1[0], X=b1[1], L=b1[2])
+    m1, v1 = p1.mean(Xt), p1.var(Xt)
+    w1 = p1.representer_weights.copy()
+    f1 = p1._factor
+    assert f1._storage is p0._factor._storage  # 64 + 600 rows fit the reserve (>= 1024 rows) of the first factor
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_allocated()
+    f2 = f1.extended(130)
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_allocated() == before  # no allocation, no copy
+    assert f2._storage is f1._storage and f2.L.data_ptr() == f1.L.data_ptr()
+    p2 = p1.condition_on_observations(b2[0], X=b2[1])
+    # p1's factor is no longer the tip of the storage (f2 claimed rows): p2 had to branch into its own storage
+    assert p2._factor._storage is not f1._storage
+    assert np.array_equal(p1.mean(Xt), m1) and np.array_equal(p1.var(Xt), v1)
+    assert np.array_equal(p1.representer_weights, w1)
+    # both branches agree with one-shot conditioning on all three batches
+    import linpde_gp_b200 as lg
+
+    ref = lg.ConditionalGaussianProcess.from_observation_batches(prior, [b0, b1, b2])
+    sc = max(np.max(np.abs(ref.mean(Xt))), 4.0)
+    assert np.max(np.abs(p2.mean(Xt) - ref.mean(Xt))) <= 1e-8 * sc
+    assert np.max(np.abs(p2.var(Xt) - ref.var(Xt))) <= 1e-8 * sc
+
+
+def test_append_beyond_capacity_moves_only_the_lower_triangle():
+    from linpde_gp_b200 import backend
+
+    rng = np.random.default_rng(3)
+    n, extra = 384, 130
+    A = rng.standard_normal((n + extra, n + extra))
+    G = A @ A.T / (n + extra) + np.eye(n + extra)
+    f = backend.DeviceFactor([n], reserve_rows=0)
+    f.L.copy_(backend.to_device(G[:n, :n]))
+    f.potrf()
+    g = f.extended(extra)  # no capacity: new storage
+    assert g._storage is not f._storage and g.capacity >= n + extra
+    g.L[n:, :].copy_(backend.to_device(G[n:, :]))
+    g.append_last()
+    L = torch.tril(g.L).cpu().numpy()
+    assert np.max(np.abs(L @ L.T - G)) <= 1e-12 * np.max(np.abs(G))
+    # the old factor is untouched
+    L0 = torch.tril(f.L).cpu().numpy()
+    assert np.max(np.abs(L0 @ L0.T - G[:n, :n])) <= 1e-12 * np.max(np.abs(G))
+
+
+def test_posterior_objects_hold_no_reference_cycles():
+    """The factor of a dropped posterior is released by reference counting (cyclic GC disabled): dead 34 GB factors must
+    not pile up between conditioning steps."""
+    import gc
+    import weakref
+
+    prior, b0, b1, _ = _poisson_prior_and_batches()
+    gc.collect()
+    gc.disable()
+    try:
+        post = prior.condition_on_observations(b0[0], X=b0[1])
+        post.mean(b0[1])
+        ref = weakref.ref(post._factor._storage)
+        del post
+        assert ref() is None
+    finally:
+        gc.enable()
