@@ -34,6 +34,8 @@ extern "C" {
 /* dimension types of the (product-form) kernel descriptor */
 #define LPGP_DIM_MATERN 0  /* half-integer Matern factor:  v = s*|dx|, weight exp(-v),  s = sqrt(2 nu)/ell   */
 #define LPGP_DIM_EXPQUAD 1 /* exponentiated-quadratic factor: v = dx/ell (signed), weight exp(-v^2/2)          */
+#define LPGP_DIM_RADIAL 2  /* isotropic (radial) half-integer Matern on R^d, see lpgp_kernel_desc                */
+#define LPGP_RADIAL_NQ 6   /* coefficients per radial polynomial (degree <= 5)                                 */
 
 /* output modes of lpgp_gram */
 #define LPGP_GRAM_FULL 0  /* every entry of the n0 x n1 block                                             */
@@ -53,6 +55,19 @@ extern "C" {
  * with 1-D factors from diffops/_matern.py:17-639 and diffops/_expquad.py:12-432, and of the base kernels
  * pn/randprocs/covfuncs/_matern.py:175-195, _exponentiated_quadratic.py:89-100.
  * `coef` is a dense C-order tensor of shape (nbtot_0, .., nbtot_{d-1}), nbtot_d = nbasis_d * (1 + has_odd_d).
+ *
+ * RADIAL kernels (every dim_type[d] == LPGP_DIM_RADIAL): the isotropic multi-dimensional half-integer Matern kernel
+ * and its first-order directional derivatives, which are NOT of product form:
+ *
+ *   u = s o (x - x'),  r = |u|_2,   value = exp(-r) * ( Q0(r) + <a,u> Q1(r) + <a,u> <b,u> Q2(r) )
+ *
+ * with coef = [Q0 | Q1 | Q2 | a | b], each Q of LPGP_RADIAL_NQ ascending coefficients, a and b of d entries
+ * (3*LPGP_RADIAL_NQ + 2*d doubles; nbasis / has_odd unused).  This covers  pn Matern._evaluate on input_shape (d,)
+ * (pn/randprocs/covfuncs/_matern.py:175-195 with IsotropicMixin._euclidean_distances,
+ * _covariance_function.py:783-802: Q0 = P_p), HalfIntegerMatern_Identity_DirectionalDerivative._evaluate
+ * (src/linpde_gp/randprocs/covfuncs/linfuncops/diffops/_matern.py:64-86: Q1 = P_{p,1} // r, a = -+ s o direction)
+ * and HalfIntegerMatern_DirectionalDerivative_DirectionalDerivative._evaluate (_matern.py:185-203:
+ * Q0 = <s o d0, s o d1> (-P_{p,1} // r), Q2 = -(P_{p,2} - P_{p,1} // r) // r^2, a = s o d0, b = s o d1).
  */
 typedef struct lpgp_kernel_desc {
   int32_t d;                      /* input dimension, 1..LPGP_MAX_DIM (input_shape=() -> d = 1)      */
@@ -213,6 +228,48 @@ int lpgp_gemv(int trans, int64_t m, int64_t n, double alpha, const double* A, in
 
 /* sum_i log L_ii^2 = log det G, written to *out (device double).                                           */
 int lpgp_logdet(const lpgp_factor* f, double* out, void* stream);
+
+/* (2b) FP64 GEMM / triangular solve emulated on the INT8 tensor cores (Ozaki scheme; tcgen05.mma.kind::i8 with TMEM
+ * accumulators, TMA operands) -- an opt-in alternative to the DMMA path for the O(N^2 M) posterior-variance solve
+ * X <- X L^{-T} (scipy.linalg.solve_triangular in pn/linops/_linear_operator.py:296-299 as used by
+ * src/linpde_gp/randprocs/_gaussian_process/_conditional.py:223-251), whose cost is bounded by the FP64 tensor-pipe
+ * issue rate on the native path.  Operands are first split, row by row and K-block by K-block, into `nslices` byte
+ * planes and one power-of-two exponent per (row, K-block):
+ *     x = 2^e * sum_s d_s 2^(-7 - 8 s),   d_0 int8, d_s (s >= 1) uint8      (exact; 7 + 8 (nslices - 1) bits kept)
+ * products of digit planes are exact in int32 and are recombined in FP64 (see csrc/ozaki.cu).
+ * planes: device, [nslices][rows][pitch] bytes (pitch % 16 == 0, 16-byte aligned); exps: device int32
+ * [cols / kblock][lde]; kblock: columns per K-block (multiple of 128, <= 4096).                                  */
+#define LPGP_OZAKI_MAX_SLICES 7
+typedef struct lpgp_ozaki_planes {
+  unsigned char* planes;
+  int32_t* exps;
+  int64_t rows, cols;     /* logical extent of every plane                                             */
+  int64_t pitch;          /* bytes between consecutive rows                                            */
+  int64_t plane_stride;   /* bytes between consecutive planes                                          */
+  int64_t lde;            /* leading dimension of exps (>= rows)                                       */
+  int32_t nslices;
+  int32_t kblock;
+} lpgp_ozaki_planes;
+
+/* Split the FP64 block A[rows x ncols] (row-major, lda; A points at its first element) into the planes of `P`, at
+ * rows row_off.. and columns col0.. (col0, ncols multiples of kblock).  lower_blocks != 0: only K-blocks strictly left
+ * of each row's own diagonal K-block are produced (all a factor L ever contributes to a blocked solve).        */
+int lpgp_ozaki_split(const double* A, int64_t lda, int64_t rows, int64_t row_off, int64_t col0, int64_t ncols,
+                     const lpgp_ozaki_planes* P, int lower_blocks, void* stream);
+
+/* C[m x n] = beta C + alpha A B^T with A = rows rowA0.. / columns kA0..kA0+k of the planes PA, B likewise of PB
+ * (k, kA0, kB0 multiples of kblock; both plane sets with the same kblock and nslices).                        */
+int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const lpgp_ozaki_planes* PA, int64_t rowA0,
+                       int64_t kA0, const lpgp_ozaki_planes* PB, int64_t rowB0, int64_t kB0, double beta, double* C,
+                       int64_t ldc, void* stream);
+
+/* X[m x n] <- X L^{-T} like lpgp_trsm_rlt (whole factor), blocked left-looking over column blocks of kblock columns:
+ * block j is updated with ONE emulated GEMM against all solved blocks (K = j kblock), solved against its diagonal
+ * block on the DMMA path and split into `XP` for the blocks to come.  `LP`: planes of the factor produced by
+ * lpgp_ozaki_split(L, ..., lower_blocks = 1); `XP`: workspace planes of at least m rows x n columns.  Requires every
+ * leaf boundary of the factor to be a multiple of 128 (segments of 128-multiples); returns -1 otherwise.        */
+int lpgp_trsm_rlt_ozaki(const lpgp_factor* f, double* X, int64_t m, int64_t ldx, const lpgp_ozaki_planes* LP,
+                        const lpgp_ozaki_planes* XP, void* stream);
 
 /* (3) posterior evaluation -----------------------------------------------------------------------------
  * One observation block of the conditioned process: descriptor of (k L_i^*) (test side x observation side),

@@ -17,7 +17,8 @@ MAX_DIM = 4
 MAX_COEF = 512
 LEAF = 128
 MAX_SEG = 64
-DIM_MATERN, DIM_EXPQUAD = 0, 1
+DIM_MATERN, DIM_EXPQUAD, DIM_RADIAL = 0, 1, 2
+RADIAL_NQ = 6
 GRAM_FULL, GRAM_LOWER = 0, 1
 OPT_DIRECT_EXP = 1
 OPT_NO_LOOKAHEAD = 2
@@ -58,6 +59,21 @@ class ObsBlock(ctypes.Structure):
     ]
 
 
+class OzakiPlanes(ctypes.Structure):
+    _fields_ = [
+        ("planes", ctypes.c_void_p),
+        ("exps", ctypes.c_void_p),
+        ("rows", ctypes.c_int64),
+        ("cols", ctypes.c_int64),
+        ("pitch", ctypes.c_int64),
+        ("plane_stride", ctypes.c_int64),
+        ("lde", ctypes.c_int64),
+        ("nslices", ctypes.c_int32),
+        ("kblock", ctypes.c_int32),
+    ]
+
+
+OZAKI_MAX_SLICES = 7
 MAX_INTEGRAL_COEF = 8
 
 
@@ -80,6 +96,7 @@ def _load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     i64, dbl, vp, ci = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
     KD, FP, OB = ctypes.POINTER(KernelDesc), ctypes.POINTER(Factor), ctypes.POINTER(ObsBlock)
+    OP = ctypes.POINTER(OzakiPlanes)
     sigs = {
         "lpgp_version": (ci, []),
         "lpgp_build_arch": (ctypes.c_char_p, []),
@@ -102,6 +119,9 @@ def _load() -> ctypes.CDLL:
         "lpgp_chol_append": (ci, [FP, vp]),
         "lpgp_trsm_rlt": (ci, [FP, i64, vp, i64, i64, vp]),
         "lpgp_trsm_rlt_refined": (ci, [FP, i64, vp, i64, i64, vp]),
+        "lpgp_ozaki_split": (ci, [vp, i64, i64, i64, i64, i64, OP, ci, vp]),
+        "lpgp_ozaki_gemm_nt": (ci, [i64, i64, i64, dbl, OP, i64, i64, OP, i64, i64, dbl, vp, i64, vp]),
+        "lpgp_trsm_rlt_ozaki": (ci, [FP, vp, i64, i64, OP, OP, vp]),
         "lpgp_potrs": (ci, [FP, vp, i64, i64, vp]),
         "lpgp_trsv": (ci, [FP, ci, vp, vp]),
         "lpgp_gemv": (ci, [ci, i64, i64, dbl, vp, i64, vp, vp, vp]),
@@ -123,7 +143,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTED = (
     "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_set_option lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower lpgp_kron_sum "
-    "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_trsm_rlt_refined lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
+    "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_ozaki_split lpgp_ozaki_gemm_nt lpgp_trsm_rlt_ozaki lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_trsm_rlt_refined lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
     "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq lpgp_matern_integral lpgp_matern_integral2"
 ).split()
 

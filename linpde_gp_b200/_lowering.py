@@ -192,3 +192,76 @@ def lower(factors, L0, L1, sigma2: float = 1.0) -> _lib.KernelDesc:
         desc.coef[i] = float(c)
     desc.diag_value = float(flat[0])
     return desc
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# radial kernels: isotropic multi-dimensional half-integer Matern and its first-order directional derivatives
+# ---------------------------------------------------------------------------------------------------------------
+def _floordiv_monomial(c, k: int):
+    """Quotient of the polynomial ``c`` (ascending) by ``r^k`` (the reference's ``poly // Monomial(k)``)."""
+    return tuple(c[k:]) if len(c) > k else (Fraction(0),)
+
+
+def lower_radial(nu: float, scales, dir0=None, dir1=None, sigma2: float = 1.0) -> _lib.KernelDesc:
+    """Descriptor of ``sigma2 * (D_{dir0} k D_{dir1}^*)(x, x')`` for the isotropic Matern-``nu`` kernel on R^d with
+    per-dimension scale factors ``scales = sqrt(2 nu) / lengthscales``; ``dir0`` / ``dir1``: direction of the
+    directional derivative on argument 0 / 1, or ``None`` (identity).  With u = s o (x - x'), r = |u|:
+
+      identity / identity : P_p(r) e^{-r}                              (pn/randprocs/covfuncs/_matern.py:175-195)
+      one derivative      : (P_{p,1} // r)(r) e^{-r} <+-s o dir, u>    (diffops/_matern.py:39-41, 55-86; minus sign when
+                            the operator acts on argument 1)
+      both                : [<a,b> N(r) - <a,u><b,u> Q(r)] e^{-r},  a = s o dir0, b = s o dir1,
+                            N = -P_{p,1} // r,  Q = (P_{p,2} + N) // r^2                 (diffops/_matern.py:160-203)
+    """
+    p = nu - 0.5
+    if p != int(p) or p < 0:
+        raise NotImplementedError("only half-integer Matern kernels have closed-form derivatives")
+    p = int(p)
+    s = np.asarray(scales, dtype=np.float64).reshape(-1)
+    d = s.size
+    if not 1 <= d <= _lib.MAX_DIM:
+        raise NotImplementedError(f"input dimension {d} not supported (max {_lib.MAX_DIM})")
+    nq = _lib.RADIAL_NQ
+    zero = (Fraction(0),)
+    a = np.zeros(d)
+    b = np.zeros(d)
+    if dir0 is None and dir1 is None:
+        q0, q1, q2, c0 = matern_poly(p, 0), zero, zero, 1.0
+    elif dir0 is None or dir1 is None:
+        if p < 1:
+            raise NotImplementedError("the Matern-1/2 kernel is not differentiable")
+        q0, q2, c0 = zero, zero, 1.0
+        q1 = _floordiv_monomial(matern_poly(p, 1), 1)
+        a = s * np.asarray(dir0, dtype=np.float64).reshape(-1) if dir1 is None else -s * np.asarray(dir1, dtype=np.float64).reshape(-1)
+    else:
+        if p < 1:
+            raise NotImplementedError("the Matern-1/2 kernel is not differentiable")
+        a = s * np.asarray(dir0, dtype=np.float64).reshape(-1)
+        b = s * np.asarray(dir1, dtype=np.float64).reshape(-1)
+        npd = _floordiv_monomial(tuple(-c for c in matern_poly(p, 1)), 1)
+        q0, c0 = npd, float(np.sum(a * b))
+        q1 = zero
+        q2 = tuple(-c for c in _floordiv_monomial(_poly_add(matern_poly(p, 2), npd), 2))
+    if a.size != d or b.size != d:
+        raise ValueError("direction and kernel input dimensions differ")
+    if max(len(q0), len(q1), len(q2)) > nq:
+        raise NotImplementedError(f"Matern order nu={nu} exceeds the device descriptor")
+    desc = _lib.KernelDesc()
+    desc.d = d
+    for i in range(d):
+        desc.dim_type[i] = _lib.DIM_RADIAL
+        desc.nbasis[i] = nq
+        desc.has_odd[i] = 0
+        desc.scale[i] = float(s[i])
+    sig = float(sigma2)
+    for i, c in enumerate(q0):
+        desc.coef[i] = sig * c0 * float(c)
+    for i, c in enumerate(q1):
+        desc.coef[nq + i] = sig * float(c)
+    for i, c in enumerate(q2):
+        desc.coef[2 * nq + i] = sig * float(c)
+    for i in range(d):
+        desc.coef[3 * nq + i] = float(a[i])
+        desc.coef[3 * nq + d + i] = float(b[i])
+    desc.diag_value = sig * c0 * float(q0[0])
+    return desc

@@ -387,6 +387,36 @@ class DeviceFactor:
         check(lib.lpgp_trsm_rlt(ctypes.byref(f), nlead, _ptr(X), X.shape[0], _ld(X), _stream()), "lpgp_trsm_rlt")
         return X
 
+    def ozaki_eligible(self, kblock: int) -> bool:
+        """The emulated solve cuts the factor into column blocks of ``kblock`` columns that must start on leaf boundaries:
+        every segment but the last a multiple of 128 rows, and at least two blocks."""
+        return all(o % _lib.LEAF == 0 for o in self.seg_off[:-1]) and self.n >= 2 * kblock
+
+    def ozaki_planes(self, nslices: int, kblock: int) -> OzakiPlanes:
+        """Digit planes of the factor (strictly-lower K-blocks only), computed once and cached."""
+        key = (int(nslices), int(kblock))
+        cache = self.__dict__.setdefault("_ozaki_cache", {})
+        if key not in cache:
+            P = OzakiPlanes(self.n, self.n, nslices, kblock)
+            nfull = (self.n // kblock) * kblock  # K never extends into a partial last block
+            if nfull:
+                P.split(self.L[:, :nfull], lower_blocks=True)
+            cache.clear()
+            cache[key] = P
+        return cache[key]
+
+    def trsm_rlt_ozaki(self, X: torch.Tensor, nslices: int, kblock: int = 1024, XP: Optional[OzakiPlanes] = None) -> torch.Tensor:
+        """X <- X L^{-T} in place with the O(m n^2) part emulated on the INT8 tensor cores (``lpgp_trsm_rlt_ozaki``)."""
+        assert X.shape[1] == self.n
+        LP = self.ozaki_planes(nslices, kblock)
+        if XP is None or XP.rows < X.shape[0] or XP.nslices != nslices or XP.kblock != kblock or XP.cols < self.n:
+            XP = OzakiPlanes(X.shape[0], self.n, nslices, kblock)
+        f = self._struct()
+        rc = lib.lpgp_trsm_rlt_ozaki(ctypes.byref(f), _ptr(X), X.shape[0], _ld(X), ctypes.byref(LP.struct),
+                                     ctypes.byref(XP.struct), _stream())
+        check(rc, "lpgp_trsm_rlt_ozaki")
+        return X
+
     def trsv(self, b: torch.Tensor, trans: bool = False) -> torch.Tensor:
         """b <- L^{-1} b (``trans``: L^{-T} b) in place; one contiguous right-hand side of length n."""
         assert b.numel() == self.n and b.is_contiguous()
@@ -408,6 +438,71 @@ class DeviceFactor:
         f = self._struct()
         check(lib.lpgp_logdet(ctypes.byref(f), _ptr(out), _stream()), "lpgp_logdet")
         return float(out.item())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# FP64 emulated on the INT8 tensor cores (Ozaki scheme, csrc/ozaki.cu): opt-in solver of the posterior-variance TRSM
+class OzakiPlanes:
+    """Digit planes of an FP64 matrix (``lpgp_ozaki_planes``): ``nslices`` byte planes of ``rows x cols`` plus one int32
+    exponent per (row, K-block of ``kblock`` columns).  Owns its buffers."""
+
+    def __init__(self, rows: int, cols: int, nslices: int, kblock: int = 1024):
+        dev = _require_cuda()
+        if not 1 <= nslices <= _lib.OZAKI_MAX_SLICES:
+            raise ValueError(f"nslices must be in 1..{_lib.OZAKI_MAX_SLICES}")
+        if kblock % 128 or not 128 <= kblock <= 4096:
+            raise ValueError("kblock must be a multiple of 128 in 128..4096")
+        self.rows, self.cols, self.nslices, self.kblock = int(rows), int(cols), int(nslices), int(kblock)
+        self.pitch = round_up(max(self.cols, 1), 128)
+        self.buf = torch.empty((self.nslices, max(self.rows, 1), self.pitch), dtype=torch.uint8, device=dev)
+        self.nkb = (self.cols + kblock - 1) // kblock
+        self.exps = torch.zeros((max(self.nkb, 1), max(self.rows, 1)), dtype=torch.int32, device=dev)
+        st = _lib.OzakiPlanes()
+        st.planes, st.exps = self.buf.data_ptr(), self.exps.data_ptr()
+        st.rows, st.cols, st.pitch = self.rows, self.cols, self.pitch
+        st.plane_stride = max(self.rows, 1) * self.pitch
+        st.lde = max(self.rows, 1)
+        st.nslices, st.kblock = self.nslices, self.kblock
+        self.struct = st
+
+    def split(self, A: torch.Tensor, row_off: int = 0, col0: int = 0, lower_blocks: bool = False) -> None:
+        """Digits of ``A`` (rows x ncols, ncols a multiple of kblock) -> rows ``row_off..``, columns ``col0..``."""
+        rows, ncols = A.shape
+        check(lib.lpgp_ozaki_split(_ptr(A), _ld(A), rows, int(row_off), int(col0), ncols, ctypes.byref(self.struct),
+                                   int(lower_blocks), _stream()), "lpgp_ozaki_split")
+
+    def reconstruct(self, rows: slice, cols: slice) -> torch.Tensor:
+        """FP64 value of the stored digits (tests / diagnostics; torch arithmetic, not a product path)."""
+        kb0, kb1 = cols.start // self.kblock, (cols.stop + self.kblock - 1) // self.kblock
+        out = torch.zeros((rows.stop - rows.start, cols.stop - cols.start), dtype=F64, device=self.buf.device)
+        for s in range(self.nslices):
+            d = self.buf[s, rows, cols]
+            d = d.to(torch.int8).to(F64) if s == 0 else d.to(F64)
+            out += d * 2.0 ** (-7 - 8 * s)
+        e = self.exps[kb0:kb1, rows].to(F64).T.repeat_interleave(self.kblock, dim=1)
+        e = e[:, cols.start - kb0 * self.kblock : cols.stop - kb0 * self.kblock]
+        return out * torch.exp2(e)
+
+
+def ozaki_gemm_nt(PA: OzakiPlanes, PB: OzakiPlanes, C: torch.Tensor, k: int, alpha: float = 1.0, beta: float = 0.0,
+                  rowA0: int = 0, kA0: int = 0, rowB0: int = 0, kB0: int = 0) -> torch.Tensor:
+    """C = beta C + alpha A B^T from digit planes (A = rows rowA0.. / columns kA0..kA0+k of PA, B likewise)."""
+    m, n = C.shape
+    rc = lib.lpgp_ozaki_gemm_nt(m, n, int(k), float(alpha), ctypes.byref(PA.struct), int(rowA0), int(kA0),
+                                ctypes.byref(PB.struct), int(rowB0), int(kB0), float(beta), _ptr(C), _ld(C), _stream())
+    check(rc, "lpgp_ozaki_gemm_nt")
+    return C
+
+
+# posterior-variance solver: {"ozaki_slices": 0} = native DMMA path (default); S in 1..7 = emulated on the INT8 tensor
+# cores with S digit planes (S = 6 keeps 47 bits, S = 7 all 53)
+VARIANCE_SOLVER = {"ozaki_slices": int(__import__("os").environ.get("LPGP_OZAKI_SLICES", "0")), "kblock": 1024}
+
+
+def set_variance_solver(ozaki_slices: int = 0, kblock: int = 1024) -> None:
+    if not 0 <= int(ozaki_slices) <= _lib.OZAKI_MAX_SLICES:
+        raise ValueError(f"ozaki_slices must be in 0..{_lib.OZAKI_MAX_SLICES}")
+    VARIANCE_SOLVER["ozaki_slices"], VARIANCE_SOLVER["kblock"] = int(ozaki_slices), int(kblock)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -484,12 +579,18 @@ def post_var(blocks: ObsBlocks, factor: DeviceFactor, Xt: torch.Tensor, prior_di
     chunk = max(1, min(chunk, m))
     K = alloc_matrix(chunk, factor.n)
     f = factor._struct()
+    S, kblock = VARIANCE_SOLVER["ozaki_slices"], VARIANCE_SOLVER["kblock"]
+    emulate = S > 0 and factor.ozaki_eligible(kblock)
+    XP = OzakiPlanes(chunk, factor.n, S, kblock) if emulate else None
     for i0 in range(0, m, chunk):
         mc = min(chunk, m - i0)
-        if blocks.extras:  # same three steps as lpgp_post_var, with the integral columns added in between
+        if blocks.extras or emulate:  # same three steps as lpgp_post_var, spelled out
             Kc = K[:mc]
             crosscov(blocks, factor.n, Xt[i0 : i0 + mc], out=Kc)
-            factor.trsm_rlt(Kc)
+            if emulate:
+                factor.trsm_rlt_ozaki(Kc, S, kblock, XP)
+            else:
+                factor.trsm_rlt(Kc)
             check(lib.lpgp_row_sumsq(_ptr(Kc), mc, factor.n, _ld(K), -1.0, float(prior_diag), _ptr(out[i0:]), _stream()),
                   "lpgp_row_sumsq")
             continue

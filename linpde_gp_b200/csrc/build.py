@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblpgp.so")
-SOURCES = ["api.cu", "gram.cu", "kron.cu", "gemm_dmma.cu", "cholesky.cu", "posterior.cu", "integrals.cu"]
+SOURCES = ["api.cu", "gram.cu", "kron.cu", "gemm_dmma.cu", "ozaki.cu", "cholesky.cu", "posterior.cu", "integrals.cu"]
 HEADERS = ["common.cuh", "kernel_eval.cuh", os.path.join("..", "..", "include", "lpgp.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

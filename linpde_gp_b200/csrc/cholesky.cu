@@ -974,6 +974,42 @@ extern "C" int lpgp_trsm_rlt_refined(const lpgp_factor* f, int64_t nlead, double
   return trsm_rlt_impl(f, nlead, X, m, ldx, stream, g_lpgp_trsm_refine >= 1);
 }
 
+// Blocked left-looking X <- X L^{-T}: the O(m n^2) part runs as emulated GEMMs on the INT8 tensor cores (ozaki.cu),
+// the diagonal blocks (kblock columns, 1 / (n / kblock) of the flops) on the DMMA recursion above.
+extern "C" int lpgp_trsm_rlt_ozaki(const lpgp_factor* f, double* X, int64_t m, int64_t ldx, const lpgp_ozaki_planes* LP,
+                                   const lpgp_ozaki_planes* XP, void* stream) {
+  if (check_factor(f)) return -1;
+  if (!X || ldx < f->n || (ldx % 2) || ((uintptr_t)X % 16)) return -2;
+  if (m < 0) return -3;
+  if (!LP || !XP || LP->kblock != XP->kblock || LP->nslices != XP->nslices) return -5;
+  if (LP->rows < f->n || XP->rows < m) return -5;
+  if (m == 0) return 0;
+  Leaves lv;
+  if (build_leaves(f->seg_off, f->nseg, lv)) return -1;
+  const int nl = (int)lv.off.size() - 1;
+  for (int l = 0; l < nl; ++l)
+    if (lv.off[l] % LEAF) return -1;  // column blocks must start and end on leaf boundaries
+  const int64_t n = f->n, kb = LP->kblock;
+  const int lpb = (int)(kb / LEAF);  // leaves per column block
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t c0 = 0; c0 < n; c0 += kb) {
+    const int64_t c1 = c0 + kb < n ? c0 + kb : n;
+    const int l0 = (int)(c0 / LEAF), l1 = c1 == n ? nl : l0 + lpb;
+    int rc = 0;
+    if (c0 > 0) {  // X[:, c0:c1] -= X[:, :c0] L[c0:c1, :c0]^T
+      rc = lpgp_ozaki_gemm_nt(m, c1 - c0, c0, -1.0, XP, 0, 0, LP, c0, 0, 1.0, X + c0, ldx, stream);
+      if (rc) return rc;
+    }
+    rc = trsm_rec(f, lv, l0, l1, X + c0, m, ldx, st);
+    if (rc) return rc;
+    if (c1 < n) {  // the solved block becomes part of the contraction of every later block
+      rc = lpgp_ozaki_split(X + c0, ldx, m, 0, c0, kb, XP, 0, stream);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
 namespace {
 // single right-hand-side substitution with the leaves of `f`: trans == 0: b <- L^{-1} b, else b <- L^{-T} b
 int trsv_impl(const lpgp_factor* f, const Leaves& lv, int trans, double* b, cudaStream_t st) {

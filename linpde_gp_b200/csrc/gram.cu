@@ -15,11 +15,14 @@ constexpr int TN = 128;
 constexpr int NTHREADS = 256;
 constexpr int ROWS_PER_THREAD = TM / (NTHREADS / (TN / 2));  // 16
 
-template <int D, int NB, bool ODD>
+// P: parameter pack with a compile-time dimension P::DIM and a device member eval(x0, x1) -- EvalParams (product
+// form) or RadialParams (isotropic multi-d Matern)
+template <typename P>
 __global__ void __launch_bounds__(NTHREADS)
-    gram_tile_kernel(const __grid_constant__ EvalParams<D, NB, ODD> p, const double* __restrict__ X0, int64_t n0,
+    gram_tile_kernel(const __grid_constant__ P p, const double* __restrict__ X0, int64_t n0,
                      const double* __restrict__ X1, int64_t n1, double* __restrict__ out, int64_t ld, int mode,
                      int accumulate, double alpha, int vec_ok) {
+  constexpr int D = P::DIM;
   const int64_t row0 = (int64_t)blockIdx.y * TM;
   const int64_t col0 = (int64_t)blockIdx.x * TN;
   if (mode == LPGP_GRAM_LOWER && col0 > row0 + (TM - 1)) return;  // tile strictly above the diagonal
@@ -75,10 +78,10 @@ __global__ void __launch_bounds__(NTHREADS)
       y0[d] = sx0[lr * D + d];
       y1[d] = r1_ok ? sx0[(lr + 1) * D + d] : y0[d];
     }
-    double v00 = alpha * eval_pair<D, NB, ODD>(p, y0, xa);
-    double v01 = alpha * eval_pair<D, NB, ODD>(p, y0, xb);
-    double v10 = alpha * eval_pair<D, NB, ODD>(p, y1, xa);
-    double v11 = alpha * eval_pair<D, NB, ODD>(p, y1, xb);
+    double v00 = alpha * p.eval(y0, xa);
+    double v01 = alpha * p.eval(y0, xb);
+    double v10 = alpha * p.eval(y1, xa);
+    double v11 = alpha * p.eval(y1, xb);
     double* o0 = obase + (int64_t)r * ld;
     double* o1 = o0 + ld;
     if (vec_ok && c1_ok) {
@@ -339,7 +342,19 @@ int launch_tile(const lpgp_kernel_desc& k, const double* X0, int64_t n0, const d
     return 0;
   }
   dim3 grid((unsigned)ceil_div64(n1, TN), (unsigned)ceil_div64(n0, TM));
-  gram_tile_kernel<D, NB, ODD><<<grid, NTHREADS, 0, st>>>(p, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, vec_ok);
+  gram_tile_kernel<EvalParams<D, NB, ODD>><<<grid, NTHREADS, 0, st>>>(p, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, vec_ok);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int D>
+int launch_radial(const lpgp_kernel_desc& k, const double* X0, int64_t n0, const double* X1, int64_t n1, double* out,
+                  int64_t ld, int mode, int accumulate, double alpha, cudaStream_t st) {
+  RadialParams<D> p;
+  pack_radial<D>(k, p);
+  const int vec_ok = (ld % 2 == 0) && ((uintptr_t)out % 16 == 0);
+  dim3 grid((unsigned)ceil_div64(n1, TN), (unsigned)ceil_div64(n0, TM));
+  gram_tile_kernel<RadialParams<D>><<<grid, NTHREADS, 0, st>>>(p, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, vec_ok);
   LPGP_CHECK_LAUNCH();
   return 0;
 }
@@ -419,6 +434,14 @@ extern "C" int lpgp_gram(const lpgp_kernel_desc* desc, const double* X0, int64_t
   if (mode == LPGP_GRAM_LOWER && n0 != n1) return -8;
   if (n0 == 0 || n1 == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (is_radial(*desc)) {
+    switch (desc->d) {
+      case 1: return launch_radial<1>(*desc, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, st);
+      case 2: return launch_radial<2>(*desc, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, st);
+      case 3: return launch_radial<3>(*desc, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, st);
+      default: return launch_radial<4>(*desc, X0, n0, X1, n1, out, ld, mode, accumulate, alpha, st);
+    }
+  }
   bool odd;
   const int NB = pick_nb(*desc, odd);
   int rc = -1;

@@ -12,12 +12,56 @@
 
 template <int D, int NB, bool ODD>
 struct EvalParams {
+  static constexpr int DIM = D;
   static constexpr int NBT = ODD ? 2 * NB : NB;
   static constexpr int NCOEF = (D == 1 ? NBT : (D == 2 ? NBT * NBT : NBT * NBT * NBT));
   int32_t dim_type[D];
   double scale[D];
   double coef[NCOEF];
+  __device__ __forceinline__ double eval(const double* x0, const double* x1) const;  // = eval_pair (defined below)
 };
+
+// radial (isotropic multi-d Matern) kernels, see lpgp_kernel_desc: coef = [Q0 | Q1 | Q2 | a | b]
+template <int D>
+struct RadialParams {
+  static constexpr int DIM = D;
+  double scale[D];
+  double a[D], b[D];
+  double q[3][LPGP_RADIAL_NQ];
+  __device__ __forceinline__ double eval(const double* x0, const double* x1) const {
+    double r2 = 0.0, pa = 0.0, pb = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double u = (x0[d] - x1[d]) * scale[d];
+      r2 = fma(u, u, r2);
+      pa = fma(a[d], u, pa);
+      pb = fma(b[d], u, pb);
+    }
+    const double r = sqrt(r2);
+    double h[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      double acc = q[t][LPGP_RADIAL_NQ - 1];
+#pragma unroll
+      for (int i = LPGP_RADIAL_NQ - 2; i >= 0; --i) acc = fma(acc, r, q[t][i]);
+      h[t] = acc;
+    }
+    return fma(pa, fma(pb, h[2], h[1]), h[0]) * exp(-r);
+  }
+};
+
+static inline bool is_radial(const lpgp_kernel_desc& k) { return k.dim_type[0] == LPGP_DIM_RADIAL; }
+
+template <int D>
+static inline void pack_radial(const lpgp_kernel_desc& k, RadialParams<D>& p) {
+  for (int d = 0; d < D; ++d) {
+    p.scale[d] = k.scale[d];
+    p.a[d] = k.coef[3 * LPGP_RADIAL_NQ + d];
+    p.b[d] = k.coef[3 * LPGP_RADIAL_NQ + D + d];
+  }
+  for (int t = 0; t < 3; ++t)
+    for (int i = 0; i < LPGP_RADIAL_NQ; ++i) p.q[t][i] = k.coef[t * LPGP_RADIAL_NQ + i];
+}
 
 template <int D, int NB, bool ODD, int DIM>
 struct NestedHorner {
@@ -67,6 +111,11 @@ __device__ __forceinline__ double eval_pair(const P& p, const double* x0, const 
   }
   const double poly = NestedHorner<D, NB, ODD, 0>::run(p, v, u, 0);
   return poly * exp(-g);
+}
+
+template <int D, int NB, bool ODD>
+__device__ __forceinline__ double EvalParams<D, NB, ODD>::eval(const double* x0, const double* x1) const {
+  return eval_pair<D, NB, ODD>(*this, x0, x1);
 }
 
 // ---- separable exponentials (all-Matern product kernels) ------------------------------------------------------
@@ -133,6 +182,23 @@ __host__ __device__ __forceinline__ bool all_matern(const P& p) {
 // Generic (runtime-shaped) evaluation straight from the descriptor: any d <= LPGP_MAX_DIM, any basis sizes.
 // Slow path used only for shapes without a specialised instantiation.
 __device__ __forceinline__ double eval_pair_generic(const lpgp_kernel_desc& k, const double* x0, const double* x1) {
+  if (k.dim_type[0] == LPGP_DIM_RADIAL) {
+    double r2 = 0.0, pa = 0.0, pb = 0.0;
+    for (int d = 0; d < k.d; ++d) {
+      const double uu = (x0[d] - x1[d]) * k.scale[d];
+      r2 = fma(uu, uu, r2);
+      pa = fma(k.coef[3 * LPGP_RADIAL_NQ + d], uu, pa);
+      pb = fma(k.coef[3 * LPGP_RADIAL_NQ + k.d + d], uu, pb);
+    }
+    const double r = sqrt(r2);
+    double h[3];
+    for (int t = 0; t < 3; ++t) {
+      double acc = k.coef[t * LPGP_RADIAL_NQ + LPGP_RADIAL_NQ - 1];
+      for (int i = LPGP_RADIAL_NQ - 2; i >= 0; --i) acc = fma(acc, r, k.coef[t * LPGP_RADIAL_NQ + i]);
+      h[t] = acc;
+    }
+    return fma(pa, fma(pb, h[2], h[1]), h[0]) * exp(-r);
+  }
   double v[LPGP_MAX_DIM], u[LPGP_MAX_DIM];
   int nbt[LPGP_MAX_DIM];
   double g = 0.0;
@@ -195,6 +261,7 @@ static inline void pack_params(const lpgp_kernel_desc& k, EvalParams<D, NB, ODD>
 static inline int pick_nb(const lpgp_kernel_desc& k, bool& odd) {
   int nb = 1;
   odd = false;
+  if (is_radial(k)) return 0;  // radial kernels have their own instantiations
   for (int d = 0; d < k.d; ++d) {
     if (k.nbasis[d] > nb) nb = k.nbasis[d];
     if (k.has_odd[d]) odd = true;
@@ -208,6 +275,11 @@ static inline int pick_nb(const lpgp_kernel_desc& k, bool& odd) {
 static inline int validate_desc(const lpgp_kernel_desc* k) {
   if (!k) return -1;
   if (k->d < 1 || k->d > LPGP_MAX_DIM) return -1;
+  if (k->dim_type[0] == LPGP_DIM_RADIAL) {  // all dimensions radial, fixed coefficient layout
+    for (int d = 0; d < k->d; ++d)
+      if (k->dim_type[d] != LPGP_DIM_RADIAL || !(k->scale[d] > 0.0)) return -1;
+    return 0;
+  }
   int64_t total = 1;
   for (int d = 0; d < k->d; ++d) {
     if (k->dim_type[d] != LPGP_DIM_MATERN && k->dim_type[d] != LPGP_DIM_EXPQUAD) return -1;

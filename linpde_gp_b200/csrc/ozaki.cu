@@ -1,0 +1,445 @@
+// FP64 GEMM emulated on the INT8 tensor cores (Ozaki scheme) -- the one place of this FP64 path where Blackwell's
+// tcgen05 / TMEM machinery applies (tcgen05 has no FP64 kind; the native FP64 tensor path is the warp-level DMMA of
+// gemm_dmma.cu, whose issue rate, 37 TFLOP/s, bounds 92 % of a posterior-variance step).
+//
+//   C[m x n] = beta C + alpha A[m x K] B[n x K]^T                                   (all row-major, "NT" like lpgp_gemm_nt)
+//
+// Error-free splitting.  The contraction index is cut into K-blocks of `kblock` columns.  Inside one K-block every
+// operand row x gets ONE power-of-two scale 2^e (e = smallest integer with max|x| < 2^e) and is expanded in radix 256,
+//
+//     x = 2^e * sum_{s >= 0} d_s 2^(-7 - 8 s),    d_0 = floor(x 2^(7-e)) in [-128, 127] (int8),  d_s in [0, 255] (uint8),
+//
+// exactly (S digits carry 7 + 8 (S-1) bits below the row maximum: S = 7 is all of FP64).  The digits are stored as S
+// byte planes.  Then
+//
+//     a . b = 2^(ea + eb - 14) sum_q 256^(-q) sum_{s + t = q} sum_k a_s[k] b_t[k]
+//
+// and the innermost sums are EXACT in int32 (|sum| <= (q+1) kblock 255^2 < 2^31 for kblock <= 4096, S <= 7), which is
+// what `tcgen05.mma.kind::i8` computes: all products of one level q accumulate into the same TMEM accumulator.  Levels
+// q >= S are dropped (relative truncation 2^(-7 - 8 (S-1)) against the product of the row maxima).  The levels are
+// recombined in FP64 registers: acc += double(D_q) * 2^(ea + eb - 14 - 8 q), every operation but the final sum exact.
+//
+// Kernel (one CTA = one 128 x 128 output tile, 320 threads):
+//   warp 0    TMA producer: 3-D tensor maps (k byte, row, plane), SWIZZLE_128B boxes of 128 rows x 128 bytes -> 6-stage ring
+//   warp 1    allocates TMEM (512 columns = 4 accumulators of 128 x 128 int32), one lane issues tcgen05.mma (M = 128,
+//             N = 128, K = 32 bytes, 4 per stage), tcgen05.commit releases stages / publishes finished accumulators
+//   warps 2-9 epilogue: tcgen05.ld the finished level (thread = 1 row x 64 columns), scale, accumulate in FP64 registers
+//             (64 per thread), hand the accumulator back; after the last K-block write C.
+// The MMA of level q+1 overlaps the epilogue of level q (4 accumulators in flight).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int OZ_BM = 128, OZ_BN = 128;
+constexpr int OZ_BK = 128;  // bytes of the contraction index per stage = one 128-byte swizzle row
+constexpr int OZ_STAGES = 6;
+constexpr int OZ_THREADS = 320;
+constexpr int OZ_EPI_THREADS = 256;
+constexpr int OZ_ACC = 4;  // TMEM accumulators (128 columns each)
+constexpr int OZ_A_BYTES = OZ_BM * OZ_BK, OZ_B_BYTES = OZ_BN * OZ_BK;
+constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;
+constexpr int OZ_BAR_BYTES = (2 * OZ_STAGES + 2 * OZ_ACC) * 8 + 16;
+constexpr int OZ_SMEM_BYTES = 1024 + OZ_STAGES * OZ_STAGE_BYTES + OZ_BAR_BYTES + OZ_BN * 8;
+
+__device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, int8/uint8 operands, int32 accumulation
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// all tcgen05.mma issued so far by this thread arrive (once) on the mbarrier when they have completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 2^e as a double (e clamped to the normal range)
+__device__ __forceinline__ double exp2i(int e) {
+  e = e < -1022 ? -1022 : (e > 1023 ? 1023 : e);
+  return __hiloint2double((1023 + e) << 20, 0);
+}
+
+// shared-memory matrix descriptor of a K-major tile of 128-byte rows in the SWIZZLE_128B layout TMA produces
+// (cute::UMMA::SmemDescriptor: start address >> 4 | LBO (unused for swizzled K-major layouts) = 1 | SBO = 8 rows x 128 B
+//  = 1024 B >> 4 | version 1 (sm_100) | layout type 2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): dense, no saturation, D = S32, A / B = int8 (1) or uint8 (0),
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t idesc_i8(int a_signed, int b_signed) {
+  return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(OZ_BN >> 3) << 17) |
+         ((uint32_t)(OZ_BM >> 4) << 24);
+}
+
+struct OzParams {
+  int m, n;            // output tile grid covers m x n
+  int nkb;             // K-blocks
+  int kblock;          // bytes (= columns) per K-block, multiple of OZ_BK
+  int nslices;         // S
+  int rowA0, rowB0;    // first row of A / B inside their plane arrays
+  int kA0, kB0;        // first contraction column of A / B inside their plane arrays (multiples of kblock)
+  const int* eA;       // exponents [(kA0 / kblock + kb) * ldeA + rowA0 + r]
+  const int* eB;
+  int64_t ldeA, ldeB;
+  double* C;
+  int64_t ldc;
+  double alpha, beta;
+  int tiles_n;
+};
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ OzParams p) {
+  extern __shared__ unsigned char oz_smem_raw[];
+  unsigned char* smem = oz_smem_raw + ((1024u - (smem_u32(oz_smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B: 1024-byte atoms
+  uint64_t* full = (uint64_t*)(smem + OZ_STAGES * OZ_STAGE_BYTES);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* acc_full = empty + OZ_STAGES;
+  uint64_t* acc_empty = acc_full + OZ_ACC;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + OZ_ACC);
+  double* s_sb = (double*)(smem + OZ_STAGES * OZ_STAGE_BYTES + OZ_BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tm = blockIdx.x / p.tiles_n, tn = blockIdx.x % p.tiles_n;
+  const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
+  const int S = p.nslices;
+  const int chunks = p.kblock / OZ_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < OZ_STAGES; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(empty + i, 1);
+    }
+    for (int i = 0; i < OZ_ACC; ++i) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, OZ_EPI_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // one warp allocates all 512 TMEM columns (1 CTA per SM: no contention) and later frees them
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int kb = 0; kb < p.nkb; ++kb)
+        for (int q = 0; q < S; ++q)
+          for (int s = 0; s <= q; ++s) {
+            const int t = q - s;
+            for (int c = 0; c < chunks; ++c) {
+              mbar_wait(empty + stage, phase ^ 1);
+              unsigned char* dst = smem + stage * OZ_STAGE_BYTES;
+              mbar_expect_tx(full + stage, OZ_STAGE_BYTES);
+              const int kk = kb * p.kblock + c * OZ_BK;
+              oz_tma_load_3d(dst, &tmA, p.kA0 + kk, p.rowA0 + m0, s, full + stage);
+              oz_tma_load_3d(dst + OZ_A_BYTES, &tmB, p.kB0 + kk, p.rowB0 + n0, t, full + stage);
+              if (++stage == OZ_STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      int stage = 0, phase = 0, it = 0;
+      for (int kb = 0; kb < p.nkb; ++kb)
+        for (int q = 0; q < S; ++q, ++it) {
+          const int buf = it % OZ_ACC;
+          mbar_wait(acc_empty + buf, ((it / OZ_ACC) & 1) ^ 1);  // the epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * OZ_BN);
+          uint32_t accumulate = 0;
+          for (int s = 0; s <= q; ++s) {
+            const uint32_t idesc = idesc_i8(s == 0, (q - s) == 0);
+            for (int c = 0; c < chunks; ++c) {
+              mbar_wait(full + stage, phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + stage * OZ_STAGE_BYTES);
+              const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + OZ_A_BYTES);
+#pragma unroll
+              for (int j = 0; j < OZ_BK / 32; ++j) {  // K = 32 bytes per instruction: +32 bytes = +2 in the address field
+                tc_mma_i8(tmem_d, da + 2 * j, db + 2 * j, idesc, accumulate);
+                accumulate = 1;
+              }
+              tc_commit(empty + stage);  // stage reusable once these MMAs have read it
+              if (++stage == OZ_STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          tc_commit(acc_full + buf);  // level q of K-block kb complete
+        }
+    }
+  } else {
+    // ===== epilogue: 8 warps, thread = 1 row x 64 columns, FP64 accumulation in registers =====
+    const int et = threadIdx.x - 64;
+    const int quad = warp & 3;          // TMEM lanes this warp may access: 32 * (warp % 4) ...
+    const int half = (warp - 2) >> 2;   // columns [64 half, 64 half + 64)
+    const int row = m0 + quad * 32 + lane;
+    double acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+    int it = 0;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");  // everyone is done with the previous K-block's s_sb
+      if (et < OZ_BN) {
+        const int col = n0 + et;
+        s_sb[et] = col < p.n ? exp2i(p.eB[(int64_t)(p.kB0 / p.kblock + kb) * p.ldeB + p.rowB0 + col]) : 0.0;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
+      const int ea = row < p.m ? p.eA[(int64_t)(p.kA0 / p.kblock + kb) * p.ldeA + p.rowA0 + row] : 0;
+      for (int q = 0; q < S; ++q, ++it) {
+        const int buf = it % OZ_ACC;
+        mbar_wait(acc_full + buf, (it / OZ_ACC) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * OZ_BN + half * 64);
+        const double srow = exp2i(ea - 14 - 8 * q);
+        const double* sb = s_sb + half * 64;
+        uint32_t v[32];
+        tc_ld32(taddr, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fma(__int2double_rn((int)v[j]), srow * sb[j], acc[j]);
+        tc_ld32(taddr + 32, v);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) oz_mbar_arrive(acc_empty + buf);  // accumulator may be overwritten
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[32 + j] = fma(__int2double_rn((int)v[j]), srow * sb[32 + j], acc[32 + j]);
+      }
+    }
+    if (row < p.m) {
+      double* crow = p.C + (int64_t)row * p.ldc + n0 + half * 64;
+      const int ncols = p.n - (n0 + half * 64);  // valid columns of my 64
+      const bool vec = (p.ldc % 2 == 0) && ((uintptr_t)p.C % 16 == 0);
+#pragma unroll
+      for (int j = 0; j < 64; j += 2) {
+        if (j + 1 < ncols && vec) {
+          double2 c = p.beta == 0.0 ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(crow + j);
+          c.x = fma(p.alpha, acc[j], p.beta * c.x);
+          c.y = fma(p.alpha, acc[j + 1], p.beta * c.y);
+          *reinterpret_cast<double2*>(crow + j) = c;
+        } else {
+          if (j < ncols) crow[j] = fma(p.alpha, acc[j], p.beta == 0.0 ? 0.0 : p.beta * crow[j]);
+          if (j + 1 < ncols) crow[j + 1] = fma(p.alpha, acc[j + 1], p.beta == 0.0 ? 0.0 : p.beta * crow[j + 1]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---- splitting: FP64 rows -> S digit planes + one exponent per (row, K-block) -----------------------------------
+// One warp per (row, K-block): pass 1 = row maximum over the block (warp reduction), pass 2 = digits.  Lane l handles
+// the 4 consecutive columns 4 (l + 32 i) .. +3 (32 bytes read, one 4-byte store per plane -> 128 contiguous bytes per warp).
+// lower_blocks != 0: only the K-blocks strictly left of the row's own diagonal block are produced (factor L: block
+// column jb is only ever contracted over the K-blocks < jb).
+__global__ void __launch_bounds__(256)
+    ozaki_slice_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int64_t row_off, int64_t col0, int nkb,
+                       int kblock, int nslices, unsigned char* __restrict__ planes, int64_t pitch, int64_t plane_stride,
+                       int* __restrict__ exps, int64_t lde, int lower_blocks) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp;
+  const int kb = blockIdx.y;
+  if (r >= rows) return;
+  if (lower_blocks && col0 / kblock + kb >= (r + row_off) / kblock) return;  // absolute K-block >= the row's own block
+  const double* src = A + r * lda + col0 + (int64_t)kb * kblock;
+  double mx = 0.0;
+  for (int c = lane * 4; c < kblock; c += 128) {
+    const double2 x0 = *reinterpret_cast<const double2*>(src + c), x1 = *reinterpret_cast<const double2*>(src + c + 2);
+    mx = fmax(fmax(fabs(x0.x), fabs(x0.y)), fmax(mx, fmax(fabs(x1.x), fabs(x1.y))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  // smallest e with max < 2^e; an all-zero (or non-finite) block gets e = 0 and all-zero digits
+  const bool ok = mx > 0.0 && mx < 1.7e308;
+  const int e = ok ? ilogb(mx) + 1 : 0;
+  if (lane == 0) exps[(int64_t)(col0 / kblock + kb) * lde + row_off + r] = e;
+  const double sc = exp2i(7 - e);  // |x| 2^(7-e) < 128 (e within the normal range for any data of this path)
+  unsigned char* dst = planes + (r + row_off) * pitch + col0 + (int64_t)kb * kblock;
+  for (int c = lane * 4; c < kblock; c += 128) {
+    const double2 x0 = *reinterpret_cast<const double2*>(src + c), x1 = *reinterpret_cast<const double2*>(src + c + 2);
+    double t[4] = {x0.x * sc, x0.y * sc, x1.x * sc, x1.y * sc};
+    if (!ok) t[0] = t[1] = t[2] = t[3] = 0.0;
+    for (int s = 0; s < nslices; ++s) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double d = floor(t[i]);
+        t[i] = (t[i] - d) * 256.0;  // exact: remainder in [0, 1)
+        packed |= ((uint32_t)((int)d) & 0xffu) << (8 * i);
+      }
+      *reinterpret_cast<uint32_t*>(dst + s * plane_stride + c) = packed;
+    }
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_oz_encode = nullptr;
+std::once_flag g_oz_once;
+int g_oz_init_rc = 0;
+std::atomic<int> g_oz_attr[LPGP_MAX_DEVICES];
+
+void oz_init_once() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    g_oz_init_rc = LPGP_CUDA_ERR(e != cudaSuccess ? e : cudaErrorNotSupported);
+    return;
+  }
+  g_oz_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+}
+
+int oz_ensure() {
+  std::call_once(g_oz_once, oz_init_once);
+  if (g_oz_init_rc) return g_oz_init_rc;
+  int dev = 0;
+  LPGP_CHECK(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < LPGP_MAX_DEVICES;
+  if (tracked && g_oz_attr[dev].load(std::memory_order_acquire)) return 0;
+  LPGP_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
+  if (tracked) g_oz_attr[dev].store(1, std::memory_order_release);
+  return 0;
+}
+
+// byte planes [nslices][rows][pitch] -> 3-D tensor map (k, row, plane), boxes of 128 bytes x 128 rows x 1 plane
+int oz_make_map(CUtensorMap* tm, const unsigned char* planes, int64_t cols, int64_t rows, int64_t pitch,
+                int64_t plane_stride, int nslices) {
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nslices};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)plane_stride};
+  cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)OZ_BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_oz_encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : LPGP_CUDA_ERR(cudaErrorInvalidValue);
+}
+
+int check_planes(const lpgp_ozaki_planes* P) {
+  if (!P || !P->planes || !P->exps) return -1;
+  if (P->nslices < 1 || P->nslices > LPGP_OZAKI_MAX_SLICES) return -1;
+  if (P->kblock < OZ_BK || P->kblock > 4096 || P->kblock % OZ_BK) return -1;
+  if (P->rows < 1 || P->cols < 1 || P->pitch < P->cols || P->pitch % 16 || P->plane_stride < P->rows * P->pitch ||
+      P->plane_stride % 16 || ((uintptr_t)P->planes % 16))
+    return -1;
+  if (P->lde < P->rows) return -1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int lpgp_ozaki_split(const double* A, int64_t lda, int64_t rows, int64_t row_off, int64_t col0, int64_t ncols,
+                                const lpgp_ozaki_planes* P, int lower_blocks, void* stream) {
+  if (check_planes(P)) return -7;
+  if (rows < 0 || row_off < 0 || row_off + rows > P->rows) return -3;
+  if (col0 < 0 || ncols < 0 || col0 % P->kblock || ncols % P->kblock || col0 + ncols > P->cols) return -5;
+  if (rows == 0 || ncols == 0) return 0;
+  if (!A || lda < ncols || (lda % 2) || ((uintptr_t)A % 16)) return -1;
+  const int nkb = (int)(ncols / P->kblock);
+  dim3 grid((unsigned)ceil_div64(rows, 8), (unsigned)nkb);
+  // `A` points at (row row_off, column col0) of the FP64 matrix: the kernel addresses it from there
+  ozaki_slice_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A - col0, lda, rows, row_off, col0, nkb, P->kblock, P->nslices,
+                                                            P->planes, P->pitch, P->plane_stride, P->exps, P->lde,
+                                                            lower_blocks);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const lpgp_ozaki_planes* PA, int64_t rowA0,
+                                  int64_t kA0, const lpgp_ozaki_planes* PB, int64_t rowB0, int64_t kB0, double beta,
+                                  double* C, int64_t ldc, void* stream) {
+  if (m < 0) return -1;
+  if (n < 0) return -2;
+  if (check_planes(PA)) return -5;
+  if (check_planes(PB)) return -8;
+  if (PA->kblock != PB->kblock || PA->nslices != PB->nslices) return -8;
+  const int kblock = PA->kblock;
+  if (k < 0 || k % kblock || kA0 < 0 || kA0 % kblock || kB0 < 0 || kB0 % kblock) return -3;
+  if (rowA0 < 0 || rowA0 + m > PA->rows || kA0 + k > PA->cols) return -6;
+  if (rowB0 < 0 || rowB0 + n > PB->rows || kB0 + k > PB->cols) return -9;
+  if (m == 0 || n == 0) return 0;
+  if (!C || ldc < n) return -12;
+  if (m > INT32_MAX || n > INT32_MAX || PA->cols > INT32_MAX || PB->cols > INT32_MAX) return -1;
+  int rc = oz_ensure();
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  rc = oz_make_map(&tmA, PA->planes, PA->cols, PA->rows, PA->pitch, PA->plane_stride, PA->nslices);
+  if (rc) return rc;
+  rc = oz_make_map(&tmB, PB->planes, PB->cols, PB->rows, PB->pitch, PB->plane_stride, PB->nslices);
+  if (rc) return rc;
+  OzParams p;
+  p.m = (int)m;
+  p.n = (int)n;
+  p.nkb = (int)(k / kblock);
+  p.kblock = kblock;
+  p.nslices = PA->nslices;
+  p.rowA0 = (int)rowA0;
+  p.rowB0 = (int)rowB0;
+  p.kA0 = (int)kA0;
+  p.kB0 = (int)kB0;
+  p.eA = PA->exps;
+  p.eB = PB->exps;
+  p.ldeA = PA->lde;
+  p.ldeB = PB->lde;
+  p.C = C;
+  p.ldc = ldc;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.tiles_n = (int)ceil_div64(n, OZ_BN);
+  const int64_t tiles = ceil_div64(m, OZ_BM) * p.tiles_n;
+  if (tiles > INT32_MAX) return -1;
+  ozaki_gemm_kernel<<<(unsigned)tiles, OZ_THREADS, OZ_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}

@@ -12,10 +12,11 @@ constexpr int PM_PTS = 2;       // test points per thread
 constexpr int PM_TILE = 256;    // observation points staged per shared-memory tile
 constexpr int PM_CHUNK = 8192;  // observation points per CTA (grid.y splits the sum; combined with atomics)
 
-template <int D, int NB, bool ODD>
+template <typename P>
 __global__ void __launch_bounds__(PM_THREADS)
-    post_mean_kernel(const __grid_constant__ EvalParams<D, NB, ODD> p, const double* __restrict__ Xobs, int64_t nobs,
+    post_mean_kernel(const __grid_constant__ P p, const double* __restrict__ Xobs, int64_t nobs,
                      const double* __restrict__ w, const double* __restrict__ Xt, int64_t m, double* __restrict__ out) {
+  constexpr int D = P::DIM;
   __shared__ __align__(16) double sx[PM_TILE * D];
   __shared__ double sw[PM_TILE];
   const int64_t i0 = ((int64_t)blockIdx.x * PM_THREADS + threadIdx.x) * PM_PTS;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(PM_THREADS)
       for (int d = 0; d < D; ++d) xo[d] = sx[j * D + d];
       const double wj = sw[j];
 #pragma unroll
-      for (int q = 0; q < PM_PTS; ++q) acc[q] = fma(eval_pair<D, NB, ODD>(p, xt[q], xo), wj, acc[q]);
+      for (int q = 0; q < PM_PTS; ++q) acc[q] = fma(p.eval(xt[q], xo), wj, acc[q]);
     }
   }
 #pragma unroll
@@ -141,7 +142,18 @@ int launch_mean(const lpgp_kernel_desc& k, const double* Xobs, int64_t nobs, con
     LPGP_CHECK_LAUNCH();
     return 0;
   }
-  post_mean_kernel<D, NB, ODD><<<grid, PM_THREADS, 0, st>>>(p, Xobs, nobs, w, Xt, m, out);
+  post_mean_kernel<EvalParams<D, NB, ODD>><<<grid, PM_THREADS, 0, st>>>(p, Xobs, nobs, w, Xt, m, out);
+  LPGP_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int D>
+int launch_mean_radial(const lpgp_kernel_desc& k, const double* Xobs, int64_t nobs, const double* w, const double* Xt,
+                       int64_t m, double* out, cudaStream_t st) {
+  RadialParams<D> p;
+  pack_radial<D>(k, p);
+  dim3 grid((unsigned)ceil_div64(m, PM_THREADS * PM_PTS), (unsigned)ceil_div64(nobs, PM_CHUNK));
+  post_mean_kernel<RadialParams<D>><<<grid, PM_THREADS, 0, st>>>(p, Xobs, nobs, w, Xt, m, out);
   LPGP_CHECK_LAUNCH();
   return 0;
 }
@@ -235,6 +247,15 @@ extern "C" int lpgp_post_mean(const lpgp_obs_block* blocks, int nblocks, const d
     bool odd;
     const int NB = pick_nb(k, odd);
     int rc = -1;
+    if (is_radial(k)) {
+      const double* wb = w + blk.col_off;
+      rc = k.d == 1   ? launch_mean_radial<1>(k, blk.X, blk.n, wb, Xt, m, out, st)
+           : k.d == 2 ? launch_mean_radial<2>(k, blk.X, blk.n, wb, Xt, m, out, st)
+           : k.d == 3 ? launch_mean_radial<3>(k, blk.X, blk.n, wb, Xt, m, out, st)
+                      : launch_mean_radial<4>(k, blk.X, blk.n, wb, Xt, m, out, st);
+      if (rc) return rc;
+      continue;
+    }
     if (NB) {
       if (k.d == 1) rc = dispatch_mean<1>(NB, odd, k, blk.X, blk.n, w + blk.col_off, Xt, m, out, st);
       if (k.d == 2) rc = dispatch_mean<2>(NB, odd, k, blk.X, blk.n, w + blk.col_off, Xt, m, out, st);

@@ -103,10 +103,19 @@ class CovarianceFunction:
         """``(factors, L0_terms, L1_terms, scale)`` or raise ``NotImplementedError``."""
         raise NotImplementedError(f"{type(self).__name__} has no closed product form on the device path")
 
+    def _radial_form(self):
+        """``dict(nu, scales, dir0, dir1, sigma2)`` for kernels built on an isotropic multi-dimensional Matern kernel
+        (not of product form; evaluated by the radial device family), else ``None``."""
+        return None
+
     def descriptor(self):
         if getattr(self, "_desc", None) is None:
-            factors, t0, t1, scale = self._product_form()
-            self._desc = _lowering.lower(factors, t0, t1, scale)
+            radial = self._radial_form()
+            if radial is not None:
+                self._desc = _lowering.lower_radial(**radial)
+            else:
+                factors, t0, t1, scale = self._product_form()
+                self._desc = _lowering.lower(factors, t0, t1, scale)
         return self._desc
 
     # -- evaluation ----------------------------------------------------------------------------------------
@@ -234,11 +243,21 @@ class Matern(CovarianceFunction):
     def lengthscales(self):
         return self._lengthscales
 
+    def _radial_form(self):
+        if self.input_size == 1:
+            return None
+        if self.input_ndim != 1:
+            raise NotImplementedError("Matern inputs must be scalars or vectors")
+        if not self.is_half_integer:
+            raise NotImplementedError("only half-integer Matern kernels are supported on the device")
+        ls = np.broadcast_to(self._lengthscales, (self.input_size,))
+        return {"nu": self._nu, "scales": np.sqrt(2.0 * self._nu) / ls, "dir0": None, "dir1": None, "sigma2": 1.0}
+
     def _product_form(self):
         if self.input_size != 1:
             raise NotImplementedError(
-                "isotropic multi-dimensional Matern kernels are not of product form; use "
-                "TensorProduct(Matern((), ...), ...) like the reference's PDE examples"
+                "isotropic multi-dimensional Matern kernels are not of product form (they lower to the radial "
+                "device family: plain evaluation and first-order directional derivatives, like the reference)"
             )
         if not self.is_half_integer:
             raise NotImplementedError("only half-integer Matern kernels are supported on the device")
@@ -331,6 +350,12 @@ class ScaledCovarianceFunction(CovarianceFunction):
     def _product_form(self):
         f, t0, t1, s = self._covfunc._product_form()
         return f, t0, t1, s * float(self._scalar)
+
+    def _radial_form(self):
+        radial = self._covfunc._radial_form()
+        if radial is not None:
+            radial = dict(radial, sigma2=radial["sigma2"] * float(self._scalar))
+        return radial
 
     def _evaluate(self, x0, x1, batch):
         if self.output_shape_0 != () or self.output_shape_1 != ():
@@ -433,6 +458,30 @@ class LinDiffOpCovarianceFunction(CovarianceFunction):
     def L1(self):
         return self._L1
 
+    def _radial_form(self):
+        radial = self._k._radial_form()
+        if radial is None:
+            return None
+        d = self._k.input_size
+
+        def direction(L):
+            """First-order operator -> its direction vector (the reference dispatches DirectionalDerivative only,
+            diffops/_registry.py:142-190; anything else on an isotropic multi-d Matern kernel needs its jax fallback)."""
+            if L is None:
+                return None
+            vec = np.zeros(d)
+            for mi, c in L._terms().items():
+                if len(mi) != d:
+                    raise ValueError("operator and kernel input dimensions differ")
+                if sum(mi) != 1:
+                    raise NotImplementedError(
+                        "isotropic multi-dimensional Matern kernels have closed forms for first-order (directional) "
+                        "derivatives only (diffops/_registry.py:270-280: the Laplacian falls to the reference's jax path)")
+                vec[mi.index(1)] += c
+            return vec
+
+        return dict(radial, dir0=direction(self._L0), dir1=direction(self._L1))
+
     def _product_form(self):
         f, t0, t1, s = self._k._product_form()
         assert t0 is None and t1 is None
@@ -520,6 +569,10 @@ class ExpQuad_DirectionalDerivative_WeightedLaplacian(LinDiffOpCovarianceFunctio
 
 class HalfIntegerMatern_Identity_DirectionalDerivative(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
     """diffops/_matern.py:17"""
+
+
+class HalfIntegerMatern_DirectionalDerivative_DirectionalDerivative(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
+    """diffops/_matern.py:138 (input_size > 1: radial device family)"""
 
 
 class UnivariateHalfIntegerMatern_DirectionalDerivative_DirectionalDerivative(LinDiffOpCovarianceFunction):  # pylint: disable=invalid-name
@@ -795,6 +848,8 @@ def _select_class(k, L0, L1):
     if isinstance(k, ExpQuad):
         return table_eq.get(kinds, LinDiffOpCovarianceFunction)
     if isinstance(k, Matern):
+        if k.input_size > 1 and kinds == ("DirectionalDerivative", "DirectionalDerivative"):
+            return HalfIntegerMatern_DirectionalDerivative_DirectionalDerivative  # diffops/_registry.py:156-190
         return table_m.get(kinds, LinDiffOpCovarianceFunction)
     return LinDiffOpCovarianceFunction
 
@@ -838,10 +893,14 @@ def apply_linfuncop(L, k: CovarianceFunction, argnum: int = 0) -> CovarianceFunc
             L0 = _compose(L0, L)
         else:
             L1 = _compose(L1, L)
-        return _select_class(k.k, L0, L1)(k.k, L0=L0, L1=L1)
+        out = _select_class(k.k, L0, L1)(k.k, L0=L0, L1=L1)
+        out._radial_form()  # radial kernels: first-order operators only
+        return out
     if isinstance(k, (Matern, ExpQuad, TensorProduct)):
         L0, L1 = (L, None) if argnum == 0 else (None, L)
         out = _select_class(k, L0, L1)(k, L0=L0, L1=L1)
-        out._product_form()  # validate now: raise NotImplementedError for unsupported combinations
+        # validate now: raise NotImplementedError for unsupported combinations
+        if out._radial_form() is None:
+            out._product_form()
         return out
     raise NotImplementedError(f"{type(L).__name__} applied to {type(k).__name__}")

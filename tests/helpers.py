@@ -50,9 +50,29 @@ def factors_from_base(base):
     raise ValueError(kind)
 
 
-def desc_from_spec(spec):
-    from linpde_gp_b200._lowering import lower
+def _direction(L, d):
+    """JSON op -> direction vector of a first-order operator (None = identity)."""
+    terms = flatten_op(L, d)
+    if terms is None:
+        return None
+    vec = np.zeros(d)
+    for mi, c in terms.items():
+        assert sum(mi) == 1
+        vec[mi.index(1)] += c
+    return vec
 
+
+def desc_from_spec(spec):
+    from linpde_gp_b200._lowering import lower, lower_radial
+
+    base = spec["kernel"]["base"]
+    shape = tuple(base.get("input_shape", ()))
+    if base["kind"] == "matern" and shape and int(np.prod(shape)) > 1:  # isotropic multi-d Matern: radial family
+        d = int(np.prod(shape))
+        ls = np.broadcast_to(np.asarray(base["lengthscales"], dtype=float), (d,))
+        scale = spec["kernel"].get("scale")
+        return lower_radial(base["nu"], np.sqrt(2 * base["nu"]) / ls, _direction(spec["L0"], d), _direction(spec["L1"], d),
+                            1.0 if scale is None else scale)
     factors = factors_from_base(spec["kernel"]["base"])
     d = len(factors)
     scale = spec["kernel"].get("scale")
@@ -64,6 +84,16 @@ def eval_desc_numpy(desc, X0, X1):
     d = desc.d
     X0 = np.asarray(X0, dtype=float).reshape(len(X0), d)
     X1 = np.asarray(X1, dtype=float).reshape(len(X1), d)
+    if desc.dim_type[0] == 2:  # LPGP_DIM_RADIAL: exp(-r) (Q0(r) + <a,u> Q1(r) + <a,u><b,u> Q2(r))
+        nq = 6
+        coef = np.array(desc.coef[: 3 * nq + 2 * d])
+        s = np.array(desc.scale[:d])
+        u = (X0[:, None, :] - X1[None, :, :]) * s
+        r = np.sqrt(np.sum(u * u, axis=-1))
+        a, b = coef[3 * nq : 3 * nq + d], coef[3 * nq + d : 3 * nq + 2 * d]
+        pa, pb = u @ a, u @ b
+        q = [sum(coef[t * nq + i] * r**i for i in range(nq)) for t in range(3)]
+        return (q[0] + pa * q[1] + pa * pb * q[2]) * np.exp(-r)
     nbt = [desc.nbasis[i] * (2 if desc.has_odd[i] else 1) for i in range(d)]
     coef = np.array(desc.coef[: int(np.prod(nbt))]).reshape(nbt)
     g = np.zeros((len(X0), len(X1)))

@@ -83,6 +83,12 @@ def test_dispatch_types_follow_the_reference_registry():
     assert type(out) is covfuncs.ScaledCovarianceFunction and float(out.scalar) == 4.0
     assert type(out.covfunc) is covfuncs.TensorProduct_LinDiffOp_LinDiffOp  # the -1 is folded into the operator terms
     assert out.covfunc.L1._terms() == {(2, 0): -1.0, (0, 2): -1.0}
+    # isotropic multi-d Matern: first-order operators only (diffops/_registry.py:142-190)
+    m3, d3, e3 = covfuncs.Matern((3,), nu=2.5), diffops.DirectionalDerivative(np.ones(3)), diffops.DirectionalDerivative(np.arange(3.0))
+    assert type(d3(m3, argnum=1)) is covfuncs.HalfIntegerMatern_Identity_DirectionalDerivative
+    assert type(e3(d3(m3, argnum=1), argnum=0)) is covfuncs.HalfIntegerMatern_DirectionalDerivative_DirectionalDerivative
+    assert type(e3(d3(m3, argnum=0), argnum=1)) is covfuncs.HalfIntegerMatern_DirectionalDerivative_DirectionalDerivative
+    assert type(d1(d1(m, argnum=1), argnum=0)) is covfuncs.UnivariateHalfIntegerMatern_DirectionalDerivative_DirectionalDerivative
     # isotropic multi-d Matern x Laplacian: no closed form (reference falls back to jax, _registry.py:270-280)
     with pytest.raises(NotImplementedError):
         diffops.Laplacian((2,))(covfuncs.Matern((2,), nu=2.5), argnum=1)
@@ -485,3 +491,23 @@ def test_pde_problem_definitions():
     u_xx = (ibvp.solution(tx + h * e_x) - 2 * ibvp.solution(tx) + ibvp.solution(tx - h * e_x)) / h**2
     assert np.max(np.abs(u_t - 0.1 * u_xx)) < 1e-5
     assert isinstance(pde.HeatEquationDirichletProblem(0.0, iv, T=1.0).solution, lg.functions.Zero)
+
+
+def test_api_descriptors_equal_spec_descriptors_for_every_reference_case():
+    """The reference-style objects (kernel classes + operators through the dispatch) lower to the same device
+    descriptor as the flat case specification -- all 117 frozen cases, radial family included (no GPU needed)."""
+    import json
+    import os
+
+    from tests import helpers
+
+    K = np.load(os.path.join(os.path.dirname(__file__), "golden", "kernels.npz"))
+    specs = json.loads(bytes(K["__specs__"]).decode())
+    assert len(specs) == 117
+    for spec in specs:
+        descs = covfuncs.device_descriptors(helpers.api_L0kL1(spec))
+        ref = helpers.desc_from_spec(spec)
+        assert len(descs) == 1, spec["name"]
+        a, b = np.array(ref.coef[:]), np.array(descs[0].coef[:])
+        assert np.allclose(a, b, rtol=1e-14, atol=0), spec["name"]
+        assert abs(ref.diag_value - descs[0].diag_value) <= 1e-14 * max(1.0, abs(ref.diag_value)), spec["name"]

@@ -20,12 +20,9 @@ GRAM_TOL = 1e-12   # north_star: Gram entries rel err <= 1e-12
 POST_TOL = 1e-8    # north_star: posterior mean/cov rel err <= 1e-8 after factorisation
 
 
-def _lowerable(spec):
-    base = spec["kernel"]["base"]
-    return not (base["kind"] == "matern" and int(np.prod(base.get("input_shape", ()) or (1,))) > 1)
-
-
-LOWERABLE = [s for s in SPECS if _lowerable(s)]
+# every reference case lowers to a device descriptor (product form, or the radial family for the isotropic
+# multi-dimensional Matern kernels)
+LOWERABLE = SPECS
 
 
 @pytest.mark.parametrize("spec", LOWERABLE, ids=[s["name"] for s in LOWERABLE])
@@ -864,3 +861,93 @@ def test_posterior_objects_hold_no_reference_cycles():
         assert ref() is None
     finally:
         gc.enable()
+
+
+# ---- parity AT SIZE: frozen outputs of the real reference at N = 4,096, the oracle at 16,384 ----
+def _large_golden(name):
+    from oracle import make_golden_large as mgl
+
+    path = os.path.join(GOLDEN, f"large_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    z = np.load(path)
+    spec = json.loads(bytes(z["problem_spec"]).decode())
+    return mgl.large_problem(spec), z
+
+
+@pytest.mark.parametrize("name", ["c2_4096", "c3_4096", "c2_16384"])
+def test_posterior_at_size_matches_frozen_reference(name):
+    """Scaled-down configs 2 / 3 at N = 4,096 against outputs of the REAL reference (oracle/make_golden_large.py), and
+    config 2 at its full N = 16,384 against the (reference-pinned) oracle: mean / variance / covariance within 1e-8."""
+    prob, z = _large_golden(name)
+    post, res = _api_solve_no_gram(prob)
+    sc = max(np.max(np.abs(z["mean"])), np.max(np.abs(z["var"])))
+    for key in ("mean", "var", "cov"):
+        assert np.max(np.abs(res[key] - z[key])) <= POST_TOL * sc, (name, key, np.max(np.abs(res[key] - z[key])) / sc)
+    # representer weights: compared through the residual G w = y of the reference's weights (w itself is sensitive to the
+    # conditioning of the heat problem: the oracle and the reference already differ by 7e-7 there)
+    w_ref = z["w"]
+    assert res["w"].shape == w_ref.shape
+    tol_w = 1e-8 if name.startswith("c2") else 1e-4
+    assert np.max(np.abs(res["w"] - w_ref)) <= tol_w * np.max(np.abs(w_ref)), name
+
+
+def _api_solve_no_gram(problem):
+    """helpers.api_solve without the dense Gram read-back (2.1 GB at N = 16,384)."""
+    import linpde_gp_b200 as lg
+
+    kernel = problem["kernel"]
+    shape = gcases.kernel_input_shape(kernel)
+    post = lg.GaussianProcess(lg.functions.Zero(input_shape=shape), helpers.api_kernel(kernel))
+    for blk in problem["blocks"]:
+        X, Y = np.asarray(blk["X"], dtype=float), np.asarray(blk["Y"], dtype=float)
+        b = None
+        if blk.get("noise_var") is not None:
+            nv = np.broadcast_to(np.asarray(blk["noise_var"], dtype=float), Y.shape).copy()
+            b = lg.randvars.Normal(np.zeros_like(Y), lg.linops.Scaling(nv))
+        post = post.condition_on_observations(Y, X=X, L=helpers.api_op(blk["L"]), b=b)
+    Xt = np.asarray(problem["Xt"], dtype=float)
+    return post, {"w": post.representer_weights, "mean": post.mean(Xt), "var": post.cov(Xt, None),
+                  "cov": post.cov.matrix(Xt[: problem.get("n_cov", 16)])}
+
+
+def test_inverse_rhs_conditioning_at_n4096_one_shot_and_block_rows():
+    """BASELINE.json configs[4]'s inverse-RHS variant at a size the CPU can check (N = 4,096): Gram =
+    L k_u L*(X, X) + k_f(X, X) accumulated on the device through ``from_observation_batches`` (single-GPU one-shot and
+    the block-row distributed layout), against the numpy formula built from the oracle's matrices."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.linfuncops import diffops
+    from oracle import covfuncs as ocf
+
+    rng = np.random.default_rng(5)
+    n_bc, n_pde = 256, 3840
+    ell = 4.0 / np.sqrt(n_pde)
+    ku_spec = {"scale": 4.0, "base": {"kind": "tensor_product", "factors": [
+        {"kind": "matern", "input_shape": [], "nu": 2.5, "lengthscales": ell},
+        {"kind": "matern", "input_shape": [], "nu": 2.5, "lengthscales": ell}]}}
+    kf_spec = {"scale": 100.0, "base": {"kind": "expquad", "input_shape": [2], "lengthscales": [0.3, 0.4]}}
+    u_prior = lg.GaussianProcess(lg.functions.Zero(input_shape=(2,)), helpers.api_kernel(ku_spec))
+    f_prior = lg.GaussianProcess(lg.functions.Constant(input_shape=(2,), value=1.5), helpers.api_kernel(kf_spec))
+    Xb = np.stack([np.linspace(0, 1, n_bc), np.zeros(n_bc)], -1)
+    Xp = rng.uniform(0, 1, (n_pde, 2))
+    Xt = rng.uniform(0, 1, (200, 2))
+    L = -1.0 * diffops.Laplacian((2,))
+    Yb, Yp = np.zeros(n_bc), np.zeros(n_pde)
+    batches = [(Yb, Xb), (Yp, Xp, L, -f_prior(Xp))]
+    posts = {"oneshot": lg.ConditionalGaussianProcess.from_observation_batches(u_prior, batches),
+             "blockrows": lg.ConditionalGaussianProcess.from_observation_batches(u_prior, batches, nb=512, replicate=False)}
+    lap = [(-1.0, ("wl", np.ones(2)))]
+    G = np.block([[ocf.matrix(ku_spec, None, None, Xb), ocf.matrix(ku_spec, None, lap, Xb, Xp)],
+                  [ocf.matrix(ku_spec, lap, None, Xp, Xb), ocf.matrix(ku_spec, lap, lap, Xp) + ocf.matrix(kf_spec, None, None, Xp)]])
+    KtX = np.hstack([ocf.matrix(ku_spec, None, None, Xt, Xb), ocf.matrix(ku_spec, None, lap, Xt, Xp)])
+    y = np.concatenate([Yb, Yp + 1.5])
+    import scipy.linalg
+
+    cf = scipy.linalg.cho_factor(G, lower=True)
+    mean_ref = KtX @ scipy.linalg.cho_solve(cf, y)
+    V = scipy.linalg.solve_triangular(cf[0], KtX.T, lower=True)
+    var_ref = 4.0 - np.sum(V * V, axis=0)
+    sc = max(np.max(np.abs(mean_ref)), 4.0)
+    for name, post in posts.items():
+        assert np.max(np.abs(post.mean(Xt) - mean_ref)) <= 1e-8 * sc, name
+        assert np.max(np.abs(post.var(Xt) - var_ref)) <= 1e-8 * sc, name

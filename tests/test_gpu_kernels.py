@@ -17,12 +17,9 @@ _K = np.load(os.path.join(GOLDEN, "kernels.npz"))
 SPECS = json.loads(bytes(_K["__specs__"]).decode())
 
 
-def _lowerable(spec):
-    base = spec["kernel"]["base"]
-    return not (base["kind"] == "matern" and int(np.prod(base.get("input_shape", ()) or (1,))) > 1)
-
-
-LOWERABLE = [s for s in SPECS if _lowerable(s)]
+# every reference case lowers to a device descriptor (product form, or the radial family for the isotropic
+# multi-dimensional Matern kernels)
+LOWERABLE = SPECS
 GRAM_TOL = 1e-12  # north_star: Gram entries rel err <= 1e-12 (relative to max |G|)
 
 

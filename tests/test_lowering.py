@@ -14,12 +14,9 @@ _K = np.load(os.path.join(GOLDEN, "kernels.npz"))
 SPECS = json.loads(bytes(_K["__specs__"]).decode())
 
 
-def _lowerable(spec):
-    base = spec["kernel"]["base"]
-    return not (base["kind"] == "matern" and int(np.prod(base.get("input_shape", ()) or (1,))) > 1)
-
-
-LOWERABLE = [s for s in SPECS if _lowerable(s)]
+# every reference case lowers to a device descriptor (product form, or the radial family for the isotropic
+# multi-dimensional Matern kernels)
+LOWERABLE = SPECS
 
 
 @pytest.mark.parametrize("spec", LOWERABLE, ids=[s["name"] for s in LOWERABLE])
@@ -34,10 +31,23 @@ def test_descriptor_reproduces_reference(spec):
     assert np.max(np.abs(desc.diag_value - d_ref)) <= 1e-13 * scale
 
 
-def test_isotropic_multid_matern_is_rejected():
-    spec = next(s for s in SPECS if s["name"] == "matern2.5_3_plain")
+def test_all_reference_cases_lower():
+    assert len(LOWERABLE) == len(SPECS) == 117
+    spec = next(s for s in SPECS if s["name"] == "matern2.5_3_dd_dd")
+    desc = helpers.desc_from_spec(spec)
+    assert desc.d == 3 and all(desc.dim_type[i] == 2 for i in range(3))  # LPGP_DIM_RADIAL
+
+
+def test_isotropic_multid_matern_laplacian_is_rejected_like_the_reference():
+    """diffops/_registry.py:270-280: no closed form (the reference falls to its jax path)."""
+    from linpde_gp_b200.linfuncops import diffops
+    from linpde_gp_b200.randprocs import covfuncs
+
     with pytest.raises(NotImplementedError):
-        helpers.desc_from_spec(spec)
+        diffops.Laplacian((3,))(covfuncs.Matern((3,), nu=2.5), argnum=1)
+    k = diffops.DirectionalDerivative(np.ones(3))(covfuncs.Matern((3,), nu=2.5), argnum=1)
+    with pytest.raises(NotImplementedError):
+        diffops.Laplacian((3,))(k, argnum=0)
 
 
 def test_matern32_third_derivative_is_rejected_like_the_reference():
