@@ -9,7 +9,8 @@
 //
 //     x = 2^e * sum_{s >= 0} d_s 2^(-7 - 8 s),    d_0 = floor(x 2^(7-e)) in [-128, 127] (int8),  d_s in [0, 255] (uint8),
 //
-// exactly (S digits carry 7 + 8 (S-1) bits below the row maximum: S = 7 is all of FP64).  The digits are stored as S
+// i.e. the digits of the fixed-point integer floor(x 2^(55-e)) (S digits carry 7 + 8 (S-1) bits below the row maximum,
+// truncated toward -inf; S = 7 represents every FP64 value of the block exactly).  The digits are stored as S
 // byte planes.  Then
 //
 //     a . b = 2^(ea + eb - 14) sum_q 256^(-q) sum_{s + t = q} sum_k a_s[k] b_t[k]
@@ -306,20 +307,20 @@ __global__ void __launch_bounds__(256)
   const bool ok = mx > 0.0 && mx < 1.7e308;
   const int e = ok ? ilogb(mx) + 1 : 0;
   if (lane == 0) exps[(int64_t)(col0 / kblock + kb) * lde + row_off + r] = e;
-  const double sc = exp2i(7 - e);  // |x| 2^(7-e) < 128 (e within the normal range for any data of this path)
+  // fixed point: F = floor(x 2^(55-e)) is an integer below 2^55 in magnitude (exact scaling, exact conversion), whose
+  // radix-256 digits are d_0 = F >> 48 (signed) and d_s = (F >> (48 - 8 s)) & 255.  (Peeling the digits off in floating
+  // point is NOT exact: for x = -tiny the remainder 1 - tiny rounds to 1 and the next digit overflows.)
+  const double sc = exp2i(55 - e);
   unsigned char* dst = planes + (r + row_off) * pitch + col0 + (int64_t)kb * kblock;
   for (int c = lane * 4; c < kblock; c += 128) {
     const double2 x0 = *reinterpret_cast<const double2*>(src + c), x1 = *reinterpret_cast<const double2*>(src + c + 2);
-    double t[4] = {x0.x * sc, x0.y * sc, x1.x * sc, x1.y * sc};
-    if (!ok) t[0] = t[1] = t[2] = t[3] = 0.0;
+    long long F[4] = {__double2ll_rd(x0.x * sc), __double2ll_rd(x0.y * sc), __double2ll_rd(x1.x * sc),
+                      __double2ll_rd(x1.y * sc)};
+    if (!ok) F[0] = F[1] = F[2] = F[3] = 0;
     for (int s = 0; s < nslices; ++s) {
       uint32_t packed = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const double d = floor(t[i]);
-        t[i] = (t[i] - d) * 256.0;  // exact: remainder in [0, 1)
-        packed |= ((uint32_t)((int)d) & 0xffu) << (8 * i);
-      }
+      for (int i = 0; i < 4; ++i) packed |= ((uint32_t)(F[i] >> (48 - 8 * s)) & 0xffu) << (8 * i);
       *reinterpret_cast<uint32_t*>(dst + s * plane_stride + c) = packed;
     }
   }
