@@ -150,6 +150,13 @@ int lpgp_kron_sum(int nterms, const double* const* A, const int64_t* lda, const 
 int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
                  int64_t ldb, double beta, double* C, int64_t ldc, int lower, void* stream);
 
+/* C[m x n] = beta*C + alpha * A[m x k] * B[k x n]  (all row-major; B has the contraction index as its ROW index).
+ * The product the backward half of a multi-right-hand-side Cholesky solve needs (X1 -= Y2 L21 contracts over the
+ * rows of L): numpy `A @ B` inside scipy.linalg.cho_solve, pn/linops/_linear_operator.py:303-307.  C may alias A
+ * only for n <= 128 (in-place X <- X W).                                                                     */
+int lpgp_gemm_nn(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
+                 int64_t ldb, double beta, double* C, int64_t ldc, void* stream);
+
 /* As lpgp_gemm_nt, but for every block of 128 rows only the columns j with col_base + j < col_limit[row/128] are
  * updated (col_limit: device array of ceil(m/128) ints; col_base: position of C's first column in the coordinates
  * of the limits).  Building block of the multi-GPU Cholesky, whose ranks own block rows of the lower triangle
@@ -211,8 +218,14 @@ int lpgp_trsm_rlt(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int
  * m x 128 workspace on `stream` (cudaMallocAsync / cudaFreeAsync).                                           */
 int lpgp_trsm_rlt_refined(const lpgp_factor* f, int64_t nlead, double* X, int64_t m, int64_t ldx, void* stream);
 
+/* X[m x n] <- X L^{-1}  (right side, lower, not transposed; row-major): L^{-T} b for every row b of X, the backward
+ * half of scipy.linalg.cho_solve (pn/linops/_linear_operator.py:303-307) for right-hand sides stored as rows.   */
+int lpgp_trsm_rln(const lpgp_factor* f, double* X, int64_t m, int64_t ldx, void* stream);
+
 /* B[r, :] <- G^{-1} B[r, :] for nrhs right-hand sides stored as rows of B (nrhs x n): forward and backward
- * substitution = scipy.linalg.cho_solve of pn/linops/_linear_operator.py:303-307.                          */
+ * substitution = scipy.linalg.cho_solve of pn/linops/_linear_operator.py:303-307.  Up to 3 right-hand sides (or rows
+ * that are not 16-byte aligned) run as single-vector substitution chains (HBM-bound), more as two blocked DMMA
+ * solves, lpgp_trsm_rlt followed by lpgp_trsm_rln.                                                             */
 int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t ldb, void* stream);
 
 /* One right-hand side, one triangular factor:  trans == 0: b <- L^{-1} b (forward substitution),
@@ -337,6 +350,15 @@ int lpgp_matern_integral(const lpgp_matern_integral_desc* desc, double a, double
  * (_radial_lebesgue.py:54-69) with HalfIntegerMaternRadialSecondAntiderivative (_matern_lebesgue.py:60-108).   */
 int lpgp_matern_integral2(const lpgp_matern_integral_desc* desc, double a, double b, double c, double d, double alpha,
                           double* out, int accumulate, void* stream);
+
+/* out[i * ld + j] (+)= alpha * int phi_j(t) k(x[i], t) dt  for n points x and the m piecewise-linear ("hat") basis
+ * functions phi_j on the ascending nodes grid[j], grid[j+1], grid[j+2] (device array of m + 2 nodes; phi_j peaks at
+ * grid[j+1]).  half_ends != 0: phi_0 keeps only its right half and phi_{m-1} only its left half (the reference's
+ * UnivariateLinearInterpolationBasis with zero_boundary=False and its two sentinel nodes, functions/bases/_fem.py:8-35).
+ * Un-normalised L2 projection of k(x, .): Matern32_L2Projection_UnivariateLinearInterpolationBasis._evaluate
+ * (crosscov/linfunctls/projections.py:129-170), here for every half-integer nu.                                */
+int lpgp_matern_hat_integral(const lpgp_matern_integral_desc* desc, const double* grid, int64_t m, int half_ends,
+                             const double* x, int64_t n, double alpha, double* out, int64_t ld, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,7 @@ def _load() -> ctypes.CDLL:
         "lpgp_kron_sum": (ci, [ci, ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(vp), ctypes.POINTER(i64),
                           ctypes.POINTER(dbl), i64, i64, i64, i64, vp, i64, ci, ci, vp]),
         "lpgp_gemm_nt": (ci, [i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, ci, vp]),
+        "lpgp_gemm_nn": (ci, [i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, vp]),
         "lpgp_gemm_nt_limited": (ci, [i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64, vp, i64, vp]),
         "lpgp_factor_dinv_bytes": (ctypes.c_size_t, [ctypes.POINTER(i64), ci]),
         "lpgp_potrf": (ci, [FP, vp]),
@@ -119,6 +120,7 @@ def _load() -> ctypes.CDLL:
         "lpgp_chol_append": (ci, [FP, vp]),
         "lpgp_trsm_rlt": (ci, [FP, i64, vp, i64, i64, vp]),
         "lpgp_trsm_rlt_refined": (ci, [FP, i64, vp, i64, i64, vp]),
+        "lpgp_trsm_rln": (ci, [FP, vp, i64, i64, vp]),
         "lpgp_ozaki_split": (ci, [vp, i64, i64, i64, i64, i64, OP, ci, vp]),
         "lpgp_ozaki_gemm_nt": (ci, [i64, i64, i64, dbl, OP, i64, i64, OP, i64, i64, dbl, vp, i64, vp]),
         "lpgp_trsm_rlt_ozaki": (ci, [FP, vp, i64, i64, OP, OP, vp]),
@@ -131,6 +133,7 @@ def _load() -> ctypes.CDLL:
         "lpgp_post_var": (ci, [OB, ci, FP, vp, i64, dbl, vp, i64, vp, vp]),
         "lpgp_row_sumsq": (ci, [vp, i64, i64, i64, dbl, dbl, vp, vp]),
         "lpgp_matern_integral": (ci, [ctypes.POINTER(MaternIntegralDesc), dbl, dbl, vp, i64, dbl, vp, vp, i64, ci, vp]),
+        "lpgp_matern_hat_integral": (ci, [ctypes.POINTER(MaternIntegralDesc), vp, i64, ci, vp, i64, dbl, vp, i64, ci, vp]),
         "lpgp_matern_integral2": (ci, [ctypes.POINTER(MaternIntegralDesc), dbl, dbl, dbl, dbl, dbl, vp, ci, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -143,8 +146,8 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTED = (
     "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_set_option lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower lpgp_kron_sum "
-    "lpgp_gemm_nt lpgp_gemm_nt_limited lpgp_ozaki_split lpgp_ozaki_gemm_nt lpgp_trsm_rlt_ozaki lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_trsm_rlt_refined lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
-    "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq lpgp_matern_integral lpgp_matern_integral2"
+    "lpgp_gemm_nt lpgp_gemm_nn lpgp_gemm_nt_limited lpgp_ozaki_split lpgp_ozaki_gemm_nt lpgp_trsm_rlt_ozaki lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_trsm_rlt_refined lpgp_trsm_rln lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
+    "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq lpgp_matern_integral lpgp_matern_integral2 lpgp_matern_hat_integral"
 ).split()
 
 

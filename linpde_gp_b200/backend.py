@@ -195,6 +195,16 @@ def gemm_nt(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, alpha: float = 1.
     return C
 
 
+def gemm_nn(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, alpha: float = 1.0, beta: float = 0.0) -> torch.Tensor:
+    """C = beta*C + alpha * A @ B on the DMMA path (B row-major k x n)."""
+    m, k = A.shape
+    n = B.shape[1]
+    assert B.shape[0] == k and C.shape == (m, n)
+    rc = lib.lpgp_gemm_nn(m, n, k, float(alpha), _ptr(A), _ld(A), _ptr(B), _ld(B), float(beta), _ptr(C), _ld(C), _stream())
+    check(rc, "lpgp_gemm_nn")
+    return C
+
+
 def gemm_nt_limited(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, col_limit: torch.Tensor, alpha: float = 1.0,
                     beta: float = 0.0, col_base: int = 0) -> torch.Tensor:
     """C = beta*C + alpha * A @ B.T, each block of 128 rows restricted to the columns j with
@@ -236,6 +246,19 @@ def matern_integral(desc: _lib.MaternIntegralDesc, a: float, b: float, x: torch.
     rc = lib.lpgp_matern_integral(ctypes.byref(desc), float(a), float(b), _ptr(x), x.numel(), float(alpha), _ptr(w),
                                   _ptr(out), int(out_stride), int(accumulate), _stream())
     check(rc, "lpgp_matern_integral")
+    return out
+
+
+def matern_hat_integral(desc: _lib.MaternIntegralDesc, grid: torch.Tensor, m: int, half_ends: bool, x: torch.Tensor,
+                        out: torch.Tensor, *, alpha: float = 1.0, accumulate: bool = False) -> torch.Tensor:
+    """out[i, j] (+)= alpha * int phi_j(t) k(x[i], t) dt for the m hat functions on the nodes ``grid`` (m + 2 entries)."""
+    _require_cuda()
+    x = x.reshape(-1)
+    assert x.is_contiguous() and x.dtype == F64 and grid.is_contiguous() and grid.numel() == m + 2
+    assert out.shape == (x.numel(), m)
+    rc = lib.lpgp_matern_hat_integral(ctypes.byref(desc), _ptr(grid), int(m), int(half_ends), _ptr(x), x.numel(),
+                                      float(alpha), _ptr(out), _ld(out), int(accumulate), _stream())
+    check(rc, "lpgp_matern_hat_integral")
     return out
 
 
@@ -387,6 +410,13 @@ class DeviceFactor:
         check(lib.lpgp_trsm_rlt(ctypes.byref(f), nlead, _ptr(X), X.shape[0], _ld(X), _stream()), "lpgp_trsm_rlt")
         return X
 
+    def trsm_rln(self, X: torch.Tensor) -> torch.Tensor:
+        """X <- X L^{-1} in place (L^{-T} b for every row b of X)."""
+        assert X.shape[1] == self.n
+        f = self._struct()
+        check(lib.lpgp_trsm_rln(ctypes.byref(f), _ptr(X), X.shape[0], _ld(X), _stream()), "lpgp_trsm_rln")
+        return X
+
     def ozaki_eligible(self, kblock: int) -> bool:
         """The emulated solve cuts the factor into column blocks of ``kblock`` columns that must start on leaf boundaries:
         every segment but the last a multiple of 128 rows, and at least two blocks."""
@@ -513,7 +543,9 @@ class ObsBlocks:
         self.descs = list(descs)
         self.Xs = list(Xs)
         self.n = len(self.descs)
-        # integral observations: (column, (a, b), [(alpha, MaternIntegralDesc), ...]) -- one closed-form column each
+        # columns that are not pairwise kernel evaluations: integral observations
+        # (column, (a, b), [(alpha, MaternIntegralDesc), ...]) -- one closed-form column each -- and dense column blocks
+        # (column, width, fill) with ``fill(Xt) -> (M x width) device matrix`` (L2-projection observations)
         self.extras = list(extras)
         self.arr = (_lib.ObsBlock * self.n)()
         for i, (dsc, X, off) in enumerate(zip(self.descs, self.Xs, col_offs)):
@@ -528,9 +560,12 @@ class ObsBlocks:
 
     def add_integral_columns(self, Xt: torch.Tensor, K: torch.Tensor) -> None:
         """K[:, col] += sum alpha * int_a^b k(Xt, t) dt for every integral observation (after ``lpgp_crosscov``)."""
-        for col, (a, b), terms in self.extras:
+        for col, what, terms in self.extras:
+            if callable(terms):  # dense block of `what` columns
+                K[:, col : col + what].add_(terms(Xt))
+                continue
             for alpha, dsc in terms:
-                matern_integral(dsc, a, b, Xt, K[:, col:], out_stride=_ld(K), alpha=alpha, accumulate=True)
+                matern_integral(dsc, what[0], what[1], Xt, K[:, col:], out_stride=_ld(K), alpha=alpha, accumulate=True)
 
 
 def post_mean(blocks: ObsBlocks, w: torch.Tensor, Xt: torch.Tensor, out: Optional[torch.Tensor] = None,
@@ -544,9 +579,12 @@ def post_mean(blocks: ObsBlocks, w: torch.Tensor, Xt: torch.Tensor, out: Optiona
     else:
         rc = lib.lpgp_post_mean(blocks.arr, blocks.n, _ptr(w), _ptr(Xt), m, _ptr(out), int(accumulate), _stream())
         check(rc, "lpgp_post_mean")
-    for col, (a, b), terms in blocks.extras:  # integral observations: one closed-form column each, weight folded in
-        for alpha, dsc in terms:
-            matern_integral(dsc, a, b, Xt, out, alpha=alpha, w=w[col : col + 1], accumulate=True)
+    for col, what, terms in blocks.extras:
+        if callable(terms):  # dense block of `what` columns: out += block @ w[col : col + what]
+            gemv(terms(Xt), w[col : col + what].contiguous(), out, 1.0)
+            continue
+        for alpha, dsc in terms:  # integral observations: one closed-form column each, weight folded in
+            matern_integral(dsc, what[0], what[1], Xt, out, alpha=alpha, w=w[col : col + 1], accumulate=True)
     return out
 
 

@@ -640,6 +640,7 @@ std::atomic<int> g_diag_attr_set[LPGP_MAX_DEVICES];  // per device: the opt-in s
 //     T = B;   X = B W^T;   T <- T - X L_kk^T (residual);   X += T W^T,
 // which brings the residual back to O(eps) (tests/test_gpu_kernels.py::test_potrf_backward_error_ill_conditioned).
 // The two extra GEMMs are m x 128 x 128: at most N^2 * 256 extra flops per factorisation (1.2 % at N = 64k).
+constexpr int POTRS_TRSM_MIN_RHS = 4;  // lpgp_potrs: from this many right-hand sides on, blocked solves
 constexpr double REFINE_KAPPA = 256.0;  // unrefined residual <= ~kappa eps ~ 3e-14 |B| below this
 
 struct RefineWs {
@@ -676,6 +677,24 @@ int trsm_rec(const lpgp_factor* f, const Leaves& lv, int lo, int hi, double* X, 
   rc = lpgp_gemm_nt(m, c2 - c1, c1 - c0, -1.0, X, ldx, f->L + c1 * f->ld + c0, f->ld, 1.0, X + (c1 - c0), ldx, 0, st);
   if (rc) return rc;
   return trsm_rec(f, lv, mid, hi, X + (c1 - c0), m, ldx, st, ws);
+}
+
+// X[m x (off[hi]-off[lo])] <- X * L[lo:hi, lo:hi]^{-1} (the backward half of a multi-right-hand-side solve whose
+// right-hand sides are the ROWS of X): Y2 = X2 L22^{-1};  X1 -= Y2 L21;  Y1 = X1 L11^{-1}.  The contraction runs over the
+// ROWS of L, hence the NN form of the DMMA GEMM; the leaf step multiplies with the explicit inverse W = L_kk^{-1} in place.
+int trsm_rln_rec(const lpgp_factor* f, const Leaves& lv, int lo, int hi, double* X, int64_t m, int64_t ldx, cudaStream_t st) {
+  const int64_t c0 = lv.off[lo];
+  if (hi - lo == 1) {
+    const int nb = (int)(lv.off[hi] - c0);
+    return lpgp_gemm_nn(m, nb, nb, 1.0, X, ldx, dinv_block(f, lo), LEAF, 0.0, X, ldx, st);
+  }
+  const int mid = lo + (hi - lo) / 2;
+  const int64_t c1 = lv.off[mid], c2 = lv.off[hi];
+  int rc = trsm_rln_rec(f, lv, mid, hi, X + (c1 - c0), m, ldx, st);
+  if (rc) return rc;
+  rc = lpgp_gemm_nn(m, c1 - c0, c2 - c1, -1.0, X + (c1 - c0), ldx, f->L + c1 * f->ld + c0, f->ld, 1.0, X, ldx, st);
+  if (rc) return rc;
+  return trsm_rln_rec(f, lv, lo, mid, X, m, ldx, st);
 }
 
 // refinement workspace of one call: stream-ordered allocation (no hidden persistent state; safe for concurrent
@@ -1041,6 +1060,16 @@ int trsv_impl(const lpgp_factor* f, const Leaves& lv, int trans, double* b, cuda
 }
 }  // namespace
 
+extern "C" int lpgp_trsm_rln(const lpgp_factor* f, double* X, int64_t m, int64_t ldx, void* stream) {
+  if (check_factor(f)) return -1;
+  if (!X || ldx < f->n || (ldx % 2) || ((uintptr_t)X % 16)) return -2;
+  if (m < 0) return -3;
+  if (m == 0) return 0;
+  Leaves lv;
+  if (build_leaves(f->seg_off, f->nseg, lv)) return -1;
+  return trsm_rln_rec(f, lv, 0, (int)lv.off.size() - 1, X, m, ldx, (cudaStream_t)stream);
+}
+
 extern "C" int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t ldb, void* stream) {
   if (check_factor(f)) return -1;
   if (!B) return -2;
@@ -1049,6 +1078,13 @@ extern "C" int lpgp_potrs(const lpgp_factor* f, double* B, int64_t nrhs, int64_t
   Leaves lv;
   if (build_leaves(f->seg_off, f->nseg, lv)) return -1;
   cudaStream_t st = (cudaStream_t)stream;
+  // several right-hand sides with TMA-compatible rows: two blocked DMMA solves (B L^{-T}, then B L^{-1}) that read the
+  // factor once each instead of 2 nrhs latency-bound substitution chains
+  if (nrhs >= POTRS_TRSM_MIN_RHS && ldb % 2 == 0 && (uintptr_t)B % 16 == 0) {
+    int rc = trsm_rec(f, lv, 0, (int)lv.off.size() - 1, B, nrhs, ldb, st);
+    if (rc) return rc;
+    return trsm_rln_rec(f, lv, 0, (int)lv.off.size() - 1, B, nrhs, ldb, st);
+  }
   for (int64_t r = 0; r < nrhs; ++r) {
     int rc = trsv_impl(f, lv, 0, B + r * ldb, st);
     if (rc) return rc;

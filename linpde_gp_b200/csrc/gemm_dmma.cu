@@ -16,6 +16,10 @@
 //     shared-memory load (the contraction index may be permuted as long as A and B agree), conflict-free
 //     without swizzling (lanes 0-7 cover two rows = one 128-byte bank window);
 //   * `lower != 0`: only tiles intersecting the lower triangle are launched (SYRK-style update).
+//   * `NN` variant (lpgp_gemm_nn: B given as k x n, the backward half of the multi-right-hand-side solve X <- X L^{-1}):
+//     the B stage is BN/16 boxes of 8 k-rows x 16 columns (128-byte rows, TMA SWIZZLE_128B), one box issued by each
+//     consumer warp's lane 0, so that the fragment loads B[k = 2t, 2t+1][n = g] (two LDS.64) are conflict-free: the
+//     16-byte chunk index is XORed with the row, which spreads the four k rows of a half-warp over all banks;
 // Bound: FP64 tensor pipe.  Algorithmic flops 2*m*n*k (lower: ~m*n*k); operand traffic per CTA tile and k-step
 // is (128+128)*8*8 B for 262144 flops, i.e. 0.0625 B/flop from L2.
 #include <cuda.h>
@@ -44,7 +48,7 @@ struct TileCfg {
   static constexpr int STAGE_A_BYTES = BM * BK * 8;
   static constexpr int STAGE_B_BYTES = BN * BK * 8;
   static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;  // 1024: swizzle atoms of the NN variant
 };
 //   Strip: 32 x 128, 1 x 4 warps, warp tile 32 x 32 -- in-place products X <- X W^T (C aliases A, n <= 128): the
 //           whole output row strip belongs to ONE CTA, which has consumed all of its A rows before it stores
@@ -70,7 +74,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <typename Cfg>
+template <typename Cfg, bool NN = false>
 __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int m, int n,
                    int k, double alpha, double beta, double* __restrict__ C, int64_t ldc, int lower, int tiles_m,
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   constexpr int BM = Cfg::BM, BN = Cfg::BN, NCONSUMER_WARPS = Cfg::NCONSUMER_WARPS, MI = Cfg::MI, NJ = Cfg::NJ;
   constexpr int STAGE_A_BYTES = Cfg::STAGE_A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // keeps the shared address space
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
 
@@ -151,15 +155,24 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   // ===== TMA producer = lane 0 of warp 0, PREFETCH k-blocks ahead of the DMMA loop =====
   // (no dedicated producer warp: a ninth warp would put three warps on one SM sub-partition and cap every thread
   //  at 168 registers -- less than the 128 accumulator + 48 fragment registers of the 128 x 128 tile)
+  // (NN: lane 0 of EVERY warp is a producer -- thread 0 arms the barrier and loads A, warp w loads the B boxes
+  //  w, w + NCONSUMER_WARPS, ...; bytes that land before thread 0's expect_tx only make the transaction count
+  //  transiently negative, the phase cannot complete before that one pending arrival)
   constexpr int PREFETCH = STAGES - 2;  // the slot refilled at step kb was consumed at step kb - 2
-  const bool producer = (threadIdx.x == 0);
+  const bool producer = NN ? (lane == 0) : (threadIdx.x == 0);
   auto issue = [&](int kf) {
     const int s = kf % STAGES;
     if (kf >= STAGES) mbar_wait(&empty[s], ((kf / STAGES) & 1) ^ 1);
-    mbar_expect_tx(&full[s], STAGE_BYTES);
     unsigned char* st = smem + s * STAGE_BYTES;
-    tma_load_2d(st, &tmA, kf * BK, row0, &full[s]);
-    tma_load_2d(st + STAGE_A_BYTES, &tmB, kf * BK, col0, &full[s]);
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&full[s], STAGE_BYTES);
+      tma_load_2d(st, &tmA, kf * BK, row0, &full[s]);
+      if (!NN) tma_load_2d(st + STAGE_A_BYTES, &tmB, kf * BK, col0, &full[s]);
+    }
+    if (NN) {
+      for (int gi = warp; gi < BN / 16; gi += NCONSUMER_WARPS)
+        tma_load_2d(st + STAGE_A_BYTES + gi * 1024, &tmB, col0 + gi * 16, kf * BK, &full[s]);
+    }
   };
   if (producer) {
     for (int kf = 0; kf < PREFETCH && kf < nk; ++kf) issue(kf);
@@ -173,6 +186,12 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // NN: element (k, n') of a 16-column box sits at double offset 16 k + 2 ((n' >> 1) ^ k) + (n' & 1) (SWIZZLE_128B);
+  // column 8 j + g of the warp tile has n' = 8 (j & 1) + g in box wn0 / 16 + j / 2, so per lane two offsets for
+  // k = 2t (even / odd j) and two for k = 2t + 1
+  const int hsw = (g >> 1) ^ (2 * t);
+  const int nn_e0 = 32 * t + 2 * hsw + (g & 1), nn_e1 = 32 * t + 2 * (hsw ^ 4) + (g & 1);
+  const int nn_f0 = 32 * t + 16 + 2 * (hsw ^ 1) + (g & 1), nn_f1 = 32 * t + 16 + 2 * (hsw ^ 5) + (g & 1);
 
   for (int kb = 0; kb < nk; ++kb) {
     if (producer && kb + PREFETCH < nk) issue(kb + PREFETCH);
@@ -185,8 +204,17 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     double2 a[MI], b[NJ];
 #pragma unroll
     for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double2*>(sA + (wm0 + 8 * i + g) * BK + 2 * t);
+    if (NN) {
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double2*>(sB + (wn0 + 8 * j + g) * BK + 2 * t);
+      for (int j = 0; j < NJ; ++j) {
+        const double* box = sB + (wn0 / 16 + j / 2) * 128;
+        b[j].x = box[(j & 1) ? nn_e1 : nn_e0];
+        b[j].y = box[(j & 1) ? nn_f1 : nn_f0];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double2*>(sB + (wn0 + 8 * j + g) * BK + 2 * t);
+    }
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -295,6 +323,9 @@ int ensure_device_attrs() {
   LPGP_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<BigTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigTile::SMEM_BYTES));
   LPGP_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<SmallTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallTile::SMEM_BYTES));
   LPGP_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<StripTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripTile::SMEM_BYTES));
+  LPGP_CHECK((cudaFuncSetAttribute(gemm_nt_kernel<BigTile, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigTile::SMEM_BYTES)));
+  LPGP_CHECK((cudaFuncSetAttribute(gemm_nt_kernel<SmallTile, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallTile::SMEM_BYTES)));
+  LPGP_CHECK((cudaFuncSetAttribute(gemm_nt_kernel<StripTile, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripTile::SMEM_BYTES)));
   if (tracked) g_attr_set[dev].store(1, std::memory_order_release);
   return 0;
 }
@@ -311,22 +342,34 @@ int make_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, in
   return r == CUDA_SUCCESS ? 0 : LPGP_CUDA_ERR(cudaErrorInvalidValue);
 }
 
+// row-major (k rows x n cols, ld) FP64 matrix as the B operand of the NN variant: boxes of 16 columns x BK rows,
+// 128-byte swizzle
+int make_map_kn(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  cuuint32_t box[2] = {16, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : LPGP_CUDA_ERR(cudaErrorInvalidValue);
+}
 
-template <typename Cfg>
+template <typename Cfg, bool NN = false>
 int launch(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
            double beta, double* C, int64_t ldc, int lower, void* stream, const int* col_limit = nullptr,
            int col_base = 0) {
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, A, m, k > 0 ? k : 1, lda, Cfg::BM);
   if (rc) return rc;
-  rc = make_map(&tmB, B, n, k > 0 ? k : 1, ldb, Cfg::BN);
+  rc = NN ? make_map_kn(&tmB, B, k > 0 ? k : 1, n, ldb) : make_map(&tmB, B, n, k > 0 ? k : 1, ldb, Cfg::BN);
   if (rc) return rc;
   const int64_t tiles_m = ceil_div64(m, Cfg::BM), tiles_n = ceil_div64(n, Cfg::BN);
   const int64_t bands = ceil_div64(tiles_m, 8);  // lower: whole bands of 8 tile rows (see the kernel)
   const int64_t ntiles = lower ? 32 * bands * bands + 4 * bands : tiles_m * tiles_n;
   if (ntiles > INT32_MAX) return -1;
   const int vec_ok = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
-  gemm_nt_kernel<Cfg><<<(unsigned)ntiles, Cfg::NTHREADS, Cfg::SMEM_BYTES, (cudaStream_t)stream>>>(
+  gemm_nt_kernel<Cfg, NN><<<(unsigned)ntiles, Cfg::NTHREADS, Cfg::SMEM_BYTES, (cudaStream_t)stream>>>(
       tmA, tmB, (int)m, (int)n, (int)k, alpha, beta, C, ldc, lower, (int)tiles_m, (int)tiles_n, vec_ok, col_limit, col_base);
   LPGP_CHECK_LAUNCH();
   return 0;
@@ -363,6 +406,28 @@ extern "C" int lpgp_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const
   return (use_small ? launch<SmallTile> : launch<BigTile>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower, stream, nullptr, 0);
 }
 
+// C[m x n] = beta*C + alpha * A[m x k] * B[k x n]: B row-major with the contraction index as its ROW index (the
+// backward half X <- X L^{-1} of the multi-right-hand-side solve contracts over the rows of L)
+extern "C" int lpgp_gemm_nn(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
+                            int64_t ldb, double beta, double* C, int64_t ldc, void* stream) {
+  if (m < 0) return -1;
+  if (n < 0) return -2;
+  if (k < 0) return -3;
+  if (m == 0 || n == 0) return 0;
+  if (!A || lda < k || (lda % 2) || ((uintptr_t)A % 16)) return -6;
+  if (!B || ldb < n || (ldb % 2) || ((uintptr_t)B % 16)) return -8;
+  if (!C || ldc < n) return -11;
+  if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return -1;
+  std::call_once(g_once, init_once);
+  if (g_init_rc) return g_init_rc;
+  if (const int arc = ensure_device_attrs()) return arc;
+  const bool use_small = ceil_div64(m, 128) * ceil_div64(n, 128) < 96;
+  if ((const double*)C == A) {  // in place (leaf step X <- X W): one CTA must own complete output rows
+    if (n > 128) return -11;
+    return (use_small ? launch<StripTile, true> : launch<BigTile, true>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, nullptr, 0);
+  }
+  return (use_small ? launch<SmallTile, true> : launch<BigTile, true>)(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, stream, nullptr, 0);
+}
 
 // lpgp_gemm_nt that does nothing when the device-side int *flag is 0 (library-internal; C must not alias A)
 int lpgp_gemm_nt_flagged(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,

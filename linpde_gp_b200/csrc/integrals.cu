@@ -55,6 +55,46 @@ __global__ void matern_integral2_kernel(IntegralParams P, double a, double b, do
   *out = accumulate ? *out + v : v;
 }
 
+// ---- L2 projections onto hat functions (SURVEY.md section 8f item 4 tail) ------------------------------------------
+// int phi_j(t) k(x, t) dt for the piecewise-linear basis function phi_j on the nodes g0 < g1 < g2 (centre g1):
+// integrating by parts twice turns the two linear pieces into
+//   left  = +H1(g1 - x) + (H2(g0 - x) - H2(g1 - x)) / (g1 - g0),   right = -H1(g1 - x) + (H2(g2 - x) - H2(g1 - x)) / (g2 - g1)
+// (the closed form the reference writes out for nu = 3/2 only, crosscov/linfunctls/projections.py:129-170; every other
+// kernel goes through scipy.integrate.quad there).  With E1 = exp(-v) P1(v), E2 = exp(-v) P2(v) the non-decaying parts
+// P1(0) v - P2(0) of H2 and P1(0) of H1 combine into slopes of |g - x| that are evaluated without cancellation.
+__device__ __forceinline__ double hat_slope(double a, double b, double x) {  // (|b - x| - |a - x|) / (b - a), a < b
+  return x <= a ? 1.0 : (x >= b ? -1.0 : ((a - x) + (b - x)) / (b - a));
+}
+
+__global__ void __launch_bounds__(128)
+    matern_hat_integral_kernel(IntegralParams P, const double* __restrict__ grid, int m, int half_ends,
+                               const double* __restrict__ x, int64_t n, double alpha, double* __restrict__ out, int64_t ld,
+                               int accumulate) {
+  const int64_t i = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || j >= m) return;
+  const double xi = x[i], g0 = grid[j], g1 = grid[j + 1], g2 = grid[j + 2];
+  const double v0 = P.s * fabs(g0 - xi), v1 = P.s * fabs(g1 - xi), v2 = P.s * fabs(g2 - xi);
+  const double e1 = exp(-v1);
+  const double E2_1 = e1 * horner(P.p2, P.ncoef, v1);
+  const bool left = !(half_ends && j == 0), right = !(half_ends && j == m - 1);
+  const double sgn1 = (g1 - xi >= 0.0) ? 1.0 : -1.0;
+  double lin = 0.0, dec = 0.0;  // multiples of P1(0) / s and of 1 / s^2
+  if (left) {
+    lin += sgn1 - hat_slope(g0, g1, xi);
+    dec += (exp(-v0) * horner(P.p2, P.ncoef, v0) - E2_1) / (g1 - g0);
+  }
+  if (right) {
+    lin += hat_slope(g1, g2, xi) - sgn1;
+    dec += (exp(-v2) * horner(P.p2, P.ncoef, v2) - E2_1) / (g2 - g1);
+  }
+  double v = P.inv_s * (P.p1[0] * lin + P.inv_s * dec);
+  if (left != right) v += (left ? -sgn1 : sgn1) * P.inv_s * e1 * horner(P.p1, P.ncoef, v1);  // E1 part of the unpaired H1
+  v *= alpha;
+  double* o = out + i * ld + j;
+  *o = accumulate ? *o + v : v;
+}
+
 int make_params(const lpgp_matern_integral_desc* desc, IntegralParams* P) {
   if (desc == nullptr || desc->ncoef < 1 || desc->ncoef > LPGP_MAX_INTEGRAL_COEF || !(desc->scale > 0.0)) return -1;
   P->ncoef = desc->ncoef;
@@ -93,5 +133,31 @@ extern "C" int lpgp_matern_integral2(const lpgp_matern_integral_desc* desc, doub
   if (out == nullptr) return -7;
   matern_integral2_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(P, a, b, c, d, alpha, out, accumulate);
   LPGP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int lpgp_matern_hat_integral(const lpgp_matern_integral_desc* desc, const double* grid, int64_t m, int half_ends,
+                                        const double* x, int64_t n, double alpha, double* out, int64_t ld, int accumulate,
+                                        void* stream) {
+  IntegralParams P;
+  if (make_params(desc, &P)) return -1;
+  if (m < 0 || m > INT32_MAX) return -3;
+  if (n < 0) return -6;
+  if (n == 0 || m == 0) return 0;
+  if (grid == nullptr) return -2;
+  if (x == nullptr) return -5;
+  if (out == nullptr) return -8;
+  if (ld < m) return -9;
+  const dim3 block(32, 4);
+  const int64_t gy = ceil_div64(n, block.y);
+  if (gy > 65535 * 1024LL) return -6;
+  // grid.y is capped at 65535: rows beyond that are covered by repeated launches
+  for (int64_t r0 = 0; r0 < n; r0 += 65535LL * block.y) {
+    const int64_t rows = n - r0 < 65535LL * block.y ? n - r0 : 65535LL * block.y;
+    const dim3 g((unsigned)ceil_div64(m, block.x), (unsigned)ceil_div64(rows, block.y));
+    matern_hat_integral_kernel<<<g, block, 0, (cudaStream_t)stream>>>(P, grid, (int)m, half_ends, x + r0, rows, alpha,
+                                                                    out + r0 * ld, ld, accumulate);
+    LPGP_CHECK_LAUNCH();
+  }
   return 0;
 }

@@ -306,7 +306,7 @@ class TruncatedSineSeries(Function):
     the initial values of the heat-equation problems."""
 
     def __init__(self, domain, coefficients):
-        from . import domains  # pylint: disable=import-outside-toplevel
+        from .. import domains  # pylint: disable=import-outside-toplevel
 
         domain = domains.asdomain(domain)
         if not isinstance(domain, domains.Interval):
@@ -329,3 +329,6 @@ class TruncatedSineSeries(Function):
     def _evaluate(self, x):
         l, _ = self._domain
         return np.sum(self._coefficients * np.sin(self.half_angular_frequencies * (x[..., None] - l)), axis=-1)
+
+
+from . import bases  # noqa: E402,F401  (piecewise-linear finite-element basis; imports Function from this module)

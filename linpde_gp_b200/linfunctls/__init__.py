@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .functions import Constant, Function, Polynomial, _as_shape
+from ..functions import Constant, Function, Polynomial, _as_shape
 
 
 class LinearFunctional:
@@ -55,7 +55,7 @@ class LinearFunctional:
         raise NotImplementedError(f"{type(self).__name__} cannot be used as an observation")
 
     def __call__(self, f, /, **kwargs):
-        from .randprocs import _conditional, _gaussian_process, covfuncs, crosscov
+        from ..randprocs import _conditional, _gaussian_process, covfuncs, crosscov
 
         if isinstance(f, covfuncs.CovarianceFunction):
             # L(k, argnum=1) = Cov(f(.), L[f]); argnum=0: the same object indexed the other way round (`reverse`)
@@ -102,7 +102,7 @@ class LinearFunctional:
         return NotImplemented
 
     def __matmul__(self, other):
-        from .linfuncops import LinearFunctionOperator
+        from ..linfuncops import LinearFunctionOperator
 
         if isinstance(other, LinearFunctionOperator):
             return CompositeLinearFunctional(linop=other, linfunctl=self)
@@ -127,7 +127,7 @@ def _integrate_function(g: Function, dom):
 
 class _EvaluationFunctional(LinearFunctional):
     def __init__(self, input_domain_shape, input_codomain_shape, X):
-        from .randprocs import covfuncs
+        from ..randprocs import covfuncs
 
         # an intact TensorProductGrid is remembered: conditioning assembles its Gram blocks from Kronecker factors
         self._grid = X if covfuncs._grid_factors(X) is not None else None  # pylint: disable=protected-access
@@ -209,7 +209,7 @@ class CompositeLinearFunctional(LinearFunctional):
                 for c, kind, op, payload in self._linfunctl._atoms()]  # pylint: disable=protected-access
 
     def __matmul__(self, other):
-        from .linfuncops import LinearFunctionOperator
+        from ..linfuncops import LinearFunctionOperator
 
         if isinstance(other, LinearFunctionOperator):
             return CompositeLinearFunctional(linop=self._linop @ other, linfunctl=self._linfunctl)

@@ -63,13 +63,90 @@ def _integral_terms(k: covfuncs.CovarianceFunction):
     )
 
 
+def _is_smooth(k: covfuncs.CovarianceFunction) -> bool:
+    """Kernels that are analytic in both arguments (ExpQuad and its products / sums / scalings): Gauss-Legendre
+    quadrature of their sections converges spectrally.  Matern kernels are not (kink / finite smoothness at x = x')."""
+    if isinstance(k, covfuncs.Zero):
+        return True
+    if isinstance(k, covfuncs.ScaledCovarianceFunction):
+        return _is_smooth(k.covfunc)
+    if isinstance(k, covfuncs.SumCovarianceFunction):
+        return all(_is_smooth(s) for s in k.summands)
+    if isinstance(k, covfuncs.TensorProduct):
+        return all(_is_smooth(f) for f in k.factors)
+    return isinstance(k, covfuncs.ExpQuad)
+
+
+def _proj_pts_block(k: covfuncs.CovarianceFunction, proj, X: "torch.Tensor", alpha: float = 1.0, op_pts=None,
+                    op_proj=None) -> "torch.Tensor":
+    """Device matrix ``alpha * Cov((op_pts f)(X_i), P[op_proj f]_j)`` (n x m) for ``f ~ GP(., k)`` and an L2 projection
+    ``P`` onto hat functions, normaliser included.  Half-integer Matern kernels without operators: closed form
+    (``lpgp_matern_hat_integral``; crosscov/linfunctls/projections.py:129-170 for every nu); kernels that are smooth
+    inside the elements: Gauss-Legendre nodes ``T`` per element, ``K(X, T)`` by the Gram kernel, times the
+    (basis x nodes) weight matrix on the DMMA path (the reference: scipy.integrate.quad per point and basis
+    function, projections.py:47-66)."""
+    m = len(proj.basis)
+    out = backend.alloc_matrix(X.shape[0], m)
+    terms = None
+    if op_pts is None and op_proj is None:
+        try:
+            terms = _integral_terms(k)
+        except NotImplementedError:
+            terms = None
+    if terms is not None:
+        if not terms:
+            out.zero_()
+        for t, (scale, nu, ell) in enumerate(terms):
+            backend.matern_hat_integral(_lowering.matern_integral_desc(nu, ell), proj.device_grid(), m,
+                                        not proj.basis.zero_boundary, X, out, alpha=alpha * scale, accumulate=t > 0)
+    else:
+        if not _is_smooth(k):
+            raise NotImplementedError(
+                f"L2 projection of {type(k).__name__} composed with an operator: closed forms exist for plain half-integer "
+                "Matern kernels, quadrature only for kernels that are smooth inside the elements")
+        kk = k if op_proj is None else op_proj(k, argnum=1)
+        kk = kk if op_pts is None else op_pts(kk, argnum=0)
+        T, W, _ = proj.device_quadrature()
+        K = backend.alloc_matrix(X.shape[0], T.shape[0])
+        _gram_into(kk, X, T, K)
+        backend.gemm_nt(K, W, out, alpha, 0.0)
+    return proj.normalize_rows(out)
+
+
+def _proj_proj_block(k: covfuncs.CovarianceFunction, projA, projB, alpha: float = 1.0, opA=None, opB=None) -> "torch.Tensor":
+    """``alpha * Cov(P_A[op_A f], P_B[op_B f])`` (m_A x m_B): the inner projection in closed form / by quadrature at the
+    Gauss-Legendre nodes of P_A's elements (the section ``s -> Cov(f(s), P_B f)`` is smooth INSIDE the elements when
+    both projections share their nodes), then the outer quadrature as a DMMA GEMM (the reference: scipy dblquad per
+    entry, projections.py:77-108)."""
+    if not np.all(np.isin(projA.basis.elements(), projB.basis.grid)) and not _is_smooth(k):
+        raise NotImplementedError("covariance of two L2 projections of a non-smooth kernel on different grids")
+    T, W, _ = projA.device_quadrature()
+    inner = _proj_pts_block(k, projB, T, alpha, op_pts=opA, op_proj=opB)  # (Q_A x m_B)
+    C = backend.alloc_matrix(W.shape[0], inner.shape[1])
+    backend.gemm_nn(W, inner, C, 1.0, 0.0)
+    if projA.normalized:
+        Ct = backend.alloc_matrix(C.shape[1], C.shape[0])
+        Ct.copy_(C.T)
+        projA.normalize_rows(Ct)
+        C.copy_(Ct.T)
+    return C
+
+
 class _Atom:
-    """One summand of an observation functional: ``coef * (op f)(X)`` (``kind == "pts"``) or
-    ``coef * int_a^b (op f)(t) dt`` (``kind == "int"``, one row)."""
+    """One summand of an observation functional: ``coef * (op f)(X)`` (``kind == "pts"``),
+    ``coef * int_a^b (op f)(t) dt`` (``kind == "int"``, one row) or ``coef * P[op f]`` for an L2 projection onto m hat
+    functions (``kind == "proj"``, m rows)."""
 
     def __init__(self, coef, kind, op, payload, d: int):
         self.coef, self.kind, self.op = float(coef), kind, op
-        if kind == "pts":
+        self.proj = None
+        if kind == "proj":
+            if d != 1:
+                raise NotImplementedError("L2 projections need a univariate input domain")
+            self.X_host = self.X = self.dom = None
+            self.proj = payload
+            self.n = len(payload.basis)
+        elif kind == "pts":
             self.X_host = np.asarray(payload, dtype=np.double)
             self.X = backend.points(self.X_host, d)
             self.n = self.X.shape[0]
@@ -88,8 +165,22 @@ class _Atom:
 def _atom_cov_into(k: covfuncs.CovarianceFunction, A: _Atom, B: _Atom, out: "torch.Tensor", accumulate: bool) -> None:
     """``out (+)= coef_A coef_B cov(atom_A f, atom_B f)`` for ``f ~ GP(., k)`` (out: n_A x n_B view of a row-major
     device matrix)."""
-    kk = A.apply(B.apply(k, 1), 0)
     alpha = A.coef * B.coef
+    if A.kind == "proj" or B.kind == "proj":
+        if "int" in (A.kind, B.kind):
+            raise NotImplementedError("covariance between an integral and an L2-projection observation")
+        if A.kind == "proj" and B.kind == "proj":
+            blk = _proj_proj_block(k, A.proj, B.proj, alpha, A.op, B.op)
+        elif B.kind == "proj":
+            blk = _proj_pts_block(k, B.proj, A.X, alpha, op_pts=A.op, op_proj=B.op)
+        else:
+            blk = _proj_pts_block(k, A.proj, B.X, alpha, op_pts=B.op, op_proj=A.op).T
+        if accumulate:
+            out.add_(blk)
+        else:
+            out.copy_(blk)
+        return
+    kk = A.apply(B.apply(k, 1), 0)
     if A.kind == "pts" and B.kind == "pts":
         _gram_into(kk, A.X, B.X, out, accumulate=accumulate, alpha=alpha)
         return
@@ -166,6 +257,7 @@ class _Block:
         self.n_phys = self.n + (self.n % 2)
         atom = _Atom.__new__(_Atom)
         atom.coef, atom.kind, atom.op, atom.X_host, atom.X, atom.n, atom.dom = 1.0, "pts", op, X_host, self.X, self.n, None
+        atom.proj = None
         self.atoms = [atom]
 
 
@@ -215,6 +307,9 @@ class _PosteriorState:
         descs, Xs, offs, extras = [], [], [], []
         for blk in self._blocks:
             for atom in blk.atoms:
+                if atom.kind == "proj":  # dense block of m columns: Cov((test_op f)(x), P f)
+                    extras.append((blk.col_off, atom.n, self._proj_fill(atom)))
+                    continue
                 kk = self._k_test_obs(atom)
                 if atom.kind == "int":
                     terms = [(atom.coef * sc, _lowering.matern_integral_desc(nu, ell)) for sc, nu, ell in _integral_terms(kk)]
@@ -228,6 +323,10 @@ class _PosteriorState:
                     Xs.append(atom.X)
                     offs.append(blk.col_off)
         return backend.ObsBlocks(descs, Xs, offs, extras=extras)
+
+    def _proj_fill(self, atom: _Atom):
+        k, test_op = self._base_prior.cov, self._test_op
+        return lambda Xt: _proj_pts_block(k, atom.proj, Xt, atom.coef, op_pts=test_op, op_proj=atom.op)
 
     def _obs_blocks_unique(self) -> backend.ObsBlocks:
         """Entries for the cross-covariance workspace ``k(x_test, X_obs)``: consecutive entries on the same columns

@@ -146,7 +146,13 @@ class _FunctionalCrossCovariance(ProcessVectorCrossCovariance):
         for atom in self._atoms:
             kk = self._kernel_for(atom)
             coef = alpha * atom.coef
-            if atom.kind == "pts":
+            if atom.kind == "proj":
+                blk = _conditional._proj_pts_block(self._covfunc, atom.proj, Xt, coef, op_pts=self._free_op, op_proj=atom.op)  # pylint: disable=protected-access
+                if accumulate:
+                    out[:, :n].add_(blk)
+                else:
+                    out[:, :n].copy_(blk)
+            elif atom.kind == "pts":
                 _conditional._gram_into(kk, Xt, atom.X, out[:, :n], accumulate=accumulate, alpha=coef)  # pylint: disable=protected-access
             else:
                 terms = _conditional._integral_terms(kk)  # pylint: disable=protected-access
@@ -296,7 +302,7 @@ def apply_linfunctl(linfunctl, pv: ProcessVectorCrossCovariance) -> randvars.Cov
         target = pv if atom.op is None else pv._apply_linfuncop(atom.op)  # pylint: disable=protected-access
         if atom.kind == "pts":
             target._device_matrix(atom.X, out=out, accumulate=not first, alpha=atom.coef)  # pylint: disable=protected-access
-        else:
+        else:  # integral / L2 projection of the free argument
             _integrate_free_argument(target, atom, out, accumulate=not first)
         first = False
     op = linops._Device(out[:, :n1])  # pylint: disable=protected-access
@@ -307,8 +313,9 @@ def apply_linfunctl(linfunctl, pv: ProcessVectorCrossCovariance) -> randvars.Cov
 
 
 def _integrate_free_argument(pv, atom, out, accumulate: bool) -> None:
-    """Row ``out[0, :] (+)= coef * int_a^b pv(t) dt`` for an integral atom applied to the free argument: closed forms
-    of the (double) Matern integrals, evaluated per atom of ``pv`` (crosscov/linfunctls/integrals/)."""
+    """Row ``out[0, :] (+)= coef * int_a^b pv(t) dt`` for an integral atom applied to the free argument (closed forms of
+    the (double) Matern integrals, crosscov/linfunctls/integrals/), or the ``m`` rows ``coef * P[pv]`` of an L2-projection
+    atom (crosscov/linfunctls/projections.py:69-122), evaluated per atom of ``pv``."""
     from . import _conditional  # pylint: disable=import-outside-toplevel
 
     def walk(p, alpha):
@@ -327,9 +334,9 @@ def _integrate_free_argument(pv, atom, out, accumulate: bool) -> None:
     for p, alpha in walk(pv, 1.0):
         for b_atom in p._atoms:  # pylint: disable=protected-access
             a_atom = _conditional._Atom.__new__(_conditional._Atom)  # pylint: disable=protected-access
-            a_atom.coef, a_atom.kind, a_atom.op, a_atom.X_host, a_atom.X, a_atom.n, a_atom.dom = (
-                alpha * atom.coef, "int", p._free_op, None, None, 1, atom.dom)  # pylint: disable=protected-access
-            _conditional._atom_cov_into(p.covfunc, a_atom, b_atom, out[:1, : b_atom.n], accumulate=accumulate)  # pylint: disable=protected-access
+            a_atom.coef, a_atom.kind, a_atom.op, a_atom.X_host, a_atom.X, a_atom.n, a_atom.dom, a_atom.proj = (
+                alpha * atom.coef, atom.kind, p._free_op, None, None, atom.n, atom.dom, atom.proj)  # pylint: disable=protected-access
+            _conditional._atom_cov_into(p.covfunc, a_atom, b_atom, out[: atom.n, : b_atom.n], accumulate=accumulate)  # pylint: disable=protected-access
             accumulate = True
     if not accumulate:
-        out[:1].zero_()
+        out[: atom.n].zero_()

@@ -28,6 +28,83 @@ from tests.golden import cases as gcases  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def make_projections():
+    """L2 projections onto piecewise-linear bases evaluated by the REAL reference (tests/golden/projections.npz):
+    the reference's own test case (tests/linpde_gp/randprocs/crosscov/linfunctls/projections/test_matern_l2_projection.py:
+    Matern-3/2, 7 nodes on [-1, 1], 50 points) in closed form AND through the generic quadrature class, other kernels /
+    grids through the quadrature class, the covariance of two projections (dblquad), and a GP conditioned on projection
+    observations followed by point observations."""
+    pn, lg = refshim.load()
+    from linpde_gp.randprocs.crosscov.linfunctls import projections as ref_proj
+    from oracle import projections as oproj
+
+    out, worst = {}, 0.0
+    cases = {
+        "m32_ref": dict(kernel={"kind": "matern", "input_shape": [], "nu": 1.5, "lengthscales": 1.0}, grid=np.linspace(-1.0, 1.0, 7),
+                        zero_boundary=False, normalized=True, xs=np.linspace(-1.0, 1.0, 50)),
+        "m32_zb": dict(kernel={"kind": "matern", "input_shape": [], "nu": 1.5, "lengthscales": 0.3},
+                       grid=np.array([-0.5, -0.2, 0.0, 0.35, 0.6, 1.1]), zero_boundary=True, normalized=False,
+                       xs=np.linspace(-0.8, 1.4, 23)),
+        "m52": dict(kernel={"kind": "matern", "input_shape": [], "nu": 2.5, "lengthscales": 0.7}, grid=np.linspace(0.0, 2.0, 6),
+                    zero_boundary=False, normalized=True, xs=np.linspace(-0.3, 2.3, 14)),
+        "m12": dict(kernel={"kind": "matern", "input_shape": [], "nu": 0.5, "lengthscales": 0.5}, grid=np.linspace(0.0, 1.0, 5),
+                    zero_boundary=True, normalized=True, xs=np.linspace(-0.2, 1.2, 15)),
+        "eq": dict(kernel={"kind": "expquad", "input_shape": [], "lengthscales": 0.4}, grid=np.linspace(-1.0, 1.0, 6),
+                   zero_boundary=False, normalized=True, xs=np.linspace(-1.2, 1.2, 13)),
+    }
+    for name, c in cases.items():
+        k = ref_base(c["kernel"])
+        basis = lg.functions.bases.UnivariateLinearInterpolationBasis(c["grid"], zero_boundary=c["zero_boundary"])
+        proj = basis.l2_projection(normalized=c["normalized"])
+        kPa = proj(k, argnum=1)
+        val = np.asarray(kPa(c["xs"]))
+        if c["kernel"]["kind"] == "matern" and c["kernel"]["nu"] == 1.5:
+            assert isinstance(kPa, ref_proj.Matern32_L2Projection_UnivariateLinearInterpolationBasis)
+            gen = ref_proj.CovarianceFunction_L2Projection_UnivariateLinearInterpolationBasis(k, proj, reverse=False)
+            dev = np.max(np.abs(np.asarray(gen(c["xs"])) - val))
+            print(f"projections {name}: closed form vs the reference's quadrature class {dev:.2e}")
+        rev = np.asarray(proj(k, argnum=0)(c["xs"]))
+        assert np.array_equal(rev, np.moveaxis(val, -1, 0))
+        ob = oproj.Basis(c["grid"], c["zero_boundary"])
+        oval = (oproj.crosscov_matern32(c["kernel"]["lengthscales"], ob, c["xs"], c["normalized"])
+                if c["kernel"].get("nu") == 1.5 else oproj.crosscov_quad(c["kernel"], ob, c["xs"], c["normalized"]))
+        worst = max(worst, np.max(np.abs(oval - val)) / np.max(np.abs(val)))
+        out[f"{name}_kPa"] = val
+        out[f"{name}_spec"] = np.frombuffer(json.dumps({**c, "grid": list(map(float, c["grid"])), "xs": list(map(float, c["xs"]))}).encode(), dtype=np.uint8)
+    # covariance of two projections (dblquad in the reference): small bases
+    for name, kernel, grid in (("m32", {"kind": "matern", "input_shape": [], "nu": 1.5, "lengthscales": 0.8}, np.linspace(-1.0, 1.0, 5)),
+                               ("eq", {"kind": "expquad", "input_shape": [], "lengthscales": 0.6}, np.linspace(0.0, 1.0, 4))):
+        k = ref_base(kernel)
+        proj = lg.functions.bases.UnivariateLinearInterpolationBasis(grid, zero_boundary=False).l2_projection()
+        C = np.asarray(proj(proj(k, argnum=1)).array)
+        ob = oproj.Basis(grid, False)
+        worst = max(worst, np.max(np.abs(oproj.covariance_dblquad(kernel, ob, ob) - C)) / np.max(np.abs(C)))
+        out[f"PkP_{name}"] = C
+        out[f"PkP_{name}_grid"] = grid
+        out[f"PkP_{name}_kernel"] = np.frombuffer(json.dumps(kernel).encode(), dtype=np.uint8)
+    # conditioning: projection observations first, point observations second (the order the reference supports)
+    kernel = {"kind": "matern", "input_shape": [], "nu": 1.5, "lengthscales": 0.6}
+    grid = np.linspace(-1.0, 1.0, 6)
+    k = ref_base(kernel)
+    prior = pn.randprocs.GaussianProcess(lg.functions.Constant(input_shape=(), value=0.3), 2.0 * k)
+    proj = lg.functions.bases.UnivariateLinearInterpolationBasis(grid, zero_boundary=False).l2_projection()
+    rng = np.random.default_rng(11)
+    Yp = np.sin(2.0 * grid) + 0.3
+    Xo = np.array([-0.75, 0.1, 0.55])
+    Yo = np.sin(2.0 * Xo) + 0.3
+    post1 = prior.condition_on_observations(Yp, L=proj)
+    post2 = post1.condition_on_observations(Yo, X=Xo)
+    Xt = np.linspace(-1.1, 1.1, 21)
+    out.update(gp_kernel=np.frombuffer(json.dumps(kernel).encode(), dtype=np.uint8), gp_grid=grid, gp_Yp=Yp, gp_Xo=Xo, gp_Yo=Yo,
+               gp_Xt=Xt, gp_mean1=np.asarray(post1.mean(Xt)), gp_var1=np.asarray(post1.cov(Xt, None)),
+               gp_mean2=np.asarray(post2.mean(Xt)), gp_var2=np.asarray(post2.cov(Xt, None)),
+               gp_gram2=np.asarray(post2.gram.todense()), gp_w2=np.asarray(post2.representer_weights))
+    del rng
+    np.savez(os.path.join(GOLDEN, "projections.npz"), **out)
+    print(f"projections.npz: {len(out)} arrays, worst oracle-vs-reference deviation {worst:.2e}")
+    return worst
+
+
 # ----------------------------------------------------------------------------------------
 # spec -> reference objects
 # ----------------------------------------------------------------------------------------
@@ -398,6 +475,9 @@ if __name__ == "__main__":
     if "--seams-only" in sys.argv:
         print(f"worst deviation: seams {make_seams():.2e}")
         sys.exit(0)
+    if "--projections-only" in sys.argv:
+        print(f"worst deviation: projections {make_projections():.2e}")
+        sys.exit(0)
     if "--multi-output-only" in sys.argv:
         print(f"worst deviation: multi-output {make_multi_output():.2e}")
         sys.exit(0)
@@ -410,5 +490,6 @@ if __name__ == "__main__":
     w4 = make_multi_output()
     w5 = make_integrals()
     w6 = make_seams()
+    w7 = make_projections()
     print(f"worst deviations: kernels {w1:.2e}, gp {w2:.2e}, kron {w3:.2e}, multi-output {w4:.2e}, integrals {w5:.2e}, "
-          f"seams {w6:.2e}")
+          f"seams {w6:.2e}, projections {w7:.2e}")

@@ -511,3 +511,35 @@ def test_api_descriptors_equal_spec_descriptors_for_every_reference_case():
         a, b = np.array(ref.coef[:]), np.array(descs[0].coef[:])
         assert np.allclose(a, b, rtol=1e-14, atol=0), spec["name"]
         assert abs(ref.diag_value - descs[0].diag_value) <= 1e-14 * max(1.0, abs(ref.diag_value)), spec["name"]
+
+
+def test_linear_interpolation_basis_and_l2_projection_host_side():
+    """``functions.bases.UnivariateLinearInterpolationBasis`` (src/linpde_gp/functions/bases/_fem.py:7-117) and the host
+    parts of ``L2Projection_UnivariateLinearInterpolationBasis`` (linfunctls/projections/l2/_fem.py:14-62): sentinel
+    nodes, partition of unity, support bounds, mass matrix, quadrature weights, argument errors."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.linfunctls.projections.l2 import L2Projection_UnivariateLinearInterpolationBasis
+
+    grid = np.array([0.0, 0.2, 0.5, 0.6, 1.0])
+    b = lg.functions.bases.UnivariateLinearInterpolationBasis(grid)
+    assert len(b) == 5 and b.output_shape == (5,) and not b.zero_boundary
+    assert np.allclose(b.grid, [-0.2, 0.0, 0.2, 0.5, 0.6, 1.0, 1.4])
+    x = np.linspace(0.0, 1.0, 41)
+    assert np.allclose(b(x).sum(-1), 1.0)                     # partition of unity on the grid
+    assert np.allclose(b(grid), np.eye(5))                    # nodal basis
+    assert b.support_bounds(0) == (0.0, 0.2) and b.support_bounds(4) == (0.6, 1.0) and b.support_bounds(2) == (0.2, 0.6)
+    assert np.allclose(b.eval_elem(2, x), b(x)[:, 2])
+    bz = lg.functions.bases.UnivariateLinearInterpolationBasis(grid, zero_boundary=True)
+    assert len(bz) == 3 and np.allclose(bz(grid)[:, 0], [0, 1, 0, 0, 0])
+    with pytest.raises(ValueError):
+        lg.functions.bases.UnivariateLinearInterpolationBasis([0.0, 1.0])
+    proj = b.l2_projection()
+    assert isinstance(proj, L2Projection_UnivariateLinearInterpolationBasis) and proj.normalized
+    assert proj.output_shape == (5,) and proj.input_shapes == ((), ())
+    M = proj.mass_matrix()
+    assert np.allclose(M, M.T) and np.isclose(M.sum(), 1.0)   # int (sum phi_i)(sum phi_j) = |domain|
+    nodes, W = b.gauss_legendre(6)
+    assert W.shape == (5, 24) and np.allclose(W.sum(1), M.sum(1)) and np.allclose(W @ nodes, M @ grid)
+    assert [a[1] for a in proj._atoms()] == ["proj"]
+    with pytest.raises(TypeError):
+        L2Projection_UnivariateLinearInterpolationBasis(grid)

@@ -142,6 +142,34 @@ def test_gemm_nt_vs_torch(be, m, n, k, alpha, beta):
     assert err <= 1e-13 * max(1.0, k**0.5) * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("m,n,k", [(128, 128, 8), (300, 200, 77), (1, 130, 1000), (1000, 1000, 512), (257, 511, 1030), (40, 18, 6)])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (-1.0, 1.0), (0.5, -2.0)])
+def test_gemm_nn_vs_torch(be, m, n, k, alpha, beta):
+    """``lpgp_gemm_nn`` (B row-major k x n, swizzled 16-column boxes): ragged m / n / k, sub-block views with offsets."""
+    g = torch.Generator(device="cuda").manual_seed(m + 2 * n + k)
+    A = be.alloc_matrix(m, k).normal_(generator=g)
+    Bfull = be.alloc_matrix(k + 3, n + 6).normal_(generator=g)
+    B = Bfull[2 : 2 + k, 4 : 4 + n]  # a view at an even column offset inside a larger matrix (like L21 inside L)
+    C = be.alloc_matrix(m, n).normal_(generator=g)
+    ref = beta * C + alpha * (A @ B)
+    be.gemm_nn(A, B, C, alpha, beta)
+    err = (C - ref).abs().max().item()
+    assert err <= 1e-13 * max(1.0, k**0.5) * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_nn_in_place_strip(be):
+    """X <- X W in place (n <= 128: one CTA owns complete output rows), the leaf step of ``lpgp_trsm_rln``."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for m, nb in ((7, 128), (1000, 128), (33000, 128), (300, 72)):
+        X = be.alloc_matrix(m, 200).normal_(generator=g)
+        W = be.alloc_matrix(128, 128).normal_(generator=g)
+        ref = X[:, :nb] @ W[:nb, :nb]
+        keep = X[:, nb:].clone()
+        be.gemm_nn(X[:, :nb], W[:nb, :nb], X[:, :nb], 1.0, 0.0)
+        assert (X[:, :nb] - ref).abs().max().item() <= 1e-12 * ref.abs().max().item()
+        assert torch.equal(X[:, nb:], keep)
+
+
 def test_gemm_nt_lower_only_touches_lower_tiles(be):
     n, k = 1000, 300
     A = be.alloc_matrix(n, k).normal_()
@@ -331,6 +359,35 @@ def test_trsm_and_potrs_vs_torch(be, n, m):
     f.potrs(Y)
     ref2 = torch.cholesky_solve(B[: min(m, 3)].T.contiguous(), L_ref).T
     assert (Y - ref2).abs().max().item() <= 1e-9 * ref2.abs().max().item()
+
+
+@pytest.mark.parametrize("sizes,m", [((130,), 5), ((200, 72, 300), 4), ((2, 4, 6, 130), 17), ((2304,), 700), ((5000, 2, 3002), 130)])
+def test_trsm_rln_and_multi_rhs_potrs_vs_torch(be, sizes, m):
+    """``lpgp_trsm_rln`` (X <- X L^{-1}) and ``lpgp_potrs`` with >= 4 right-hand sides (two blocked DMMA solves) against
+    torch FP64, over ragged segments; the blocked path agrees with the single-vector substitution chains."""
+    n = sum(sizes)
+    G = _spd(n, n + m)
+    f, off = None, 0
+    for s in sizes:
+        f = be.DeviceFactor([s]) if f is None else f.extended(s)
+        f.L[off : off + s, : off + s].copy_(G[off : off + s, : off + s])
+        f.potrf() if off == 0 else f.append_last()
+        off += s
+    L_ref = torch.linalg.cholesky(G)
+    B = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(n + m))
+    X = be.alloc_matrix(m, n)
+    X.copy_(B)
+    f.trsm_rln(X)
+    ref = torch.linalg.solve_triangular(L_ref.T, B.T, upper=True).T
+    assert (X - ref).abs().max().item() <= 1e-10 * ref.abs().max().item()
+    Y = be.alloc_matrix(m, n)
+    Y.copy_(B)
+    f.potrs(Y)
+    ref2 = torch.cholesky_solve(B.T.contiguous(), L_ref).T
+    assert (Y - ref2).abs().max().item() <= 1e-9 * ref2.abs().max().item()
+    assert (Y @ G - B).abs().max().item() <= 1e-11 * max(1.0, (Y.abs() @ G.abs()).max().item())
+    y1 = f.potrs(B[:2].clone())  # < 4 rows: substitution chains
+    assert (y1 - Y[:2]).abs().max().item() <= 1e-10 * Y[:2].abs().max().item()
 
 
 @pytest.mark.parametrize("sizes", [(128, 128), (200, 72, 300), (2, 4, 6, 130), (1000, 24, 1500)])

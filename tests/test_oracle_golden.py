@@ -216,3 +216,26 @@ def test_oracle_crosscov_matches_reference_seam_goldens():
         x = g[f"blk__{name}__schur_update"]
         rhs = np.concatenate([g[f"blk__{name}__u"], g[f"blk__{name}__v"]])
         assert np.max(np.abs(K @ x - rhs)) <= 1e-6 * np.max(np.abs(rhs))
+
+
+def test_oracle_projections_match_reference_golden():
+    """oracle/projections.py (quad / dblquad restatement + the Matern-3/2 closed form) against the real reference's
+    outputs frozen in tests/golden/projections.npz; the cheap cases only (the quadrature cases take seconds each)."""
+    import json
+
+    from oracle import projections as oproj
+
+    z = np.load(os.path.join(GOLDEN, "projections.npz"))
+    for name in ("m32_ref", "m32_zb", "m12"):
+        c = json.loads(bytes(z[f"{name}_spec"]).decode())
+        ob = oproj.Basis(c["grid"], c["zero_boundary"])
+        if c["kernel"]["nu"] == 1.5:
+            val = oproj.crosscov_matern32(c["kernel"]["lengthscales"], ob, c["xs"], c["normalized"])
+        else:
+            val = oproj.crosscov_quad(c["kernel"], ob, c["xs"][:4], c["normalized"])
+        ref = z[f"{name}_kPa"][: len(val)]
+        assert np.max(np.abs(val - ref)) <= 1e-12 * np.max(np.abs(ref))
+    # mass matrix of the basis: exact integrals of products of hat functions
+    ob = oproj.Basis(np.array([0.0, 0.5, 1.5, 2.0]), False)
+    M = oproj.mass_matrix(ob)
+    assert np.allclose(M.sum(), 2.0) and np.allclose(M, M.T)
