@@ -43,11 +43,18 @@ sys.path.insert(0, ROOT)
 SIGMA2 = 4.0
 NU = 2.5
 T_START = time.perf_counter()
-# DRAM traffic of the dominant kernel: taken from a committed ncu capture, never measured inside a bench run
+# DRAM traffic of the dominant kernels: taken from committed ncu captures (one launch each), never measured inside a
+# bench run (ncu replays kernels; a number printed under a profiler is not a bench value)
 GEMM_TRAFFIC = {
     "bytes": 2.786e9,
     "source": "profiles/ncu_kernels_r01d.md (ncu --set full, one launch; not measured in this run)",
     "launch": "gemm_nt_kernel 8192x8192x2048 beta=1: 2.26 GB read + 0.53 GB written (algorithmic 1.34 GB)",
+}
+OZAKI_TRAFFIC = {
+    "bytes": 3.016e9,
+    "source": "profiles/ncu_ozaki_r02d.md (ncu --set full, one launch; not measured in this run)",
+    "launch": "ozaki_gemm_kernel 16384x1024x16384, 7 digit planes, beta=1: 2.88 GB read + 0.13 GB written "
+              "(algorithmic 2.27 GB: 7 x (16384 + 1024) x 16384 plane bytes + C read and written)",
 }
 
 
@@ -263,6 +270,26 @@ def dmma_peak_tflops(torch, backend):
     return best
 
 
+def i8_peak_tops(torch):
+    """INT8 tensor-pipe issue rate (tcgen05.mma.kind::i8, operands resident in shared memory), TOP/s: best of 4."""
+    import ctypes
+
+    from linpde_gp_b200._lib import lib
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    ops = ctypes.c_double(0.0)
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = lib.lpgp_i8_peak_probe(sms, 20000, ctypes.byref(ops), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        e1.record()
+        torch.cuda.synchronize()
+        assert rc == 0
+        best = max(best, ops.value / e0.elapsed_time(e1) * 1e-9)
+    return best
+
+
 def gram_kernel_alone(torch, backend, prob):
     """The assembly kernel on its own (one L k L* block of 16,384 x N_pde entries written to HBM), best of 4."""
     from linpde_gp_b200._lowering import Factor1D, lower
@@ -353,6 +380,8 @@ def run_b200(args):
     # ---- before the GPU loop: bounded CPU baseline (N = 1 only), roofline denominators ----
     cpu_est, cpu_detail = (cpu_sample(prob, budget_s=args.cpu_budget_s) if (world == 1 and rank == 0) else (None, {}))
     peak = dmma_peak_tflops(torch, backend) if rank == 0 else None
+    emulated = backend.VARIANCE_SOLVER["ozaki_slices"] > 0
+    peak_i8 = i8_peak_tops(torch) if (rank == 0 and emulated) else None
     gram_kernel = gram_kernel_alone(torch, backend, prob) if rank == 0 else None
 
     # ---- first warm-up step doubles as the estimate of the step time the plan is made from ----
@@ -368,6 +397,10 @@ def run_b200(args):
     # ---- the timed loop: wall clock around it -> e2e, CUDA-event phase timers inside it -> device-only value ----
     barrier()
     lib.lpgp_launch_count(1)
+    import ctypes
+
+    lib.lpgp_ozaki_gemm_stats(1, None, None, None, None)
+    lib.lpgp_set_option(4, 1)  # LPGP_OPT_TIME_OZAKI: CUDA events around every emulated-GEMM launch of the timed loop
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -379,6 +412,9 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - t0
     launches = lib.lpgp_launch_count(0)
+    oz_ms, oz_ops, oz_flops, oz_n = ctypes.c_double(0.0), ctypes.c_double(0.0), ctypes.c_double(0.0), ctypes.c_longlong(0)
+    lib.lpgp_ozaki_gemm_stats(1, ctypes.byref(oz_ms), ctypes.byref(oz_ops), ctypes.byref(oz_flops), ctypes.byref(oz_n))
+    lib.lpgp_set_option(4, 0)
     clocks = sampler.stop() if rank == 0 else None
     phases = {k: v / k_steps for k, v in timer.totals_ms().items()}
     ms_dev, ms_e2e = max_over_ranks(sum(phases.values()), wall * 1e3 / k_steps)
@@ -388,13 +424,45 @@ def run_b200(args):
 
     if rank == 0:
         m_shard = parallel.shard_bounds(M, 0, world)[1]
-        flops_tensor = N**3 / 3.0 / world + float(m_shard) * N * N  # per rank: Cholesky share + variance TRSM
-        t_tensor = (phases["factor"] + phases["var"]) * 1e-3
-        achieved = flops_tensor / t_tensor * 1e-12
         h2d = sum(e.nbytes for e in prob["edges"]) + sum(y.nbytes for y in prob["Y_bc"]) + prob["X_pde"].nbytes \
             + prob["Y_pde"].nbytes + prob["Xt"].nbytes * 2 // world
         threads, cores = host_threads()
         prior_var = SIGMA2
+        # DMMA GEMM kernel: Cholesky trailing updates (+ the variance solve when it runs on the native FP64 path)
+        flops_dmma = N**3 / 3.0 / world + (0.0 if emulated else float(m_shard) * N * N)
+        t_dmma = (phases["factor"] + (0.0 if emulated else phases["var"])) * 1e-3
+        roofline_dmma = {
+            "bound": "tensor", "achieved": flops_dmma / t_dmma * 1e-12, "peak": peak, "unit": "TFLOP/s",
+            "frac": flops_dmma / t_dmma * 1e-12 / peak, "traffic": GEMM_TRAFFIC["bytes"],
+            "traffic_source": GEMM_TRAFFIC["source"], "traffic_launch": GEMM_TRAFFIC["launch"],
+            "kernel": "gemm_nt_kernel (DMMA m8n8k4.f64) inside lpgp_potrf / lpgp_chol_append"
+                      + ("" if emulated else " + lpgp_post_var"),
+            "peak_source": "FP64 tensor-pipe issue rate measured live (lpgp_dmma_peak_probe); MEASURED_PEAKS.json holds "
+                           "no FP64 figure",
+            "flops": flops_dmma, "seconds": t_dmma,
+        }
+        if emulated and oz_n.value > 0:
+            # the dominant kernel of the step: per-launch CUDA events on the launching stream, summed over the timed loop
+            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            mp = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+            ach = oz_ops.value / (oz_ms.value * 1e-3) * 1e-12
+            roofline = {
+                "bound": "tensor", "achieved": ach, "peak": peak_i8, "unit": "TFLOP/s", "frac": ach / peak_i8,
+                "traffic": OZAKI_TRAFFIC["bytes"], "traffic_source": OZAKI_TRAFFIC["source"],
+                "traffic_launch": OZAKI_TRAFFIC["launch"],
+                "kernel": "ozaki_gemm_kernel (tcgen05.mma.kind::i8, TMEM accumulators, TMA operands): the O(M N^2) part of "
+                          "the posterior-variance solve; `achieved` / `peak` count INT8 multiply-adds x 2 (TOP/s)",
+                "peak_source": "INT8 tensor-pipe issue rate measured live (lpgp_i8_peak_probe, operands resident in shared "
+                               "memory); MEASURED_PEAKS.json holds bf16 only",
+                "peak_2x_measured_bf16_burst": (2.0 * mp["bf16_tflops"]) if mp.get("bf16_tflops") else None,
+                "peak_2x_measured_bf16_sustained": (2.0 * mp["bf16_tflops_sustained"]) if mp.get("bf16_tflops_sustained") else None,
+                "int8_ops": oz_ops.value / k_steps, "launches_per_step": oz_n.value / k_steps,
+                "kernel_seconds_per_step": oz_ms.value * 1e-3 / k_steps,
+                "share_of_step": oz_ms.value / k_steps / ms_dev,
+                "fp64_equivalent_tflops": oz_flops.value / (oz_ms.value * 1e-3) * 1e-12,
+            }
+        else:
+            roofline = dict(roofline_dmma)
         out = {
             "metric": "s per GP-PDE solve (2D Poisson N=64k)",
             "value": ms_dev * 1e-3,
@@ -434,19 +502,13 @@ def run_b200(args):
             "clocks": clocks,
             "checks": {"mean_finite": bool(np.all(np.isfinite(gm))), "var_min": float(np.min(gv)), "var_max": float(np.max(gv)),
                        "var_within_prior": bool(np.min(gv) >= -1e-8 * prior_var and np.max(gv) <= prior_var * (1 + 1e-12))},
-            "roofline": {
-                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # NOT measured in this run: dram__bytes_read+write of ONE representative launch (8192 x 8192 x 2048,
-                # beta = 1) from the committed ncu --set full capture named in `traffic_source`; its algorithmic
-                # bytes are 1.34e9 (A + B once, C read + written)
-                "traffic": GEMM_TRAFFIC["bytes"],
-                "traffic_source": GEMM_TRAFFIC["source"],
-                "traffic_launch": GEMM_TRAFFIC["launch"],
-                "kernel": "gemm_nt_kernel (DMMA m8n8k4.f64) inside lpgp_potrf/lpgp_chol_append + lpgp_post_var",
-                "peak_source": "FP64 tensor-pipe issue rate measured live (lpgp_dmma_peak_probe); MEASURED_PEAKS.json "
-                               "holds no FP64 figure",
-                "flops": flops_tensor,
-            },
+            "roofline": roofline,
+            "roofline_cholesky": roofline_dmma,
+            "variance_solver": ({"kind": "INT8-emulated FP64 (Ozaki splitting, tcgen05.mma.kind::i8)",
+                                 "digit_planes": backend.VARIANCE_SOLVER["ozaki_slices"],
+                                 "kblock": backend.VARIANCE_SOLVER["kblock"],
+                                 "bits_kept": 7 + 8 * (backend.VARIANCE_SOLVER["ozaki_slices"] - 1)}
+                                if emulated else {"kind": "DMMA"}),
             "cpu_baseline": ({"value": cpu_est, "unit": "s", "cores": cores, "threads": threads, "kind": "port",
                               **cpu_detail} if cpu_est is not None else None),
         }

@@ -101,6 +101,13 @@ long long lpgp_launch_count(int reset); /* kernels launched by the library so fa
  * the residual perturbs the Gram matrix itself and decides whether a nearly singular matrix still factors, as it
  * does with the reference's dpotrf); 2 = as 1, also in lpgp_trsm_rlt; 3 = as 2 for every leaf (A/B tests).     */
 #define LPGP_OPT_TRSM_REFINE 3
+/* LPGP_OPT_TIME_OZAKI != 0: every lpgp_ozaki_gemm_nt launch is bracketed by two CUDA events on its stream (no
+ * synchronisation added); lpgp_ozaki_gemm_stats reads them back (bench.py: live duration of the dominant kernel). */
+#define LPGP_OPT_TIME_OZAKI 4
+/* LPGP_OPT_OZAKI_KERNEL: 2 (default) = emulated-GEMM kernel that keeps the digit planes of a K-chunk resident in shared
+ * memory and reuses them across the (s, t) plane pairs of a group of levels; 1 = the first version, which streams one
+ * pair of tiles per pipeline stage (A/B timing, profiles/).                                                       */
+#define LPGP_OPT_OZAKI_KERNEL 5
 int lpgp_set_option(int key, int value);
 /* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and
  * reports the flop count; timed by the caller it yields the roofline denominator of the DMMA kernels on the
@@ -283,6 +290,16 @@ int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const lpgp
  * leaf boundary of the factor to be a multiple of 128 (segments of 128-multiples); returns -1 otherwise.        */
 int lpgp_trsm_rlt_ozaki(const lpgp_factor* f, double* X, int64_t m, int64_t ldx, const lpgp_ozaki_planes* LP,
                         const lpgp_ozaki_planes* XP, void* stream);
+
+/* Sum of the CUDA-event durations (ms), INT8 operation count (2 m n k x digit-plane pairs), FP64-equivalent flops
+ * (2 m n k) and number of the lpgp_ozaki_gemm_nt launches recorded since the last reset (LPGP_OPT_TIME_OZAKI);
+ * waits for the recorded launches to finish.                                                                   */
+int lpgp_ozaki_gemm_stats(int reset, double* ms, double* int8_ops, double* fp64_flops, long long* launches);
+
+/* INT8 tensor-pipe issue-rate probe: `blocks` CTAs each issue iters x 4 tcgen05.mma.kind::i8 (128 x 128 x 32) on
+ * operands resident in shared memory; reports the operation count -- timed by the caller it is the roofline
+ * denominator of the emulated GEMM on the box at hand (MEASURED_PEAKS.json holds a bf16 figure only).           */
+int lpgp_i8_peak_probe(int blocks, int iters, double* ops, void* stream);
 
 /* (3) posterior evaluation -----------------------------------------------------------------------------
  * One observation block of the conditioned process: descriptor of (k L_i^*) (test side x observation side),

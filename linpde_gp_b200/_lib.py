@@ -124,6 +124,8 @@ def _load() -> ctypes.CDLL:
         "lpgp_ozaki_split": (ci, [vp, i64, i64, i64, i64, i64, OP, ci, vp]),
         "lpgp_ozaki_gemm_nt": (ci, [i64, i64, i64, dbl, OP, i64, i64, OP, i64, i64, dbl, vp, i64, vp]),
         "lpgp_trsm_rlt_ozaki": (ci, [FP, vp, i64, i64, OP, OP, vp]),
+        "lpgp_ozaki_gemm_stats": (ci, [ci, ctypes.POINTER(dbl), ctypes.POINTER(dbl), ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_longlong)]),
+        "lpgp_i8_peak_probe": (ci, [ci, ci, ctypes.POINTER(dbl), vp]),
         "lpgp_potrs": (ci, [FP, vp, i64, i64, vp]),
         "lpgp_trsv": (ci, [FP, ci, vp, vp]),
         "lpgp_gemv": (ci, [ci, i64, i64, dbl, vp, i64, vp, vp, vp]),
@@ -146,7 +148,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTED = (
     "lpgp_version lpgp_build_arch lpgp_error_string lpgp_launch_count lpgp_set_option lpgp_dmma_peak_probe lpgp_gram lpgp_gram_pairs lpgp_gram_diag lpgp_add_diag lpgp_symmetrize_lower lpgp_kron_sum "
-    "lpgp_gemm_nt lpgp_gemm_nn lpgp_gemm_nt_limited lpgp_ozaki_split lpgp_ozaki_gemm_nt lpgp_trsm_rlt_ozaki lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_trsm_rlt_refined lpgp_trsm_rln lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
+    "lpgp_gemm_nt lpgp_gemm_nn lpgp_gemm_nt_limited lpgp_ozaki_split lpgp_ozaki_gemm_nt lpgp_ozaki_gemm_stats lpgp_i8_peak_probe lpgp_trsm_rlt_ozaki lpgp_factor_dinv_bytes lpgp_potrf lpgp_potrf_async lpgp_chol_append lpgp_trsm_rlt lpgp_trsm_rlt_refined lpgp_trsm_rln lpgp_potrs lpgp_trsv lpgp_gemv lpgp_logdet "
     "lpgp_post_mean lpgp_crosscov lpgp_post_var lpgp_row_sumsq lpgp_matern_integral lpgp_matern_integral2 lpgp_matern_hat_integral"
 ).split()
 

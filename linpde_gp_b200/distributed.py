@@ -203,9 +203,12 @@ class DistributedCholesky:
             dist.broadcast(t, src=dist.get_global_rank(self.group, src) if self.group is not None else src, group=self.group)
 
     # -- factorisation -------------------------------------------------------------------------------------
-    def factor(self, L_full: Optional[torch.Tensor] = None) -> None:
+    def factor(self, L_full: Optional[torch.Tensor] = None, profile: Optional[dict] = None) -> None:
         """Factor in place (``A_loc`` holds this rank's block rows of L afterwards).  ``L_full`` (n x n row-major,
-        optional): receives the lower triangle of the complete factor on every rank."""
+        optional): receives the lower triangle of the complete factor on every rank.  ``profile`` (a dict, optional):
+        receives the CUDA-event time of every stage of the panel chain summed over the panels (``potrf``, ``bcast``,
+        ``trsm``, ``gather``, ``rotate``, ``update_next`` on the panel stream; ``update_rest`` on the update stream) and
+        the total -- the timeline that says what the critical path of the pipeline is made of."""
         lay, ops, P, rank, nb, n = self.layout, self.ops, self.world, self.rank, self.nb, self.n
         dev = self.A_loc.device
         nblk = lay.nblk
@@ -221,7 +224,23 @@ class DistributedCholesky:
         ev_first = [None, None]   # update stream: block column k+2 of step k done
         ev_rest = [None, None]    # update stream: all of step k done (panel buffer k%2 free again)
 
+        marks = []  # (stage, start event, end event)
+
+        def mark(stage, ev0):
+            """close `stage` (started at event ev0) at the current point of the current stream; returns the new event"""
+            if profile is None:
+                return None
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record(torch.cuda.current_stream())
+            if ev0 is not None:
+                marks.append((stage, ev0, ev1))
+            return ev1
+
         ops.fork()
+        t_begin = None
+        if profile is not None:
+            t_begin = torch.cuda.Event(enable_timing=True)
+            t_begin.record(torch.cuda.current_stream())
         for k in range(nblk):
             k0, k1 = lay.block_bounds(k)
             bk = k1 - k0
@@ -234,6 +253,7 @@ class DistributedCholesky:
             dinv_k = self.dinv[leaf0 * LEAF * LEAF : (leaf0 + nleaf) * LEAF * LEAF]
             with ops.on("panel"):
                 ops.wait(ev_rest[k % 2])  # step k-2 no longer reads pack / panel buffer k%2
+                e = mark("", None)
                 # (1) diagonal block on its owner; [L_kk | inverted leaves | info] travels in one broadcast
                 if rank == owner:
                     D = self.local_block_rows(k)[:, k0:k1]
@@ -242,7 +262,9 @@ class DistributedCholesky:
                     pack[-1:].add_(float(k0) * (pack[-1:] > 0))  # position inside the whole matrix
                     Lkk.copy_(D)
                     Wk.copy_(dt[: nleaf * LEAF * LEAF])
+                e = mark("potrf", e)
                 self._bcast(pack, owner)
+                e = mark("bcast", e)
                 info_all.copy_(torch.where(info_all > 0, info_all, pack[-1:]))
                 dinv_k.copy_(Wk)
                 if L_full is not None:
@@ -255,6 +277,7 @@ class DistributedCholesky:
                 m_loc = lay.rows_after(rank, k)
                 X = self.A_loc[r_lo : r_lo + m_loc, k0:k1]
                 ops.trsm_block(Lkk, Wk, X, refine=True)
+                e = mark("trsm", e)
                 # (3) all-gather the panel pieces; slot (r, j) = j-th block below k of rank r.  Global block
                 #     k+1+t sits in slot ((k+1+t) % P, t // P): rotating the rank axis and swapping it with the
                 #     slot axis puts the panel into global row order.
@@ -265,6 +288,7 @@ class DistributedCholesky:
                 if P > 1:
                     rview = recv[: P * J * nb * bk]
                     dist.all_gather_into_tensor(rview, send[: J * nb * bk], group=self.group)
+                    e = mark("gather", e)
                     R = rview.view(P, J, nb, bk)
                     pv = pbuf[: J * P * nb * bk].view(J, P, nb, bk)
                     s = (k + 1) % P
@@ -274,6 +298,7 @@ class DistributedCholesky:
                 else:
                     pbuf[: J * nb * bk].copy_(send[: J * nb * bk])
                 panel = pbuf[: (n - k1) * bk].view(n - k1, bk)
+                e = mark("rotate", e)
                 ev_panel = ops.record()
                 # (4a) block column k+1 (the next panel) right away, on the panel stream
                 k2 = lay.block_bounds(k + 1)[1]
@@ -281,8 +306,10 @@ class DistributedCholesky:
                 if m_loc > 0:
                     ops.wait(ev_first[(k + 1) % 2])  # step k-1 has finished with block column k+1
                     ops.update_limited(self.A_loc[r_lo : r_lo + m_loc, k1:k2], X, panel[: k2 - k1], lim, k1)
+                e = mark("update_next", e)
             with ops.on("update"):
                 ops.wait(ev_panel)
+                eu = mark("", None)
                 if L_full is not None:
                     L_full[k1:n, k0:k1].copy_(panel)
                 # (4b) block column k+2, then everything to the right of it
@@ -295,7 +322,17 @@ class DistributedCholesky:
                 else:
                     ev_first[k % 2] = ops.record()
                 ev_rest[k % 2] = ops.record()
+                mark("update_rest", eu)
         ops.join()
+        if profile is not None:
+            t_end = torch.cuda.Event(enable_timing=True)
+            t_end.record(torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            profile.clear()
+            for stage, e0, e1 in marks:
+                profile[stage] = profile.get(stage, 0.0) + e0.elapsed_time(e1)
+            profile["total"] = t_begin.elapsed_time(t_end)
+            profile["panels"] = nblk
         info = int(info_all.item())
         if info > 0:  # every rank raises together (pn/linops/_linear_operator.py:823-839 semantics)
             import numpy as np

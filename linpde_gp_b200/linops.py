@@ -126,6 +126,13 @@ class LinearOperator:
     def _triangular_solve(self, B):
         raise NotImplementedError(f"{type(self).__name__} has no triangular solve")
 
+    def _solve_rows_device(self, R: torch.Tensor) -> torch.Tensor:
+        """Device matrix whose rows are ``A^{-1} r`` for the rows ``r`` of the device matrix ``R`` (building block of the
+        structured Kronecker solve): symmetric operators through their cached Cholesky factor."""
+        if not self.is_symmetric:
+            raise NotImplementedError(f"row solves with {type(self).__name__} (not flagged symmetric)")
+        return self.cholesky(True)._spd_rows_device(R)  # pylint: disable=protected-access
+
     def inv(self) -> "LinearOperator":
         """Lazy inverse (pn/linops/_linear_operator.py:1009-1028, 1474-1521): ``inv() @ B`` is ``solve(B)``."""
         if not self.is_square:
@@ -195,6 +202,11 @@ class _Transposed(LinearOperator):
 
     def _triangular_solve(self, B):
         return self._op._triangular_solve(B, trans=True)  # pylint: disable=protected-access
+
+    def _solve_rows_device(self, R):
+        if isinstance(self._op, CholeskyFactor):
+            return self._op._solve_rows_device(R, trans=True)  # pylint: disable=protected-access
+        return super()._solve_rows_device(R)
 
 
 class _InverseLinearOperator(LinearOperator):
@@ -419,17 +431,40 @@ class CholeskyFactor(LinearOperator):
         self.factor.potrs(dev)  # forward + backward substitution per right-hand side
         return back(dev[:, self._dev_index()].cpu().numpy())
 
+    def _apply_rows_device(self, R: torch.Tensor, how: str) -> torch.Tensor:
+        """Rows of the device matrix ``R`` (logical width) through ``potrs`` / ``L^{-1}`` / ``L^{-T}`` of the physical
+        factor (zero-padded columns for the identity padding rows); returns a device matrix of the logical width."""
+        n = self.shape[0]
+        direct = n == self.factor.n and R.stride(0) % 2 == 0 and R.data_ptr() % 16 == 0 and R.stride(1) == 1
+        if direct:
+            dev = R
+        else:
+            dev = backend.alloc_matrix(R.shape[0], self.factor.n).zero_()
+            dev[:, self._dev_index()] = R
+        if how == "spd":
+            self.factor.potrs(dev)
+        elif how == "fwd":
+            self.factor.trsm_rlt(dev)  # rows <- rows L^{-T}, i.e. L^{-1} b for every right-hand side b
+        elif dev.shape[0] >= 4:
+            self.factor.trsm_rln(dev)  # rows <- rows L^{-1}, i.e. L^{-T} b: blocked DMMA solve
+        else:
+            for r in range(dev.shape[0]):
+                self.factor.trsv(dev[r], trans=True)
+        return dev if direct else dev[:, self._dev_index()]
+
+    def _spd_rows_device(self, R: torch.Tensor) -> torch.Tensor:
+        return self._apply_rows_device(R, "spd")
+
+    def _solve_rows_device(self, R: torch.Tensor, trans: bool = False) -> torch.Tensor:
+        return self._apply_rows_device(R, "bwd" if trans else "fwd")
+
     def _triangular_solve(self, B, trans: bool = False):
         """``L^{-1} B`` (``trans``: ``L^{-T} B``).  The padding rows of the physical factor are identity rows, so
         substituting with the physical factor on zero-padded right-hand sides gives the logical solution."""
         rows, back = _rows_of(B, self.shape[0])
-        dev = self._scatter(rows)
-        if not trans:
-            self.factor.trsm_rlt(dev)  # rows <- rows L^{-T}, i.e. L^{-1} b for every right-hand side b
-        else:
-            for r in range(dev.shape[0]):
-                self.factor.trsv(dev[r], trans=True)
-        return back(dev[:, self._dev_index()].cpu().numpy())
+        R = backend.alloc_matrix(*rows.shape)
+        R.copy_(backend.to_device(np.ascontiguousarray(rows)))
+        return back(self._apply_rows_device(R, "bwd" if trans else "fwd").cpu().numpy())
 
     def logabsdet(self) -> float:
         return 0.5 * self.factor.logdet()
@@ -551,6 +586,53 @@ class Kronecker(LinearOperator):
     def kron_terms(self):
         A, B = self._factor_matrices()
         return [(1.0, A, B)]
+
+    # -- structure-preserving algebra (pn/linops/_kronecker.py:122-166, 233-242): nothing of size N x N is formed -----
+    @property
+    def T(self):
+        return self if self.is_symmetric else Kronecker(self.A.T, self.B.T)
+
+    def cholesky(self, lower: bool = True) -> "Kronecker":
+        """``chol(A (x) B) = chol(A) (x) chol(B)`` (_kronecker.py:233-242)."""
+        if not (self.A.is_symmetric and self.B.is_symmetric):
+            raise np.linalg.LinAlgError("The Cholesky decomposition is only defined for symmetric matrices.")
+        K = Kronecker(self.A.cholesky(lower), self.B.cholesky(lower))
+        K.is_lower_triangular, K.is_upper_triangular = bool(lower), not lower
+        return K
+
+    def inv(self) -> "Kronecker":
+        """``(A (x) B)^{-1} = A^{-1} (x) B^{-1}`` (_kronecker.py:135-140)."""
+        if not (self.A.is_square and self.B.is_square):
+            raise np.linalg.LinAlgError("Only square operators can be inverted.")
+        return Kronecker(self.A.inv(), self.B.inv())
+
+    def solve(self, B):
+        """``(A (x) B)^{-1} vec(X) = vec(A^{-1} X B^{-T})``: two multi-right-hand-side solves with the SMALL factors (their
+        cached Cholesky factors, blocked DMMA substitutions), O(n1 n2 (n1 + n2)) instead of O((n1 n2)^3)."""
+        if not (self.A.is_square and self.B.is_square):
+            raise np.linalg.LinAlgError("Only square operators can be solved with.")
+        rows, back = _rows_of(B, self.shape[0])
+        return back(self._solve_rows_device(backend.to_device(np.ascontiguousarray(rows))).cpu().numpy())
+
+    def _solve_rows_device(self, R: torch.Tensor) -> torch.Tensor:
+        n1, n2 = self.A.shape[0], self.B.shape[0]
+        k = R.shape[0]
+        X = backend.alloc_matrix(k * n1, n2)
+        X.copy_(R.reshape(k * n1, n2))
+        Y = self.B._solve_rows_device(X)  # pylint: disable=protected-access  (rows (c, i1): B^{-1} X[c, i1, :])
+        Yt = backend.alloc_matrix(k * n2, n1)
+        Yt.copy_(Y.reshape(k, n1, n2).permute(0, 2, 1).reshape(k * n2, n1))
+        Z = self.A._solve_rows_device(Yt)  # pylint: disable=protected-access  (rows (c, i2): A^{-1} Y[c, :, i2])
+        return Z.reshape(k, n2, n1).permute(0, 2, 1).reshape(k, n1 * n2)
+
+    def logabsdet(self) -> float:
+        return self.B.shape[0] * self.A.logabsdet() + self.A.shape[0] * self.B.logabsdet()  # _kronecker.py:159-167
+
+    def det(self) -> float:
+        return float(self.A.det() ** self.B.shape[0] * self.B.det() ** self.A.shape[0])  # _kronecker.py:152-157
+
+    def trace(self) -> float:
+        return self.A.trace() * self.B.trace()
 
     def device_dense(self):
         return backend.kron_sum(self.kron_terms())

@@ -126,6 +126,8 @@ def test_posterior_variance_with_the_emulated_solver_matches_the_frozen_referenc
     batches = [(np.asarray(b["Y"]), np.asarray(b["X"]), helpers.api_op(b["L"])) for b in prob["blocks"]]
     post = lg.ConditionalGaussianProcess.from_observation_batches(prior, batches)
     Xt = np.asarray(prob["Xt"])
+    prev = dict(be.VARIANCE_SOLVER)
+    be.set_variance_solver(ozaki_slices=0)
     var_dmma = post.var(Xt)
     try:
         for S in (5, 6, 7):  # S = 5 (39 bits) is measurably outside the 1e-8 gate here (7e-8): never a default
@@ -134,4 +136,4 @@ def test_posterior_variance_with_the_emulated_solver_matches_the_frozen_referenc
             assert np.max(np.abs(var_oz - z["var"])) <= {5: 1e-6, 6: 1e-8, 7: 1e-8}[S] * 4.0, S
             assert np.max(np.abs(var_oz - var_dmma)) <= {5: 1e-6, 6: 1e-9, 7: 1e-11}[S] * 4.0, S
     finally:
-        be.set_variance_solver(ozaki_slices=0)
+        be.set_variance_solver(ozaki_slices=prev["ozaki_slices"], kblock=prev["kblock"])
