@@ -104,10 +104,6 @@ long long lpgp_launch_count(int reset); /* kernels launched by the library so fa
 /* LPGP_OPT_TIME_OZAKI != 0: every lpgp_ozaki_gemm_nt launch is bracketed by two CUDA events on its stream (no
  * synchronisation added); lpgp_ozaki_gemm_stats reads them back (bench.py: live duration of the dominant kernel). */
 #define LPGP_OPT_TIME_OZAKI 4
-/* LPGP_OPT_OZAKI_KERNEL: 2 (default) = emulated-GEMM kernel that keeps the digit planes of a K-chunk resident in shared
- * memory and reuses them across the (s, t) plane pairs of a group of levels; 1 = the first version, which streams one
- * pair of tiles per pipeline stage (A/B timing, profiles/).                                                       */
-#define LPGP_OPT_OZAKI_KERNEL 5
 int lpgp_set_option(int key, int value);
 /* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and
  * reports the flop count; timed by the caller it yields the roofline denominator of the DMMA kernels on the

@@ -21,8 +21,6 @@ extern int g_lpgp_no_lookahead;
 extern int g_lpgp_trsm_refine;
 // != 0: lpgp_ozaki_gemm_nt brackets its launches with CUDA events (lpgp_ozaki_gemm_stats)
 extern int g_lpgp_time_ozaki;
-// emulated GEMM kernel: 2 = digit planes reused from shared memory (default), 1 = one tile pair per stage
-extern int g_lpgp_ozaki_kernel;
 #define LPGP_MAX_DEVICES 32
 
 #define LPGP_CHECK_LAUNCH()                            \

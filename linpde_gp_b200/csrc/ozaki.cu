@@ -27,6 +27,14 @@
 //   warps 2-9 epilogue: tcgen05.ld the finished level (thread = 1 row x 64 columns), scale, accumulate in FP64 registers
 //             (64 per thread), hand the accumulator back; after the last K-block write C.
 // The MMA of level q+1 overlaps the epilogue of level q (4 accumulators in flight).
+//
+// Measured (profiles/ncu_ozaki_r02d.md, profiles/perf_ozaki_r02g.txt): 2.46-2.49 INT8 POP/s on a 16384 x 1024 x 16384
+// launch (tensor pipe active 61 %, L2 -> shared memory 18.9 TB/s = 72 % of the L2 peak, DRAM 6 %); inside the
+// seconds-long variance solve the part sits at the 1 kW power cap (SM clock ~1.57 GHz) and sustains 2.13 POP/s.  A
+// variant that keeps the digit planes of a K-chunk resident in shared memory and reuses them across the plane pairs of
+// a level group (30 instead of 56 tile loads per chunk, one 16 KB slot per plane) was built and measured in round 2:
+// bit-identical results, but 1.46 POP/s -- with one slot per plane the refill latency of a slot (~2,200 cycles from L2
+// under load) is exposed once per chunk; it was removed again (git history: "plane-reuse kernel v2").
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -283,244 +291,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   }
 }
 
-// ================================================================================================================
-// Version 2 of the kernel: digit planes are REUSED from shared memory.
-//
-// In the kernel above every (s, t) pair of digit planes streams its own A_s and B_t tiles: 2 tile loads per 128 x 128 x 128
-// product, 128 B per tensor-core cycle and SM -- ncu (profiles/ncu_ozaki_r02d.md): 18.9 TB/s from L2 into shared memory,
-// L2 throughput 72 %, tensor pipe 59 %.  Here the levels q = s + t of one K-block are processed in GROUPS ({0,1,2}, {3,4},
-// {5,6} for S = 7) whose accumulators are live in TMEM at the same time; inside a group and a 128-byte chunk of the
-// contraction index, plane A_s is loaded ONCE and multiplied with every B_t of the group (t = q0 - s .. q1 - s), and B_t
-// stays resident for the two or three s that need it: 30 tile loads per chunk instead of 56.  Shared memory holds one
-// 16 KB slot per plane (7 A + 7 B = 224 KB), each with its own full / empty mbarrier; the producer refills a slot for the
-// next chunk as soon as the last MMA that reads it has retired (tcgen05.commit), so the slots form a software pipeline
-// about one chunk deep.  Accumulator buffers, the epilogue warps and the exactness argument are those of version 1
-// (level q of K-block kb lives in TMEM buffer (kb S + q) mod 4).
-constexpr int OZ2_SLOTS = 2 * LPGP_OZAKI_MAX_SLICES;  // slot s = plane s of A, slot 7 + t = plane t of B
-constexpr int OZ2_SLOT_BYTES = OZ_BM * OZ_BK;
-constexpr int OZ2_BAR_BYTES = (2 * OZ2_SLOTS + 2 * OZ_ACC) * 8 + 16;
-constexpr int OZ2_SMEM_BYTES = 1024 + OZ2_SLOTS * OZ2_SLOT_BYTES + OZ2_BAR_BYTES + OZ_BN * 8;
-constexpr int OZ2_MAX_GROUPS = 4, OZ2_MAX_PAIRS = 16;
-enum { OZ2_WAIT_A = 1, OZ2_WAIT_B = 2, OZ2_FREE_A = 4, OZ2_FREE_B = 8, OZ2_FIRST = 16, OZ2_LAST = 32 };
-
-struct Oz2Schedule {  // host-built, identical for the producer and the MMA issuer
-  int ngroups;
-  int npairs[OZ2_MAX_GROUPS];
-  unsigned char ps[OZ2_MAX_GROUPS][OZ2_MAX_PAIRS];     // plane of A
-  unsigned char pt[OZ2_MAX_GROUPS][OZ2_MAX_PAIRS];     // plane of B
-  unsigned char flags[OZ2_MAX_GROUPS][OZ2_MAX_PAIRS];  // OZ2_* bits
-};
-
-__global__ void __launch_bounds__(OZ_THREADS, 1)
-    ozaki_gemm_kernel2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ OzParams p, const __grid_constant__ Oz2Schedule sch) {
-  extern __shared__ unsigned char oz_smem_raw[];
-  unsigned char* smem = oz_smem_raw + ((1024u - (smem_u32(oz_smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = (uint64_t*)(smem + OZ2_SLOTS * OZ2_SLOT_BYTES);
-  uint64_t* empty = full + OZ2_SLOTS;
-  uint64_t* acc_full = empty + OZ2_SLOTS;
-  uint64_t* acc_empty = acc_full + OZ_ACC;
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + OZ_ACC);
-  double* s_sb = (double*)(smem + OZ2_SLOTS * OZ2_SLOT_BYTES + OZ2_BAR_BYTES);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tm = blockIdx.x / p.tiles_n, tn = blockIdx.x % p.tiles_n;
-  const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
-  const int S = p.nslices;
-  const int chunks = p.kblock / OZ_BK;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < OZ2_SLOTS; ++i) {
-      mbar_init(full + i, 1);
-      mbar_init(empty + i, 1);
-    }
-    for (int i = 0; i < OZ_ACC; ++i) {
-      mbar_init(acc_full + i, 1);
-      mbar_init(acc_empty + i, OZ_EPI_THREADS / 32);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===== TMA producer: planes in the order of their first use, one slot per plane =====
-    if (lane == 0) {
-      uint32_t parity = 0;  // bit i: phase of empty[i] this thread waits for next (flips with every use of the slot)
-      for (int kb = 0; kb < p.nkb; ++kb)
-        for (int g = 0; g < sch.ngroups; ++g)
-          for (int c = 0; c < chunks; ++c) {
-            const int kk = kb * p.kblock + c * OZ_BK;
-            for (int i = 0; i < sch.npairs[g]; ++i) {
-              const int fl = sch.flags[g][i];
-              if (fl & OZ2_WAIT_A) {
-                const int slot = sch.ps[g][i];
-                mbar_wait(empty + slot, ((parity >> slot) & 1u) ^ 1u);
-                parity ^= 1u << slot;
-                mbar_expect_tx(full + slot, OZ2_SLOT_BYTES);
-                oz_tma_load_3d(smem + slot * OZ2_SLOT_BYTES, &tmA, p.kA0 + kk, p.rowA0 + m0, sch.ps[g][i], full + slot);
-              }
-              if (fl & OZ2_WAIT_B) {
-                const int slot = LPGP_OZAKI_MAX_SLICES + sch.pt[g][i];
-                mbar_wait(empty + slot, ((parity >> slot) & 1u) ^ 1u);
-                parity ^= 1u << slot;
-                mbar_expect_tx(full + slot, OZ2_SLOT_BYTES);
-                oz_tma_load_3d(smem + slot * OZ2_SLOT_BYTES, &tmB, p.kB0 + kk, p.rowB0 + n0, sch.pt[g][i], full + slot);
-              }
-            }
-          }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (one lane) =====
-    if (lane == 0) {
-      uint32_t parity = 0;  // bit i: phase of full[i] expected next
-      for (int kb = 0; kb < p.nkb; ++kb)
-        for (int g = 0; g < sch.ngroups; ++g)
-          for (int c = 0; c < chunks; ++c)
-            for (int i = 0; i < sch.npairs[g]; ++i) {
-              const int fl = sch.flags[g][i];
-              const int s = sch.ps[g][i], t = sch.pt[g][i];
-              const int it = kb * S + s + t;  // level q = s + t of K-block kb
-              const int buf = it % OZ_ACC;
-              const bool first = (c == 0) && (fl & OZ2_FIRST);
-              if (first) {
-                mbar_wait(acc_empty + buf, ((it / OZ_ACC) & 1) ^ 1);  // the epilogue has drained this accumulator
-                tc_fence_after();
-              }
-              const int sa_slot = s, sb_slot = LPGP_OZAKI_MAX_SLICES + t;
-              if (fl & OZ2_WAIT_A) {
-                mbar_wait(full + sa_slot, (parity >> sa_slot) & 1u);
-                parity ^= 1u << sa_slot;
-              }
-              if (fl & OZ2_WAIT_B) {
-                mbar_wait(full + sb_slot, (parity >> sb_slot) & 1u);
-                parity ^= 1u << sb_slot;
-              }
-              tc_fence_after();
-              const uint64_t da = smem_desc_sw128(smem_u32(smem + sa_slot * OZ2_SLOT_BYTES));
-              const uint64_t db = smem_desc_sw128(smem_u32(smem + sb_slot * OZ2_SLOT_BYTES));
-              const uint32_t idesc = idesc_i8(s == 0, t == 0);
-              const uint32_t tmem_d = tmem_base + (uint32_t)(buf * OZ_BN);
-#pragma unroll
-              for (int j = 0; j < OZ_BK / 32; ++j) tc_mma_i8(tmem_d, da + 2 * j, db + 2 * j, idesc, (first && j == 0) ? 0u : 1u);
-              if (fl & OZ2_FREE_A) tc_commit(empty + sa_slot);
-              if (fl & OZ2_FREE_B) tc_commit(empty + sb_slot);
-              if (c == chunks - 1 && (fl & OZ2_LAST)) tc_commit(acc_full + buf);  // level complete for this K-block
-            }
-    }
-  } else {
-    // ===== epilogue: identical to version 1 =====
-    const int et = threadIdx.x - 64;
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = m0 + quad * 32 + lane;
-    double acc[64];
-#pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.0;
-    int it = 0;
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
-      if (et < OZ_BN) {
-        const int col = n0 + et;
-        s_sb[et] = col < p.n ? exp2i(p.eB[(int64_t)(p.kB0 / p.kblock + kb) * p.ldeB + p.rowB0 + col]) : 0.0;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
-      const int ea = row < p.m ? p.eA[(int64_t)(p.kA0 / p.kblock + kb) * p.ldeA + p.rowA0 + row] : 0;
-      for (int q = 0; q < S; ++q, ++it) {
-        const int buf = it % OZ_ACC;
-        mbar_wait(acc_full + buf, (it / OZ_ACC) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * OZ_BN + half * 64);
-        const double srow = exp2i(ea - 14 - 8 * q);
-        const double* sb = s_sb + half * 64;
-        uint32_t v[32];
-        tc_ld32(taddr, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = fma(__int2double_rn((int)v[j]), srow * sb[j], acc[j]);
-        tc_ld32(taddr + 32, v);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) oz_mbar_arrive(acc_empty + buf);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[32 + j] = fma(__int2double_rn((int)v[j]), srow * sb[32 + j], acc[32 + j]);
-      }
-    }
-    if (row < p.m) {
-      double* crow = p.C + (int64_t)row * p.ldc + n0 + half * 64;
-      const int ncols = p.n - (n0 + half * 64);
-      const bool vec = (p.ldc % 2 == 0) && ((uintptr_t)p.C % 16 == 0);
-#pragma unroll
-      for (int j = 0; j < 64; j += 2) {
-        if (j + 1 < ncols && vec) {
-          double2 c = p.beta == 0.0 ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(crow + j);
-          c.x = fma(p.alpha, acc[j], p.beta * c.x);
-          c.y = fma(p.alpha, acc[j + 1], p.beta * c.y);
-          *reinterpret_cast<double2*>(crow + j) = c;
-        } else {
-          if (j < ncols) crow[j] = fma(p.alpha, acc[j], p.beta == 0.0 ? 0.0 : p.beta * crow[j]);
-          if (j + 1 < ncols) crow[j + 1] = fma(p.alpha, acc[j + 1], p.beta == 0.0 ? 0.0 : p.beta * crow[j + 1]);
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-  }
-}
-
-// Level groups from the top: pairs of levels, the (cheap) lowest two or three levels together; inside a group the pairs
-// run s-major so that A_s is live for one row of pairs and B_t for as many rows as the group has levels.
-void oz2_build_schedule(int S, Oz2Schedule* sch) {
-  int groups[OZ2_MAX_GROUPS][2];
-  int ng = 0, q = S;
-  while (q > 3) {
-    groups[ng][0] = q - 2;
-    groups[ng][1] = q - 1;
-    ++ng;
-    q -= 2;
-  }
-  groups[ng][0] = 0;
-  groups[ng][1] = q - 1;
-  ++ng;
-  sch->ngroups = ng;
-  for (int g = 0; g < ng; ++g) {  // ascending level order: group 0 = lowest levels
-    const int q0 = groups[ng - 1 - g][0], q1 = groups[ng - 1 - g][1];
-    int n = 0;
-    for (int s = 0; s < S; ++s)
-      for (int t = (q0 - s > 0 ? q0 - s : 0); t <= q1 - s && t < S; ++t) {
-        sch->ps[g][n] = (unsigned char)s;
-        sch->pt[g][n] = (unsigned char)t;
-        sch->flags[g][n] = 0;
-        ++n;
-      }
-    sch->npairs[g] = n;
-    for (int i = 0; i < n; ++i) {
-      bool firstA = true, firstB = true, lastA = true, lastB = true, firstL = true, lastL = true;
-      for (int j = 0; j < n; ++j) {
-        if (j == i) continue;
-        const bool before = j < i;
-        if (sch->ps[g][j] == sch->ps[g][i]) (before ? firstA : lastA) = false;
-        if (sch->pt[g][j] == sch->pt[g][i]) (before ? firstB : lastB) = false;
-        if (sch->ps[g][j] + sch->pt[g][j] == sch->ps[g][i] + sch->pt[g][i]) (before ? firstL : lastL) = false;
-      }
-      sch->flags[g][i] = (unsigned char)((firstA ? OZ2_WAIT_A : 0) | (firstB ? OZ2_WAIT_B : 0) | (lastA ? OZ2_FREE_A : 0) |
-                                         (lastB ? OZ2_FREE_B : 0) | (firstL ? OZ2_FIRST : 0) | (lastL ? OZ2_LAST : 0));
-    }
-  }
-}
-
 // ---- splitting: FP64 rows -> S digit planes + one exponent per (row, K-block) -----------------------------------
 // One warp per (row, K-block): pass 1 = row maximum over the block (warp reduction), pass 2 = digits.  Lane l handles
 // the 4 consecutive columns 4 (l + 32 i) .. +3 (32 bytes read, one 4-byte store per plane -> 128 contiguous bytes per warp).
@@ -590,7 +360,6 @@ int oz_ensure() {
   const bool tracked = dev >= 0 && dev < LPGP_MAX_DEVICES;
   if (tracked && g_oz_attr[dev].load(std::memory_order_acquire)) return 0;
   LPGP_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
-  LPGP_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM_BYTES));
   if (tracked) g_oz_attr[dev].store(1, std::memory_order_release);
   return 0;
 }
@@ -792,13 +561,7 @@ extern "C" int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha,
     g_oz_timing.ops += 2.0 * (double)m * (double)n * (double)k * pairs;
     LPGP_CHECK(cudaEventRecord(e0, (cudaStream_t)stream));
   }
-  if (g_lpgp_ozaki_kernel == 1) {
-    ozaki_gemm_kernel<<<(unsigned)tiles, OZ_THREADS, OZ_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
-  } else {
-    Oz2Schedule sch;
-    oz2_build_schedule(p.nslices, &sch);
-    ozaki_gemm_kernel2<<<(unsigned)tiles, OZ_THREADS, OZ2_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p, sch);
-  }
+  ozaki_gemm_kernel<<<(unsigned)tiles, OZ_THREADS, OZ_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
   LPGP_CHECK_LAUNCH();
   if (e1) LPGP_CHECK(cudaEventRecord(e1, (cudaStream_t)stream));
   return 0;

@@ -516,6 +516,17 @@ class ScaledLinearOperator(LinearOperator):
     def __matmul__(self, other):
         return self._scalar * (self._linop @ other)
 
+    # a scalar multiple of a structured (Kronecker) operator keeps its structure: (c A)^{-1} = A^{-1} / c
+    def solve(self, B):
+        if isinstance(self._linop, Kronecker):
+            return self._linop.solve(B) / self._scalar
+        return super().solve(B)
+
+    def logabsdet(self) -> float:
+        if isinstance(self._linop, Kronecker):
+            return self._linop.logabsdet() + self.shape[0] * float(np.log(abs(self._scalar)))
+        return super().logabsdet()
+
 
 class SumLinearOperator(LinearOperator):
     """``A + B + ...`` (pn/linops/_arithmetic_fallbacks.py:63-117); nested sums are flattened."""

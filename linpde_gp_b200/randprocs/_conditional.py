@@ -261,6 +261,103 @@ class _Block:
         self.atoms = [atom]
 
 
+STRUCTURED_MIN_N = int(__import__("os").environ.get("LPGP_STRUCTURED_MIN_N", "20000"))  # below: dense factor (general)
+
+
+class KroneckerFactor:
+    """Cached factor of a Gram matrix that IS a Kronecker product, ``G = alpha * K_1 (x) K_2`` -- plain observations of a
+    (scaled) two-factor ``TensorProduct`` kernel on an intact ``TensorProductGrid`` (the reference keeps
+    this Gram matrix a lazy ``pn.linops.Kronecker``, covfuncs/_tensor_product.py:64-82, whose ``solve`` / ``cholesky``
+    act on the factors, pn/linops/_kronecker.py:122-140, 233-242).  Nothing of size N x N is ever formed:
+
+    * representer weights: two multi-right-hand-side Cholesky solves with the n_1 x n_1 and n_2 x n_2 factors;
+    * pointwise variance: ``k(X, x) = alpha k_1(X_1, x_1) (x) k_2(X_2, x_2)`` and ``L = sqrt(alpha) L_1 (x) L_2`` give
+      ``|L^{-1} k(X, x)|^2 = alpha q_1(x_1) q_2(x_2)`` with ``q_i = |L_i^{-1} k_i(X_i, x_i)|^2`` -- O(M (n_1^2 + n_2^2))
+      instead of O(M N^2);
+    * covariance blocks: Hadamard product of the per-dimension ``V_i V_i'^T``.
+
+    N = n_1 n_2 can exceed what a dense factor could hold (1024 x 1024 grid: a dense FP64 Gram matrix would be 8.8 TB)."""
+
+    structured = True
+
+    def __init__(self, alpha: float, kernels, grids):
+        from .. import linops as _linops  # pylint: disable=import-outside-toplevel
+
+        self.alpha = float(alpha)
+        self.kernels = tuple(kernels)
+        self.grids = tuple(backend.points(np.asarray(g, dtype=np.double), 1) for g in grids)
+        self.sizes = tuple(int(g.shape[0]) for g in self.grids)
+        self.n = int(np.prod(self.sizes))
+        ops = []
+        for k, g in zip(self.kernels, self.grids):
+            Ki = backend.alloc_matrix(g.shape[0], g.shape[0])
+            _gram_into(k, g, None, Ki, lower=True)
+            backend.symmetrize_lower(Ki)
+            op = _linops._Device(Ki)  # pylint: disable=protected-access
+            op.is_symmetric = True
+            ops.append(op)
+        self.op = _linops.Kronecker(ops[0], ops[1])
+        self.chol = [o.cholesky(True) for o in ops]  # small dense factors (LinAlgError if a factor is not SPD)
+
+    def potrs(self, B: "torch.Tensor") -> "torch.Tensor":
+        if B.dim() == 1:
+            B = B.reshape(1, -1)
+        B.copy_(self.op._solve_rows_device(B))  # pylint: disable=protected-access
+        return B.mul_(1.0 / self.alpha)
+
+    def logdet(self) -> float:
+        return self.op.logabsdet() + self.n * float(np.log(self.alpha))
+
+    def _dim_rows(self, i: int, x: "torch.Tensor") -> "torch.Tensor":
+        """``V_i = k_i(x, X_i) L_i^{-T}`` for the i-th coordinates ``x`` (M,) of the test points: (M x n_i)."""
+        Ki = backend.alloc_matrix(x.shape[0], self.sizes[i])
+        _gram_into(self.kernels[i], x.reshape(-1, 1).contiguous(), self.grids[i], Ki)
+        return self.chol[i]._solve_rows_device(Ki)  # pylint: disable=protected-access
+
+    def post_var(self, Xt: "torch.Tensor", prior_diag: float) -> "torch.Tensor":
+        q = None
+        for i in range(2):
+            qi = backend.row_sumsq(self._dim_rows(i, Xt[:, i].contiguous()))
+            q = qi if q is None else q * qi
+        return prior_diag - self.alpha * q
+
+    def post_cov_sub(self, X0: "torch.Tensor", X1, C: "torch.Tensor") -> None:
+        """``C -= alpha * prod_i V_i(X0) V_i(X1)^T`` (Hadamard product over the dimensions)."""
+        H = None
+        for i in range(2):
+            V0 = self._dim_rows(i, X0[:, i].contiguous())
+            V1 = V0 if X1 is None else self._dim_rows(i, X1[:, i].contiguous())
+            Gi = backend.alloc_matrix(*C.shape)
+            backend.gemm_nt(V0, V1, Gi, 1.0, 0.0)
+            H = Gi if H is None else H.mul_(Gi)
+        C.sub_(H.mul_(self.alpha))
+
+    def extended(self, new_size: int):
+        raise NotImplementedError(
+            "a posterior with a Kronecker-structured Gram factor cannot be extended by bordering (the bordered matrix is no "
+            "Kronecker product); condition on the gridded batch LAST, or set LPGP_STRUCTURED_MIN_N above its size to "
+            "use the dense appendable factor")
+
+
+def _kronecker_structure(prior, atoms, noise):
+    """``(alpha, [k_1, k_2], [grid_1, grid_2])`` if the Gram matrix of this single batch is ``alpha K_1 (x) K_2``."""
+    if noise is not None or len(atoms) != 1:
+        return None
+    coef, kind, op, payload = atoms[0]
+    if kind != "pts" or op is not None or coef != 1.0:
+        return None
+    grids = covfuncs._grid_factors(payload)  # pylint: disable=protected-access
+    k, alpha = prior.cov, 1.0
+    while isinstance(k, covfuncs.ScaledCovarianceFunction):
+        alpha *= float(k.scalar)
+        k = k.covfunc
+    if grids is None or len(grids) != 2 or not isinstance(k, covfuncs.TensorProduct) or len(k.factors) != 2:
+        return None
+    if int(np.prod([len(g) for g in grids])) < STRUCTURED_MIN_N or alpha <= 0.0:
+        return None
+    return alpha, list(k.factors), list(grids)
+
+
 class _PosteriorState:
     """Everything a conditioned process needs to evaluate itself: prior, observation blocks, the device-resident
     factor, residuals and representer weights.  ``ConditionalGaussianProcess``, its ``Mean`` and its
@@ -291,6 +388,8 @@ class _PosteriorState:
     def gram(self) -> "GramFactorOperator":
         if getattr(self._factor, "distributed", False):
             raise NotImplementedError("the Gram factor is distributed over several GPUs (replicate=False)")
+        if getattr(self._factor, "structured", False):  # the lazy Kronecker product itself (solve / cholesky on the factors)
+            return self._factor.alpha * self._factor.op
         if self._gram_op is None:
             self._gram_op = GramFactorOperator(self._factor, self._logical_index)
         return self._gram_op
@@ -360,6 +459,14 @@ class ConditionalGaussianProcess(GaussianProcess):
     def from_observations(cls, prior: GaussianProcess, Y, X=None, *, L=None, b=None):
         Y, Lf, b, atoms, resid, noise = cls._preprocess_observations(prior=prior, Y=Y, X=X, L=L, b=b)
         blk = _Block(None, None, prior.cov.input_size, 0, atoms=atoms)
+        structure = _kronecker_structure(prior, atoms, noise)
+        if structure is not None:  # Gram matrix = alpha K_1 (x) K_2: factor the two small matrices only
+            with backend.phase("factor"):
+                factor = KroneckerFactor(*structure)
+            y = backend.to_device(resid).clone()
+            with backend.phase("solve"):
+                w = factor.potrs(y.clone().reshape(1, -1)).reshape(-1)
+            return cls(prior=prior, Ys=(Y,), Ls=(Lf,), bs=(b,), blocks=(blk,), factor=factor, resid=y, weights=w)
         factor = backend.DeviceFactor([blk.n_phys])
         with backend.phase("assemble"):
             cls._assemble_rows(prior, [], blk, factor, noise)
@@ -568,6 +675,12 @@ class ConditionalGaussianProcess(GaussianProcess):
                     with backend.phase("var"):
                         var = post._var_distributed(Xt, diag)
                     return var.cpu().numpy().reshape(batch)
+                if getattr(post._factor, "structured", False):
+                    if post._test_op is not None:
+                        raise NotImplementedError("operator push-forwards of a posterior with a Kronecker-structured factor")
+                    with backend.phase("var"):
+                        var = post._factor.post_var(Xt, diag)
+                    return var.cpu().numpy().reshape(batch)
                 chunk = backend.var_chunk_rows(n, Xt.shape[0], max_bytes=VAR_CHUNK_BYTES)
                 with backend.phase("var"):
                     var = backend.post_var(post._obs_blocks_unique(), post._factor, Xt, diag, chunk=chunk)
@@ -595,6 +708,11 @@ class ConditionalGaussianProcess(GaussianProcess):
             _gram_into(post._prior.cov, X0, X1, C)
             blocks = post._obs_blocks_unique()
             if blocks.empty:
+                return C
+            if getattr(post._factor, "structured", False):
+                if post._test_op is not None:
+                    raise NotImplementedError("operator push-forwards of a posterior with a Kronecker-structured factor")
+                post._factor.post_cov_sub(X0, X1, C)
                 return C
             V0 = backend.crosscov(blocks, post._factor.n, X0)
             post._factor.trsm_rlt(V0)

@@ -951,3 +951,49 @@ def test_inverse_rhs_conditioning_at_n4096_one_shot_and_block_rows():
     for name, post in posts.items():
         assert np.max(np.abs(post.mean(Xt) - mean_ref)) <= 1e-8 * sc, name
         assert np.max(np.abs(post.var(Xt) - var_ref)) <= 1e-8 * sc, name
+
+
+def test_gridded_observations_of_a_product_kernel_use_the_kronecker_factor(monkeypatch):
+    """SURVEY 8f item 3 beyond dense N: plain observations on an intact TensorProductGrid under a TensorProduct prior have
+    the Gram matrix ``alpha K_1 (x) K_2`` (covfuncs/_tensor_product.py:64-82, pn/linops/_kronecker.py:122-140); the
+    structured factor (two small Cholesky factors) gives the same posterior as the dense bordered factor -- checked at a
+    size where both run -- and conditions on a 1000 x 1200 grid (N = 1.2 M; a dense FP64 Gram matrix would be 11.5 TB)."""
+    import linpde_gp_b200 as lg
+    from linpde_gp_b200.randprocs import _conditional, covfuncs
+
+    k = 1.7 * covfuncs.TensorProduct(covfuncs.Matern((), nu=2.5, lengthscales=0.3), covfuncs.Matern((), nu=1.5, lengthscales=0.5))
+    prior = lg.GaussianProcess(lg.functions.Constant(input_shape=(2,), value=0.2), k)
+    g1, g2 = np.linspace(0.0, 1.0, 33), np.linspace(-1.0, 1.0, 41)
+    grid = covfuncs.TensorProductGrid(g1, g2)
+    f = lambda x: np.sin(3 * x[..., 0]) * np.cos(2 * x[..., 1]) + 0.2  # noqa: E731
+    Y = f(np.asarray(grid))
+    rng = np.random.default_rng(5)
+    Xt = rng.uniform([0.0, -1.0], [1.0, 1.0], (300, 2))
+    monkeypatch.setattr(_conditional, "STRUCTURED_MIN_N", 10**9)
+    dense = prior.condition_on_observations(Y, X=grid)
+    assert not getattr(dense._factor, "structured", False)
+    monkeypatch.setattr(_conditional, "STRUCTURED_MIN_N", 1000)
+    post = prior.condition_on_observations(Y, X=grid)
+    assert post._factor.structured and post._factor.n == 33 * 41
+    assert np.max(np.abs(post.representer_weights - dense.representer_weights)) <= 1e-7 * np.max(np.abs(dense.representer_weights))
+    assert np.max(np.abs(post.mean(Xt) - dense.mean(Xt))) <= 1e-9
+    assert np.max(np.abs(post.var(Xt) - dense.var(Xt))) <= 1e-9 * 1.7
+    C, Cd = post.cov.linop(Xt[:40]).todense(), dense.cov.linop(Xt[:40]).todense()
+    assert np.max(np.abs(C - Cd)) <= 1e-9 * 1.7
+    C01, Cd01 = post.cov.linop(Xt[:40], Xt[40:90]).todense(), dense.cov.linop(Xt[:40], Xt[40:90]).todense()
+    assert np.max(np.abs(C01 - Cd01)) <= 1e-9 * 1.7
+    b = rng.standard_normal(33 * 41)
+    assert np.max(np.abs(post.gram.solve(b) - dense.gram.solve(b))) <= 1e-7 * np.max(np.abs(dense.gram.solve(b)))
+    with pytest.raises(NotImplementedError):
+        post.condition_on_observations(np.zeros(3), X=rng.uniform(0, 1, (3, 2)))
+    # far beyond dense size: N = 1.2 M observations, interpolation at grid nodes, variance ~ 0 there and within the prior
+    G1, G2 = np.linspace(0.0, 1.0, 1000), np.linspace(-1.0, 1.0, 1200)
+    big = covfuncs.TensorProductGrid(G1, G2)
+    kb = 1.7 * covfuncs.TensorProduct(covfuncs.Matern((), nu=1.5, lengthscales=0.05), covfuncs.Matern((), nu=1.5, lengthscales=0.08))
+    pb = lg.GaussianProcess(lg.functions.Constant(input_shape=(2,), value=0.2), kb).condition_on_observations(f(np.asarray(big)), X=big)
+    assert pb._factor.structured and pb._factor.n == 1_200_000
+    nodes = np.stack([G1[[0, 17, 500, 999]], G2[[3, 600, 601, 1199]]], -1)
+    assert np.max(np.abs(pb.mean(nodes) - f(nodes))) <= 1e-6
+    v = pb.var(np.concatenate([nodes, Xt]))
+    assert np.all(np.abs(v[:4]) <= 1e-7) and np.all(v >= -1e-7) and np.all(v <= 1.7)
+    assert np.max(np.abs(pb.mean(Xt) - f(Xt))) <= 1e-3  # h = 1e-3 grid of a smooth function

@@ -295,4 +295,6 @@ def test_kronecker_gram_of_a_gridded_product_kernel_solves_beyond_dense_size():
     b = rng.standard_normal(630000)
     x = K.solve(b)
     r = K @ x - b
-    assert np.max(np.abs(r)) <= 1e-8 * np.max(np.abs(b))
+    # backward error: the factors are fine-grid Matern Gram matrices (condition number ~1e7), so |x| >> |b|
+    normK = np.abs(K.A.todense()).sum(1).max() * np.abs(K.B.todense()).sum(1).max()
+    assert np.max(np.abs(r)) <= 1e-13 * normK * np.max(np.abs(x)), (np.max(np.abs(r)), normK, np.max(np.abs(x)))
