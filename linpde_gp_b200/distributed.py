@@ -157,6 +157,21 @@ class DeviceOps:
     def row_sumsq(self, A: torch.Tensor, scale: float, offset: float) -> torch.Tensor:
         return self.be.row_sumsq(A, scale, offset)
 
+    # -- FP64 emulated on the INT8 tensor cores (csrc/ozaki.cu): the O(m n^2) part of the streamed solve -------------------
+    def emu_slices(self) -> int:
+        return int(self.be.VARIANCE_SOLVER["ozaki_slices"])
+
+    def emu_planes(self, rows: int, cols: int, kblock: int):
+        return self.be.OzakiPlanes(rows, cols, self.emu_slices(), kblock)
+
+    def emu_split(self, P, A: torch.Tensor, col0: int) -> None:
+        """digit planes of ``A`` (rows x ncols, ncols a multiple of the K-block) into columns col0.. of ``P``"""
+        P.split(A, row_off=0, col0=col0)
+
+    def emu_gemm_update(self, XP, RP, C: torch.Tensor, k: int) -> None:
+        """C -= X[:, :k] R[:, :k]^T from the digit planes of X and R."""
+        self.be.ozaki_gemm_nt(XP, RP, C, k, alpha=-1.0, beta=1.0)
+
     def update_limited(self, C: torch.Tensor, A: torch.Tensor, B: torch.Tensor, col_limit: torch.Tensor,
                        col_base: int) -> None:
         """C -= A B^T, each block of 128 rows restricted to the columns j with col_base + j < col_limit[block]."""
@@ -389,6 +404,15 @@ class DistributedCholesky:
         dev = self.A_loc.device
         bufs = [torch.empty(nb * n, dtype=torch.float64, device=dev) for _ in range(2)]
         ev_ready, ev_free = [None, None], [None, None]
+        # INT8-emulated update: the streamed block row and the solved column blocks of K are split into
+        # digit planes (K-block = nb columns) and the O(m n^2) products run on the tcgen05 tensor cores; the nb x nb
+        # diagonal solves stay on DMMA.  Every rank splits the block rows it receives itself (15 B per entry, HBM-bound).
+        emulate = (K.shape[0] > 0 and hasattr(ops, "emu_slices") and ops.emu_slices() > 0 and 128 <= nb <= 4096
+                   and n >= 2 * nb and K.stride(0) % 2 == 0)
+        XP = RP = None
+        if emulate:
+            XP = ops.emu_planes(K.shape[0], n, nb)
+            RP = [ops.emu_planes(nb, n, nb) for _ in range(2)]
         ops.fork()
         for k in range(lay.nblk):
             k0, k1 = lay.block_bounds(k)
@@ -404,8 +428,14 @@ class DistributedCholesky:
                 ops.wait(ev_ready[k % 2])
                 if K.shape[0] > 0:
                     Kk = K[:, k0:k1]
-                    ops.gemm_update(Kk, K[:, :k0], row[:, :k0])
+                    if emulate and k0 > 0:
+                        ops.emu_split(RP[k % 2], row[:, :k0], 0)
+                        ops.emu_gemm_update(XP, RP[k % 2], Kk, k0)
+                    else:
+                        ops.gemm_update(Kk, K[:, :k0], row[:, :k0])
                     ops.trsm_block(row[:, k0:k1], self._dinv_block(k), Kk)
+                    if emulate and bk == nb and k + 1 < lay.nblk:
+                        ops.emu_split(XP, Kk, k0)
                 ev_free[k % 2] = ops.record()
         ops.join()
         return K
@@ -466,7 +496,9 @@ class DistributedFactor:
 
         n = self.n
         free = torch.cuda.mem_get_info()[0]
-        budget = max(min_chunk_bytes, min(int(0.5 * free), 64 << 30))
+        # with the emulated update the digit planes of the chunk (7 B per entry) sit next to it (8 B per entry)
+        emulated = hasattr(self.ch.ops, "emu_slices") and self.ch.ops.emu_slices() > 0
+        budget = max(min_chunk_bytes, min(int((0.27 if emulated else 0.5) * free), 64 << 30))
         chunk = int(max(256, budget // (8 * backend.round_up(n, 16))))
         m = Xt.shape[0]
         out = torch.empty(m, dtype=torch.float64, device=Xt.device)

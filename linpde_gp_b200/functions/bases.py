@@ -12,19 +12,30 @@ from . import Function
 
 
 class UnivariateLinearInterpolationBasis(Function):
+    """``phi_i(x) = max(0, min(rise_i(x), fall_i(x)))`` with the two ramps through the neighbours of node ``c_i``.
+
+    ``zero_boundary=True``: one function per INTERIOR node.  ``zero_boundary=False``: one function per node; the ramps of
+    the first / last function are continued to a mirrored sentinel node and the function is cut off outside the grid, so
+    that the basis is a partition of unity on ``[grid[0], grid[-1]]`` (the reference adds the same sentinels, which is why
+    ``grid`` / ``x_im1`` / ``x_i`` / ``x_ip1`` below include them)."""
+
     def __init__(self, grid, zero_boundary: bool = False) -> None:
-        grid = np.asarray(grid, dtype=np.double)
-        zero_boundary = bool(zero_boundary)
-        if grid.ndim != 1 or grid.size < 3:
+        nodes = np.array(grid, dtype=np.double)
+        if nodes.ndim != 1 or nodes.size < 3:
             raise ValueError("`grid` must be a one-dimensional array of at least 3 nodes")
-        if not np.all(np.diff(grid) > 0):
+        steps = np.diff(nodes)
+        if not np.all(steps > 0):
             raise ValueError("`grid` must be strictly increasing")
-        if not zero_boundary:  # sentinel nodes (_fem.py:17-25)
-            grid = np.concatenate(([grid[0] - (grid[1] - grid[0])], grid, [grid[-1] + (grid[-1] - grid[-2])]))
-        self._grid = grid
-        self._zero_boundary = zero_boundary
-        self._left_normalization_factors = 1.0 / (self.x_i - self.x_im1)
-        self._right_normalization_factors = 1.0 / (self.x_ip1 - self.x_i)
+        self._zero_boundary = bool(zero_boundary)
+        self._domain = (float(nodes[0]), float(nodes[-1]))
+        if self._zero_boundary:
+            self._grid = nodes
+        else:
+            self._grid = np.empty(nodes.size + 2)
+            self._grid[1:-1] = nodes
+            self._grid[0], self._grid[-1] = nodes[0] - steps[0], nodes[-1] + steps[-1]
+        self._inv_rise = 1.0 / (self._grid[1:-1] - self._grid[:-2])
+        self._inv_fall = 1.0 / (self._grid[2:] - self._grid[1:-1])
         super().__init__(input_shape=(), output_shape=(self._grid.size - 2,))
 
     grid = property(lambda self: self._grid)
@@ -33,45 +44,31 @@ class UnivariateLinearInterpolationBasis(Function):
     x_ip1 = property(lambda self: self._grid[2:])
     zero_boundary = property(lambda self: self._zero_boundary)
 
+    def _hats(self, x, which=slice(None)):
+        x = np.asarray(x, dtype=np.double)[..., None]
+        rise = (x - self.x_im1[which]) * self._inv_rise[which]
+        fall = (self.x_ip1[which] - x) * self._inv_fall[which]
+        vals = np.clip(np.minimum(rise, fall), 0.0, None)
+        if not self._zero_boundary:  # the outer halves of the first / last function lie outside the grid
+            vals = np.where((x < self._domain[0]) | (x > self._domain[1]), 0.0, vals)
+        return vals
+
     def _evaluate(self, x):
-        x = np.asarray(x, dtype=np.double)
-        res = np.maximum(
-            0.0,
-            np.where(
-                x[..., None] < self.x_i,
-                (x[..., None] - self.x_im1) * self._left_normalization_factors,
-                (self.x_ip1 - x[..., None]) * self._right_normalization_factors,
-            ),
-        )
-        if not self._zero_boundary:
-            res[x < self._grid[1], 0] = 0.0
-            res[x > self._grid[-2], -1] = 0.0
-        return res
+        return self._hats(x)
 
     def eval_elem(self, idx: int, x):
-        x = np.asarray(x, dtype=np.double)
-        res = np.asarray(np.maximum(
-            0.0,
-            np.where(
-                x < self.x_i[idx],
-                (x - self.x_im1[idx]) * self._left_normalization_factors[idx],
-                (self.x_ip1[idx] - x) * self._right_normalization_factors[idx],
-            ),
-        ))
-        if not self._zero_boundary:
-            res[x < self._grid[1]] = 0.0
-            res[x > self._grid[-2]] = 0.0
-        return res
+        idx = int(idx) % len(self)
+        return self._hats(x, slice(idx, idx + 1))[..., 0]
 
     def support_bounds(self, idx: int):
-        if not -len(self) <= idx < len(self):
+        m = len(self)
+        if not -m <= idx < m:
             raise IndexError(idx)
+        idx %= m
+        lo, hi = self._grid[idx], self._grid[idx + 2]
         if not self._zero_boundary:
-            if idx in (0, -len(self)):
-                return self.x_i[0], self.x_ip1[0]
-            if idx in (len(self) - 1, -1):
-                return self.x_im1[-1], self.x_i[-1]
-        return self.x_im1[idx], self.x_ip1[idx]
+            lo, hi = max(lo, self._domain[0]), min(hi, self._domain[1])
+        return lo, hi
 
     def __len__(self):
         return self._output_shape[0]

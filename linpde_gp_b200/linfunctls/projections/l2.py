@@ -37,14 +37,24 @@ class L2Projection_UnivariateLinearInterpolationBasis(LinearFunctional):  # pyli
 
     # -- mass matrix / normaliser (_fem.py:38-62) -----------------------------------------------------------------
     def mass_matrix(self) -> np.ndarray:
+        """``M_ij = int phi_i phi_j``, assembled element by element: an element of length h contributes h/3 to the two
+        diagonal entries of its end nodes and h/6 to their coupling (the tridiagonal matrix of _fem.py:38-62)."""
         b = self._basis
-        diag = (b.x_ip1 - b.x_im1) / 3.0
-        offdiag = (b.x_ip1[:-1] - b.x_i[:-1]) / 6.0
-        if not b.zero_boundary:
-            diag = diag.copy()
-            diag[0] = (b.x_ip1[0] - b.x_i[0]) / 3.0
-            diag[-1] = (b.x_i[-1] - b.x_im1[-1]) / 3.0
-        return np.diag(diag) + np.diag(offdiag, 1) + np.diag(offdiag, -1)
+        e = b.elements()
+        h = np.diff(e)
+        first = 1 if b.zero_boundary else 0  # index (among the element nodes) of the first node that carries a function
+        m = len(b)
+        M = np.zeros((m, m))
+        for el, hl in enumerate(h):
+            i, j = el - first, el + 1 - first  # basis functions of the element's left / right node
+            if 0 <= i < m:
+                M[i, i] += hl / 3.0
+            if 0 <= j < m:
+                M[j, j] += hl / 3.0
+            if 0 <= i < m and 0 <= j < m:
+                M[i, j] += hl / 6.0
+                M[j, i] += hl / 6.0
+        return M
 
     def _device_mass_factor(self):
         """Device Cholesky factor of the mass matrix (SPD, tridiagonal; factored densely -- m x m is small)."""
@@ -124,6 +134,19 @@ class L2Projection_UnivariateLinearInterpolationBasis(LinearFunctional):  # pyli
                 raise NotImplementedError("L2 projections of scalar functions on the real line only")
             nodes, W = self._basis.gauss_legendre(32)
             return self.normalizer(W @ np.asarray(f(nodes), dtype=np.double), axis=-1)
+        from ...randprocs import covfuncs, crosscov  # pylint: disable=import-outside-toplevel
+
+        if isinstance(f, covfuncs.CovarianceFunction) and not isinstance(f, covfuncs.Zero):
+            # dispatch of covfuncs/linfunctls/_registry.py:198-238
+            argnum = kwargs.get("argnum", 0)
+            if argnum not in (0, 1):
+                raise ValueError("`argnum` must either be 0 or 1.")
+            if f.input_shape != ():
+                raise ValueError("L2 projections onto a univariate basis need a process on the real line")
+            cls = (crosscov.Matern32_L2Projection_UnivariateLinearInterpolationBasis
+                   if isinstance(f, covfuncs.Matern) and f.nu == 1.5
+                   else crosscov.CovarianceFunction_L2Projection_UnivariateLinearInterpolationBasis)
+            return cls(f, self, reverse=(argnum == 0))
         return super().__call__(f, **kwargs)
 
     def _atoms(self):

@@ -312,7 +312,8 @@ class KroneckerFactor:
         """``V_i = k_i(x, X_i) L_i^{-T}`` for the i-th coordinates ``x`` (M,) of the test points: (M x n_i)."""
         Ki = backend.alloc_matrix(x.shape[0], self.sizes[i])
         _gram_into(self.kernels[i], x.reshape(-1, 1).contiguous(), self.grids[i], Ki)
-        return self.chol[i]._solve_rows_device(Ki)  # pylint: disable=protected-access
+        # (odd n_i: the small factor is padded by an identity row and the solve returns a gathered copy -> re-align for TMA)
+        return linops._aligned(self.chol[i]._solve_rows_device(Ki))  # pylint: disable=protected-access
 
     def post_var(self, Xt: "torch.Tensor", prior_diag: float) -> "torch.Tensor":
         q = None

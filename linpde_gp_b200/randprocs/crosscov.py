@@ -173,6 +173,22 @@ class _FunctionalCrossCovariance(ProcessVectorCrossCovariance):
         return [(1.0, self, None)]
 
 
+class CovarianceFunction_L2Projection_UnivariateLinearInterpolationBasis(_FunctionalCrossCovariance):  # pylint: disable=invalid-name
+    """``Cov(f(.), P[f])`` for an L2 projection ``P`` onto hat functions (crosscov/linfunctls/projections.py:18-69): what
+    ``proj(k, argnum)`` returns.  Evaluation: closed-form hat integrals for half-integer Matern kernels of every order,
+    Gauss-Legendre per element for smooth kernels (``_conditional._proj_pts_block``), normaliser included."""
+
+    def __init__(self, covfunc, proj, reverse: bool = True):
+        super().__init__(covfunc, proj, reverse)
+
+    projection = property(lambda self: self._linfunctl)
+
+
+class Matern32_L2Projection_UnivariateLinearInterpolationBasis(CovarianceFunction_L2Projection_UnivariateLinearInterpolationBasis):  # pylint: disable=invalid-name
+    """The class the reference returns for ``nu = 3/2`` (projections.py:125-170, its only closed form); here the same
+    device kernel serves every half-integer order."""
+
+
 class ScaledProcessVectorCrossCovariance(ProcessVectorCrossCovariance):
     """``scalar * pv_crosscov`` (crosscov/_arithmetic.py:12-60)."""
 

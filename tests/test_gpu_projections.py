@@ -48,6 +48,11 @@ def test_projection_crosscov_matches_reference(name):
     proj = _proj(c["grid"], c["zero_boundary"], c["normalized"])
     xs = np.asarray(c["xs"])
     kPa = proj(k, argnum=1)
+    from linpde_gp_b200.randprocs import crosscov
+
+    assert isinstance(kPa, crosscov.CovarianceFunction_L2Projection_UnivariateLinearInterpolationBasis)
+    assert isinstance(kPa, crosscov.Matern32_L2Projection_UnivariateLinearInterpolationBasis) == (c["kernel"].get("nu") == 1.5)
+    assert kPa.projection is proj and kPa.covfunc is k
     assert kPa.randvar_shape == (len(proj.basis),) and not kPa.reverse
     val = kPa(xs)
     ref = z[f"{name}_kPa"]
