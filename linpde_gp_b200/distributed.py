@@ -519,3 +519,219 @@ class DistributedFactor:
         if self.ch.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.ch.group)
         return int(t.item())
+
+
+# ================================================================================================================
+# 2-D block-cyclic variant of the factorisation (the layout BASELINE.json's north star names)
+# ================================================================================================================
+class Grid2DLayout:
+    """Block (i, j) of the lower triangle (``nb x nb``) lives on the rank at grid position (i % pr, j % pc) of a
+    ``pr x pc`` process grid (rank = row * pc + column), stored at local block position (i // pr, j // pc)."""
+
+    def __init__(self, n: int, nb: int, pr: int, pc: int):
+        if nb % LEAF:
+            raise ValueError("nb must be a multiple of 128")
+        if n % nb:
+            raise ValueError("the 2-D layout needs n to be a multiple of nb")
+        self.n, self.nb, self.pr, self.pc = int(n), int(nb), int(pr), int(pc)
+        self.nblk = n // nb
+
+    def coords(self, rank: int) -> Tuple[int, int]:
+        return rank // self.pc, rank % self.pc
+
+    def rank_of(self, r: int, c: int) -> int:
+        return r * self.pc + c
+
+    def owner(self, i: int, j: int) -> int:
+        return self.rank_of(i % self.pr, j % self.pc)
+
+    def n_local_rows(self, r: int) -> int:
+        return len(range(r, self.nblk, self.pr))
+
+    def n_local_cols(self, c: int) -> int:
+        return len(range(c, self.nblk, self.pc))
+
+    @staticmethod
+    def count_le(k: int, first: int, step: int) -> int:
+        """number of indices first, first + step, ... that are <= k"""
+        return 0 if k < first else (k - first) // step + 1
+
+
+class BlockCyclic2DCholesky:
+    """Right-looking Cholesky on a ``pr x pc`` process grid with one panel of lookahead (same two-stream pipeline as
+    :class:`DistributedCholesky`).  Per panel ``k``:
+
+      1. the owner of block (k, k) factors it and broadcasts ``[L_kk | inverted leaves | info]`` down its process COLUMN;
+      2. the ``pr`` ranks of that column solve their blocks of the panel, ``X <- X L_kk^{-T}``;
+      3. the panel is broadcast along the process ROWS (every rank receives the blocks ``L_ik`` of its own block rows),
+         then the blocks whose index also belongs to a rank's block COLUMNS are all-gathered inside each process column
+         (the "transposed" panel ``L_jk``, j = c mod pc);
+      4. every rank updates its local blocks, ``A_ij -= L_ik L_jk^T`` for i >= j > k, with one row-limited DMMA GEMM
+         (the local lower "staircase" is expressed through the per-row column limits of ``lpgp_gemm_nt_limited``).
+
+    Compared with the 1-D block-row layout every rank receives ``(1/pr + 1/pc)`` of each panel instead of all of it, but
+    only ``pr`` ranks share a panel's triangular solve.  Built to MEASURE the layout the north star names against the 1-D
+    one on one NVSwitch domain (tools/dist_bench2d.py); posterior evaluation uses the 1-D class."""
+
+    def __init__(self, n: int, nb: int, pr: int, pc: int, ops=None):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        if pr * pc != self.world:
+            raise ValueError(f"process grid {pr} x {pc} does not match the world size {self.world}")
+        self.layout = lay = Grid2DLayout(n, nb, pr, pc)
+        self.ops = DeviceOps() if ops is None else ops
+        self.n, self.nb = n, nb
+        self.r, self.c = lay.coords(self.rank)
+        # sub-communicators: every rank creates every group, in the same order
+        self.row_group = self.col_group = None
+        if self.world > 1:
+            for r in range(pr):
+                g = dist.new_group([lay.rank_of(r, c) for c in range(pc)])
+                if r == self.r:
+                    self.row_group = g
+            for c in range(pc):
+                g = dist.new_group([lay.rank_of(r, c) for r in range(pr)])
+                if c == self.c:
+                    self.col_group = g
+        self.nbr, self.nbc = lay.n_local_rows(self.r), lay.n_local_cols(self.c)
+        self.A_loc = self.ops.empty(max(self.nbr, 1) * nb, max(self.nbc, 1) * nb)
+        dev = self.A_loc.device
+        # per local 128-row block: end (in local columns) of the blocks j <= i of its block row i
+        lim = []
+        for li in range(self.nbr):
+            i = li * pr + self.r
+            lim += [lay.count_le(i, self.c, pc) * nb] * (nb // LEAF)
+        self.col_limit = torch.tensor(lim or [0], dtype=torch.int32).to(dev)
+
+    def local_block(self, i: int, j: int) -> torch.Tensor:
+        nb = self.nb
+        li, lj = i // self.layout.pr, j // self.layout.pc
+        return self.A_loc[li * nb : (li + 1) * nb, lj * nb : (lj + 1) * nb]
+
+    def owns(self, i: int, j: int) -> bool:
+        return self.layout.owner(i, j) == self.rank
+
+    def factor(self, profile: Optional[dict] = None) -> None:
+        lay, ops, nb, rank = self.layout, self.ops, self.nb, self.rank
+        pr, pc, r, c, nblk = lay.pr, lay.pc, self.r, self.c, lay.nblk
+        dev = self.A_loc.device
+        wlen = (nb // LEAF) * LEAF * LEAF
+        packs = [torch.zeros(nb * nb + wlen + 2, dtype=torch.float64, device=dev) for _ in range(2)]
+        dtmp = torch.zeros(wlen + 8, dtype=torch.float64, device=dev)
+        info_all = torch.zeros(1, dtype=torch.float64, device=dev)
+        lrows = [torch.zeros(max(self.nbr, 1) * nb * nb, dtype=torch.float64, device=dev) for _ in range(2)]
+        lcols = [torch.zeros(max(self.nbc, 1) * nb * nb, dtype=torch.float64, device=dev) for _ in range(2)]
+        # blocks of my rows whose index is also one of my columns: i = r (mod pr) and i = c (mod pc)
+        period = pr * pc // _gcd(pr, pc)
+        cnt_max = (nblk + period - 1) // period + 1
+        send = torch.zeros(cnt_max * nb * nb, dtype=torch.float64, device=dev)
+        recv = torch.zeros(pr * cnt_max * nb * nb, dtype=torch.float64, device=dev)
+        ev_first, ev_rest = [None, None], [None, None]
+        t_begin = t_end = None
+        if profile is not None:
+            t_begin = torch.cuda.Event(enable_timing=True)
+            t_begin.record(torch.cuda.current_stream())
+
+        def both(ii: int, rr: int) -> bool:
+            return ii % pr == rr and ii % pc == c
+
+        ops.fork()
+        for k in range(nblk):
+            rk, ck = k % pr, k % pc
+            in_col = c == ck
+            lr0, lc0 = lay.count_le(k, r, pr), lay.count_le(k, c, pc)  # local rows / columns with index <= k
+            m_loc, n_loc = (self.nbr - lr0) * nb, (self.nbc - lc0) * nb
+            pack = packs[k % 2]
+            Lkk = pack[: nb * nb].view(nb, nb)
+            Wk = pack[nb * nb : nb * nb + wlen]
+            with ops.on("panel"):
+                ops.wait(ev_rest[k % 2])
+                if in_col:
+                    if r == rk:
+                        D = self.local_block(k, k)
+                        ops.potrf_block(D, dtmp, pack[-1:])
+                        pack[-1:].add_(float(k * nb) * (pack[-1:] > 0))
+                        Lkk.copy_(D)
+                        Wk.copy_(dtmp[:wlen])
+                    if self.col_group is not None and pr > 1:
+                        dist.broadcast(pack, src=lay.rank_of(rk, ck), group=self.col_group)
+                    info_all.copy_(torch.where(info_all > 0, info_all, pack[-1:]))
+                if k == nblk - 1:
+                    break
+                Lrow = lrows[k % 2][: m_loc * nb].view(m_loc, nb)
+                if in_col and m_loc > 0:
+                    X = self.A_loc[lr0 * nb : lr0 * nb + m_loc, (k // pc) * nb : (k // pc + 1) * nb]
+                    ops.trsm_block(Lkk, Wk, X, refine=True)
+                    Lrow.copy_(X)
+                # (3a) along my process row: the blocks L_ik of my block rows
+                if self.row_group is not None and pc > 1 and m_loc > 0:
+                    dist.broadcast(lrows[k % 2][: m_loc * nb], src=lay.rank_of(r, ck), group=self.row_group)
+                # (3b) inside my process column: the blocks L_jk of my block columns (j = c mod pc), from whichever
+                #      process row holds them (j mod pr)
+                Lcol = lcols[k % 2][: n_loc * nb].view(n_loc, nb)
+                if n_loc > 0:
+                    # both index sets are arithmetic progressions with the period lcm(pr, pc): strided block copies
+                    sv = send.view(cnt_max, nb, nb)
+                    mine = [t for t in range(self.nbr - lr0) if both((lr0 + t) * pr + r, r)]
+                    if mine:
+                        sv[: len(mine)].copy_(Lrow.view(-1, nb, nb)[mine[0] :: period // pr][: len(mine)])
+                    if self.col_group is not None and pr > 1:
+                        dist.all_gather_into_tensor(recv, send, group=self.col_group)
+                        rv = recv.view(pr, cnt_max, nb, nb)
+                    else:
+                        rv = sv.view(1, cnt_max, nb, nb)
+                    Lc3 = Lcol.view(-1, nb, nb)
+                    for rr in range(pr):
+                        dst = [lj - lc0 for lj in range(lc0, self.nbc) if (lj * pc + c) % pr == rr]
+                        if dst:
+                            Lc3[dst[0] :: period // pc][: len(dst)].copy_(rv[rr, : len(dst)])
+                ev_panel = ops.record()
+                lim = self.col_limit[lr0 * (nb // LEAF) :]
+                C = self.A_loc[lr0 * nb : lr0 * nb + m_loc, lc0 * nb : lc0 * nb + n_loc]
+                first_cols = 0
+                if m_loc > 0 and n_loc > 0 and (k + 1) % pc == c:  # (4a) block column k+1 = the next panel, right away
+                    ops.wait(ev_first[(k + 1) % 2])
+                    ops.update_limited(C[:, :nb], Lrow, Lcol[:nb], lim, lc0 * nb)
+                    first_cols = 1
+            with ops.on("update"):
+                ops.wait(ev_panel)
+                done = first_cols
+                if m_loc > 0 and n_loc > done * nb and k + 2 < nblk and (k + 2) % pc == c:  # block column k+2 first
+                    ops.update_limited(C[:, done * nb : (done + 1) * nb], Lrow, Lcol[done * nb : (done + 1) * nb], lim,
+                                       (lc0 + done) * nb)
+                    done += 1
+                ev_first[k % 2] = ops.record()
+                if m_loc > 0 and n_loc > done * nb:
+                    ops.update_limited(C[:, done * nb :], Lrow, Lcol[done * nb :], lim, (lc0 + done) * nb)
+                ev_rest[k % 2] = ops.record()
+        ops.join()
+        if profile is not None:
+            t_end = torch.cuda.Event(enable_timing=True)
+            t_end.record(torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            profile["total"] = t_begin.elapsed_time(t_end)
+        if self.world > 1:
+            dist.all_reduce(info_all, op=dist.ReduceOp.MAX)
+        info = int(info_all.item())
+        if info > 0:
+            import numpy as np
+
+            raise np.linalg.LinAlgError(f"{info}-th leading minor of the array is not positive definite")
+
+    def gather_full(self, L_full: torch.Tensor) -> None:
+        """Every rank receives every block of the factor (validation at small sizes: one broadcast per block)."""
+        lay, nb = self.layout, self.nb
+        tmp = torch.zeros((nb, nb), dtype=torch.float64, device=self.A_loc.device)
+        for i in range(lay.nblk):
+            for j in range(i + 1):
+                if self.owns(i, j):
+                    tmp.copy_(self.local_block(i, j))
+                if self.world > 1:
+                    dist.broadcast(tmp, src=lay.owner(i, j))
+                L_full[i * nb : (i + 1) * nb, j * nb : (j + 1) * nb].copy_(tmp)
+
+
+def _gcd(a: int, b: int) -> int:
+    while b:
+        a, b = b, a % b
+    return a

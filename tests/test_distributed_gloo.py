@@ -106,3 +106,58 @@ def test_world2_gloo(n, nb):
     for p in procs:
         p.join(timeout=60)
     assert all(err < 1e-11 and werr < 1e-10 for _, err, werr in res), res
+
+
+# ---- 2-D block-cyclic variant ------------------------------------------------------------------------------------------
+def _run2d(rank, world, port, n, nb, pr, pc, q):
+    from linpde_gp_b200.distributed import BlockCyclic2DCholesky
+
+    if world > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    G = _spd(n, 5)
+    ch = BlockCyclic2DCholesky(n, nb, pr, pc, ops=HostOps())
+    lay = ch.layout
+    for i in range(lay.nblk):
+        for j in range(i + 1):
+            if ch.owns(i, j):
+                ch.local_block(i, j).copy_(G[i * nb : (i + 1) * nb, j * nb : (j + 1) * nb])
+    ch.factor()
+    L = torch.zeros((n, n), dtype=torch.float64)
+    ch.gather_full(L)
+    err = float((torch.tril(L) - torch.linalg.cholesky(G)).abs().max())
+    # a matrix that is not positive definite: every rank raises, with LAPACK's info
+    bad = BlockCyclic2DCholesky(n, nb, pr, pc, ops=HostOps())
+    Gb = G.clone()
+    Gb[nb + 3, nb + 3] = -1.0
+    for i in range(lay.nblk):
+        for j in range(i + 1):
+            if bad.owns(i, j):
+                bad.local_block(i, j).copy_(Gb[i * nb : (i + 1) * nb, j * nb : (j + 1) * nb])
+    raised = False
+    try:
+        bad.factor()
+    except np.linalg.LinAlgError:
+        raised = True
+    q.put((rank, err, raised))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,pr,pc,n,nb", [(1, 1, 1, 512, 128), (2, 2, 1, 768, 128), (2, 1, 2, 768, 128), (4, 2, 2, 1152, 128),
+                                              (6, 2, 3, 1024, 128), (6, 3, 2, 896, 128)])
+def test_2d_block_cyclic_cholesky(world, pr, pc, n, nb):
+    """``BlockCyclic2DCholesky`` on pr x pc process grids (row broadcast + column all-gather of the panel, staircase row
+    limits, lookahead bookkeeping) against torch's dense Cholesky; non-positive-definite input raises on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run2d, args=(rk, world, port, n, nb, pr, pc, q)) for rk in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for _, err, raised in res:
+        assert err < 1e-11 and raised
