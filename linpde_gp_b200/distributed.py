@@ -557,6 +557,9 @@ class Grid2DLayout:
         return 0 if k < first else (k - first) // step + 1
 
 
+_GRID_GROUPS: dict = {}  # (pr, pc, world) -> (row groups, column groups) of the default process group
+
+
 class BlockCyclic2DCholesky:
     """Right-looking Cholesky on a ``pr x pc`` process grid with one panel of lookahead (same two-stream pipeline as
     :class:`DistributedCholesky`).  Per panel ``k``:
@@ -582,17 +585,21 @@ class BlockCyclic2DCholesky:
         self.ops = DeviceOps() if ops is None else ops
         self.n, self.nb = n, nb
         self.r, self.c = lay.coords(self.rank)
-        # sub-communicators: every rank creates every group, in the same order
+        # sub-communicators: every rank creates every group, in the same order; cached per grid shape and warmed up
+        # with one tiny collective each (NCCL builds a communicator lazily at its first use -- hundreds of milliseconds
+        # that must not land inside a factorisation)
         self.row_group = self.col_group = None
         if self.world > 1:
-            for r in range(pr):
-                g = dist.new_group([lay.rank_of(r, c) for c in range(pc)])
-                if r == self.r:
-                    self.row_group = g
-            for c in range(pc):
-                g = dist.new_group([lay.rank_of(r, c) for r in range(pr)])
-                if c == self.c:
-                    self.col_group = g
+            key = (pr, pc, self.world)
+            if key not in _GRID_GROUPS:
+                rows = [dist.new_group([lay.rank_of(r, c) for c in range(pc)]) for r in range(pr)]
+                cols = [dist.new_group([lay.rank_of(r, c) for r in range(pr)]) for c in range(pc)]
+                _GRID_GROUPS[key] = (rows, cols)
+                warm = torch.zeros(1, dtype=torch.float64, device=self.ops.device)
+                dist.all_reduce(warm, group=rows[self.r])
+                dist.all_reduce(warm, group=cols[self.c])
+            rows, cols = _GRID_GROUPS[key]
+            self.row_group, self.col_group = rows[self.r], cols[self.c]
         self.nbr, self.nbc = lay.n_local_rows(self.r), lay.n_local_cols(self.c)
         self.A_loc = self.ops.empty(max(self.nbr, 1) * nb, max(self.nbc, 1) * nb)
         dev = self.A_loc.device

@@ -47,8 +47,8 @@ def main():
     t = timed(dmma) - t_copy
     Xd = X.clone()
     print(f"DMMA trsm  m={m} n={n}: {t:9.1f} ms  {flops / t * 1e-9:7.2f} TFLOP/s")
-    for kblock in (1024, 2048):
-        for S in (5, 6, 7):
+    for kblock in (512, 1024):
+        for S in (6, 7):
             XP = be.OzakiPlanes(m, n, S, kblock)
             t_split = timed(lambda: f.__dict__.pop("_ozaki_cache", None) or f.ozaki_planes(S, kblock), reps=1)
 
