@@ -55,6 +55,7 @@ constexpr int OZ_ACC = 4;  // TMEM accumulators (128 columns each)
 constexpr int OZ_A_BYTES = OZ_BM * OZ_BK, OZ_B_BYTES = OZ_BN * OZ_BK;
 constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;
 constexpr int OZ_BAR_BYTES = (2 * OZ_STAGES + 2 * OZ_ACC) * 8 + 16;
+constexpr int OZ_BAD_EXP = 1 << 20;  // exponent sentinel of a (row, K-block) that holds a NaN or an infinity: the products become NaN
 constexpr int OZ_SMEM_BYTES = 1024 + OZ_STAGES * OZ_STAGE_BYTES + OZ_BAR_BYTES + OZ_BN * 8;
 
 __device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
@@ -239,7 +240,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");  // everyone is done with the previous K-block's s_sb
       if (et < OZ_BN) {
         const int col = n0 + et;
-        s_sb[et] = col < p.n ? exp2i(p.eB[(int64_t)(p.kB0 / p.kblock + kb) * p.ldeB + p.rowB0 + col]) : 0.0;
+        const int eb = col < p.n ? p.eB[(int64_t)(p.kB0 / p.kblock + kb) * p.ldeB + p.rowB0 + col] : 0;
+        s_sb[et] = col < p.n ? (eb >= OZ_BAD_EXP ? __longlong_as_double(0x7ff8000000000000LL) : exp2i(eb)) : 0.0;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
       const int ea = row < p.m ? p.eA[(int64_t)(p.kA0 / p.kblock + kb) * p.ldeA + p.rowA0 + row] : 0;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         mbar_wait(acc_full + buf, (it / OZ_ACC) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * OZ_BN + half * 64);
-        const double srow = exp2i(ea - 14 - 8 * q);
+        const double srow = ea >= OZ_BAD_EXP ? __longlong_as_double(0x7ff8000000000000LL) : exp2i(ea - 14 - 8 * q);
         const double* sb = s_sb + half * 64;
         uint32_t v[32];
         tc_ld32(taddr, v);
@@ -307,20 +309,25 @@ __global__ void __launch_bounds__(256)
   if (lower_blocks && col0 / kblock + kb >= (r + row_off) / kblock) return;  // absolute K-block >= the row's own block
   const double* src = A + r * lda + col0 + (int64_t)kb * kblock;
   double mx = 0.0;
+  int bad = 0;  // NaN or infinity anywhere in the block (fmax would silently drop a NaN)
   for (int c = lane * 4; c < kblock; c += 128) {
     const double2 x0 = *reinterpret_cast<const double2*>(src + c), x1 = *reinterpret_cast<const double2*>(src + c + 2);
     mx = fmax(fmax(fabs(x0.x), fabs(x0.y)), fmax(mx, fmax(fabs(x1.x), fabs(x1.y))));
+    bad |= !(fabs(x0.x) <= 1.7976931348623157e308) | !(fabs(x0.y) <= 1.7976931348623157e308) |
+           !(fabs(x1.x) <= 1.7976931348623157e308) | !(fabs(x1.y) <= 1.7976931348623157e308);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  // smallest e with max < 2^e; an all-zero (or non-finite) block gets e = 0 and all-zero digits
-  const bool ok = mx > 0.0 && mx < 1.7e308;
-  const int e = ok ? ilogb(mx) + 1 : 0;
+  bad = __any_sync(0xffffffffu, bad);
+  // smallest e with max < 2^e; an all-zero block gets e = 0 and all-zero digits; a block with a non-finite entry gets the
+  // sentinel exponent, which turns every product it takes part in into NaN (what an FP64 GEMM would propagate)
+  const bool ok = mx > 0.0 && !bad;
+  const int e = bad ? OZ_BAD_EXP : (ok ? ilogb(mx) + 1 : 0);
   if (lane == 0) exps[(int64_t)(col0 / kblock + kb) * lde + row_off + r] = e;
   // fixed point: F = floor(x 2^(55-e)) is an integer below 2^55 in magnitude (exact scaling, exact conversion), whose
   // radix-256 digits are d_0 = F >> 48 (signed) and d_s = (F >> (48 - 8 s)) & 255.  (Peeling the digits off in floating
   // point is NOT exact: for x = -tiny the remainder 1 - tiny rounds to 1 and the next digit overflows.)
-  const double sc = exp2i(55 - e);
+  const double sc = exp2i(bad ? 0 : 55 - e);
   unsigned char* dst = planes + (r + row_off) * pitch + col0 + (int64_t)kb * kblock;
   for (int c = lane * 4; c < kblock; c += 128) {
     const double2 x0 = *reinterpret_cast<const double2*>(src + c), x1 = *reinterpret_cast<const double2*>(src + c + 2);

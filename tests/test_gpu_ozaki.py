@@ -137,3 +137,26 @@ def test_posterior_variance_with_the_emulated_solver_matches_the_frozen_referenc
             assert np.max(np.abs(var_oz - var_dmma)) <= {5: 1e-6, 6: 1e-9, 7: 1e-11}[S] * 4.0, S
     finally:
         be.set_variance_solver(ozaki_slices=prev["ozaki_slices"], kblock=prev["kblock"])
+
+
+def test_non_finite_entries_propagate_like_an_fp64_gemm(be):
+    """A NaN or an infinity in an operand turns the affected rows / columns of the product into NaN (an FP64 GEMM would
+    give NaN or inf there); everything else stays exact."""
+    rng = np.random.default_rng(9)
+    m, n, k = 130, 140, 2048
+    A, B = be.to_device(rng.standard_normal((m, k))), be.to_device(rng.standard_normal((n, k)))
+    A[3, 1500] = float("nan")
+    A[7, 10] = float("inf")
+    B[5, 100] = -float("inf")
+    PA, PB = be.OzakiPlanes(m, k, 7, 1024), be.OzakiPlanes(n, k, 7, 1024)
+    PA.split(A)
+    PB.split(B)
+    C = be.alloc_matrix(m, n).zero_()
+    be.ozaki_gemm_nt(PA, PB, C, k)
+    bad = torch.zeros((m, n), dtype=torch.bool, device=C.device)
+    bad[3, :] = bad[7, :] = True
+    bad[:, 5] = True
+    assert torch.all(torch.isnan(C[bad]))
+    ref = torch.nan_to_num(A, nan=0.0, posinf=0.0, neginf=0.0) @ torch.nan_to_num(B, nan=0.0, posinf=0.0, neginf=0.0).T
+    assert torch.all(torch.isfinite(C[~bad]))
+    assert (C[~bad] - ref[~bad]).abs().max() <= 1e-12 * ref.abs().max()
