@@ -104,6 +104,10 @@ long long lpgp_launch_count(int reset); /* kernels launched by the library so fa
 /* LPGP_OPT_TIME_OZAKI != 0: every lpgp_ozaki_gemm_nt launch is bracketed by two CUDA events on its stream (no
  * synchronisation added); lpgp_ozaki_gemm_stats reads them back (bench.py: live duration of the dominant kernel). */
 #define LPGP_OPT_TIME_OZAKI 4
+/* LPGP_OPT_OZAKI_CLUSTER: CTAs per thread-block cluster of the emulated GEMM.  2 (default): the two CTAs of a cluster
+ * compute vertically adjacent 128 x 128 tiles and share their B tile -- each loads half of it and TMA multicasts the
+ * half into both CTAs' shared memory (24 KB instead of 32 KB from L2 per CTA and pipeline stage); 1: no clusters.   */
+#define LPGP_OPT_OZAKI_CLUSTER 5
 int lpgp_set_option(int key, int value);
 /* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and
  * reports the flop count; timed by the caller it yields the roofline denominator of the DMMA kernels on the

@@ -531,6 +531,10 @@ def ozaki_gemm_nt(PA: OzakiPlanes, PB: OzakiPlanes, C: torch.Tensor, k: int, alp
 VARIANCE_SOLVER = {"ozaki_slices": int(__import__("os").environ.get("LPGP_OZAKI_SLICES", "7")), "kblock": 1024}
 
 
+if "LPGP_OZAKI_CLUSTER" in __import__("os").environ:  # A/B switch of the emulated GEMM's cluster size (1 or 2, default 2)
+    check(lib.lpgp_set_option(5, int(__import__("os").environ["LPGP_OZAKI_CLUSTER"])), "lpgp_set_option(LPGP_OPT_OZAKI_CLUSTER)")
+
+
 def set_variance_solver(ozaki_slices: int = 0, kblock: int = 1024) -> None:
     if not 0 <= int(ozaki_slices) <= _lib.OZAKI_MAX_SLICES:
         raise ValueError(f"ozaki_slices must be in 0..{_lib.OZAKI_MAX_SLICES}")

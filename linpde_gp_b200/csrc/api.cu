@@ -17,6 +17,7 @@ int g_lpgp_no_sep = 0;
 int g_lpgp_no_lookahead = 0;
 int g_lpgp_trsm_refine = 1;
 int g_lpgp_time_ozaki = 0;
+int g_lpgp_ozaki_cluster = 2;
 
 extern "C" int lpgp_set_option(int key, int value) {
   if (key == LPGP_OPT_DIRECT_EXP) {
@@ -30,6 +31,11 @@ extern "C" int lpgp_set_option(int key, int value) {
   if (key == LPGP_OPT_TRSM_REFINE) {
     if (value < 0 || value > 3) return -2;
     g_lpgp_trsm_refine = value;
+    return 0;
+  }
+  if (key == LPGP_OPT_OZAKI_CLUSTER) {
+    if (value != 1 && value != 2 && value != 4) return -2;
+    g_lpgp_ozaki_cluster = value;
     return 0;
   }
   if (key == LPGP_OPT_TIME_OZAKI) {

@@ -21,6 +21,8 @@ extern int g_lpgp_no_lookahead;
 extern int g_lpgp_trsm_refine;
 // != 0: lpgp_ozaki_gemm_nt brackets its launches with CUDA events (lpgp_ozaki_gemm_stats)
 extern int g_lpgp_time_ozaki;
+// emulated GEMM: CTAs per cluster (1, or 2 = B tile loaded once per pair of vertically adjacent tiles, TMA multicast)
+extern int g_lpgp_ozaki_cluster;
 #define LPGP_MAX_DEVICES 32
 
 #define LPGP_CHECK_LAUNCH()                            \

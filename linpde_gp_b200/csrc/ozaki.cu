@@ -48,7 +48,10 @@ namespace {
 
 constexpr int OZ_BM = 128, OZ_BN = 128;
 constexpr int OZ_BK = 128;  // bytes of the contraction index per stage = one 128-byte swizzle row
-constexpr int OZ_STAGES = 6;
+#ifndef LPGP_OZ_STAGES
+#define LPGP_OZ_STAGES 6
+#endif
+constexpr int OZ_STAGES = LPGP_OZ_STAGES;  // 6 x 32 KB = all the shared memory one CTA can have; fewer only for latency experiments
 constexpr int OZ_THREADS = 320;
 constexpr int OZ_EPI_THREADS = 256;
 constexpr int OZ_ACC = 4;  // TMEM accumulators (128 columns each)
@@ -68,6 +71,24 @@ __device__ __forceinline__ void oz_tma_load_3d(void* dst, const CUtensorMap* tm,
       "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
+// the same copy delivered to the same shared-memory offset of every CTA in `mask` (bits = ranks in the cluster); each
+// destination's own mbarrier at that offset receives the complete_tx
+__device__ __forceinline__ void oz_tma_load_3d_mc(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, "
+      "%4}], [%5], %6;" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T, int8/uint8 operands, int32 accumulation
@@ -84,6 +105,13 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint
 // all tcgen05.mma issued so far by this thread arrive (once) on the mbarrier when they have completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// as tc_commit, arriving on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -133,6 +161,13 @@ struct OzParams {
   int tiles_n;
 };
 
+// CLM x CLN = CTAs per cluster (1 x 1, 2 x 1 or 2 x 2), computing a CLM x CLN patch of adjacent output tiles.  CTAs in
+// the same patch column need the SAME B tile and CTAs in the same patch row the SAME A tile: each loads 1 / CLM of B
+// (1 / CLN of A) and TMA multicasts its share into the shared memory of every CTA that needs it -- 24 KB (2 x 1) or 16 KB
+// (2 x 2) instead of 32 KB from L2 per CTA and stage.  A stage may only be refilled when every CTA that receives a share
+// of it has consumed it, so the MMA issuer's tcgen05.commit arrives on the `empty` barriers of all CTAs that write into
+// this one (itself, its A partners, its B partners).
+template <int CLM, int CLN>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ OzParams p) {
@@ -146,15 +181,27 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   double* s_sb = (double*)(smem + OZ_STAGES * OZ_STAGE_BYTES + OZ_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tm = blockIdx.x / p.tiles_n, tn = blockIdx.x % p.tiles_n;
+  constexpr int CL = CLM * CLN;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int rm = crank % CLM, rn = crank / CLM;  // position inside the patch
+  const int cid = blockIdx.x / CL;               // clusters walk the patch grid row-major
+  const int patches_n = (p.tiles_n + CLN - 1) / CLN;
+  const int tm = (cid / patches_n) * CLM + rm, tn = (cid % patches_n) * CLN + rn;
   const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
   const int S = p.nslices;
   const int chunks = p.kblock / OZ_BK;
+  // ranks that share my A tile (same rm) / my B tile (same rn)
+  uint16_t mask_a = 0, mask_b = 0;
+#pragma unroll
+  for (int j = 0; j < CLN; ++j) mask_a |= (uint16_t)(1u << (rm + CLM * j));
+#pragma unroll
+  for (int i = 0; i < CLM; ++i) mask_b |= (uint16_t)(1u << (i + CLM * rn));
+  const uint16_t mask_all = mask_a | mask_b;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < OZ_STAGES; ++i) {
       mbar_init(full + i, 1);
-      mbar_init(empty + i, 1);
+      mbar_init(empty + i, CLM + CLN - 1);
     }
     for (int i = 0; i < OZ_ACC; ++i) {
       mbar_init(acc_full + i, 1);
@@ -168,6 +215,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA multicasts into a peer whose barriers are not initialised yet
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -184,8 +232,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
               unsigned char* dst = smem + stage * OZ_STAGE_BYTES;
               mbar_expect_tx(full + stage, OZ_STAGE_BYTES);
               const int kk = kb * p.kblock + c * OZ_BK;
-              oz_tma_load_3d(dst, &tmA, p.kA0 + kk, p.rowA0 + m0, s, full + stage);
-              oz_tma_load_3d(dst + OZ_A_BYTES, &tmB, p.kB0 + kk, p.rowB0 + n0, t, full + stage);
+              // my shares of the A and B tiles (whole 1 KB swizzle atoms), delivered to every CTA that needs them
+              if (CLN == 1)
+                oz_tma_load_3d(dst, &tmA, p.kA0 + kk, p.rowA0 + m0, s, full + stage);
+              else
+                oz_tma_load_3d_mc(dst + rn * (OZ_A_BYTES / CLN), &tmA, p.kA0 + kk, p.rowA0 + m0 + rn * (OZ_BM / CLN), s,
+                                  full + stage, mask_a);
+              if (CLM == 1)
+                oz_tma_load_3d(dst + OZ_A_BYTES, &tmB, p.kB0 + kk, p.rowB0 + n0, t, full + stage);
+              else
+                oz_tma_load_3d_mc(dst + OZ_A_BYTES + rm * (OZ_B_BYTES / CLM), &tmB, p.kB0 + kk,
+                                  p.rowB0 + n0 + rm * (OZ_BN / CLM), t, full + stage, mask_b);
               if (++stage == OZ_STAGES) {
                 stage = 0;
                 phase ^= 1;
@@ -216,7 +273,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                 tc_mma_i8(tmem_d, da + 2 * j, db + 2 * j, idesc, accumulate);
                 accumulate = 1;
               }
-              tc_commit(empty + stage);  // stage reusable once these MMAs have read it
+              if (CL == 1) tc_commit(empty + stage);  // stage reusable once these MMAs have read it
+              else tc_commit_mc(empty + stage, mask_all);  // ... in every CTA whose producer writes into it
               if (++stage == OZ_STAGES) {
                 stage = 0;
                 phase ^= 1;
@@ -287,6 +345,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers may still signal my barriers / I may still signal theirs until everyone is done
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -366,17 +425,19 @@ int oz_ensure() {
   LPGP_CHECK(cudaGetDevice(&dev));
   const bool tracked = dev >= 0 && dev < LPGP_MAX_DEVICES;
   if (tracked && g_oz_attr[dev].load(std::memory_order_acquire)) return 0;
-  LPGP_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
+  LPGP_CHECK((cudaFuncSetAttribute(ozaki_gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)));
+  LPGP_CHECK((cudaFuncSetAttribute(ozaki_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)));
+  LPGP_CHECK((cudaFuncSetAttribute(ozaki_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)));
   if (tracked) g_oz_attr[dev].store(1, std::memory_order_release);
   return 0;
 }
 
 // byte planes [nslices][rows][pitch] -> 3-D tensor map (k, row, plane), boxes of 128 bytes x 128 rows x 1 plane
 int oz_make_map(CUtensorMap* tm, const unsigned char* planes, int64_t cols, int64_t rows, int64_t pitch,
-                int64_t plane_stride, int nslices) {
+                int64_t plane_stride, int nslices, int box_rows = OZ_BM) {
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nslices};
   cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)plane_stride};
-  cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)OZ_BM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_oz_encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -526,10 +587,14 @@ extern "C" int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha,
   if (m > INT32_MAX || n > INT32_MAX || PA->cols > INT32_MAX || PB->cols > INT32_MAX) return -1;
   int rc = oz_ensure();
   if (rc) return rc;
+  // cluster shape: 2 x 2 / 2 x 1 patches of tiles when the tile grid has the rows / columns for it
+  const int64_t tiles_m = ceil_div64(m, OZ_BM), tiles_n0 = ceil_div64(n, OZ_BN);
+  const int clm = (g_lpgp_ozaki_cluster >= 2 && tiles_m >= 2) ? 2 : 1;
+  const int cln = (g_lpgp_ozaki_cluster >= 4 && clm == 2 && tiles_n0 >= 2) ? 2 : 1;
   CUtensorMap tmA, tmB;
-  rc = oz_make_map(&tmA, PA->planes, PA->cols, PA->rows, PA->pitch, PA->plane_stride, PA->nslices);
+  rc = oz_make_map(&tmA, PA->planes, PA->cols, PA->rows, PA->pitch, PA->plane_stride, PA->nslices, OZ_BM / cln);
   if (rc) return rc;
-  rc = oz_make_map(&tmB, PB->planes, PB->cols, PB->rows, PB->pitch, PB->plane_stride, PB->nslices);
+  rc = oz_make_map(&tmB, PB->planes, PB->cols, PB->rows, PB->pitch, PB->plane_stride, PB->nslices, OZ_BN / clm);
   if (rc) return rc;
   OzParams p;
   p.m = (int)m;
@@ -550,7 +615,8 @@ extern "C" int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha,
   p.alpha = alpha;
   p.beta = beta;
   p.tiles_n = (int)ceil_div64(n, OZ_BN);
-  const int64_t tiles = ceil_div64(m, OZ_BM) * p.tiles_n;
+  // whole patches (padding tiles run the pipeline -- their shares of A / B are needed by their partners -- but store nothing)
+  const int64_t tiles = ceil_div64(tiles_m, clm) * clm * ceil_div64(tiles_n0, cln) * cln;
   if (tiles > INT32_MAX) return -1;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_lpgp_time_ozaki) {
@@ -568,7 +634,26 @@ extern "C" int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha,
     g_oz_timing.ops += 2.0 * (double)m * (double)n * (double)k * pairs;
     LPGP_CHECK(cudaEventRecord(e0, (cudaStream_t)stream));
   }
-  ozaki_gemm_kernel<<<(unsigned)tiles, OZ_THREADS, OZ_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+  if (clm == 1) {
+    ozaki_gemm_kernel<1, 1><<<(unsigned)tiles, OZ_THREADS, OZ_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.blockDim = dim3(OZ_THREADS);
+    cfg.dynamicSmemBytes = OZ_SMEM_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)(clm * cln);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cln == 1)
+      LPGP_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<2, 1>, tmA, tmB, p));
+    else
+      LPGP_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<2, 2>, tmA, tmB, p));
+  }
   LPGP_CHECK_LAUNCH();
   if (e1) LPGP_CHECK(cudaEventRecord(e1, (cudaStream_t)stream));
   return 0;

@@ -17,6 +17,9 @@ PA, PB = be.OzakiPlanes(m, k, S, 1024), be.OzakiPlanes(n, k, S, 1024)
 PA.split(A)
 PB.split(B)
 del A, B
+from linpde_gp_b200._lib import lib
+cl = int(sys.argv[5]) if len(sys.argv) > 5 else 2
+assert lib.lpgp_set_option(5, cl) == 0  # LPGP_OPT_OZAKI_CLUSTER
 for _ in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -25,5 +28,5 @@ for _ in range(3):
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1)
     pairs = S * (S + 1) // 2
-    print(f"ozaki gemm {m}x{n}x{k} S={S}: {t:.2f} ms  {2.0 * m * n * k / t * 1e-9:.1f} TFLOP/s-equivalent  "
+    print(f"ozaki gemm (cluster {cl}) {m}x{n}x{k} S={S}: {t:.2f} ms  {2.0 * m * n * k / t * 1e-9:.1f} TFLOP/s-equivalent  "
           f"{2.0 * m * n * k * pairs / t * 1e-12:.2f} INT8 POP/s")
