@@ -51,9 +51,9 @@ GEMM_TRAFFIC = {
     "launch": "gemm_nt_kernel 8192x8192x2048 beta=1: 2.26 GB read + 0.53 GB written (algorithmic 1.34 GB)",
 }
 OZAKI_TRAFFIC = {
-    "bytes": 3.016e9,
-    "source": "profiles/ncu_ozaki_r02d.md (ncu --set full, one launch; not measured in this run)",
-    "launch": "ozaki_gemm_kernel 16384x1024x16384, 7 digit planes, beta=1: 2.88 GB read + 0.13 GB written "
+    "bytes": 3.118e9,
+    "source": "profiles/ncu_ozaki_r02u.md (ncu --set full, one launch; not measured in this run)",
+    "launch": "ozaki_gemm_kernel<2, 1> 16384x1024x16384, 7 digit planes, beta=1: 2.98 GB read + 0.13 GB written "
               "(algorithmic 2.27 GB: 7 x (16384 + 1024) x 16384 plane bytes + C read and written)",
 }
 

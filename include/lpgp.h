@@ -108,6 +108,11 @@ long long lpgp_launch_count(int reset); /* kernels launched by the library so fa
  * compute vertically adjacent 128 x 128 tiles and share their B tile -- each loads half of it and TMA multicasts the
  * half into both CTAs' shared memory (24 KB instead of 32 KB from L2 per CTA and pipeline stage); 1: no clusters.   */
 #define LPGP_OPT_OZAKI_CLUSTER 5
+/* LPGP_OPT_OZAKI_PAIR_LEVELS: 1 (default): the emulated GEMM accumulates two digit levels q, q+1 per pass over a K-block --
+ * pipeline stage j holds the planes (A_j, B_{q+1-j}); A_j B_{q+1-j} goes to level q+1 and A_{j-1} B_{q+1-j} (the previous
+ * stage's A tile) to level q, so 16 instead of 28 operand-stage loads per K-chunk at 7 planes; 0: one level per pass.
+ * Both orders add the same exact int32 sums: results are bit-identical.                                              */
+#define LPGP_OPT_OZAKI_PAIR_LEVELS 6
 int lpgp_set_option(int key, int value);
 /* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and
  * reports the flop count; timed by the caller it yields the roofline denominator of the DMMA kernels on the

@@ -23,6 +23,8 @@ extern int g_lpgp_trsm_refine;
 extern int g_lpgp_time_ozaki;
 // emulated GEMM: CTAs per cluster (1, or 2 = B tile loaded once per pair of vertically adjacent tiles, TMA multicast)
 extern int g_lpgp_ozaki_cluster;
+// emulated GEMM: != 0 = two digit levels per pass over a K-block (operand tiles shared between them), 0 = one level per pass
+extern int g_lpgp_ozaki_pair_levels;
 #define LPGP_MAX_DEVICES 32
 
 #define LPGP_CHECK_LAUNCH()                            \

@@ -159,6 +159,7 @@ struct OzParams {
   int64_t ldc;
   double alpha, beta;
   int tiles_n;
+  int pair_levels;     // != 0: two levels per pass over the K-block, operand tiles shared between them (see the kernel)
 };
 
 // CLM x CLN = CTAs per cluster (1 x 1, 2 x 1 or 2 x 2), computing a CLM x CLN patch of adjacent output tiles.  CTAs in
@@ -223,66 +224,123 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int kb = 0; kb < p.nkb; ++kb)
-        for (int q = 0; q < S; ++q)
-          for (int s = 0; s <= q; ++s) {
-            const int t = q - s;
-            for (int c = 0; c < chunks; ++c) {
-              mbar_wait(empty + stage, phase ^ 1);
-              unsigned char* dst = smem + stage * OZ_STAGE_BYTES;
-              mbar_expect_tx(full + stage, OZ_STAGE_BYTES);
-              const int kk = kb * p.kblock + c * OZ_BK;
-              // my shares of the A and B tiles (whole 1 KB swizzle atoms), delivered to every CTA that needs them
-              if (CLN == 1)
-                oz_tma_load_3d(dst, &tmA, p.kA0 + kk, p.rowA0 + m0, s, full + stage);
-              else
-                oz_tma_load_3d_mc(dst + rn * (OZ_A_BYTES / CLN), &tmA, p.kA0 + kk, p.rowA0 + m0 + rn * (OZ_BM / CLN), s,
-                                  full + stage, mask_a);
-              if (CLM == 1)
-                oz_tma_load_3d(dst + OZ_A_BYTES, &tmB, p.kB0 + kk, p.rowB0 + n0, t, full + stage);
-              else
-                oz_tma_load_3d_mc(dst + OZ_A_BYTES + rm * (OZ_B_BYTES / CLM), &tmB, p.kB0 + kk,
-                                  p.rowB0 + n0 + rm * (OZ_BN / CLM), t, full + stage, mask_b);
-              if (++stage == OZ_STAGES) {
-                stage = 0;
-                phase ^= 1;
-              }
-            }
+      // one pipeline stage = (plane sa of my A tile, plane sb of my B tile) at K-chunk c of K-block kb
+      auto load = [&](int kb, int c, int sa, int sb) {
+        mbar_wait(empty + stage, phase ^ 1);
+        unsigned char* dst = smem + stage * OZ_STAGE_BYTES;
+        mbar_expect_tx(full + stage, OZ_STAGE_BYTES);
+        const int kk = kb * p.kblock + c * OZ_BK;
+        // my shares of the A and B tiles (whole 1 KB swizzle atoms), delivered to every CTA that needs them
+        if (CLN == 1)
+          oz_tma_load_3d(dst, &tmA, p.kA0 + kk, p.rowA0 + m0, sa, full + stage);
+        else
+          oz_tma_load_3d_mc(dst + rn * (OZ_A_BYTES / CLN), &tmA, p.kA0 + kk, p.rowA0 + m0 + rn * (OZ_BM / CLN), sa,
+                            full + stage, mask_a);
+        if (CLM == 1)
+          oz_tma_load_3d(dst + OZ_A_BYTES, &tmB, p.kB0 + kk, p.rowB0 + n0, sb, full + stage);
+        else
+          oz_tma_load_3d_mc(dst + OZ_A_BYTES + rm * (OZ_B_BYTES / CLM), &tmB, p.kB0 + kk, p.rowB0 + n0 + rm * (OZ_BN / CLM),
+                            sb, full + stage, mask_b);
+        if (++stage == OZ_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      if (p.pair_levels) {
+        for (int kb = 0; kb < p.nkb; ++kb)
+          for (int q0 = 0; q0 < S;) {
+            const int nl = (q0 == 0 && (S & 1)) ? 1 : 2;  // levels of this group
+            const int top = q0 + nl - 1;                  // its highest level: stage j holds (A_j, B_{top-j})
+            for (int c = 0; c < chunks; ++c)
+              for (int j = 0; j <= top; ++j) load(kb, c, j, top - j);
+            q0 += nl;
           }
+      } else {
+        for (int kb = 0; kb < p.nkb; ++kb)
+          for (int q = 0; q < S; ++q)
+            for (int s = 0; s <= q; ++s)
+              for (int c = 0; c < chunks; ++c) load(kb, c, s, q - s);
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one lane) =====
     if (lane == 0) {
       int stage = 0, phase = 0, it = 0;
-      for (int kb = 0; kb < p.nkb; ++kb)
-        for (int q = 0; q < S; ++q, ++it) {
-          const int buf = it % OZ_ACC;
-          mbar_wait(acc_empty + buf, ((it / OZ_ACC) & 1) ^ 1);  // the epilogue has drained this accumulator
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * OZ_BN);
-          uint32_t accumulate = 0;
-          for (int s = 0; s <= q; ++s) {
-            const uint32_t idesc = idesc_i8(s == 0, (q - s) == 0);
-            for (int c = 0; c < chunks; ++c) {
-              mbar_wait(full + stage, phase);
-              tc_fence_after();
-              const uint32_t sa = smem_u32(smem + stage * OZ_STAGE_BYTES);
-              const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + OZ_A_BYTES);
+      // the four K = 32-byte instructions of one 128 x 128 x 128-byte product (+32 bytes = +2 in the address field)
+      auto mma4 = [&](uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, uint32_t& accumulate) {
+        const uint64_t da = smem_desc_sw128(a_addr), db = smem_desc_sw128(b_addr);
 #pragma unroll
-              for (int j = 0; j < OZ_BK / 32; ++j) {  // K = 32 bytes per instruction: +32 bytes = +2 in the address field
-                tc_mma_i8(tmem_d, da + 2 * j, db + 2 * j, idesc, accumulate);
-                accumulate = 1;
+        for (int j = 0; j < OZ_BK / 32; ++j) {
+          tc_mma_i8(tmem_d, da + 2 * j, db + 2 * j, idesc, accumulate);
+          accumulate = 1;
+        }
+      };
+      auto release = [&](int st) {  // stage reusable once the MMAs issued so far have read it ...
+        if (CL == 1) tc_commit(empty + st);
+        else tc_commit_mc(empty + st, mask_all);  // ... in every CTA whose producer writes into it
+      };
+      if (p.pair_levels) {
+        // Levels top-1 and top in ONE pass over the K-block: stage j of a chunk holds (A_j, B_{top-j}); the product with its
+        // own B tile belongs to level top, the product of the PREVIOUS stage's A tile (A_{j-1}) with this B tile to level
+        // top-1 -- every pair of both levels from top+1 stage loads instead of 2 top+1: 16 instead of 28 stage loads per
+        // chunk at S = 7 (groups (0), (1,2), (3,4), (5,6)), 512 instead of 256 tensor-pipe cycles per 32 KB stage.
+        for (int kb = 0; kb < p.nkb; ++kb)
+          for (int q0 = 0; q0 < S;) {
+            const int nl = (q0 == 0 && (S & 1)) ? 1 : 2;
+            const int top = q0 + nl - 1;
+            for (int l = 0; l < nl; ++l) mbar_wait(acc_empty + (it + l) % OZ_ACC, (((it + l) / OZ_ACC) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_hi = tmem_base + (uint32_t)(((it + nl - 1) % OZ_ACC) * OZ_BN);
+            const uint32_t tmem_lo = tmem_base + (uint32_t)((it % OZ_ACC) * OZ_BN);  // level top-1 (nl == 2 only)
+            uint32_t acc_hi = 0, acc_lo = 0;
+            int prev = 0;
+            for (int c = 0; c < chunks; ++c)
+              for (int j = 0; j <= top; ++j) {
+                mbar_wait(full + stage, phase);
+                tc_fence_after();
+                const uint32_t cur_addr = smem_u32(smem + stage * OZ_STAGE_BYTES);
+                mma4(tmem_hi, cur_addr, cur_addr + OZ_A_BYTES, idesc_i8(j == 0, top - j == 0), acc_hi);
+                if (nl == 2 && j >= 1) {
+                  mma4(tmem_lo, smem_u32(smem + prev * OZ_STAGE_BYTES), cur_addr + OZ_A_BYTES,
+                       idesc_i8(j - 1 == 0, top - j == 0), acc_lo);
+                  release(prev);
+                }
+                if (nl == 1 || j == top) release(stage);
+                prev = stage;
+                if (++stage == OZ_STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
-              if (CL == 1) tc_commit(empty + stage);  // stage reusable once these MMAs have read it
-              else tc_commit_mc(empty + stage, mask_all);  // ... in every CTA whose producer writes into it
-              if (++stage == OZ_STAGES) {
-                stage = 0;
-                phase ^= 1;
+            for (int l = 0; l < nl; ++l) tc_commit(acc_full + (it + l) % OZ_ACC);  // the levels of K-block kb are complete
+            it += nl;
+            q0 += nl;
+          }
+      } else {
+        for (int kb = 0; kb < p.nkb; ++kb)
+          for (int q = 0; q < S; ++q, ++it) {
+            const int buf = it % OZ_ACC;
+            mbar_wait(acc_empty + buf, ((it / OZ_ACC) & 1) ^ 1);  // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * OZ_BN);
+            uint32_t accumulate = 0;
+            for (int s = 0; s <= q; ++s) {
+              const uint32_t idesc = idesc_i8(s == 0, (q - s) == 0);
+              for (int c = 0; c < chunks; ++c) {
+                mbar_wait(full + stage, phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * OZ_STAGE_BYTES);
+                mma4(tmem_d, sa, sa + OZ_A_BYTES, idesc, accumulate);
+                release(stage);
+                if (++stage == OZ_STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
             }
+            tc_commit(acc_full + buf);  // level q of K-block kb complete
           }
-          tc_commit(acc_full + buf);  // level q of K-block kb complete
-        }
+      }
     }
   } else {
     // ===== epilogue: 8 warps, thread = 1 row x 64 columns, FP64 accumulation in registers =====
@@ -615,6 +673,7 @@ extern "C" int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha,
   p.alpha = alpha;
   p.beta = beta;
   p.tiles_n = (int)ceil_div64(n, OZ_BN);
+  p.pair_levels = g_lpgp_ozaki_pair_levels;
   // whole patches (padding tiles run the pipeline -- their shares of A / B are needed by their partners -- but store nothing)
   const int64_t tiles = ceil_div64(tiles_m, clm) * clm * ceil_div64(tiles_n0, cln) * cln;
   if (tiles > INT32_MAX) return -1;

@@ -77,6 +77,37 @@ def test_emulated_gemm_matches_fp64(be, m, n, k, kb, S):
         assert (C - ref7).abs().max() <= 1e-12 * (A.abs() @ B.abs().T).max()
 
 
+@pytest.mark.parametrize("S", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("m,n", [(128, 128), (300, 260), (1000, 130)])
+def test_level_orders_of_the_emulated_gemm_are_bit_identical(be, m, n, S):
+    """LPGP_OPT_OZAKI_PAIR_LEVELS: two digit levels per pass over a K-block (operand tiles shared between the levels) or
+    one -- the same exact int32 sums recombined in the same order, so the outputs must agree bit for bit; both against
+    the FP64 product of the reconstructed digits.  (m = 128: no cluster; m > 128: clusters of two CTAs.)"""
+    from linpde_gp_b200._lib import lib
+
+    rng = np.random.default_rng(100 * S + m)
+    k, kb = 3072, 1024
+    A, B = be.to_device(_rand(rng, m, k, 4.0)), be.to_device(_rand(rng, n, k, 4.0))
+    PA, PB = be.OzakiPlanes(m, k, S, kb), be.OzakiPlanes(n, k, S, kb)
+    PA.split(A)
+    PB.split(B)
+    out = []
+    try:
+        for order in (0, 1):
+            assert lib.lpgp_set_option(6, order) == 0
+            C = be.alloc_matrix(m, n)
+            C.fill_(0.25)
+            be.ozaki_gemm_nt(PA, PB, C, k, alpha=1.0, beta=-2.0)
+            torch.cuda.synchronize()
+            out.append(C.clone())
+    finally:
+        assert lib.lpgp_set_option(6, 1) == 0
+    assert torch.equal(out[0], out[1])
+    if S == 7:
+        RA, RB = PA.reconstruct(slice(0, m), slice(0, k)), PB.reconstruct(slice(0, n), slice(0, k))
+        assert (out[1] - (RA @ RB.T - 0.5)).abs().max() <= 1e-12 * (A.abs() @ B.abs().T).max()
+
+
 def test_emulated_gemm_offsets_into_the_planes(be):
     rng = np.random.default_rng(0)
     kb, S = 1024, 6
