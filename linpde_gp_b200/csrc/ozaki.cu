@@ -20,21 +20,24 @@
 // q >= S are dropped (relative truncation 2^(-7 - 8 (S-1)) against the product of the row maxima).  The levels are
 // recombined in FP64 registers: acc += double(D_q) * 2^(ea + eb - 14 - 8 q), every operation but the final sum exact.
 //
-// Kernel (one CTA = one 128 x 128 output tile, 320 threads):
+// Kernel (one CTA = one 128 x 128 output tile, 320 threads; clusters of two CTAs on vertically adjacent tiles):
 //   warp 0    TMA producer: 3-D tensor maps (k byte, row, plane), SWIZZLE_128B boxes of 128 rows x 128 bytes -> 6-stage ring
+//             of (A plane tile, B plane tile) pairs; the B tile is shared by the cluster (each CTA loads half, multicast)
 //   warp 1    allocates TMEM (512 columns = 4 accumulators of 128 x 128 int32), one lane issues tcgen05.mma (M = 128,
-//             N = 128, K = 32 bytes, 4 per stage), tcgen05.commit releases stages / publishes finished accumulators
+//             N = 128, K = 32 bytes, 4 per product), tcgen05.commit releases stages / publishes finished accumulators
 //   warps 2-9 epilogue: tcgen05.ld the finished level (thread = 1 row x 64 columns), scale, accumulate in FP64 registers
 //             (64 per thread), hand the accumulator back; after the last K-block write C.
-// The MMA of level q+1 overlaps the epilogue of level q (4 accumulators in flight).
+// Two levels q, q+1 are accumulated per pass over a K-block (stage j holds the planes (A_j, B_{q+1-j}); A_j B_{q+1-j} goes
+// to level q+1 and the previous stage's A_{j-1} with the same B tile to level q): 16 instead of 28 stage loads per
+// K-chunk at S = 7.  The MMAs of the next level group overlap the epilogue of the last one (4 accumulators).
 //
-// Measured (profiles/ncu_ozaki_r02d.md, profiles/perf_ozaki_r02g.txt): 2.46-2.49 INT8 POP/s on a 16384 x 1024 x 16384
-// launch (tensor pipe active 61 %, L2 -> shared memory 18.9 TB/s = 72 % of the L2 peak, DRAM 6 %); inside the
-// seconds-long variance solve the part sits at the 1 kW power cap (SM clock ~1.57 GHz) and sustains 2.13 POP/s.  A
-// variant that keeps the digit planes of a K-chunk resident in shared memory and reuses them across the plane pairs of
-// a level group (30 instead of 56 tile loads per chunk, one 16 KB slot per plane) was built and measured in round 2:
-// bit-identical results, but 1.46 POP/s -- with one slot per plane the refill latency of a slot (~2,200 cycles from L2
-// under load) is exposed once per chunk; it was removed again (git history: "plane-reuse kernel v2").
+// Measured (profiles/ncu_ozaki_r02d.md, ncu_ozaki_r02u.md, perf_ozaki_*_r02*.txt; DESIGN.md section 3 "Data path"): one
+// 32768 x 1024 x 32768 launch 24.95 ms (no clusters, one level per pass: tensor pipe 61 %, L2 72 %) -> 24.7 ms (clusters:
+// L2 reads -31 %) -> 22.3 ms = 2.76 INT8 POP/s (two levels per pass); inside the seconds-long variance solve the part
+// sits at the 1 kW power cap and sustains 2.07 -> 2.33 -> 2.53 POP/s (SM clock 1.55 -> 1.63 -> 1.71 GHz).  A variant that
+// keeps the digit planes of a K-chunk resident in shared memory (one 16 KB slot per plane) was built and measured in
+// round 2: bit-identical results, but 1.46 POP/s -- the refill latency of a slot (~2,200 cycles from L2 under load) is
+// exposed once per chunk; it was removed again (git history: "plane-reuse kernel v2").
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
