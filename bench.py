@@ -51,9 +51,9 @@ GEMM_TRAFFIC = {
     "launch": "gemm_nt_kernel 8192x8192x2048 beta=1: 2.26 GB read + 0.53 GB written (algorithmic 1.34 GB)",
 }
 OZAKI_TRAFFIC = {
-    "bytes": 3.118e9,
-    "source": "profiles/ncu_ozaki_r02u.md (ncu --set full, one launch; not measured in this run)",
-    "launch": "ozaki_gemm_kernel<2, 1> 16384x1024x16384, 7 digit planes, beta=1: 2.98 GB read + 0.13 GB written "
+    "bytes": 3.122e9,
+    "source": "profiles/ncu_ozaki_r02w.md (ncu --set full, one launch; not measured in this run)",
+    "launch": "ozaki_gemm2_kernel 16384x1024x16384, 7 digit planes, beta=1: 2.99 GB read + 0.13 GB written "
               "(algorithmic 2.27 GB: 7 x (16384 + 1024) x 16384 plane bytes + C read and written)",
 }
 
@@ -456,7 +456,7 @@ def run_b200(args):
                 "bound": "tensor", "achieved": ach, "peak": peak_val, "unit": "TFLOP/s", "frac": ach / peak_val,
                 "traffic": OZAKI_TRAFFIC["bytes"], "traffic_source": OZAKI_TRAFFIC["source"],
                 "traffic_launch": OZAKI_TRAFFIC["launch"],
-                "kernel": "ozaki_gemm_kernel (tcgen05.mma.kind::i8, TMEM accumulators, TMA operands): the O(M N^2) part of "
+                "kernel": "ozaki_gemm2_kernel (tcgen05.mma.cta_group::2.kind::i8 over CTA pairs, TMEM accumulators, TMA operands): the O(M N^2) part of "
                           "the posterior-variance solve; `achieved` / `peak` count INT8 multiply-adds x 2 (TOP/s)",
                 "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (of measured; INT8 tcgen05 rate = 2 x bf16; "
                                 "sustained because the kernel runs inside a seconds-long power-capped phase)") if sustained

@@ -111,8 +111,13 @@ long long lpgp_launch_count(int reset); /* kernels launched by the library so fa
 /* LPGP_OPT_OZAKI_PAIR_LEVELS: 1 (default): the emulated GEMM accumulates two digit levels q, q+1 per pass over a K-block --
  * pipeline stage j holds the planes (A_j, B_{q+1-j}); A_j B_{q+1-j} goes to level q+1 and A_{j-1} B_{q+1-j} (the previous
  * stage's A tile) to level q, so 16 instead of 28 operand-stage loads per K-chunk at 7 planes; 0: one level per pass.
- * Both orders add the same exact int32 sums: results are bit-identical.                                              */
+ * Both orders add the same exact int32 sums: results are bit-identical.  (The CTA-pair kernel below always pairs levels.) */
 #define LPGP_OPT_OZAKI_PAIR_LEVELS 6
+/* LPGP_OPT_OZAKI_CTA_PAIR: 1 (default): the emulated GEMM runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256: each CTA
+ * of a cluster keeps its 128 rows of A and half of the B tile in shared memory, the leader issues the instructions for
+ * both tensor cores); 0: one tensor-core instruction stream per CTA (LPGP_OPT_OZAKI_CLUSTER then picks the multicast
+ * shape).  Bit-identical results either way.                                                                        */
+#define LPGP_OPT_OZAKI_CTA_PAIR 7
 int lpgp_set_option(int key, int value);
 /* FP64 tensor-pipe (DMMA) issue-rate probe: launches blocks x 8 warps x iters x 8 independent DMMA.8x8x4 and
  * reports the flop count; timed by the caller it yields the roofline denominator of the DMMA kernels on the

@@ -533,6 +533,8 @@ VARIANCE_SOLVER = {"ozaki_slices": int(__import__("os").environ.get("LPGP_OZAKI_
 
 if "LPGP_OZAKI_CLUSTER" in __import__("os").environ:  # A/B switch of the emulated GEMM's cluster size (1 or 2, default 2)
     check(lib.lpgp_set_option(5, int(__import__("os").environ["LPGP_OZAKI_CLUSTER"])), "lpgp_set_option(LPGP_OPT_OZAKI_CLUSTER)")
+if "LPGP_OZAKI_CTA_PAIR" in __import__("os").environ:  # A/B switch: CTA-pair kernel (tcgen05 cta_group::2) on (1, default) or off (0)
+    check(lib.lpgp_set_option(7, int(__import__("os").environ["LPGP_OZAKI_CTA_PAIR"])), "lpgp_set_option(LPGP_OPT_OZAKI_CTA_PAIR)")
 if "LPGP_OZAKI_PAIR_LEVELS" in __import__("os").environ:  # A/B switch: two digit levels per pass (1, default) or one (0)
     check(lib.lpgp_set_option(6, int(__import__("os").environ["LPGP_OZAKI_PAIR_LEVELS"])), "lpgp_set_option(LPGP_OPT_OZAKI_PAIR_LEVELS)")
 

@@ -19,6 +19,7 @@ int g_lpgp_trsm_refine = 1;
 int g_lpgp_time_ozaki = 0;
 int g_lpgp_ozaki_cluster = 2;
 int g_lpgp_ozaki_pair_levels = 1;
+int g_lpgp_ozaki_cta_pair = 1;
 
 extern "C" int lpgp_set_option(int key, int value) {
   if (key == LPGP_OPT_DIRECT_EXP) {
@@ -37,6 +38,10 @@ extern "C" int lpgp_set_option(int key, int value) {
   if (key == LPGP_OPT_OZAKI_CLUSTER) {
     if (value != 1 && value != 2 && value != 4) return -2;
     g_lpgp_ozaki_cluster = value;
+    return 0;
+  }
+  if (key == LPGP_OPT_OZAKI_CTA_PAIR) {
+    g_lpgp_ozaki_cta_pair = value != 0;
     return 0;
   }
   if (key == LPGP_OPT_OZAKI_PAIR_LEVELS) {

@@ -25,6 +25,8 @@ extern int g_lpgp_time_ozaki;
 extern int g_lpgp_ozaki_cluster;
 // emulated GEMM: != 0 = two digit levels per pass over a K-block (operand tiles shared between them), 0 = one level per pass
 extern int g_lpgp_ozaki_pair_levels;
+// emulated GEMM: != 0 = CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256)
+extern int g_lpgp_ozaki_cta_pair;
 #define LPGP_MAX_DEVICES 32
 
 #define LPGP_CHECK_LAUNCH()                            \

@@ -413,6 +413,239 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   }
 }
 
+// ---- CTA-pair variant (the default, LPGP_OPT_OZAKI_CTA_PAIR): tcgen05.mma.cta_group::2, M = 256 -------------------------
+// The two CTAs of a cluster (one TPC) compute a 256 x 128 patch with ONE tensor-core instruction stream issued by the
+// leader (rank 0): each CTA keeps its own 128 rows of A and HALF of the B tile (64 of its 128 rows) in shared memory and
+// its own 128 x 128 accumulators in TMEM -- 24 KB instead of 32 KB per stage written into shared memory and 6 KB instead
+// of 8 KB read from it per instruction (the 2 x 1 cluster above saves the L2 reads only).  Barriers: `full` lives in the
+// leader (both producers' TMA loads complete_tx there, .cta_group::2), the leader's tcgen05.commit multicasts to `empty`
+// and `acc_full` of both CTAs, the epilogue warps of both CTAs arrive on the leader's `acc_empty`.  Same level order
+// (two levels per pass) and the same epilogue as ozaki_gemm_kernel: bit-identical results.
+constexpr int OZ2_STAGES = 8;
+constexpr int OZ2_B_BYTES = OZ_B_BYTES / 2;
+constexpr int OZ2_STAGE_BYTES = OZ_A_BYTES + OZ2_B_BYTES;  // 24 KB, a multiple of the 1 KB swizzle atom
+constexpr int OZ2_BAR_BYTES = (2 * OZ2_STAGES + 2 * OZ_ACC) * 8 + 16;
+constexpr int OZ2_SMEM_BYTES = 1024 + OZ2_STAGES * OZ2_STAGE_BYTES + OZ2_BAR_BYTES + OZ_BN * 8;
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into MY shared memory, completion bytes counted on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void oz_tma_load_3d_2sm(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster_addr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t idesc_i8_m256(int a_signed, int b_signed) {
+  return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(OZ_BN >> 3) << 17) |
+         ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    ozaki_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ OzParams p) {
+  extern __shared__ unsigned char oz_smem_raw[];
+  unsigned char* smem = oz_smem_raw + ((1024u - (smem_u32(oz_smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = (uint64_t*)(smem + OZ2_STAGES * OZ2_STAGE_BYTES);
+  uint64_t* empty = full + OZ2_STAGES;
+  uint64_t* acc_full = empty + OZ2_STAGES;
+  uint64_t* acc_empty = acc_full + OZ_ACC;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + OZ_ACC);
+  double* s_sb = (double*)(smem + OZ2_STAGES * OZ2_STAGE_BYTES + OZ2_BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+  const int cid = blockIdx.x >> 1;
+  const int tm = (cid / p.tiles_n) * 2 + crank, tn = cid % p.tiles_n;
+  const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
+  const int S = p.nslices;
+  const int chunks = p.kblock / OZ_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < OZ2_STAGES; ++i) {
+      mbar_init(full + i, 1);   // the leader's own arrive.expect_tx (both CTAs' bytes)
+      mbar_init(empty + i, 1);  // the leader's commit
+    }
+    for (int i = 0; i < OZ_ACC; ++i) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, 2 * (OZ_EPI_THREADS / 32));  // the epilogue warps of both CTAs (used in the leader only)
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // the same warp of both CTAs allocates (and later frees) the pair's TMEM columns
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): my 128 rows of A, my 64 rows of the B tile =====
+    if (lane == 0) {
+      const uint32_t full_leader = mapa_u32(smem_u32(full), 0);
+      int stage = 0, phase = 0;
+      auto load = [&](int kb, int c, int sa, int sb) {
+        mbar_wait(empty + stage, phase ^ 1);
+        unsigned char* dst = smem + stage * OZ2_STAGE_BYTES;
+        if (leader) mbar_expect_tx(full + stage, 2 * OZ2_STAGE_BYTES);
+        const int kk = kb * p.kblock + c * OZ_BK;
+        oz_tma_load_3d_2sm(dst, &tmA, p.kA0 + kk, p.rowA0 + m0, sa, full_leader + 8u * stage);
+        oz_tma_load_3d_2sm(dst + OZ_A_BYTES, &tmB, p.kB0 + kk, p.rowB0 + n0 + crank * (OZ_BN / 2), sb, full_leader + 8u * stage);
+        if (++stage == OZ2_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int kb = 0; kb < p.nkb; ++kb)
+        for (int q0 = 0; q0 < S;) {
+          const int nl = (q0 == 0 && (S & 1)) ? 1 : 2;
+          const int top = q0 + nl - 1;
+          for (int c = 0; c < chunks; ++c)
+            for (int j = 0; j <= top; ++j) load(kb, c, j, top - j);
+          q0 += nl;
+        }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one lane of the leader CTA drives the tensor cores of both SMs =====
+    if (lane == 0 && leader) {
+      int stage = 0, phase = 0, it = 0;
+      auto mma4 = [&](uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, uint32_t& accumulate) {
+        const uint64_t da = smem_desc_sw128(a_addr), db = smem_desc_sw128(b_addr);
+#pragma unroll
+        for (int j = 0; j < OZ_BK / 32; ++j) {
+          tc_mma_i8_2sm(tmem_d, da + 2 * j, db + 2 * j, idesc, accumulate);
+          accumulate = 1;
+        }
+      };
+      for (int kb = 0; kb < p.nkb; ++kb)
+        for (int q0 = 0; q0 < S;) {
+          const int nl = (q0 == 0 && (S & 1)) ? 1 : 2;
+          const int top = q0 + nl - 1;
+          for (int l = 0; l < nl; ++l) mbar_wait(acc_empty + (it + l) % OZ_ACC, (((it + l) / OZ_ACC) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_hi = tmem_base + (uint32_t)(((it + nl - 1) % OZ_ACC) * OZ_BN);
+          const uint32_t tmem_lo = tmem_base + (uint32_t)((it % OZ_ACC) * OZ_BN);
+          uint32_t acc_hi = 0, acc_lo = 0;
+          int prev = 0;
+          for (int c = 0; c < chunks; ++c)
+            for (int j = 0; j <= top; ++j) {
+              mbar_wait(full + stage, phase);
+              tc_fence_after();
+              const uint32_t cur_addr = smem_u32(smem + stage * OZ2_STAGE_BYTES);
+              mma4(tmem_hi, cur_addr, cur_addr + OZ_A_BYTES, idesc_i8_m256(j == 0, top - j == 0), acc_hi);
+              if (nl == 2 && j >= 1) {
+                mma4(tmem_lo, smem_u32(smem + prev * OZ2_STAGE_BYTES), cur_addr + OZ_A_BYTES,
+                     idesc_i8_m256(j - 1 == 0, top - j == 0), acc_lo);
+                tc_commit_2sm(empty + prev);
+              }
+              if (nl == 1 || j == top) tc_commit_2sm(empty + stage);
+              prev = stage;
+              if (++stage == OZ2_STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          for (int l = 0; l < nl; ++l) tc_commit_2sm(acc_full + (it + l) % OZ_ACC);
+          it += nl;
+          q0 += nl;
+        }
+    }
+  } else {
+    // ===== epilogue (both CTAs, as in ozaki_gemm_kernel; accumulators are handed back to the leader's barrier) =====
+    const uint32_t acc_empty_leader = mapa_u32(smem_u32(acc_empty), 0);
+    const int et = threadIdx.x - 64;
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = m0 + quad * 32 + lane;
+    double acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+    int it = 0;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
+      if (et < OZ_BN) {
+        const int col = n0 + et;
+        const int eb = col < p.n ? p.eB[(int64_t)(p.kB0 / p.kblock + kb) * p.ldeB + p.rowB0 + col] : 0;
+        s_sb[et] = col < p.n ? (eb >= OZ_BAD_EXP ? __longlong_as_double(0x7ff8000000000000LL) : exp2i(eb)) : 0.0;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
+      const int ea = row < p.m ? p.eA[(int64_t)(p.kA0 / p.kblock + kb) * p.ldeA + p.rowA0 + row] : 0;
+      for (int q = 0; q < S; ++q, ++it) {
+        const int buf = it % OZ_ACC;
+        mbar_wait(acc_full + buf, (it / OZ_ACC) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * OZ_BN + half * 64);
+        const double srow = ea >= OZ_BAD_EXP ? __longlong_as_double(0x7ff8000000000000LL) : exp2i(ea - 14 - 8 * q);
+        const double* sb = s_sb + half * 64;
+        uint32_t v[32];
+        tc_ld32(taddr, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fma(__int2double_rn((int)v[j]), srow * sb[j], acc[j]);
+        tc_ld32(taddr + 32, v);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * buf);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[32 + j] = fma(__int2double_rn((int)v[j]), srow * sb[32 + j], acc[32 + j]);
+      }
+    }
+    if (row < p.m) {
+      double* crow = p.C + (int64_t)row * p.ldc + n0 + half * 64;
+      const int ncols = p.n - (n0 + half * 64);
+      const bool vec = (p.ldc % 2 == 0) && ((uintptr_t)p.C % 16 == 0);
+#pragma unroll
+      for (int j = 0; j < 64; j += 2) {
+        if (j + 1 < ncols && vec) {
+          double2 c = p.beta == 0.0 ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(crow + j);
+          c.x = fma(p.alpha, acc[j], p.beta * c.x);
+          c.y = fma(p.alpha, acc[j + 1], p.beta * c.y);
+          *reinterpret_cast<double2*>(crow + j) = c;
+        } else {
+          if (j < ncols) crow[j] = fma(p.alpha, acc[j], p.beta == 0.0 ? 0.0 : p.beta * crow[j]);
+          if (j + 1 < ncols) crow[j + 1] = fma(p.alpha, acc[j + 1], p.beta == 0.0 ? 0.0 : p.beta * crow[j + 1]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ---- splitting: FP64 rows -> S digit planes + one exponent per (row, K-block) -----------------------------------
 // One warp per (row, K-block): pass 1 = row maximum over the block (warp reduction), pass 2 = digits.  Lane l handles
 // the 4 consecutive columns 4 (l + 32 i) .. +3 (32 bytes read, one 4-byte store per plane -> 128 contiguous bytes per warp).
@@ -489,6 +722,7 @@ int oz_ensure() {
   LPGP_CHECK((cudaFuncSetAttribute(ozaki_gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)));
   LPGP_CHECK((cudaFuncSetAttribute(ozaki_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)));
   LPGP_CHECK((cudaFuncSetAttribute(ozaki_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)));
+  LPGP_CHECK(cudaFuncSetAttribute(ozaki_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM_BYTES));
   if (tracked) g_oz_attr[dev].store(1, std::memory_order_release);
   return 0;
 }
@@ -650,8 +884,9 @@ extern "C" int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha,
   if (rc) return rc;
   // cluster shape: 2 x 2 / 2 x 1 patches of tiles when the tile grid has the rows / columns for it
   const int64_t tiles_m = ceil_div64(m, OZ_BM), tiles_n0 = ceil_div64(n, OZ_BN);
-  const int clm = (g_lpgp_ozaki_cluster >= 2 && tiles_m >= 2) ? 2 : 1;
-  const int cln = (g_lpgp_ozaki_cluster >= 4 && clm == 2 && tiles_n0 >= 2) ? 2 : 1;
+  const bool cta_pair = g_lpgp_ozaki_cta_pair && tiles_m >= 2;  // ozaki_gemm2_kernel (2 x 1 patches, tcgen05 cta_group::2)
+  const int clm = (cta_pair || (g_lpgp_ozaki_cluster >= 2 && tiles_m >= 2)) ? 2 : 1;
+  const int cln = (!cta_pair && g_lpgp_ozaki_cluster >= 4 && clm == 2 && tiles_n0 >= 2) ? 2 : 1;
   CUtensorMap tmA, tmB;
   rc = oz_make_map(&tmA, PA->planes, PA->cols, PA->rows, PA->pitch, PA->plane_stride, PA->nslices, OZ_BM / cln);
   if (rc) return rc;
@@ -702,7 +937,7 @@ extern "C" int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha,
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)tiles);
     cfg.blockDim = dim3(OZ_THREADS);
-    cfg.dynamicSmemBytes = OZ_SMEM_BYTES;
+    cfg.dynamicSmemBytes = cta_pair ? OZ2_SMEM_BYTES : OZ_SMEM_BYTES;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -711,7 +946,9 @@ extern "C" int lpgp_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cln == 1)
+    if (cta_pair)
+      LPGP_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm2_kernel, tmA, tmB, p));
+    else if (cln == 1)
       LPGP_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<2, 1>, tmA, tmB, p));
     else
       LPGP_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<2, 2>, tmA, tmB, p));

@@ -93,6 +93,7 @@ def test_level_orders_of_the_emulated_gemm_are_bit_identical(be, m, n, S):
     PB.split(B)
     out = []
     try:
+        assert lib.lpgp_set_option(7, 0) == 0  # the one-stream-per-CTA kernel (the CTA-pair kernel always pairs levels)
         for order in (0, 1):
             assert lib.lpgp_set_option(6, order) == 0
             C = be.alloc_matrix(m, n)
@@ -102,10 +103,45 @@ def test_level_orders_of_the_emulated_gemm_are_bit_identical(be, m, n, S):
             out.append(C.clone())
     finally:
         assert lib.lpgp_set_option(6, 1) == 0
+        assert lib.lpgp_set_option(7, 1) == 0
     assert torch.equal(out[0], out[1])
     if S == 7:
         RA, RB = PA.reconstruct(slice(0, m), slice(0, k)), PB.reconstruct(slice(0, n), slice(0, k))
         assert (out[1] - (RA @ RB.T - 0.5)).abs().max() <= 1e-12 * (A.abs() @ B.abs().T).max()
+
+
+@pytest.mark.parametrize("S", [1, 2, 7])
+@pytest.mark.parametrize("m,n", [(256, 128), (300, 260), (1000, 130)])
+def test_cta_pair_kernel_is_bit_identical(be, m, n, S):
+    """LPGP_OPT_OZAKI_CTA_PAIR: the tcgen05 cta_group::2 variant (M = 256 over the two CTAs of a cluster) against the
+    one-stream-per-CTA kernel: same exact sums, same recombination order -> bit-identical."""
+    from linpde_gp_b200._lib import lib
+
+    rng = np.random.default_rng(1000 * S + m)
+    k, kb = 3072, 1024
+    A, B = be.to_device(_rand(rng, m, k, 4.0)), be.to_device(_rand(rng, n, k, 4.0))
+    PA, PB = be.OzakiPlanes(m, k, S, kb), be.OzakiPlanes(n, k, S, kb)
+    PA.split(A)
+    PB.split(B)
+    out = []
+    try:
+        for pair in (0, 1):
+            assert lib.lpgp_set_option(7, pair) == 0
+            C = be.alloc_matrix(m, n)
+            C.fill_(0.25)
+            be.ozaki_gemm_nt(PA, PB, C, k, alpha=1.0, beta=-2.0)
+            torch.cuda.synchronize()
+            out.append(C.clone())
+    finally:
+        assert lib.lpgp_set_option(7, 1) == 0
+    if not torch.equal(out[0], out[1]):  # where: (128-row block, 64-column block) -> share of differing entries
+        bad = (out[0] != out[1]).double()
+        rb, cb = -(-m // 128), -(-n // 64)
+        pad = torch.zeros((rb * 128, cb * 64), dtype=torch.float64, device=bad.device)
+        pad[:m, :n] = bad
+        share = pad.reshape(rb, 128, cb, 64).mean(dim=(1, 3)).cpu().numpy()
+        raise AssertionError(f"CTA-pair kernel differs: max |d| = {(out[0] - out[1]).abs().max().item():.3e}, "
+                             f"share of differing entries per (row block, column block):\n{np.round(share, 3)}")
 
 
 def test_emulated_gemm_offsets_into_the_planes(be):

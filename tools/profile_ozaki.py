@@ -22,6 +22,8 @@ cl = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 assert lib.lpgp_set_option(5, cl) == 0  # LPGP_OPT_OZAKI_CLUSTER
 pl = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 assert lib.lpgp_set_option(6, pl) == 0  # LPGP_OPT_OZAKI_PAIR_LEVELS
+cp = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+assert lib.lpgp_set_option(7, cp) == 0  # LPGP_OPT_OZAKI_CTA_PAIR
 for _ in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -30,5 +32,5 @@ for _ in range(3):
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1)
     pairs = S * (S + 1) // 2
-    print(f"ozaki gemm (cluster {cl}, levels per pass {1 + pl}) {m}x{n}x{k} S={S}: {t:.2f} ms  {2.0 * m * n * k / t * 1e-9:.1f} TFLOP/s-equivalent  "
+    print(f"ozaki gemm (cluster {cl}, levels per pass {1 + pl}, cta pair {cp}) {m}x{n}x{k} S={S}: {t:.2f} ms  {2.0 * m * n * k / t * 1e-9:.1f} TFLOP/s-equivalent  "
           f"{2.0 * m * n * k * pairs / t * 1e-12:.2f} INT8 POP/s")
