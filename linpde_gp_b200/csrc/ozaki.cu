@@ -20,7 +20,9 @@
 // q >= S are dropped (relative truncation 2^(-7 - 8 (S-1)) against the product of the row maxima).  The levels are
 // recombined in FP64 registers: acc += double(D_q) * 2^(ea + eb - 14 - 8 q), every operation but the final sum exact.
 //
-// Kernel (one CTA = one 128 x 128 output tile, 320 threads; clusters of two CTAs on vertically adjacent tiles):
+// Two kernels, bit-identical results: ozaki_gemm2_kernel (CTA pairs on tcgen05.mma.cta_group::2, the default, further
+// down) and ozaki_gemm_kernel -- one CTA = one 128 x 128 output tile, 320 threads; clusters of two CTAs on vertically
+// adjacent tiles:
 //   warp 0    TMA producer: 3-D tensor maps (k byte, row, plane), SWIZZLE_128B boxes of 128 rows x 128 bytes -> 6-stage ring
 //             of (A plane tile, B plane tile) pairs; the B tile is shared by the cluster (each CTA loads half, multicast)
 //   warp 1    allocates TMEM (512 columns = 4 accumulators of 128 x 128 int32), one lane issues tcgen05.mma (M = 128,
@@ -33,8 +35,9 @@
 //
 // Measured (profiles/ncu_ozaki_r02d.md, ncu_ozaki_r02u.md, perf_ozaki_*_r02*.txt; DESIGN.md section 3 "Data path"): one
 // 32768 x 1024 x 32768 launch 24.95 ms (no clusters, one level per pass: tensor pipe 61 %, L2 72 %) -> 24.7 ms (clusters:
-// L2 reads -31 %) -> 22.3 ms = 2.76 INT8 POP/s (two levels per pass); inside the seconds-long variance solve the part
-// sits at the 1 kW power cap and sustains 2.07 -> 2.33 -> 2.53 POP/s (SM clock 1.55 -> 1.63 -> 1.71 GHz).  A variant that
+// L2 reads -31 %) -> 22.3 ms = 2.76 INT8 POP/s (two levels per pass) -> 21.5 ms (CTA pairs); inside the seconds-long
+// variance solve the part sits at the 1 kW power cap and sustains 2.07 -> 2.33 -> 2.53 -> 2.59 POP/s (SM clock 1.55 ->
+// 1.63 -> 1.71 -> 1.74 GHz; profiles/ncu_ozaki_r02w.md).  A variant that
 // keeps the digit planes of a K-chunk resident in shared memory (one 16 KB slot per plane) was built and measured in
 // round 2: bit-identical results, but 1.46 POP/s -- the refill latency of a slot (~2,200 cycles from L2 under load) is
 // exposed once per chunk; it was removed again (git history: "plane-reuse kernel v2").
