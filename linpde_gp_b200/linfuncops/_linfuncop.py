@@ -94,12 +94,13 @@ class LinearFunctionOperator:
         from .. import linfunctls
 
         return linfunctls.CompositeLinearFunctional(
-            linop=self,
+            linop=None,
             linfunctl=linfunctls._EvaluationFunctional(  # pylint: disable=protected-access
                 input_domain_shape=self.output_domain_shape,
                 input_codomain_shape=self.output_codomain_shape,
                 X=X,
             ),
+            linfuncop=self,
         )
 
     def __rmul__(self, other):

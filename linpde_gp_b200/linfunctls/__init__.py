@@ -2,8 +2,9 @@
 Lebesgue integrals, and their arithmetic.
 
 ``_EvaluationFunctional`` (src/linpde_gp/linfunctls/_evaluation.py:10-60) evaluates a function at the points ``X``
-(output layout: codomain_shape + batch_shape); ``CompositeLinearFunctional`` (``_arithmetic.py:92-140``) is
-``linfunctl @ linop``, which is what ``LinearFunctionOperator.to_linfunctl(X)`` returns; ``LebesgueIntegral``
+(output layout: codomain_shape + batch_shape); ``CompositeLinearFunctional`` (``_arithmetic.py:92-174``) is
+``linop @ linfunctl @ linfuncop`` (matrix, functional, function operator; ``LinearFunctionOperator.to_linfunctl(X)``
+returns one without a matrix); ``LebesgueIntegral``
 (``_integrals.py:13-62``) integrates over an interval; ``ScaledLinearFunctional`` / ``SumLinearFunctional``
 (``_arithmetic.py:12-90``) combine them, e.g. the stationarity condition of
 experiments/0000_cpu_stationary_1d.ipynb cell 65.
@@ -105,7 +106,15 @@ class LinearFunctional:
         from ..linfuncops import LinearFunctionOperator
 
         if isinstance(other, LinearFunctionOperator):
-            return CompositeLinearFunctional(linop=other, linfunctl=self)
+            return CompositeLinearFunctional(linop=None, linfunctl=self, linfuncop=other)
+        return NotImplemented
+
+    def __rmatmul__(self, other):
+        """``A @ linfunctl`` for a matrix ``A`` acting on the (1-D) output (``_linfunctl.py:117-129``)."""
+        from .. import linops  # pylint: disable=import-outside-toplevel
+
+        if isinstance(other, (np.ndarray, linops.LinearOperator)):
+            return CompositeLinearFunctional(linop=other, linfunctl=self, linfuncop=None)
         return NotImplemented
 
 
@@ -176,43 +185,105 @@ class DiracFunctional(LinearFunctional):
 
 
 class CompositeLinearFunctional(LinearFunctional):
-    """``linfunctl @ linop``: apply the function operator first (``_arithmetic.py:92-174``; the reference's keyword
-    for the operator is ``linfuncop``, accepted as an alias)."""
+    """``linop @ linfunctl @ linfuncop`` (``_arithmetic.py:92-174``): the function operator ``linfuncop`` acts first, then
+    the functional, then the finite-dimensional matrix ``linop`` on the functional's (1-D) output -- the reference's
+    keywords and meaning.  ``linfunctl @ L`` and ``A @ linfunctl`` build these (``_linfunctl.py:103-129``).
+
+    Without a matrix the object flattens into the atoms of ``linfunctl`` with ``linfuncop`` composed in (the observation
+    functionals of the conditioning path, ``LinearFunctionOperator.to_linfunctl``).  With a matrix it can be applied to
+    functions, covariance functions (-> ``crosscov.LinOpProcessVectorCrossCovariance``), cross-covariances
+    (-> ``Covariance``) and Gaussian processes (-> ``Normal``); conditioning a process on such a functional is not lowered
+    to the device path (``NotImplementedError``; the reference's own use of it, the mass-matrix normaliser of L2
+    projections, is built into the projection atoms)."""
 
     def __init__(self, *, linop=None, linfunctl, linfuncop=None):
-        if linfuncop is not None:
-            if linop is not None:
-                raise NotImplementedError("matrix @ functional compositions are not supported")
-            linop = linfuncop
-        if tuple(linop.output_shapes[0]) != tuple(linfunctl.input_domain_shape) or tuple(
-                linop.output_shapes[1]) != tuple(linfunctl.input_codomain_shape):
+        from ..linfuncops import LinearFunctionOperator
+
+        if isinstance(linop, LinearFunctionOperator):  # round-1 spelling of this class: the operator passed as `linop`
+            if linfuncop is not None:
+                raise TypeError("`linop` is the matrix applied last; pass the function operator as `linfuncop`")
+            linop, linfuncop = None, linop
+        if linfuncop is not None and (
+                tuple(linfuncop.output_shapes[0]) != tuple(linfunctl.input_domain_shape)
+                or tuple(linfuncop.output_shapes[1]) != tuple(linfunctl.input_codomain_shape)):
             raise ValueError("shape mismatch between operator output and functional input")
-        super().__init__(linop.input_shapes, linfunctl.output_shape)
-        self._linop = linop
+        if linop is not None:
+            from .. import linops  # pylint: disable=import-outside-toplevel
+
+            linop = linop.todense() if isinstance(linop, linops.LinearOperator) else np.asarray(linop, dtype=np.double)
+            if linop.ndim != 2 or len(linfunctl.output_shape) != 1 or linop.shape[1:] != tuple(linfunctl.output_shape):
+                raise ValueError(f"a matrix of shape {linop.shape} cannot act on the output (shape "
+                                 f"{tuple(linfunctl.output_shape)}) of the functional")
+        super().__init__(linfunctl.input_shapes if linfuncop is None else linfuncop.input_shapes,
+                         linfunctl.output_shape if linop is None else linop.shape[0:1])
+        self._matrix = linop
+        self._linfuncop = linfuncop
         self._linfunctl = linfunctl
 
     @property
     def linop(self):
-        return self._linop
+        """The matrix applied last (an array; ``None`` if absent)."""
+        return self._matrix
 
     @property
     def linfuncop(self):
-        return self._linop
+        return self._linfuncop
 
     @property
     def linfunctl(self):
         return self._linfunctl
 
+    def _without_matrix(self):
+        if self._linfuncop is None:
+            return self._linfunctl
+        return CompositeLinearFunctional(linop=None, linfunctl=self._linfunctl, linfuncop=self._linfuncop)
+
     def _atoms(self):
-        # (inner.op @ linop): the function operator of this composite acts first
-        return [(c, kind, self._linop if op is None else op @ self._linop, payload)
+        if self._matrix is not None:
+            raise NotImplementedError("observations of the form matrix @ functional are not lowered to the device path; "
+                                      "condition on the functional itself and transform the data instead")
+        if self._linfuncop is None:
+            return self._linfunctl._atoms()  # pylint: disable=protected-access
+        # (inner.op @ linfuncop): the function operator of this composite acts first
+        return [(c, kind, self._linfuncop if op is None else op @ self._linfuncop, payload)
                 for c, kind, op, payload in self._linfunctl._atoms()]  # pylint: disable=protected-access
+
+    def __call__(self, f, /, **kwargs):
+        if self._matrix is None:
+            return super().__call__(f, **kwargs)
+        from .. import randvars  # pylint: disable=import-outside-toplevel
+        from ..randprocs import crosscov  # pylint: disable=import-outside-toplevel
+
+        A = self._matrix
+        res = self._without_matrix()(f, **kwargs)
+        if isinstance(res, crosscov.ProcessVectorCrossCovariance):  # covfuncs/linfunctls/_registry.py:42-61
+            return crosscov.LinOpProcessVectorCrossCovariance(A, res)
+        if isinstance(res, randvars.Covariance):  # f was a cross-covariance: A acts on this functional's axis
+            M = np.asarray(res.matrix)
+            if isinstance(f, crosscov.ProcessVectorCrossCovariance) and f.reverse:  # (randvar, functional) layout
+                return randvars.ArrayCovariance((M @ A.T).reshape(res.shape0 + self.output_shape), res.shape0,
+                                                self.output_shape)
+            return randvars.ArrayCovariance((A @ M).reshape(self.output_shape + res.shape1), self.output_shape, res.shape1)
+        if isinstance(res, randvars.Normal):
+            return randvars.Normal(A @ res.mean.reshape(-1), A @ res.dense_cov @ A.T)
+        return np.tensordot(np.asarray(res), A, axes=([-1], [1]))  # functions: A along the last axis (_arithmetic.py:150-151)
 
     def __matmul__(self, other):
         from ..linfuncops import LinearFunctionOperator
 
         if isinstance(other, LinearFunctionOperator):
-            return CompositeLinearFunctional(linop=self._linop @ other, linfunctl=self._linfunctl)
+            return CompositeLinearFunctional(
+                linop=self._matrix, linfunctl=self._linfunctl,
+                linfuncop=other if self._linfuncop is None else self._linfuncop @ other)
+        return NotImplemented
+
+    def __rmatmul__(self, other):
+        from .. import linops  # pylint: disable=import-outside-toplevel
+
+        if isinstance(other, (np.ndarray, linops.LinearOperator)):
+            other = other.todense() if isinstance(other, linops.LinearOperator) else np.asarray(other, dtype=np.double)
+            return CompositeLinearFunctional(linop=other if self._matrix is None else other @ self._matrix,
+                                             linfunctl=self._linfunctl, linfuncop=self._linfuncop)
         return NotImplemented
 
 

@@ -163,6 +163,8 @@ class LinearOperator:
         return _Transposed(self)
 
     def __matmul__(self, other):
+        if hasattr(other, "input_shapes") and hasattr(other, "_atoms"):  # LinearFunctional: its __rmatmul__ builds A @ l
+            return NotImplemented
         if isinstance(other, LinearOperator):
             other = other.todense()
         x = np.asarray(other, dtype=np.double)

@@ -215,6 +215,40 @@ class ScaledProcessVectorCrossCovariance(ProcessVectorCrossCovariance):
         return NotImplemented
 
 
+class LinOpProcessVectorCrossCovariance(ProcessVectorCrossCovariance):
+    """``linop @ pv_crosscov``: the cross-covariance with the random vector ``A L[f]`` for a matrix ``A`` acting on the
+    (1-D) random vector of ``pv_crosscov`` (crosscov/_arithmetic.py:91-130) -- what ``(A @ linfunctl)(k, argnum)`` returns
+    (covfuncs/linfunctls/_registry.py:42-61).  Evaluation: the inner (M x n) matrix on the device, then one DMMA GEMM
+    with ``A`` (m x n)."""
+
+    def __init__(self, linop, pv_crosscov: ProcessVectorCrossCovariance):
+        A = linop.todense() if isinstance(linop, linops.LinearOperator) else np.asarray(linop, dtype=np.double)
+        if pv_crosscov.randvar_ndim != 1 or A.ndim != 2 or A.shape[1:] != pv_crosscov.randvar_shape:
+            raise ValueError(f"a matrix of shape {A.shape} cannot act on a random vector of shape {pv_crosscov.randvar_shape}")
+        super().__init__(pv_crosscov.randproc_input_shape, pv_crosscov.randproc_output_shape, A.shape[0:1],
+                         reverse=pv_crosscov.reverse)
+        self._linop = A
+        self._pv_crosscov = pv_crosscov
+        self._A_dev = None
+
+    linop = property(lambda self: self._linop)
+    pv_crosscov = property(lambda self: self._pv_crosscov)
+
+    def _device_matrix(self, Xt, out=None, accumulate: bool = False, alpha: float = 1.0):
+        if self._A_dev is None:
+            self._A_dev = backend.alloc_matrix(*self._linop.shape)
+            self._A_dev.copy_(backend.to_device(self._linop))
+        inner = self._pv_crosscov._device_matrix(Xt)[:, : self._pv_crosscov.randvar_size]  # pylint: disable=protected-access
+        if out is None:
+            out = backend.alloc_matrix(Xt.shape[0], self.randvar_size)
+            accumulate = False
+        backend.gemm_nt(inner, self._A_dev, out[:, : self.randvar_size], alpha=alpha, beta=1.0 if accumulate else 0.0)
+        return out
+
+    def _apply_linfuncop(self, L):
+        return LinOpProcessVectorCrossCovariance(self._linop, self._pv_crosscov._apply_linfuncop(L))  # pylint: disable=protected-access
+
+
 class SumProcessVectorCrossCovariance(ProcessVectorCrossCovariance):
     """``pv_1 + ... + pv_n`` (crosscov/_arithmetic.py:63-120); nested sums are flattened."""
 

@@ -2,6 +2,8 @@
 the finite-dimensional marginals returned by ``GaussianProcess.__call__``."""
 from __future__ import annotations
 
+from typing import Optional
+
 import numpy as np
 
 from . import linops
@@ -196,3 +198,48 @@ def asrandvar(b):
     if isinstance(b, (Normal, Constant)):
         return b
     return Constant(np.asarray(b, dtype=np.double))
+
+
+def condition_normal_on_observations(prior: "Normal", observations, noise: "Optional[Normal]", transform=None) -> "Normal":
+    r"""Conditions a Gaussian random vector on linearly transformed observations ``y = A x + eps`` with
+    ``x ~ N(mu, Sigma)``, ``eps ~ N(b, Lambda)`` (src/linpde_gp/randvars/_normal.py:8-71; the finite-dimensional analogue
+    of ``condition_on_observations``; also installed as ``Normal.condition_on_observations`` like the reference does).
+
+    The Gram matrix ``A Sigma A^T + Lambda`` is factored by the device Cholesky and the gain computed by a multi-right-hand
+    side ``potrs``; the matrix products run through the DMMA GEMM (``linops.Matrix @``)."""
+    y = np.asarray(observations, dtype=np.double)
+    mu = prior.mean.reshape(-1)
+    Sigma = np.asarray(prior.dense_cov, dtype=np.double)
+    A = transform
+    if A is not None:
+        A = A.todense() if isinstance(A, linops.LinearOperator) else np.asarray(A, dtype=np.double)
+        if A.ndim == 1:  # one scalar observation (_normal.py:26-29)
+            A = A[None, :]
+            y = y.reshape(1)
+            if noise is not None:
+                noise = Normal(np.reshape(noise.mean, (1,)), np.reshape(noise.dense_cov, (1, 1)))
+        if A.ndim != 2 or A.shape[1] != mu.size:
+            raise ValueError(f"`transform` must have shape (m, {mu.size}), got {A.shape}")
+    y = y.reshape(-1)
+    if A is None:
+        cross, pred_mean, pred_cov = Sigma, mu, Sigma  # Cov(y, x)
+    else:
+        cross = linops.Matrix(A) @ Sigma
+        pred_mean, pred_cov = A @ mu, linops.Matrix(cross) @ A.T
+    if noise is not None:
+        if noise.mean.size != pred_mean.size:
+            raise ValueError("`noise` must have the shape of the observations")
+        pred_mean = pred_mean + noise.mean.reshape(-1)
+        pred_cov = pred_cov + np.asarray(noise.dense_cov, dtype=np.double)
+    if y.size != pred_mean.size:
+        raise ValueError(f"{pred_mean.size} observations expected, got {y.size}")
+    gram = linops.Matrix(0.5 * (pred_cov + pred_cov.T))
+    gram.is_symmetric = True
+    gram.is_positive_definite = True
+    gain_t = gram.solve(cross)  # (m, n): G^{-1} Cov(y, x)
+    mean = mu + gain_t.T @ (y - pred_mean)
+    cov = Sigma - linops.Matrix(np.ascontiguousarray(cross.T)) @ gain_t
+    return Normal(mean.reshape(prior.mean.shape), 0.5 * (cov + cov.T))
+
+
+Normal.condition_on_observations = condition_normal_on_observations

@@ -228,6 +228,51 @@ def test_multi_output_dispatch_follows_the_reference_registry():
         prior.condition_on_observations(np.zeros((3, 4)), X=np.zeros(4))  # vector-valued observation
 
 
+def test_composite_linear_functional_keywords_follow_the_reference():
+    """src/linpde_gp/linfunctls/_arithmetic.py:92-174, _linfunctl.py:103-129: ``linop`` is the MATRIX applied last,
+    ``linfuncop`` the function operator applied first; ``A @ linfunctl`` / ``linfunctl @ L`` build the composite."""
+    from linpde_gp_b200 import functions, linfunctls, linops
+    from linpde_gp_b200.linfuncops import diffops
+
+    X = np.linspace(0.0, 1.0, 5)
+    ev = linfunctls._EvaluationFunctional(input_domain_shape=(), input_codomain_shape=(), X=X)
+    D = diffops.Derivative(1)
+    A = np.arange(15.0).reshape(3, 5)
+    f = functions.Polynomial([1.0, 2.0, 3.0])
+    plain = linfunctls.CompositeLinearFunctional(linop=None, linfunctl=ev, linfuncop=D)  # the reference's spelling
+    assert plain.linop is None and plain.linfuncop is D and plain.linfunctl is ev and plain.output_shape == (5,)
+    assert len(plain._atoms()) == 1 and plain._atoms()[0][2] is D
+    assert type(ev @ D) is linfunctls.CompositeLinearFunctional and (ev @ D).linfuncop is D
+    comp = A @ ev
+    assert type(comp) is linfunctls.CompositeLinearFunctional
+    assert comp.output_shape == (3,) and comp.input_shapes == ((), ()) and comp.linfuncop is None
+    np.testing.assert_allclose(comp.linop, A)
+    np.testing.assert_allclose(comp(f), A @ f(X), rtol=1e-14)
+    comp2 = np.ones((2, 3)) @ (comp @ D)  # (B A) @ ev @ D
+    assert comp2.output_shape == (2,) and comp2.linfuncop is D
+    np.testing.assert_allclose(comp2.linop, np.ones((2, 3)) @ A)
+    np.testing.assert_allclose(comp2(f), np.ones((2, 3)) @ A @ D(f)(X), rtol=1e-14)
+
+    class _HostOp(linops.LinearOperator):  # a LinearOperator is accepted like an array (densified once)
+        def __init__(self):
+            super().__init__(A.shape)
+
+        def todense(self, cache=True):
+            return A
+
+    np.testing.assert_allclose((_HostOp() @ ev).linop, A)
+    with pytest.raises(NotImplementedError):  # conditioning on matrix @ functional is not lowered to the device
+        comp._atoms()
+    with pytest.raises(ValueError):
+        linfunctls.CompositeLinearFunctional(linop=np.ones((3, 4)), linfunctl=ev, linfuncop=None)
+    with pytest.raises(ValueError):  # the matrix needs a 1-D functional output
+        np.ones((2, 1)) @ linfunctls.LebesgueIntegral((0.0, 1.0))
+    legacy = linfunctls.CompositeLinearFunctional(linop=D, linfunctl=ev)  # round-1 spelling still understood
+    assert legacy.linop is None and legacy.linfuncop is D
+    with pytest.raises(TypeError):
+        linfunctls.CompositeLinearFunctional(linop=D, linfunctl=ev, linfuncop=D)
+
+
 def test_linear_functional_arithmetic_and_atoms():
     """src/linpde_gp/linfunctls/_linfunctl.py:74-129, _arithmetic.py:12-174, _integrals.py:13-62 (host-side, symbolic):
     the stationarity functional of experiments/0000_cpu_stationary_1d.ipynb cell 65."""

@@ -298,3 +298,44 @@ def test_kronecker_gram_of_a_gridded_product_kernel_solves_beyond_dense_size():
     # backward error: the factors are fine-grid Matern Gram matrices (condition number ~1e7), so |x| >> |b|
     normK = np.abs(K.A.todense()).sum(1).max() * np.abs(K.B.todense()).sum(1).max()
     assert np.max(np.abs(r)) <= 1e-13 * normK * np.max(np.abs(x)), (np.max(np.abs(r)), normK, np.max(np.abs(x)))
+
+
+@pytest.mark.parametrize("with_transform,with_noise", [(True, True), (True, False), (False, True)])
+def test_condition_normal_on_observations_matches_numpy(with_transform, with_noise):
+    """``randvars.condition_normal_on_observations`` (src/linpde_gp/randvars/_normal.py:8-71) against the same formulas
+    in numpy / scipy (``cho_solve``), 1e-10 of the largest entry; also as ``Normal.condition_on_observations`` and with a
+    single-row transform."""
+    from linpde_gp_b200 import randvars
+
+    rng = np.random.default_rng(5 + 2 * with_transform + with_noise)
+    n, m = 40, 12
+    R = rng.standard_normal((n, n))
+    Sigma, mu = R @ R.T / n + 0.1 * np.eye(n), rng.standard_normal(n)
+    A = rng.standard_normal((m, n)) if with_transform else None
+    k = m if with_transform else n
+    noise = randvars.Normal(rng.standard_normal(k), np.diag(rng.uniform(0.05, 0.2, k))) if with_noise else None
+    y = rng.standard_normal(k)
+
+    def numpy_posterior(A_, y_, noise_):
+        cross = Sigma if A_ is None else A_ @ Sigma
+        pm = mu if A_ is None else A_ @ mu
+        pc = Sigma if A_ is None else cross @ A_.T
+        if noise_ is not None:
+            pm, pc = pm + noise_.mean.reshape(-1), pc + noise_.dense_cov
+        gain = scipy.linalg.cho_solve((scipy.linalg.cholesky(pc, lower=True), True), cross).T
+        return mu + gain @ (y_ - pm), Sigma - cross.T @ gain.T
+
+    prior = randvars.Normal(mu, Sigma)
+    post = randvars.condition_normal_on_observations(prior, y, noise, A)
+    m_ref, C_ref = numpy_posterior(A, y, noise)
+    assert np.max(np.abs(post.mean - m_ref)) <= 1e-10 * np.max(np.abs(m_ref))
+    assert np.max(np.abs(post.dense_cov - C_ref)) <= 1e-10 * np.max(np.abs(Sigma))
+    post2 = prior.condition_on_observations(y, noise, A)
+    assert np.array_equal(post2.mean, post.mean)
+    if with_transform:  # one scalar observation through a single row (the reference's 1-D `transform`)
+        eps = randvars.Normal(np.asarray(0.3), np.asarray(0.01).reshape(1, 1)) if with_noise else None
+        post1 = randvars.condition_normal_on_observations(prior, np.asarray(0.7), eps, A[0])
+        eps1 = randvars.Normal(np.asarray([0.3]), np.asarray([[0.01]])) if with_noise else None
+        m1, C1 = numpy_posterior(A[:1], np.asarray([0.7]), eps1)
+        assert np.max(np.abs(post1.mean - m1)) <= 1e-10 * np.max(np.abs(m1))
+        assert np.max(np.abs(post1.dense_cov - C1)) <= 1e-10 * np.max(np.abs(Sigma))
