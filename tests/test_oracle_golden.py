@@ -218,6 +218,21 @@ def test_oracle_crosscov_matches_reference_seam_goldens():
         assert np.max(np.abs(K @ x - rhs)) <= 1e-6 * np.max(np.abs(rhs))
 
 
+def test_oracle_crosscov_matches_reference_linop_goldens():
+    """tests/golden/seams_linop.npz (real reference: ``(B @ (A @ linfunctl))(k, argnum=1)(x)``, a
+    ``LinOpProcessVectorCrossCovariance``, crosscov/_arithmetic.py:91-130) against the oracle's kernel matrix times
+    ``(B A)^T``."""
+    g = np.load(os.path.join(GOLDEN, "seams_linop.npz"))
+    X, Xt, BA = g["X"], g["Xt"], g["B"] @ g["A"]
+    n = 0
+    for kname, kspec in gcases.SEAM_KERNELS.items():
+        for oname, ospec in gcases.SEAM_OPS.items():
+            K = ocf.matrix(kspec, None, gcases.spec_to_oracle_op(ospec), Xt.reshape(-1, 2), X) @ BA.T
+            assert np.max(np.abs(g[f"pv__{kname}__{oname}"] - K.reshape(5, 4, 2))) <= 1e-13 * np.max(np.abs(K))
+            n += 1
+    assert n == len([k for k in g.files if k.startswith("pv__")])
+
+
 def test_oracle_projections_match_reference_golden():
     """oracle/projections.py (quad / dblquad restatement + the Matern-3/2 closed form) against the real reference's
     outputs frozen in tests/golden/projections.npz; the cheap cases only (the quadrature cases take seconds each)."""
