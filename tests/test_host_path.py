@@ -54,6 +54,13 @@ from tests.test_gpu_linops import (  # noqa: F401
     test_not_positive_definite_block_raises,
     test_spd_block_quantities,
 )
+from tests.test_gpu_projections import (  # noqa: F401
+    test_conditioning_on_projection_then_point_observations_matches_reference,
+    test_covariance_of_two_projections_matches_reference,
+    test_projection_crosscov_matches_reference,
+    test_projection_observation_of_an_expquad_process_interpolates,
+    test_projection_of_functions,
+)
 from tests.test_gpu_seam_goldens import (  # noqa: F401
     test_block_matrix_2x2_matches_the_reference,
     test_crosscov_and_covariance_match_the_reference,
